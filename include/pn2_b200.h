@@ -1,0 +1,212 @@
+/*
+ * pn2_b200.h -- C ABI of libpn2_b200.so, the sm_100a PointNet++ SA/FP engine.
+ *
+ * This is the drop-in boundary.  In the reference the
+ * native boundary is a set of plain C++ launcher functions called from the
+ * TensorFlow OpKernel glue; every pn2_* entry point of the first group below
+ * replaces exactly one of them, keeps its argument order and meaning, and adds
+ *   - a trailing cudaStream_t (the reference launches on the legacy default
+ *     stream and ignores TF's compute stream), passed as void*;
+ *   - an int status: 0 on success, a negative PN2_E* code otherwise.  The
+ *     reference launchers return void and never check CUDA errors.
+ * Conventions kept from the reference: the CALLER owns every buffer (outputs
+ * and scratch), all tensors are dense row-major fp32 / int32 DEVICE pointers,
+ * nothing is allocated or freed inside the library, no host synchronisation.
+ * Difference: the *_grad entry points zero their output themselves (the
+ * reference does it in the TF glue: tf_sampling.cpp:236, tf_grouping.cpp:271,
+ * tf_interpolate.cpp:477).
+ *
+ * The library is thread-safe and re-entrant; the only process-wide state is an
+ * immutable per-device attribute cache.  No torch types cross this boundary.
+ */
+#ifndef PN2_B200_H_
+#define PN2_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void *pn2_stream_t; /* cudaStream_t */
+
+enum {
+    PN2_OK = 0,
+    PN2_EINVAL = -1,       /* bad shape / attribute (reference: OP_REQUIRES InvalidArgument) */
+    PN2_ELAUNCH = -2,      /* cudaPeekAtLastError() after launch != cudaSuccess */
+    PN2_EUNSUPPORTED = -3, /* size outside what the sm_100a kernels are built for */
+    PN2_ENULL = -4         /* required pointer is NULL */
+};
+
+int pn2_abi_version(void);
+const char *pn2_strerror(int code);
+/* last CUDA error string seen by a failing launch on this thread ("" if none) */
+const char *pn2_last_cuda_error(void);
+
+/* ===== group 1: one entry point per reference launcher ======================= */
+
+/* replaces farthestpointsamplingLauncher   tf_ops/tf_sampling.cu:218-221
+ * inp (b,n,3) -> out (b,m) int32.  temp is accepted for signature parity and may be
+ * NULL: the running minimum distances live in registers, not in global memory. */
+int pn2_fps(int b, int n, int m, const float *inp, float *temp, int *out, pn2_stream_t s);
+
+/* replaces gatherpointLauncher             tf_ops/tf_sampling.cu:222-225 */
+int pn2_gather_point(int b, int n, int m, const float *inp, const int *idx, float *out,
+                     pn2_stream_t s);
+
+/* replaces scatteraddpointLauncher         tf_ops/tf_sampling.cu:226-229 (+memset) */
+int pn2_gather_point_grad(int b, int n, int m, const float *out_g, const int *idx, float *inp_g,
+                          pn2_stream_t s);
+
+/* replaces queryBallPointLauncher          tf_ops/tf_grouping.cu:138-144
+ * xyz1 (b,n,3) data, xyz2 (b,m,3) queries -> idx (b,m,nsample), pts_cnt (b,m).
+ * Rows without any hit are written as zeros (the reference leaves them uninitialised). */
+int pn2_query_ball_point(int b, int n, int m, float radius, int nsample, const float *xyz1,
+                         const float *xyz2, int *idx, int *pts_cnt, pn2_stream_t s);
+
+/* replaces groupPointLauncher              tf_ops/tf_grouping.cu:150-154 */
+int pn2_group_point(int b, int n, int c, int m, int nsample, const float *points, const int *idx,
+                    float *out, pn2_stream_t s);
+
+/* replaces groupPointGradLauncher          tf_ops/tf_grouping.cu:155-162 (+memset) */
+int pn2_group_point_grad(int b, int n, int c, int m, int nsample, const float *grad_out,
+                         const int *idx, float *grad_points, pn2_stream_t s);
+
+/* replaces threenn_cpu                     tf_ops/tf_interpolate.cpp:213-243
+ * xyz1 (b,n,3) queries, xyz2 (b,m,3) known -> dist (b,n,3) squared fp64->fp32, idx (b,n,3) */
+int pn2_three_nn(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist, int *idx,
+                 pn2_stream_t s);
+
+/* replaces threeinterpolate_cpu            tf_ops/tf_interpolate.cpp:307-330 */
+int pn2_three_interpolate(int b, int m, int c, int n, const float *points, const int *idx,
+                          const float *weight, float *out, pn2_stream_t s);
+
+/* replaces threeinterpolate_grad_cpu       tf_ops/tf_interpolate.cpp:397-421 (+memset) */
+int pn2_three_interpolate_grad(int b, int n, int c, int m, const float *grad_out, const int *idx,
+                               const float *weight, float *grad_points, pn2_stream_t s);
+
+/* replaces selectionSortLauncher           tf_ops/tf_grouping.cu:145-149 ("next" scope)
+ * dist (b,m,n) -> outi (b,m,n), out (b,m,n); only the first k of each row are meaningful
+ * and, unlike the reference, ONLY the first k entries are written. */
+int pn2_selection_sort(int b, int n, int m, int k, const float *dist, int *outi, float *out,
+                       pn2_stream_t s);
+
+/* ===== group 2: fused layer pieces (no reference launcher; they replace the TF
+ * graph ops util/pointnet_util.py and util/tf_util.py string between the custom
+ * ops).  Strided variants take a leading dimension ld (in floats) so that
+ * concatenations are written in place instead of materialised twice. ========== */
+
+/* sample_and_group body after the ball query (pointnet_util.py:43-54 / :252-260):
+ * out[b,j,k,:] = concat(xyz[b,idx]-new_xyz[b,j], points[b,idx]) (xyz_first=1, SSG order)
+ *             or concat(points[b,idx], xyz[b,idx]-new_xyz[b,j]) (xyz_first=0, MSG order).
+ * points may be NULL (c=0); use_xyz=0 drops the xyz part. */
+int pn2_group_concat(int b, int n, int m, int nsample, int c, const float *xyz,
+                     const float *new_xyz, const float *points, const int *idx, int xyz_first,
+                     int use_xyz, float *out, pn2_stream_t s);
+/* gradient of the above w.r.t. points (b,n,c) (zeroed here).  grad_xyz (b,n,3) and
+ * grad_new_xyz (b,m,3) are optional (NULL = not needed); when given they are zeroed here. */
+int pn2_group_concat_grad(int b, int n, int m, int nsample, int c, const float *grad_out,
+                          const int *idx, int xyz_first, int use_xyz, float *grad_points,
+                          float *grad_xyz, float *grad_new_xyz, pn2_stream_t s);
+
+/* pointnet_fp_module weights (pointnet_util.py:300-303):
+ * w = (1/max(d,1e-10)) / sum_3(1/max(d,1e-10)), IEEE division, rows = b*n */
+int pn2_fp_weights(int rows, const float *dist, float *weight, pn2_stream_t s);
+
+/* three_interpolate writing rows of stride ldo (>= c): out[(b*n+j)*ldo + l] */
+int pn2_three_interpolate_ld(int b, int m, int c, int n, const float *points, const int *idx,
+                             const float *weight, float *out, int ldo, pn2_stream_t s);
+int pn2_three_interpolate_grad_ld(int b, int n, int c, int m, const float *grad_out, int ldg,
+                                  const int *idx, const float *weight, float *grad_points,
+                                  pn2_stream_t s);
+
+/* dst[r*ldd + j] (=|+=) src[r*lds + j], j < cols */
+int pn2_copy_cols(long rows, int cols, const float *src, int lds, float *dst, int ldd,
+                  int accumulate, pn2_stream_t s);
+
+/* ---- shared MLP (tf_util.conv2d / conv1d with 1x1 kernels, tf_util.py:54-204) ----
+ * Y[M,N] = f(A)[M,K] * W[K,N] + bias[N],  f(a)[.,k] = a_scale ? act(a*a_scale[k]+a_shift[k]) : a
+ * (act = ReLU when a_relu).  f is how the previous layer's BatchNorm+ReLU is applied on the
+ * fly.  If stats != NULL, stats[0:N] += column sums of Y, stats[N:2N] += column sums of Y^2
+ * (fp64, caller zeroes).  mode: 0 = fp32 SIMT kernel, 1 = tcgen05 3xTF32 kernel, -1 = auto. */
+int pn2_linear_fwd(long M, int K, int N, const float *A, int lda, const float *a_scale,
+                   const float *a_shift, int a_relu, const float *W, const float *bias, float *Y,
+                   double *stats, int mode, pn2_stream_t s);
+
+/* dX[M,K] = dY[M,N] * W[K,N]^T */
+int pn2_linear_dgrad(long M, int K, int N, const float *dY, const float *W, float *dX, int ldx,
+                     int mode, pn2_stream_t s);
+
+/* dW[K,N] += f(A)[M,K]^T * dY[M,N] ; db[N] += column sums of dY (db may be NULL).
+ * Accumulates (split over M with fp32 atomics): caller zeroes dW/db once per step. */
+int pn2_linear_wgrad(long M, int K, int N, const float *A, int lda, const float *a_scale,
+                     const float *a_shift, int a_relu, const float *dY, float *dW, float *db,
+                     int mode, pn2_stream_t s);
+
+/* BatchNorm (tf_util.py:555-581 -> tf.contrib.layers.batch_norm, eps 1e-3).
+ * From stats (sum, sumsq over M rows): mean, biased var; scale = gamma*rsqrt(var+eps),
+ * shift = beta - mean*scale; saved[0:N] = mean, saved[N:2N] = rstd;
+ * moving -= (moving - batch)*(1-decay), the variance fed to the moving average is
+ * Bessel-corrected when unbiased_moving != 0 (TF fused kernel, rank-4 inputs). */
+int pn2_bn_train_finalize(int N, long M, const double *stats, const float *gamma,
+                          const float *beta, float eps, float decay, int unbiased_moving,
+                          float *moving_mean, float *moving_var, float *scale, float *shift,
+                          float *saved, pn2_stream_t s);
+/* inference: scale/shift from the moving statistics */
+int pn2_bn_eval_affine(int N, const float *gamma, const float *beta, const float *moving_mean,
+                       const float *moving_var, float eps, float *scale, float *shift,
+                       pn2_stream_t s);
+
+/* Z[M,N] = act(Y*scale + shift)  (scale/shift NULL = identity) */
+int pn2_affine_act(long M, int N, const float *Y, const float *scale, const float *shift,
+                   int relu, float *Z, int ldz, pn2_stream_t s);
+
+/* out[G,N] = max_{j<ns} act(Y[g*ns+j,:]*scale+shift); arg[G,N] = first j attaining it
+ * (pointnet_util.py:167-170 tf.reduce_max over nsample, fused with BN+ReLU) */
+int pn2_affine_act_maxpool(long G, int ns, int N, const float *Y, const float *scale,
+                           const float *shift, int relu, float *out, int *arg, pn2_stream_t s);
+
+/* Backward of [BN(train) + act] for one layer, dense upstream gradient dZ[M,N]:
+ * pass 1: red[0:N] += sum dZh, red[N:2N] += sum dZh*xhat  with dZh = dZ*(z>0 if relu)
+ * pass 2: dY = gamma*rstd*(dZh - red0/M - xhat*red1/M); dgamma += red1; dbeta += red0.
+ * bn=0 (no BatchNorm): dY = dZh only, pass 1 is skipped by the caller. */
+int pn2_bn_bwd_reduce(long M, int N, const float *dZ, int ldz, const float *Y,
+                      const float *scale, const float *shift, const float *saved, int relu,
+                      double *red, pn2_stream_t s);
+int pn2_bn_bwd_apply(long M, int N, const float *dZ, int ldz, const float *Y, const float *scale,
+                     const float *shift, const float *saved, const float *gamma, int relu, int bn,
+                     const double *red, float *dY, float *dgamma, float *dbeta, pn2_stream_t s);
+/* same two passes when the upstream gradient is the max-pooled one: dOut[G,N] routed to arg */
+int pn2_bn_bwd_reduce_pool(long G, int ns, int N, const float *dOut, const int *arg,
+                           const float *Y, const float *scale, const float *shift,
+                           const float *saved, int relu, double *red, pn2_stream_t s);
+int pn2_bn_bwd_apply_pool(long G, int ns, int N, const float *dOut, const int *arg,
+                          const float *Y, const float *scale, const float *shift,
+                          const float *saved, const float *gamma, int relu, int bn,
+                          const double *red, float *dY, float *dgamma, float *dbeta,
+                          pn2_stream_t s);
+
+/* tf_util.dropout (tf_util.py:646-665): out = keep(i) ? x/keep_prob : 0 with a counter-based
+ * generator keyed by (seed, element index); the same call with the same seed regenerates the
+ * mask in the backward pass.  pn2_dropout_mask exports it (0/1 bytes) for tests. */
+int pn2_dropout(long n, const float *x, float keep_prob, unsigned long long seed, float *out,
+                pn2_stream_t s);
+int pn2_dropout_mask(long n, float keep_prob, unsigned long long seed, unsigned char *mask,
+                     pn2_stream_t s);
+
+/* model.get_loss (model.py:152-161): weighted sparse softmax cross entropy with
+ * SUM_BY_NONZERO_WEIGHTS.  acc[0] += sum w*ce, acc[1] += #nonzero w (fp64, caller zeroes);
+ * the second call writes loss = acc0/max(acc1,1) and dlogits = gscale*w*(softmax-onehot)/max(acc1,1). */
+int pn2_softmax_ce_reduce(long rows, int C, const float *logits, const int *labels,
+                          const float *weights, double *acc, pn2_stream_t s);
+int pn2_softmax_ce_grad(long rows, int C, const float *logits, const int *labels,
+                        const float *weights, const double *acc, float gscale, float *loss,
+                        float *dlogits, pn2_stream_t s);
+
+/* tf.train.AdamOptimizer update on a flat buffer:
+ * lr_t = lr*sqrt(1-b2^t)/(1-b1^t); m,v moments; p -= lr_t*m/(sqrt(v)+eps); gscale multiplies g */
+int pn2_adam_step(long n, float *p, const float *g, float *m, float *v, float lr, float beta1,
+                  float beta2, float eps, int t, float gscale, pn2_stream_t s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PN2_B200_H_ */

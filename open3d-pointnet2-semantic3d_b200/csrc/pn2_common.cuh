@@ -1,0 +1,62 @@
+// pn2_common.cuh -- shared helpers for the sm_100a kernels behind include/pn2_b200.h
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/pn2_b200.h"
+
+#define PN2_API extern "C" __attribute__((visibility("default")))
+
+namespace pn2 {
+
+constexpr int kNumSMsB200 = 148;
+
+// Remember the CUDA error text of a failing launch for pn2_last_cuda_error().
+void set_last_cuda_error(const char *msg);
+
+inline int finish_launch() {
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) {
+        set_last_cuda_error(cudaGetErrorString(e));
+        cudaGetLastError();  // clear the sticky-less error so later calls start clean
+        return PN2_ELAUNCH;
+    }
+    return PN2_OK;
+}
+
+inline int cuda_status(cudaError_t e) {
+    if (e != cudaSuccess) {
+        set_last_cuda_error(cudaGetErrorString(e));
+        cudaGetLastError();
+        return PN2_ELAUNCH;
+    }
+    return PN2_OK;
+}
+
+inline cudaStream_t as_stream(pn2_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// Number of SMs of the current device (cached, immutable).
+int num_sms();
+
+template <typename T>
+__host__ __device__ constexpr T ceil_div(T a, T b) {
+    return (a + b - 1) / b;
+}
+
+// Squared distance exactly as the nvcc-compiled reference kernels evaluate it
+// (FMUL dy,dy ; FFMA dx,dx ; FFMA dz,dz -- see oracle/pn2_oracle.c).  Explicit
+// intrinsics so no compiler flag can change the rounding sequence.
+__device__ __forceinline__ float sqdist_ref(float dx, float dy, float dz) {
+    return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+}
+
+}  // namespace pn2
+
+#define PN2_REQUIRE(cond)                \
+    do {                                 \
+        if (!(cond)) return PN2_EINVAL;  \
+    } while (0)
+#define PN2_REQUIRE_PTR(p)              \
+    do {                                \
+        if ((p) == nullptr) return PN2_ENULL; \
+    } while (0)

@@ -1,0 +1,683 @@
+// pn2_dense.cu -- shared-MLP layer pieces for sm_100a: linear fwd/dgrad/wgrad dispatch,
+// train/eval BatchNorm, fused affine+ReLU(+max-pool), their backward passes, dropout, the
+// weighted softmax cross-entropy and the Adam update.
+//
+// These replace the TensorFlow graph ops the reference strings between its custom ops
+// (util/tf_util.py:54-204, 555-581, 646-665; util/pointnet_util.py:150-170, 313-324;
+// model.py:132-161; train.py:387-388).  Nothing here has a reference kernel to follow.
+#include <math.h>
+
+#include "pn2_common.cuh"
+#include "pn2_gemm_simt.cuh"
+
+namespace pn2 {
+
+// implemented in pn2_gemm_tc.cu (tcgen05 3xTF32 path); returns PN2_EUNSUPPORTED for shapes it
+// does not cover so that the caller can fall back to the exact fp32 kernel.
+int tc_linear_fwd(long M, int K, int N, const float *A, int lda, const float *a_scale,
+                  const float *a_shift, int a_relu, const float *W, const float *bias, float *Y,
+                  double *stats, cudaStream_t st);
+int tc_linear_dgrad(long M, int K, int N, const float *dY, const float *W, float *dX, int ldx,
+                    cudaStream_t st);
+
+// ---- SIMT GEMM dispatch ----------------------------------------------------------------------
+template <bool A_KC, bool B_NC, bool ATOMIC>
+static int launch_gemm(int Mp, int Np, long Kp, const float *A, long a_sm, long a_sk,
+                       const float *B, long b_sk, long b_sn, const float *a_scale,
+                       const float *a_shift, int a_relu, const float *bias, float *C, long ldc,
+                       double *stats, int splits, cudaStream_t st) {
+    const int bm = Mp > 64 ? 128 : (Mp > 32 ? 64 : 32);
+    const int bn = Np > 64 ? 128 : (Np > 32 ? 64 : 32);
+    long k_chunk = ceil_div<long>(Kp, splits);
+    k_chunk = ceil_div<long>(k_chunk, G_BK) * G_BK;
+    splits = (int)ceil_div<long>(Kp, k_chunk);
+    if (splits < 1) splits = 1;
+    dim3 grid((unsigned)ceil_div(Mp, bm), (unsigned)ceil_div(Np, bn), (unsigned)splits);
+#define PN2_G(BM_, BN_)                                                                        \
+    gemm_simt_kernel<BM_, BN_, A_KC, B_NC, ATOMIC><<<grid, G_THREADS, 0, st>>>(                 \
+        Mp, Np, Kp, A, a_sm, a_sk, B, b_sk, b_sn, a_scale, a_shift, a_relu, bias, C, ldc, stats, \
+        k_chunk)
+    if (bm == 128 && bn == 128) PN2_G(128, 128);
+    else if (bm == 128 && bn == 64) PN2_G(128, 64);
+    else if (bm == 128 && bn == 32) PN2_G(128, 32);
+    else if (bm == 64 && bn == 128) PN2_G(64, 128);
+    else if (bm == 64 && bn == 64) PN2_G(64, 64);
+    else if (bm == 64 && bn == 32) PN2_G(64, 32);
+    else if (bm == 32 && bn == 128) PN2_G(32, 128);
+    else if (bm == 32 && bn == 64) PN2_G(32, 64);
+    else PN2_G(32, 32);
+#undef PN2_G
+    return finish_launch();
+}
+
+// ---- column-wise helpers over a row-major [M,N] matrix ------------------------------------------
+// Block = 256 threads owning a slab of rows; thread t works on columns c = cx, cx+lanes, ... and
+// rows r = ry, ry+rpp, ... so that a warp reads contiguous columns of one (or a few) rows.
+struct Slab {
+    int lanes, rpp, cx, ry;
+    long r0, r1;
+    bool active;
+};
+__device__ __forceinline__ Slab make_slab(long M, int N, long rows_per_block) {
+    Slab s;
+    s.lanes = N < (int)blockDim.x ? N : (int)blockDim.x;
+    s.rpp = blockDim.x / s.lanes;
+    s.cx = threadIdx.x % s.lanes;
+    s.ry = threadIdx.x / s.lanes;
+    s.active = s.ry < s.rpp;
+    s.r0 = (long)blockIdx.x * rows_per_block;
+    s.r1 = s.r0 + rows_per_block < M ? s.r0 + rows_per_block : M;
+    return s;
+}
+
+// dZh, xhat for one element
+__device__ __forceinline__ void bn_elem(float y, float dz, float sc, float sh, float mean,
+                                        float rstd, int relu, float &dzh, float &xhat) {
+    const float z = __fmaf_rn(y, sc, sh);
+    dzh = (relu && !(z > 0.f)) ? 0.f : dz;
+    xhat = (y - mean) * rstd;
+}
+
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_kernel(long M, int N, long rpb, const float *__restrict__ dZ, int ldz,
+                     const float *__restrict__ Y, const float *__restrict__ scale,
+                     const float *__restrict__ shift, const float *__restrict__ saved, int relu,
+                     double *__restrict__ red) {
+    const Slab s = make_slab(M, N, rpb);
+    if (!s.active) return;
+    for (int c = s.cx; c < N; c += s.lanes) {
+        const float sc = __ldg(scale + c), sh = __ldg(shift + c);
+        const float mean = __ldg(saved + c), rstd = __ldg(saved + N + c);
+        float a0 = 0.f, a1 = 0.f;
+        for (long r = s.r0 + s.ry; r < s.r1; r += s.rpp) {
+            float dzh, xh;
+            bn_elem(__ldg(Y + r * N + c), __ldg(dZ + r * ldz + c), sc, sh, mean, rstd, relu, dzh, xh);
+            a0 += dzh;
+            a1 = __fmaf_rn(dzh, xh, a1);
+        }
+        atomicAdd(red + c, (double)a0);
+        atomicAdd(red + N + c, (double)a1);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(long M, int N, long rpb, const float *__restrict__ dZ, int ldz,
+                    const float *__restrict__ Y, const float *__restrict__ scale,
+                    const float *__restrict__ shift, const float *__restrict__ saved,
+                    const float *__restrict__ gamma, int relu, int bn,
+                    const double *__restrict__ red, float *__restrict__ dY,
+                    float *__restrict__ dgamma, float *__restrict__ dbeta) {
+    const Slab s = make_slab(M, N, rpb);
+    if (!s.active) return;
+    const double invM = 1.0 / (double)M;
+    for (int c = s.cx; c < N; c += s.lanes) {
+        float sc = 1.f, sh = 0.f, mean = 0.f, rstd = 1.f, gs = 1.f, m0 = 0.f, m1 = 0.f;
+        if (scale) {
+            sc = __ldg(scale + c);
+            sh = __ldg(shift + c);
+        }
+        if (bn) {
+            mean = __ldg(saved + c);
+            rstd = __ldg(saved + N + c);
+            gs = __ldg(gamma + c) * rstd;
+            m0 = (float)(red[c] * invM);
+            m1 = (float)(red[N + c] * invM);
+            if (blockIdx.x == 0 && s.ry == 0) {
+                if (dgamma) dgamma[c] += (float)red[N + c];
+                if (dbeta) dbeta[c] += (float)red[c];
+            }
+        }
+        for (long r = s.r0 + s.ry; r < s.r1; r += s.rpp) {
+            float dzh, xh;
+            bn_elem(__ldg(Y + r * N + c), __ldg(dZ + r * ldz + c), sc, sh, mean, rstd, relu, dzh, xh);
+            dY[r * N + c] = bn ? gs * (dzh - m0 - xh * m1) : dzh;
+        }
+    }
+}
+
+// pooled upstream gradient: dZh[g*ns+j, c] = dOut[g,c] if arg[g,c]==j (and z>0) else 0
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_pool_kernel(long G, int ns, int N, const float *__restrict__ dOut,
+                          const int *__restrict__ arg, const float *__restrict__ Y,
+                          const float *__restrict__ scale, const float *__restrict__ shift,
+                          const float *__restrict__ saved, int relu, double *__restrict__ red) {
+    const long rpb = ceil_div<long>(G, (long)gridDim.x);
+    const Slab s = make_slab(G, N, rpb);
+    if (!s.active) return;
+    for (int c = s.cx; c < N; c += s.lanes) {
+        const float sc = __ldg(scale + c), sh = __ldg(shift + c);
+        const float mean = __ldg(saved + c), rstd = __ldg(saved + N + c);
+        float a0 = 0.f, a1 = 0.f;
+        for (long g = s.r0 + s.ry; g < s.r1; g += s.rpp) {
+            const int j = __ldg(arg + g * N + c);
+            float dzh, xh;
+            bn_elem(__ldg(Y + (g * ns + j) * N + c), __ldg(dOut + g * N + c), sc, sh, mean, rstd,
+                    relu, dzh, xh);
+            a0 += dzh;
+            a1 = __fmaf_rn(dzh, xh, a1);
+        }
+        atomicAdd(red + c, (double)a0);
+        atomicAdd(red + N + c, (double)a1);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_pool_kernel(long G, int ns, int N, long rpb, const float *__restrict__ dOut,
+                         const int *__restrict__ arg, const float *__restrict__ Y,
+                         const float *__restrict__ scale, const float *__restrict__ shift,
+                         const float *__restrict__ saved, const float *__restrict__ gamma,
+                         int relu, int bn, const double *__restrict__ red,
+                         float *__restrict__ dY, float *__restrict__ dgamma,
+                         float *__restrict__ dbeta) {
+    const long M = G * ns;
+    const Slab s = make_slab(M, N, rpb);
+    if (!s.active) return;
+    const double invM = 1.0 / (double)M;
+    for (int c = s.cx; c < N; c += s.lanes) {
+        float sc = 1.f, sh = 0.f, mean = 0.f, rstd = 1.f, gs = 1.f, m0 = 0.f, m1 = 0.f;
+        if (scale) {
+            sc = __ldg(scale + c);
+            sh = __ldg(shift + c);
+        }
+        if (bn) {
+            mean = __ldg(saved + c);
+            rstd = __ldg(saved + N + c);
+            gs = __ldg(gamma + c) * rstd;
+            m0 = (float)(red[c] * invM);
+            m1 = (float)(red[N + c] * invM);
+            if (blockIdx.x == 0 && s.ry == 0) {
+                if (dgamma) dgamma[c] += (float)red[N + c];
+                if (dbeta) dbeta[c] += (float)red[c];
+            }
+        }
+        for (long r = s.r0 + s.ry; r < s.r1; r += s.rpp) {
+            const long g = r / ns;
+            const int j = (int)(r - g * ns);
+            const float dz = (__ldg(arg + g * N + c) == j) ? __ldg(dOut + g * N + c) : 0.f;
+            float dzh, xh;
+            bn_elem(__ldg(Y + r * N + c), dz, sc, sh, mean, rstd, relu, dzh, xh);
+            dY[r * N + c] = bn ? gs * (dzh - m0 - xh * m1) : dzh;
+        }
+    }
+}
+
+__global__ void bn_train_finalize_kernel(int N, long M, const double *__restrict__ stats,
+                                         const float *__restrict__ gamma,
+                                         const float *__restrict__ beta, float eps, float decay,
+                                         int unbiased_moving, float *__restrict__ moving_mean,
+                                         float *__restrict__ moving_var, float *__restrict__ scale,
+                                         float *__restrict__ shift, float *__restrict__ saved) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= N) return;
+    const double mean = stats[c] / (double)M;
+    double var = stats[N + c] / (double)M - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const double rstd = 1.0 / sqrt(var + (double)eps);
+    const float sc = (float)((double)gamma[c] * rstd);
+    scale[c] = sc;
+    shift[c] = (float)((double)beta[c] - mean * (double)gamma[c] * rstd);
+    saved[c] = (float)mean;
+    saved[N + c] = (float)rstd;
+    if (moving_mean) {
+        const double uv = unbiased_moving && M > 1 ? var * ((double)M / (double)(M - 1)) : var;
+        // assign_moving_average: v -= (v - value) * (1 - decay)
+        moving_mean[c] = (float)((double)moving_mean[c] - ((double)moving_mean[c] - mean) * (1.0 - (double)decay));
+        moving_var[c] = (float)((double)moving_var[c] - ((double)moving_var[c] - uv) * (1.0 - (double)decay));
+    }
+}
+
+__global__ void bn_eval_affine_kernel(int N, const float *__restrict__ gamma,
+                                      const float *__restrict__ beta,
+                                      const float *__restrict__ mm, const float *__restrict__ mv,
+                                      float eps, float *__restrict__ scale,
+                                      float *__restrict__ shift) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= N) return;
+    const double rstd = 1.0 / sqrt((double)mv[c] + (double)eps);
+    scale[c] = (float)((double)gamma[c] * rstd);
+    shift[c] = (float)((double)beta[c] - (double)mm[c] * (double)gamma[c] * rstd);
+}
+
+__global__ void affine_act_kernel(long total, int N, const float *__restrict__ Y,
+                                  const float *__restrict__ scale,
+                                  const float *__restrict__ shift, int relu,
+                                  float *__restrict__ Z, int ldz) {
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total;
+         e += (long)gridDim.x * blockDim.x) {
+        const long r = e / N;
+        const int c = (int)(e - r * N);
+        float v = __ldg(Y + e);
+        if (scale) v = __fmaf_rn(v, __ldg(scale + c), __ldg(shift + c));
+        if (relu) v = fmaxf(v, 0.f);
+        Z[r * ldz + c] = v;
+    }
+}
+
+__global__ void affine_act_maxpool_kernel(long total, int ns, int N, const float *__restrict__ Y,
+                                          const float *__restrict__ scale,
+                                          const float *__restrict__ shift, int relu,
+                                          float *__restrict__ out, int *__restrict__ arg) {
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total;
+         e += (long)gridDim.x * blockDim.x) {
+        const long g = e / N;
+        const int c = (int)(e - g * N);
+        const float sc = scale ? __ldg(scale + c) : 1.f, sh = scale ? __ldg(shift + c) : 0.f;
+        const float *y = Y + g * ns * N + c;
+        float best = -INFINITY;
+        int bj = 0;
+#pragma unroll 4
+        for (int j = 0; j < ns; ++j) {
+            float v = __fmaf_rn(__ldg(y + (long)j * N), sc, sh);
+            if (relu) v = fmaxf(v, 0.f);
+            if (v > best) {
+                best = v;
+                bj = j;
+            }
+        }
+        out[e] = best;
+        if (arg) arg[e] = bj;
+    }
+}
+
+// ---- dropout: counter-based generator (splitmix64 finaliser over seed ^ index) -------------------
+__device__ __forceinline__ bool dropout_keep(unsigned long long seed, long i, float keep_prob) {
+    unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(i + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z = z ^ (z >> 31);
+    const float u = (float)(z >> 40) * (1.0f / 16777216.0f);  // [0,1)
+    return u < keep_prob;
+}
+__global__ void dropout_kernel(long n, const float *__restrict__ x, float keep_prob, float inv,
+                               unsigned long long seed, float *__restrict__ out) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n;
+         i += (long)gridDim.x * blockDim.x)
+        out[i] = dropout_keep(seed, i, keep_prob) ? __fmul_rn(__ldg(x + i), inv) : 0.f;
+}
+__global__ void dropout_mask_kernel(long n, float keep_prob, unsigned long long seed,
+                                    unsigned char *__restrict__ mask) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n;
+         i += (long)gridDim.x * blockDim.x)
+        mask[i] = dropout_keep(seed, i, keep_prob) ? 1 : 0;
+}
+
+// ---- weighted sparse softmax cross entropy ---------------------------------------------------------
+__global__ void softmax_ce_reduce_kernel(long rows, int C, const float *__restrict__ logits,
+                                         const int *__restrict__ labels,
+                                         const float *__restrict__ weights,
+                                         double *__restrict__ acc) {
+    double s = 0.0, nz = 0.0;
+    for (long r = blockIdx.x * (long)blockDim.x + threadIdx.x; r < rows;
+         r += (long)gridDim.x * blockDim.x) {
+        const float *x = logits + r * C;
+        float mx = -INFINITY;
+        for (int c = 0; c < C; ++c) mx = fmaxf(mx, __ldg(x + c));
+        float se = 0.f;
+        for (int c = 0; c < C; ++c) se += expf(__ldg(x + c) - mx);
+        const float lse = mx + logf(se);
+        const float w = weights ? __ldg(weights + r) : 1.f;
+        const float ce = lse - __ldg(x + __ldg(labels + r));
+        s += (double)(ce * w);
+        nz += (w != 0.f) ? 1.0 : 0.0;
+    }
+#pragma unroll
+    for (int off = 16; off; off >>= 1) {
+        s += __shfl_xor_sync(0xFFFFFFFFu, s, off);
+        nz += __shfl_xor_sync(0xFFFFFFFFu, nz, off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(acc, s);
+        atomicAdd(acc + 1, nz);
+    }
+}
+__global__ void softmax_ce_grad_kernel(long rows, int C, const float *__restrict__ logits,
+                                       const int *__restrict__ labels,
+                                       const float *__restrict__ weights,
+                                       const double *__restrict__ acc, float gscale,
+                                       float *__restrict__ loss, float *__restrict__ dlogits) {
+    const double nz = acc[1] > 0.0 ? acc[1] : 1.0;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && loss) *loss = (float)(acc[0] / nz);
+    if (!dlogits) return;
+    const float inv = (float)((double)gscale / nz);
+    for (long r = blockIdx.x * (long)blockDim.x + threadIdx.x; r < rows;
+         r += (long)gridDim.x * blockDim.x) {
+        const float *x = logits + r * C;
+        float mx = -INFINITY;
+        for (int c = 0; c < C; ++c) mx = fmaxf(mx, __ldg(x + c));
+        float se = 0.f;
+        for (int c = 0; c < C; ++c) se += expf(__ldg(x + c) - mx);
+        const float w = (weights ? __ldg(weights + r) : 1.f) * inv;
+        const int lab = __ldg(labels + r);
+        const float rse = 1.f / se;
+        for (int c = 0; c < C; ++c) {
+            const float p = expf(__ldg(x + c) - mx) * rse;
+            dlogits[r * C + c] = w * (p - (c == lab ? 1.f : 0.f));
+        }
+    }
+}
+
+__global__ void adam_kernel(long n, float *__restrict__ p, const float *__restrict__ g,
+                            float *__restrict__ m, float *__restrict__ v, float lr_t, float b1,
+                            float b2, float eps, float gscale) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n;
+         i += (long)gridDim.x * blockDim.x) {
+        const float gi = g[i] * gscale;
+        const float mi = m[i] + (gi - m[i]) * (1.f - b1);
+        const float vi = v[i] + (gi * gi - v[i]) * (1.f - b2);
+        m[i] = mi;
+        v[i] = vi;
+        p[i] -= lr_t * mi / (sqrtf(vi) + eps);
+    }
+}
+
+__global__ void colsum_kernel(long M, int N, long rpb, const float *__restrict__ X,
+                              float *__restrict__ out) {
+    const Slab s = make_slab(M, N, rpb);
+    if (!s.active) return;
+    for (int c = s.cx; c < N; c += s.lanes) {
+        float a = 0.f;
+        for (long r = s.r0 + s.ry; r < s.r1; r += s.rpp) a += __ldg(X + r * N + c);
+        atomicAdd(out + c, a);
+    }
+}
+
+static inline int grid_for(long total, int threads) {
+    long blocks = ceil_div<long>(total, threads);
+    long cap = 148L * 16;
+    return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
+}
+// rows per block for the slab kernels: aim at ~148*8 blocks, at least 32 rows each
+static inline long slab_rows(long M, int *blocks) {
+    long rpb = ceil_div<long>(M, 148L * 8);
+    if (rpb < 32) rpb = 32;
+    *blocks = (int)ceil_div<long>(M, rpb);
+    return rpb;
+}
+
+}  // namespace pn2
+
+using namespace pn2;
+
+static bool tc_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("PN2_DISABLE_TC");
+        v = (e && e[0] == '1') ? 0 : 1;
+    }
+    return v == 1;
+}
+
+PN2_API int pn2_linear_fwd(long M, int K, int N, const float *A, int lda, const float *a_scale,
+                           const float *a_shift, int a_relu, const float *W, const float *bias,
+                           float *Y, double *stats, int mode, pn2_stream_t s) {
+    PN2_REQUIRE(M >= 0 && K > 0 && N > 0 && lda >= K && M < (1L << 31));
+    PN2_REQUIRE(mode >= -1 && mode <= 1);
+    if (M == 0) return PN2_OK;
+    PN2_REQUIRE_PTR(A);
+    PN2_REQUIRE_PTR(W);
+    PN2_REQUIRE_PTR(Y);
+    PN2_REQUIRE((a_scale == nullptr) == (a_shift == nullptr));
+    cudaStream_t st = as_stream(s);
+    if (mode == 1 || (mode == -1 && tc_enabled())) {
+        int rc = tc_linear_fwd(M, K, N, A, lda, a_scale, a_shift, a_relu, W, bias, Y, stats, st);
+        if (rc != PN2_EUNSUPPORTED || mode == 1) return rc;
+    }
+    return launch_gemm<true, true, false>((int)M, N, K, A, lda, 1, W, N, 1, a_scale, a_shift,
+                                          a_relu, bias, Y, N, stats, 1, st);
+}
+
+PN2_API int pn2_linear_dgrad(long M, int K, int N, const float *dY, const float *W, float *dX,
+                             int ldx, int mode, pn2_stream_t s) {
+    PN2_REQUIRE(M >= 0 && K > 0 && N > 0 && ldx >= K && M < (1L << 31));
+    PN2_REQUIRE(mode >= -1 && mode <= 1);
+    if (M == 0) return PN2_OK;
+    PN2_REQUIRE_PTR(dY);
+    PN2_REQUIRE_PTR(W);
+    PN2_REQUIRE_PTR(dX);
+    cudaStream_t st = as_stream(s);
+    if (mode == 1 || (mode == -1 && tc_enabled())) {
+        int rc = tc_linear_dgrad(M, K, N, dY, W, dX, ldx, st);
+        if (rc != PN2_EUNSUPPORTED || mode == 1) return rc;
+    }
+    // C[M,K] = sum_n dY(m,n) * W(k,n):  M'=M, N'=K, K'=N ; B(k'=n, n'=k) = W + k*N + n
+    return launch_gemm<true, false, false>((int)M, K, N, dY, N, 1, W, 1, N, nullptr, nullptr, 0,
+                                           nullptr, dX, ldx, nullptr, 1, st);
+}
+
+PN2_API int pn2_linear_wgrad(long M, int K, int N, const float *A, int lda, const float *a_scale,
+                             const float *a_shift, int a_relu, const float *dY, float *dW,
+                             float *db, int mode, pn2_stream_t s) {
+    PN2_REQUIRE(M >= 0 && K > 0 && N > 0 && lda >= K && M < (1L << 31));
+    PN2_REQUIRE(mode >= -1 && mode <= 1);
+    if (M == 0) return PN2_OK;
+    PN2_REQUIRE_PTR(A);
+    PN2_REQUIRE_PTR(dY);
+    PN2_REQUIRE_PTR(dW);
+    PN2_REQUIRE((a_scale == nullptr) == (a_shift == nullptr));
+    cudaStream_t st = as_stream(s);
+    // C[K,N] += sum_m f(A)(m,k) dY(m,n): M'=K, N'=N, K'=M ; A(m'=k, k'=m) = A + m*lda + k
+    const int tiles = ceil_div(K, K > 64 ? 128 : (K > 32 ? 64 : 32)) *
+                      ceil_div(N, N > 64 ? 128 : (N > 32 ? 64 : 32));
+    int splits = (int)ceil_div<long>(148L * 4, tiles);
+    const long max_splits = ceil_div<long>(M, 256);
+    if (splits > max_splits) splits = (int)max_splits;
+    if (splits < 1) splits = 1;
+    int rc = launch_gemm<false, true, true>(K, N, M, A, 1, lda, dY, N, 1, a_scale, a_shift, a_relu,
+                                            nullptr, dW, N, nullptr, splits, st);
+    if (rc) return rc;
+    if (db) {
+        int blocks;
+        long rpb = slab_rows(M, &blocks);
+        colsum_kernel<<<blocks, 256, 0, st>>>(M, N, rpb, dY, db);
+        rc = finish_launch();
+    }
+    return rc;
+}
+
+PN2_API int pn2_bn_train_finalize(int N, long M, const double *stats, const float *gamma,
+                                  const float *beta, float eps, float decay, int unbiased_moving,
+                                  float *moving_mean, float *moving_var, float *scale,
+                                  float *shift, float *saved, pn2_stream_t s) {
+    PN2_REQUIRE(N > 0 && M > 0);
+    PN2_REQUIRE_PTR(stats);
+    PN2_REQUIRE_PTR(gamma);
+    PN2_REQUIRE_PTR(beta);
+    PN2_REQUIRE_PTR(scale);
+    PN2_REQUIRE_PTR(shift);
+    PN2_REQUIRE_PTR(saved);
+    PN2_REQUIRE((moving_mean == nullptr) == (moving_var == nullptr));
+    bn_train_finalize_kernel<<<ceil_div(N, 128), 128, 0, as_stream(s)>>>(
+        N, M, stats, gamma, beta, eps, decay, unbiased_moving, moving_mean, moving_var, scale, shift,
+        saved);
+    return finish_launch();
+}
+
+PN2_API int pn2_bn_eval_affine(int N, const float *gamma, const float *beta,
+                               const float *moving_mean, const float *moving_var, float eps,
+                               float *scale, float *shift, pn2_stream_t s) {
+    PN2_REQUIRE(N > 0);
+    PN2_REQUIRE_PTR(gamma);
+    PN2_REQUIRE_PTR(beta);
+    PN2_REQUIRE_PTR(moving_mean);
+    PN2_REQUIRE_PTR(moving_var);
+    PN2_REQUIRE_PTR(scale);
+    PN2_REQUIRE_PTR(shift);
+    bn_eval_affine_kernel<<<ceil_div(N, 128), 128, 0, as_stream(s)>>>(
+        N, gamma, beta, moving_mean, moving_var, eps, scale, shift);
+    return finish_launch();
+}
+
+PN2_API int pn2_affine_act(long M, int N, const float *Y, const float *scale, const float *shift,
+                           int relu, float *Z, int ldz, pn2_stream_t s) {
+    PN2_REQUIRE(M >= 0 && N > 0 && ldz >= N);
+    PN2_REQUIRE((scale == nullptr) == (shift == nullptr));
+    if (M == 0) return PN2_OK;
+    PN2_REQUIRE_PTR(Y);
+    PN2_REQUIRE_PTR(Z);
+    const long total = M * N;
+    affine_act_kernel<<<grid_for(total, 256), 256, 0, as_stream(s)>>>(total, N, Y, scale, shift,
+                                                                      relu, Z, ldz);
+    return finish_launch();
+}
+
+PN2_API int pn2_affine_act_maxpool(long G, int ns, int N, const float *Y, const float *scale,
+                                   const float *shift, int relu, float *out, int *arg,
+                                   pn2_stream_t s) {
+    PN2_REQUIRE(G >= 0 && ns > 0 && N > 0);
+    PN2_REQUIRE((scale == nullptr) == (shift == nullptr));
+    if (G == 0) return PN2_OK;
+    PN2_REQUIRE_PTR(Y);
+    PN2_REQUIRE_PTR(out);
+    const long total = G * N;
+    affine_act_maxpool_kernel<<<grid_for(total, 128), 128, 0, as_stream(s)>>>(
+        total, ns, N, Y, scale, shift, relu, out, arg);
+    return finish_launch();
+}
+
+PN2_API int pn2_bn_bwd_reduce(long M, int N, const float *dZ, int ldz, const float *Y,
+                              const float *scale, const float *shift, const float *saved,
+                              int relu, double *red, pn2_stream_t s) {
+    PN2_REQUIRE(M >= 0 && N > 0 && ldz >= N);
+    if (M == 0) return PN2_OK;
+    PN2_REQUIRE_PTR(dZ);
+    PN2_REQUIRE_PTR(Y);
+    PN2_REQUIRE_PTR(scale);
+    PN2_REQUIRE_PTR(shift);
+    PN2_REQUIRE_PTR(saved);
+    PN2_REQUIRE_PTR(red);
+    int blocks;
+    long rpb = slab_rows(M, &blocks);
+    bn_bwd_reduce_kernel<<<blocks, 256, 0, as_stream(s)>>>(M, N, rpb, dZ, ldz, Y, scale, shift,
+                                                           saved, relu, red);
+    return finish_launch();
+}
+
+PN2_API int pn2_bn_bwd_apply(long M, int N, const float *dZ, int ldz, const float *Y,
+                             const float *scale, const float *shift, const float *saved,
+                             const float *gamma, int relu, int bn, const double *red, float *dY,
+                             float *dgamma, float *dbeta, pn2_stream_t s) {
+    PN2_REQUIRE(M >= 0 && N > 0 && ldz >= N);
+    if (M == 0) return PN2_OK;
+    PN2_REQUIRE_PTR(dZ);
+    PN2_REQUIRE_PTR(Y);
+    PN2_REQUIRE_PTR(dY);
+    if (bn) {
+        PN2_REQUIRE_PTR(scale);
+        PN2_REQUIRE_PTR(shift);
+        PN2_REQUIRE_PTR(saved);
+        PN2_REQUIRE_PTR(gamma);
+        PN2_REQUIRE_PTR(red);
+    }
+    PN2_REQUIRE((scale == nullptr) == (shift == nullptr));
+    int blocks;
+    long rpb = slab_rows(M, &blocks);
+    bn_bwd_apply_kernel<<<blocks, 256, 0, as_stream(s)>>>(M, N, rpb, dZ, ldz, Y, scale, shift, saved,
+                                                          gamma, relu, bn, red, dY, dgamma, dbeta);
+    return finish_launch();
+}
+
+PN2_API int pn2_bn_bwd_reduce_pool(long G, int ns, int N, const float *dOut, const int *arg,
+                                   const float *Y, const float *scale, const float *shift,
+                                   const float *saved, int relu, double *red, pn2_stream_t s) {
+    PN2_REQUIRE(G >= 0 && ns > 0 && N > 0);
+    if (G == 0) return PN2_OK;
+    PN2_REQUIRE_PTR(dOut);
+    PN2_REQUIRE_PTR(arg);
+    PN2_REQUIRE_PTR(Y);
+    PN2_REQUIRE_PTR(scale);
+    PN2_REQUIRE_PTR(shift);
+    PN2_REQUIRE_PTR(saved);
+    PN2_REQUIRE_PTR(red);
+    int blocks;
+    (void)slab_rows(G, &blocks);
+    bn_bwd_reduce_pool_kernel<<<blocks, 256, 0, as_stream(s)>>>(G, ns, N, dOut, arg, Y, scale, shift,
+                                                                saved, relu, red);
+    return finish_launch();
+}
+
+PN2_API int pn2_bn_bwd_apply_pool(long G, int ns, int N, const float *dOut, const int *arg,
+                                  const float *Y, const float *scale, const float *shift,
+                                  const float *saved, const float *gamma, int relu, int bn,
+                                  const double *red, float *dY, float *dgamma, float *dbeta,
+                                  pn2_stream_t s) {
+    PN2_REQUIRE(G >= 0 && ns > 0 && N > 0);
+    if (G == 0) return PN2_OK;
+    PN2_REQUIRE_PTR(dOut);
+    PN2_REQUIRE_PTR(arg);
+    PN2_REQUIRE_PTR(Y);
+    PN2_REQUIRE_PTR(dY);
+    if (bn) {
+        PN2_REQUIRE_PTR(scale);
+        PN2_REQUIRE_PTR(shift);
+        PN2_REQUIRE_PTR(saved);
+        PN2_REQUIRE_PTR(gamma);
+        PN2_REQUIRE_PTR(red);
+    }
+    PN2_REQUIRE((scale == nullptr) == (shift == nullptr));
+    int blocks;
+    long rpb = slab_rows(G * ns, &blocks);
+    bn_bwd_apply_pool_kernel<<<blocks, 256, 0, as_stream(s)>>>(G, ns, N, rpb, dOut, arg, Y, scale,
+                                                               shift, saved, gamma, relu, bn, red, dY,
+                                                               dgamma, dbeta);
+    return finish_launch();
+}
+
+PN2_API int pn2_dropout(long n, const float *x, float keep_prob, unsigned long long seed,
+                        float *out, pn2_stream_t s) {
+    PN2_REQUIRE(n >= 0 && keep_prob > 0.f && keep_prob <= 1.f);
+    if (n == 0) return PN2_OK;
+    PN2_REQUIRE_PTR(x);
+    PN2_REQUIRE_PTR(out);
+    dropout_kernel<<<grid_for(n, 256), 256, 0, as_stream(s)>>>(n, x, keep_prob, 1.0f / keep_prob,
+                                                               seed, out);
+    return finish_launch();
+}
+
+PN2_API int pn2_dropout_mask(long n, float keep_prob, unsigned long long seed,
+                             unsigned char *mask, pn2_stream_t s) {
+    PN2_REQUIRE(n >= 0 && keep_prob > 0.f && keep_prob <= 1.f);
+    if (n == 0) return PN2_OK;
+    PN2_REQUIRE_PTR(mask);
+    dropout_mask_kernel<<<grid_for(n, 256), 256, 0, as_stream(s)>>>(n, keep_prob, seed, mask);
+    return finish_launch();
+}
+
+PN2_API int pn2_softmax_ce_reduce(long rows, int C, const float *logits, const int *labels,
+                                  const float *weights, double *acc, pn2_stream_t s) {
+    PN2_REQUIRE(rows >= 0 && C > 0);
+    if (rows == 0) return PN2_OK;
+    PN2_REQUIRE_PTR(logits);
+    PN2_REQUIRE_PTR(labels);
+    PN2_REQUIRE_PTR(acc);
+    softmax_ce_reduce_kernel<<<grid_for(rows, 256), 256, 0, as_stream(s)>>>(rows, C, logits, labels,
+                                                                           weights, acc);
+    return finish_launch();
+}
+
+PN2_API int pn2_softmax_ce_grad(long rows, int C, const float *logits, const int *labels,
+                                const float *weights, const double *acc, float gscale,
+                                float *loss, float *dlogits, pn2_stream_t s) {
+    PN2_REQUIRE(rows >= 0 && C > 0);
+    if (rows == 0) return PN2_OK;
+    PN2_REQUIRE_PTR(logits);
+    PN2_REQUIRE_PTR(labels);
+    PN2_REQUIRE_PTR(acc);
+    softmax_ce_grad_kernel<<<grid_for(rows, 256), 256, 0, as_stream(s)>>>(
+        rows, C, logits, labels, weights, acc, gscale, loss, dlogits);
+    return finish_launch();
+}
+
+PN2_API int pn2_adam_step(long n, float *p, const float *g, float *m, float *v, float lr,
+                          float beta1, float beta2, float eps, int t, float gscale,
+                          pn2_stream_t s) {
+    PN2_REQUIRE(n >= 0 && t >= 1);
+    if (n == 0) return PN2_OK;
+    PN2_REQUIRE_PTR(p);
+    PN2_REQUIRE_PTR(g);
+    PN2_REQUIRE_PTR(m);
+    PN2_REQUIRE_PTR(v);
+    const double lr_t = (double)lr * sqrt(1.0 - pow((double)beta2, t)) / (1.0 - pow((double)beta1, t));
+    adam_kernel<<<grid_for(n, 256), 256, 0, as_stream(s)>>>(n, p, g, m, v, (float)lr_t, beta1, beta2,
+                                                            eps, gscale);
+    return finish_launch();
+}

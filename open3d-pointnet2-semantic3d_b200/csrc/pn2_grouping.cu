@@ -1,0 +1,566 @@
+// pn2_grouping.cu -- ball query, group_point(+grad), fused group+centre+concat (+grad),
+// selection sort, for sm_100a.
+//
+// Replaces tf_ops/tf_grouping.cu of the reference (not a translation):
+//
+// Ball query.  The reference runs b*256 threads in total and re-reads every data point from
+// global memory for every query.  Here a CTA owns 128 queries of one cloud and streams the
+// cloud through shared memory in 1024-point tiles staged by the TMA engine
+// (cp.async.bulk + mbarrier, double buffered); each thread scans the tile with broadcast
+// LDS.128 reads, 4 points per iteration.  When b*m is too small to fill 148 SMs the cloud is
+// made fully resident and SPLIT lanes share one query (contiguous chunks, in-order merge).
+//
+// Bit-exactness: the reference tests  max(sqrtf(d2), 1e-20f) < radius  with IEEE sqrt.  sqrt is
+// monotone and correctly rounded, so that predicate equals  !(d2 >= T)  where T is the smallest
+// float whose correctly rounded sqrt is >= radius; T is found on the host (pn2_ball_threshold).
+// d2 itself is fma(dz,dz,fma(dx,dx,dy*dy)) as in the compiled reference.  The NaN behaviour
+// (CUDA max(NaN,1e-20f) = 1e-20f, hence a hit) is preserved by the negated comparison.
+#include <math.h>
+
+#include "pn2_common.cuh"
+
+namespace pn2 {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LAB_DONE;\n"
+        "bra LAB_WAIT;\n"
+        "LAB_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes,
+                                            uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+constexpr int BQ_THREADS = 128;
+constexpr int BQ_TILE = 1024;  // points per shared-memory stage (12 KB)
+
+// One thread per query, cloud streamed through two TMA-filled stages.
+template <bool USE_TMA>
+__global__ void __launch_bounds__(BQ_THREADS)
+ball_query_stream_kernel(int n, int m, float thr, int nsample, const float *__restrict__ xyz1,
+                         const float *__restrict__ xyz2, int *__restrict__ idx,
+                         int *__restrict__ pts_cnt) {
+    __shared__ __align__(128) float tile[2][BQ_TILE * 3];
+    __shared__ __align__(8) uint64_t full[2];
+
+    const int cloud = blockIdx.y;
+    const int j = blockIdx.x * BQ_THREADS + threadIdx.x;
+    const float *data = xyz1 + (size_t)cloud * n * 3;
+    const int ntiles = (n + BQ_TILE - 1) / BQ_TILE;
+
+    if (USE_TMA) {
+        if (threadIdx.x == 0) {
+            mbar_init(&full[0], 1);
+            mbar_init(&full[1], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int t = 0; t < 2 && t < ntiles; ++t) {
+                int cntp = min(BQ_TILE, n - t * BQ_TILE);
+                mbar_expect_tx(&full[t], cntp * 12);
+                tma_load_1d(tile[t], data + (size_t)t * BQ_TILE * 3, cntp * 12, &full[t]);
+            }
+        }
+    }
+
+    const bool valid = j < m;
+    float qx = 0.f, qy = 0.f, qz = 0.f;
+    if (valid) {
+        const float *q = xyz2 + ((size_t)cloud * m + j) * 3;
+        qx = __ldg(q);
+        qy = __ldg(q + 1);
+        qz = __ldg(q + 2);
+    }
+    int *row = idx + ((size_t)cloud * m + (valid ? j : 0)) * nsample;
+    int cnt = 0, first = 0;
+    bool done = !valid;
+
+    for (int t = 0; t < ntiles; ++t) {
+        const int base = t * BQ_TILE;
+        const int cntp = min(BQ_TILE, n - base);
+        float *buf = tile[t & 1];
+        if (USE_TMA) {
+            mbar_wait(&full[t & 1], (t >> 1) & 1);
+        } else {
+            for (int e = threadIdx.x; e < cntp * 3; e += BQ_THREADS)
+                buf[e] = __ldg(data + (size_t)base * 3 + e);
+            __syncthreads();
+        }
+        if (!done) {
+            const int k4 = cntp & ~3;
+            const float4 *b4 = reinterpret_cast<const float4 *>(buf);
+            int k = 0;
+            for (; k < k4 && cnt < nsample; k += 4) {
+                // 4 points = 12 floats = 3 broadcast LDS.128
+                float4 a = b4[(k >> 2) * 3 + 0], bb = b4[(k >> 2) * 3 + 1], c = b4[(k >> 2) * 3 + 2];
+                float d0 = sqdist_ref(qx - a.x, qy - a.y, qz - a.z);
+                float d1 = sqdist_ref(qx - a.w, qy - bb.x, qz - bb.y);
+                float d2 = sqdist_ref(qx - bb.z, qy - bb.w, qz - c.x);
+                float d3 = sqdist_ref(qx - c.y, qy - c.z, qz - c.w);
+                bool h0 = !(d0 >= thr), h1 = !(d1 >= thr), h2 = !(d2 >= thr), h3 = !(d3 >= thr);
+                if (h0 | h1 | h2 | h3) {
+                    if (h0 && cnt < nsample) { if (cnt == 0) first = base + k; row[cnt++] = base + k; }
+                    if (h1 && cnt < nsample) { if (cnt == 0) first = base + k + 1; row[cnt++] = base + k + 1; }
+                    if (h2 && cnt < nsample) { if (cnt == 0) first = base + k + 2; row[cnt++] = base + k + 2; }
+                    if (h3 && cnt < nsample) { if (cnt == 0) first = base + k + 3; row[cnt++] = base + k + 3; }
+                }
+            }
+            for (; k < cntp && cnt < nsample; ++k) {
+                float d0 = sqdist_ref(qx - buf[k * 3], qy - buf[k * 3 + 1], qz - buf[k * 3 + 2]);
+                if (!(d0 >= thr)) {
+                    if (cnt == 0) first = base + k;
+                    row[cnt++] = base + k;
+                }
+            }
+            done = cnt >= nsample;
+        }
+        // everyone is finished with this stage; stop early when the whole CTA is done
+        const int all_done = __syncthreads_and(done ? 1 : 0);
+        if (all_done) {
+            // never leave the CTA with a bulk copy still in flight towards its shared memory
+            if (USE_TMA && t + 1 < ntiles) mbar_wait(&full[(t + 1) & 1], ((t + 1) >> 1) & 1);
+            break;
+        }
+        if (USE_TMA && threadIdx.x == 0 && t + 2 < ntiles) {
+            int c2 = min(BQ_TILE, n - (t + 2) * BQ_TILE);
+            mbar_expect_tx(&full[t & 1], c2 * 12);
+            tma_load_1d(buf, data + (size_t)(t + 2) * BQ_TILE * 3, c2 * 12, &full[t & 1]);
+        }
+    }
+    if (valid) {
+        for (int l = cnt; l < nsample; ++l) row[l] = first;  // pad with the first hit (0 if none)
+        pts_cnt[(size_t)cloud * m + j] = cnt;
+    }
+}
+
+// Small-grid variant: whole cloud resident in shared memory (one TMA bulk copy), SPLIT lanes
+// per query each scanning a contiguous chunk; per-lane hit lists live in shared memory and
+// are concatenated in chunk order (== index order) at the end.
+template <int SPLIT>
+__global__ void __launch_bounds__(BQ_THREADS)
+ball_query_resident_kernel(int n, int m, float thr, int nsample, int use_tma,
+                           const float *__restrict__ xyz1, const float *__restrict__ xyz2,
+                           int *__restrict__ idx, int *__restrict__ pts_cnt) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int QPB = BQ_THREADS / SPLIT;
+    const int npad4 = (n + 3) & ~3;
+    float *pts = reinterpret_cast<float *>(smem_raw);                    // npad4*3 floats
+    int *hits = reinterpret_cast<int *>(pts + (size_t)npad4 * 3);        // [BQ_THREADS][nsample]
+    __shared__ __align__(8) uint64_t full;
+
+    const int cloud = blockIdx.y;
+    const float *data = xyz1 + (size_t)cloud * n * 3;
+    if (use_tma) {
+        if (threadIdx.x == 0) {
+            mbar_init(&full, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            // bulk copies are limited by the mbarrier tx-count (2^20-1 bytes): chunk it
+            uint32_t total = (uint32_t)n * 12u;
+            mbar_expect_tx(&full, total);
+            for (uint32_t off = 0; off < total; off += 65536u) {
+                uint32_t bytes = min(65536u, total - off);
+                tma_load_1d(reinterpret_cast<unsigned char *>(pts) + off,
+                            reinterpret_cast<const unsigned char *>(data) + off, bytes, &full);
+            }
+        }
+        mbar_wait(&full, 0);
+    } else {
+        for (int e = threadIdx.x; e < n * 3; e += BQ_THREADS) pts[e] = __ldg(data + e);
+        __syncthreads();
+    }
+
+    const int q = threadIdx.x / SPLIT, sub = threadIdx.x % SPLIT;
+    const int j = blockIdx.x * QPB + q;
+    const bool valid = j < m;
+    float qx = 0.f, qy = 0.f, qz = 0.f;
+    if (valid) {
+        const float *qp = xyz2 + ((size_t)cloud * m + j) * 3;
+        qx = __ldg(qp);
+        qy = __ldg(qp + 1);
+        qz = __ldg(qp + 2);
+    }
+    // chunk boundaries are multiples of 4 points so float4 reads stay aligned
+    const int chunk = ((n + SPLIT - 1) / SPLIT + 3) & ~3;
+    const int k0 = min(sub * chunk, n), k1 = min(k0 + chunk, n);
+    int *mine = hits + (size_t)threadIdx.x * nsample;
+    int cnt = 0;
+    if (valid) {
+        const float4 *b4 = reinterpret_cast<const float4 *>(pts);
+        int k = k0;
+        const int kend4 = k0 + ((k1 - k0) & ~3);
+        for (; k < kend4 && cnt < nsample; k += 4) {
+            float4 a = b4[(k >> 2) * 3 + 0], bb = b4[(k >> 2) * 3 + 1], c = b4[(k >> 2) * 3 + 2];
+            float d0 = sqdist_ref(qx - a.x, qy - a.y, qz - a.z);
+            float d1 = sqdist_ref(qx - a.w, qy - bb.x, qz - bb.y);
+            float d2 = sqdist_ref(qx - bb.z, qy - bb.w, qz - c.x);
+            float d3 = sqdist_ref(qx - c.y, qy - c.z, qz - c.w);
+            bool h0 = !(d0 >= thr), h1 = !(d1 >= thr), h2 = !(d2 >= thr), h3 = !(d3 >= thr);
+            if (h0 | h1 | h2 | h3) {
+                if (h0 && cnt < nsample) mine[cnt++] = k;
+                if (h1 && cnt < nsample) mine[cnt++] = k + 1;
+                if (h2 && cnt < nsample) mine[cnt++] = k + 2;
+                if (h3 && cnt < nsample) mine[cnt++] = k + 3;
+            }
+        }
+        for (; k < k1 && cnt < nsample; ++k) {
+            float d0 = sqdist_ref(qx - pts[k * 3], qy - pts[k * 3 + 1], qz - pts[k * 3 + 2]);
+            if (!(d0 >= thr)) mine[cnt++] = k;
+        }
+    }
+    // in-order merge inside the SPLIT-lane group (groups never straddle a warp: SPLIT | 32)
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned gbase = lane & ~(unsigned)(SPLIT - 1);
+    int offset = 0, total = 0, first = 0;
+    bool have_first = false;
+#pragma unroll
+    for (int s = 0; s < SPLIT; ++s) {
+        int c = __shfl_sync(0xFFFFFFFFu, cnt, gbase + s);
+        int f = __shfl_sync(0xFFFFFFFFu, cnt > 0 ? mine[0] : 0, gbase + s);
+        if (s < sub) offset += c;
+        if (!have_first && c > 0) {
+            first = f;
+            have_first = true;
+        }
+        total += c;
+    }
+    if (valid) {
+        int *row = idx + ((size_t)cloud * m + j) * nsample;
+        for (int l = 0; l < cnt && offset + l < nsample; ++l) row[offset + l] = mine[l];
+        const int tot = min(total, nsample);
+        // padding slots are shared out among the group's lanes
+        for (int l = tot + sub; l < nsample; l += SPLIT) row[l] = first;
+        if (sub == 0) pts_cnt[(size_t)cloud * m + j] = tot;
+    }
+}
+
+// ---- group_point / grad ------------------------------------------------------------------
+template <typename VT>
+__global__ void group_point_kernel(int n, int cv, long rows_per_cloud, long total,
+                                   const VT *__restrict__ points, const int *__restrict__ idx,
+                                   VT *__restrict__ out) {
+    // cv = channels in units of VT; e = row*cv + l
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total;
+         e += (long)gridDim.x * blockDim.x) {
+        long row = e / cv;
+        int l = (int)(e - row * cv);
+        long cloud = row / rows_per_cloud;
+        int ii = __ldg(idx + row);
+        out[e] = __ldg(points + (cloud * n + ii) * cv + l);
+    }
+}
+
+__global__ void group_point_grad_kernel(int n, int c, long rows_per_cloud, long total,
+                                        const float *__restrict__ grad_out,
+                                        const int *__restrict__ idx,
+                                        float *__restrict__ grad_points) {
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total;
+         e += (long)gridDim.x * blockDim.x) {
+        long row = e / c;
+        int l = (int)(e - row * c);
+        long cloud = row / rows_per_cloud;
+        int ii = __ldg(idx + row);
+        atomicAdd(grad_points + (cloud * n + ii) * c + l, __ldg(grad_out + e));
+    }
+}
+
+// out[row, :] = [xyz[idx]-new_xyz | points[idx]]  (or [points | xyz] when !xyz_first)
+__global__ void group_concat_kernel(int n, int m, int ns, int c, int w, int xoff, int poff,
+                                    int use_xyz, long total, const float *__restrict__ xyz,
+                                    const float *__restrict__ new_xyz,
+                                    const float *__restrict__ points,
+                                    const int *__restrict__ idx, float *__restrict__ out) {
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total;
+         e += (long)gridDim.x * blockDim.x) {
+        long row = e / w;
+        int col = (int)(e - row * w);
+        long grp = row / ns;          // cloud*m + j
+        long cloud = grp / m;
+        int ii = __ldg(idx + row);
+        float v;
+        if (use_xyz && col >= xoff && col < xoff + 3) {
+            int a = col - xoff;
+            v = __fsub_rn(__ldg(xyz + (cloud * n + ii) * 3 + a), __ldg(new_xyz + grp * 3 + a));
+        } else {
+            v = __ldg(points + (cloud * n + ii) * c + (col - poff));
+        }
+        out[e] = v;
+    }
+}
+
+__global__ void group_concat_grad_kernel(int n, int m, int ns, int c, int w, int xoff, int poff,
+                                         int use_xyz, long total,
+                                         const float *__restrict__ grad_out,
+                                         const int *__restrict__ idx,
+                                         float *__restrict__ grad_points,
+                                         float *__restrict__ grad_xyz,
+                                         float *__restrict__ grad_new_xyz) {
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total;
+         e += (long)gridDim.x * blockDim.x) {
+        long row = e / w;
+        int col = (int)(e - row * w);
+        long grp = row / ns;
+        long cloud = grp / m;
+        int ii = __ldg(idx + row);
+        float g = __ldg(grad_out + e);
+        if (use_xyz && col >= xoff && col < xoff + 3) {
+            int a = col - xoff;
+            if (grad_xyz) atomicAdd(grad_xyz + (cloud * n + ii) * 3 + a, g);
+            if (grad_new_xyz) atomicAdd(grad_new_xyz + grp * 3 + a, -g);
+        } else if (grad_points) {
+            atomicAdd(grad_points + (cloud * n + ii) * c + (col - poff), g);
+        }
+    }
+}
+
+// ---- selection sort ("next" scope, tf_grouping.cu:95-136): k passes of arg-min ------------
+// one warp per (b,m) row; out/outi get the k smallest in ascending order, ties -> earliest.
+__global__ void selection_topk_kernel(long rows, int n, int k, const float *__restrict__ dist,
+                                      int *__restrict__ outi, float *__restrict__ out) {
+    long row = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float *d = dist + row * n;
+    float *o = out + row * n;
+    int *oi = outi + row * n;
+    // The reference's swap-based selection sort equals: repeatedly take the minimum of the
+    // not-yet-selected entries, earliest position (in the CURRENT, swapped order) on ties.
+    // For distinct values that is the k smallest ascending; exact tie order of the swapped
+    // array is reproduced by tests only on tie-free data.
+    float prev_v = -INFINITY;
+    int prev_i = -1;
+    for (int s = 0; s < k && s < n; ++s) {
+        float bv = INFINITY;
+        int bi = 0x7FFFFFFF;
+        for (int t = lane; t < n; t += 32) {
+            float v = __ldg(d + t);
+            bool after = (v > prev_v) || (v == prev_v && t > prev_i);
+            if (after && (v < bv || (v == bv && t < bi))) {
+                bv = v;
+                bi = t;
+            }
+        }
+#pragma unroll
+        for (int off = 16; off; off >>= 1) {
+            float ov = __shfl_xor_sync(0xFFFFFFFFu, bv, off);
+            int oi2 = __shfl_xor_sync(0xFFFFFFFFu, bi, off);
+            if (ov < bv || (ov == bv && oi2 < bi)) {
+                bv = ov;
+                bi = oi2;
+            }
+        }
+        if (lane == 0) {
+            o[s] = bv;
+            oi[s] = bi;
+        }
+        prev_v = bv;
+        prev_i = bi;
+    }
+}
+
+static inline int grid_for(long total, int threads) {
+    long blocks = ceil_div<long>(total, threads);
+    long cap = 148L * 32;
+    return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
+}
+
+}  // namespace pn2
+
+using namespace pn2;
+
+// smallest float T >= 0 such that sqrtf(T) >= radius (host sqrtf is IEEE, correctly rounded)
+static float ball_threshold(float radius) {
+    if (!(radius > 1e-20f)) return 0.f;  // max(d,1e-20f) < radius can never hold
+    if (isinf(radius)) return INFINITY;
+    float t = (float)((double)radius * (double)radius);
+    while (t > 0.f && sqrtf(nextafterf(t, 0.f)) >= radius) t = nextafterf(t, 0.f);
+    while (sqrtf(t) < radius) t = nextafterf(t, INFINITY);
+    return t;
+}
+
+PN2_API float pn2_ball_threshold(float radius) { return ball_threshold(radius); }
+
+PN2_API int pn2_query_ball_point(int b, int n, int m, float radius, int nsample,
+                                 const float *xyz1, const float *xyz2, int *idx, int *pts_cnt,
+                                 pn2_stream_t s) {
+    // tf_grouping.cpp:80-87: "QueryBallPoint expects positive radius / nsample"
+    PN2_REQUIRE(radius > 0.f && nsample > 0);
+    PN2_REQUIRE(b >= 0 && n > 0 && m >= 0);
+    if (b == 0 || m == 0) return PN2_OK;
+    PN2_REQUIRE_PTR(xyz1);
+    PN2_REQUIRE_PTR(xyz2);
+    PN2_REQUIRE_PTR(idx);
+    PN2_REQUIRE_PTR(pts_cnt);
+    cudaStream_t st = as_stream(s);
+    const float thr = ball_threshold(radius);
+    // TMA bulk copies need 16-byte aligned sources and sizes: every cloud starts at n*12 bytes
+    const bool tma_ok = (reinterpret_cast<uintptr_t>(xyz1) % 16 == 0) && (n % 4 == 0);
+
+    // small grids: make the cloud resident and split each query over SPLIT lanes
+    const long queries = (long)b * m;
+    int split = 1;
+    while (split < 8 && queries * split < 148L * 512) split *= 2;
+    const size_t res_smem = (size_t)((n + 3) & ~3) * 12 + (size_t)BQ_THREADS * nsample * 4;
+    if (split > 1 && res_smem <= 200 * 1024) {
+        dim3 grid((unsigned)ceil_div(m, BQ_THREADS / split), (unsigned)b);
+        int rc = PN2_OK;
+#define PN2_LAUNCH_RES(SP)                                                                      \
+    do {                                                                                        \
+        auto kern = ball_query_resident_kernel<SP>;                                             \
+        rc = cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                              (int)res_smem));                                  \
+        if (rc) return rc;                                                                      \
+        kern<<<grid, BQ_THREADS, res_smem, st>>>(n, m, thr, nsample, tma_ok ? 1 : 0, xyz1,     \
+                                                 xyz2, idx, pts_cnt);                           \
+    } while (0)
+        if (split == 2) PN2_LAUNCH_RES(2);
+        else if (split == 4) PN2_LAUNCH_RES(4);
+        else PN2_LAUNCH_RES(8);
+#undef PN2_LAUNCH_RES
+        return finish_launch();
+    }
+    dim3 grid((unsigned)ceil_div(m, BQ_THREADS), (unsigned)b);
+    if (tma_ok)
+        ball_query_stream_kernel<true><<<grid, BQ_THREADS, 0, st>>>(n, m, thr, nsample, xyz1, xyz2,
+                                                                    idx, pts_cnt);
+    else
+        ball_query_stream_kernel<false><<<grid, BQ_THREADS, 0, st>>>(n, m, thr, nsample, xyz1,
+                                                                     xyz2, idx, pts_cnt);
+    return finish_launch();
+}
+
+PN2_API int pn2_group_point(int b, int n, int c, int m, int nsample, const float *points,
+                            const int *idx, float *out, pn2_stream_t s) {
+    PN2_REQUIRE(b >= 0 && n > 0 && c >= 0 && m >= 0 && nsample >= 0);
+    long rows = (long)b * m * nsample;
+    if (rows == 0 || c == 0) return PN2_OK;
+    PN2_REQUIRE_PTR(points);
+    PN2_REQUIRE_PTR(idx);
+    PN2_REQUIRE_PTR(out);
+    cudaStream_t st = as_stream(s);
+    const bool vec = (c % 4 == 0) && (reinterpret_cast<uintptr_t>(points) % 16 == 0) &&
+                     (reinterpret_cast<uintptr_t>(out) % 16 == 0);
+    if (vec) {
+        long total = rows * (c / 4);
+        group_point_kernel<float4><<<grid_for(total, 256), 256, 0, st>>>(
+            n, c / 4, (long)m * nsample, total, reinterpret_cast<const float4 *>(points), idx,
+            reinterpret_cast<float4 *>(out));
+    } else {
+        long total = rows * c;
+        group_point_kernel<float><<<grid_for(total, 256), 256, 0, st>>>(
+            n, c, (long)m * nsample, total, points, idx, out);
+    }
+    return finish_launch();
+}
+
+PN2_API int pn2_group_point_grad(int b, int n, int c, int m, int nsample, const float *grad_out,
+                                 const int *idx, float *grad_points, pn2_stream_t s) {
+    PN2_REQUIRE(b >= 0 && n > 0 && c >= 0 && m >= 0 && nsample >= 0);
+    if (b == 0 || c == 0) return PN2_OK;
+    PN2_REQUIRE_PTR(grad_points);
+    cudaStream_t st = as_stream(s);
+    int rc = cuda_status(cudaMemsetAsync(grad_points, 0, sizeof(float) * (size_t)b * n * c, st));
+    if (rc) return rc;
+    long total = (long)b * m * nsample * c;
+    if (total == 0) return PN2_OK;
+    PN2_REQUIRE_PTR(grad_out);
+    PN2_REQUIRE_PTR(idx);
+    group_point_grad_kernel<<<grid_for(total, 256), 256, 0, st>>>(n, c, (long)m * nsample, total,
+                                                                  grad_out, idx, grad_points);
+    return finish_launch();
+}
+
+PN2_API int pn2_group_concat(int b, int n, int m, int nsample, int c, const float *xyz,
+                             const float *new_xyz, const float *points, const int *idx,
+                             int xyz_first, int use_xyz, float *out, pn2_stream_t s) {
+    PN2_REQUIRE(b >= 0 && n > 0 && m >= 0 && nsample >= 0 && c >= 0);
+    PN2_REQUIRE(use_xyz || c > 0);
+    const int w = (use_xyz ? 3 : 0) + c;
+    long total = (long)b * m * nsample * w;
+    if (total == 0) return PN2_OK;
+    PN2_REQUIRE_PTR(idx);
+    PN2_REQUIRE_PTR(out);
+    if (use_xyz) {
+        PN2_REQUIRE_PTR(xyz);
+        PN2_REQUIRE_PTR(new_xyz);
+    }
+    if (c > 0) PN2_REQUIRE_PTR(points);
+    const int xoff = xyz_first ? 0 : c, poff = (use_xyz && xyz_first) ? 3 : 0;
+    group_concat_kernel<<<grid_for(total, 256), 256, 0, as_stream(s)>>>(
+        n, m, nsample, c, w, xoff, poff, use_xyz, total, xyz, new_xyz, points, idx, out);
+    return finish_launch();
+}
+
+PN2_API int pn2_group_concat_grad(int b, int n, int m, int nsample, int c, const float *grad_out,
+                                  const int *idx, int xyz_first, int use_xyz, float *grad_points,
+                                  float *grad_xyz, float *grad_new_xyz, pn2_stream_t s) {
+    PN2_REQUIRE(b >= 0 && n > 0 && m >= 0 && nsample >= 0 && c >= 0);
+    if (b == 0) return PN2_OK;
+    cudaStream_t st = as_stream(s);
+    int rc;
+    if (grad_points && c > 0) {
+        rc = cuda_status(cudaMemsetAsync(grad_points, 0, sizeof(float) * (size_t)b * n * c, st));
+        if (rc) return rc;
+    }
+    if (grad_xyz) {
+        rc = cuda_status(cudaMemsetAsync(grad_xyz, 0, sizeof(float) * (size_t)b * n * 3, st));
+        if (rc) return rc;
+    }
+    if (grad_new_xyz) {
+        rc = cuda_status(cudaMemsetAsync(grad_new_xyz, 0, sizeof(float) * (size_t)b * m * 3, st));
+        if (rc) return rc;
+    }
+    const int w = (use_xyz ? 3 : 0) + c;
+    long total = (long)b * m * nsample * w;
+    if (total == 0) return PN2_OK;
+    PN2_REQUIRE_PTR(grad_out);
+    PN2_REQUIRE_PTR(idx);
+    const int xoff = xyz_first ? 0 : c, poff = (use_xyz && xyz_first) ? 3 : 0;
+    group_concat_grad_kernel<<<grid_for(total, 256), 256, 0, st>>>(
+        n, m, nsample, c, w, xoff, poff, use_xyz, total, grad_out, idx, grad_points, grad_xyz,
+        grad_new_xyz);
+    return finish_launch();
+}
+
+PN2_API int pn2_selection_sort(int b, int n, int m, int k, const float *dist, int *outi,
+                               float *out, pn2_stream_t s) {
+    PN2_REQUIRE(k > 0);  // tf_grouping.cpp:142-144 "SelectionSort expects positive k"
+    PN2_REQUIRE(b >= 0 && n > 0 && m >= 0);
+    long rows = (long)b * m;
+    if (rows == 0) return PN2_OK;
+    PN2_REQUIRE_PTR(dist);
+    PN2_REQUIRE_PTR(outi);
+    PN2_REQUIRE_PTR(out);
+    int threads = 128;
+    long blocks = ceil_div<long>(rows * 32, threads);
+    selection_topk_kernel<<<(unsigned)blocks, threads, 0, as_stream(s)>>>(rows, n, k, dist, outi,
+                                                                         out);
+    return finish_launch();
+}

@@ -1,0 +1,315 @@
+// pn2_sampling.cu -- farthest point sampling + gather_point(+grad) for sm_100a.
+//
+// Replaces tf_ops/tf_sampling.cu:111-206 of the reference (not a translation):
+//
+// FPS: one persistent CTA per cloud.  The cloud is staged once (coalesced AoS read ->
+// SoA shared memory), every thread then keeps its points AND their running minimum
+// distance in registers for all m-1 rounds -- the reference re-reads a (32,n) global
+// scratch row and most of the cloud every round.  The per-round arg-max is two
+// `redux.sync` instructions per level (max over the distance bit pattern, then min over a
+// tie key among the lanes holding the max) with ONE __syncthreads per round (double-buffered
+// per-warp slots) instead of the reference's 9-level shared-memory tree with 18 barriers.
+//
+// Bit-exactness contract: distance = fma(dz,dz,fma(dx,dx,dy*dy)), running
+// min by fminf, strict '>' arg-max whose ties resolve to the lowest (k mod 512) then lowest
+// k -- exactly the order the reference's 512-thread strided scan + left-biased tree gives.
+#include "pn2_common.cuh"
+
+namespace pn2 {
+
+// ---- tie key: smaller wins.  (k mod 512) major, (k div 512) minor ----------------------
+__device__ __forceinline__ unsigned tie_key(int k) {
+    return ((unsigned)(k & 511) << 22) | (unsigned)(k >> 9);
+}
+__device__ __forceinline__ int key_to_k(unsigned key) {
+    return (int)(((key & 0x3FFFFFu) << 9) | (key >> 22));
+}
+
+template <int THREADS, int PPT>
+__global__ void __launch_bounds__(THREADS, 1)
+fps_reg_kernel(int n, int m, const float *__restrict__ inp, int *__restrict__ out) {
+    constexpr int NW = THREADS / 32;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned long long *slots = reinterpret_cast<unsigned long long *>(smem_raw);  // [2][32]
+    float *xs = reinterpret_cast<float *>(slots + 64);
+    const int npad = THREADS * PPT;
+    float *ys = xs + npad;
+    float *zs = ys + npad;
+
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const float *src = inp + (size_t)blockIdx.x * n * 3;
+    int *dst = out + (size_t)blockIdx.x * m;
+
+    // stage the cloud: coalesced AoS global read -> SoA shared memory
+    for (int e = t; e < n * 3; e += THREADS) {
+        float v = __ldg(src + e);
+        int k = e / 3, c = e - k * 3;
+        (c == 0 ? xs : (c == 1 ? ys : zs))[k] = v;
+    }
+    __syncthreads();
+
+    float px[PPT], py[PPT], pz[PPT], pd[PPT];
+#pragma unroll
+    for (int i = 0; i < PPT; ++i) {
+        int k = t + i * THREADS;
+        bool ok = k < n;
+        px[i] = ok ? xs[k] : 0.f;
+        py[i] = ok ? ys[k] : 0.f;
+        pz[i] = ok ? zs[k] : 0.f;
+        pd[i] = ok ? 1e38f : -1.f;  // padding lanes can never exceed best (= -1, strict >)
+    }
+
+    int old = 0;
+    if (t == 0) dst[0] = 0;
+    // visiting order inside a thread must follow the tie order: classes of (k mod 512)
+    constexpr int R = (THREADS >= 512) ? 1 : 512 / THREADS;
+    for (int j = 1; j < m; ++j) {
+        const float x1 = xs[old], y1 = ys[old], z1 = zs[old];
+        float best = -1.f;
+        int besti = 0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+#pragma unroll
+            for (int i = r; i < PPT; i += R) {
+                float d = sqdist_ref(px[i] - x1, py[i] - y1, pz[i] - z1);
+                float d2 = fminf(d, pd[i]);
+                pd[i] = d2;
+                if (d2 > best) {
+                    best = d2;
+                    besti = i;
+                }
+            }
+        }
+        const bool has = best >= 0.f;
+        unsigned db = has ? __float_as_uint(best) : 0u;
+        unsigned key = has ? tie_key(t + besti * THREADS) : 0xFFFFFFFFu;
+        unsigned wmax = __reduce_max_sync(0xFFFFFFFFu, db);
+        unsigned wkey = __reduce_min_sync(0xFFFFFFFFu, db == wmax ? key : 0xFFFFFFFFu);
+        unsigned long long *sl = slots + (j & 1) * 32;
+        if (lane == 0) sl[warp] = ((unsigned long long)wmax << 32) | wkey;
+        __syncthreads();
+        unsigned long long v = lane < NW ? sl[lane] : 0x00000000FFFFFFFFull;
+        unsigned d2 = (unsigned)(v >> 32), k2 = (unsigned)v;
+        unsigned gmax = __reduce_max_sync(0xFFFFFFFFu, d2);
+        unsigned gkey = __reduce_min_sync(0xFFFFFFFFu, d2 == gmax ? k2 : 0xFFFFFFFFu);
+        old = gkey == 0xFFFFFFFFu ? 0 : key_to_k(gkey);
+        if (t == 0) dst[j] = old;
+    }
+}
+
+// Variant for 8192 < n <= 16384: coordinates stay in shared memory (196 KB), only the
+// running minimum lives in registers.
+template <int THREADS, int PPT>
+__global__ void __launch_bounds__(THREADS, 1)
+fps_smem_kernel(int n, int m, const float *__restrict__ inp, int *__restrict__ out) {
+    constexpr int NW = THREADS / 32;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned long long *slots = reinterpret_cast<unsigned long long *>(smem_raw);
+    float *xs = reinterpret_cast<float *>(slots + 64);
+    const int npad = THREADS * PPT;
+    float *ys = xs + npad;
+    float *zs = ys + npad;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const float *src = inp + (size_t)blockIdx.x * n * 3;
+    int *dst = out + (size_t)blockIdx.x * m;
+    for (int e = t; e < npad * 3; e += THREADS) {
+        int k = e / 3, c = e - k * 3;
+        float v = e < n * 3 ? __ldg(src + e) : 0.f;
+        (c == 0 ? xs : (c == 1 ? ys : zs))[k] = v;
+    }
+    __syncthreads();
+    float pd[PPT];
+#pragma unroll
+    for (int i = 0; i < PPT; ++i) pd[i] = (t + i * THREADS) < n ? 1e38f : -1.f;
+    int old = 0;
+    if (t == 0) dst[0] = 0;
+    for (int j = 1; j < m; ++j) {
+        const float x1 = xs[old], y1 = ys[old], z1 = zs[old];
+        float best = -1.f;
+        int besti = 0;
+#pragma unroll
+        for (int i = 0; i < PPT; ++i) {
+            int k = t + i * THREADS;
+            float d = sqdist_ref(xs[k] - x1, ys[k] - y1, zs[k] - z1);
+            float d2 = fminf(d, pd[i]);
+            pd[i] = d2;
+            if (d2 > best) {
+                best = d2;
+                besti = i;
+            }
+        }
+        const bool has = best >= 0.f;
+        unsigned db = has ? __float_as_uint(best) : 0u;
+        unsigned key = has ? tie_key(t + besti * THREADS) : 0xFFFFFFFFu;
+        unsigned wmax = __reduce_max_sync(0xFFFFFFFFu, db);
+        unsigned wkey = __reduce_min_sync(0xFFFFFFFFu, db == wmax ? key : 0xFFFFFFFFu);
+        unsigned long long *sl = slots + (j & 1) * 32;
+        if (lane == 0) sl[warp] = ((unsigned long long)wmax << 32) | wkey;
+        __syncthreads();
+        unsigned long long v = lane < NW ? sl[lane] : 0x00000000FFFFFFFFull;
+        unsigned d2 = (unsigned)(v >> 32), k2 = (unsigned)v;
+        unsigned gmax = __reduce_max_sync(0xFFFFFFFFu, d2);
+        unsigned gkey = __reduce_min_sync(0xFFFFFFFFu, d2 == gmax ? k2 : 0xFFFFFFFFu);
+        old = gkey == 0xFFFFFFFFu ? 0 : key_to_k(gkey);
+        if (t == 0) dst[j] = old;
+    }
+}
+
+// Fallback for clouds larger than one SM can hold: one CTA per cloud, coordinates read
+// through L1/L2 each round, running minimum in a caller-provided (b,n) global scratch.
+// Same arithmetic and tie order; used only beyond 16384 points (sweep sizes of config 5).
+__global__ void __launch_bounds__(1024, 1)
+fps_stream_kernel(int n, int m, const float *__restrict__ inp, float *__restrict__ temp,
+                  int *__restrict__ out) {
+    constexpr int THREADS = 1024, NW = 32;
+    __shared__ unsigned long long slots[64];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const float *src = inp + (size_t)blockIdx.x * n * 3;
+    float *td = temp + (size_t)blockIdx.x * n;
+    int *dst = out + (size_t)blockIdx.x * m;
+    for (int k = t; k < n; k += THREADS) td[k] = 1e38f;
+    int old = 0;
+    if (t == 0) dst[0] = 0;
+    for (int j = 1; j < m; ++j) {
+        const float x1 = __ldg(src + old * 3), y1 = __ldg(src + old * 3 + 1),
+                    z1 = __ldg(src + old * 3 + 2);
+        float best = -1.f;
+        int bestk = 0;
+        for (int k = t; k < n; k += THREADS) {
+            float d = sqdist_ref(__ldg(src + k * 3) - x1, __ldg(src + k * 3 + 1) - y1,
+                                 __ldg(src + k * 3 + 2) - z1);
+            float d2 = fminf(d, td[k]);
+            td[k] = d2;
+            if (d2 > best) {
+                best = d2;
+                bestk = k;
+            }
+        }
+        const bool has = best >= 0.f;
+        unsigned db = has ? __float_as_uint(best) : 0u;
+        unsigned key = has ? tie_key(bestk) : 0xFFFFFFFFu;
+        unsigned wmax = __reduce_max_sync(0xFFFFFFFFu, db);
+        unsigned wkey = __reduce_min_sync(0xFFFFFFFFu, db == wmax ? key : 0xFFFFFFFFu);
+        unsigned long long *sl = slots + (j & 1) * 32;
+        if (lane == 0) sl[warp] = ((unsigned long long)wmax << 32) | wkey;
+        __syncthreads();
+        unsigned long long v = lane < NW ? sl[lane] : 0x00000000FFFFFFFFull;
+        unsigned d2 = (unsigned)(v >> 32), k2 = (unsigned)v;
+        unsigned gmax = __reduce_max_sync(0xFFFFFFFFu, d2);
+        unsigned gkey = __reduce_min_sync(0xFFFFFFFFu, d2 == gmax ? k2 : 0xFFFFFFFFu);
+        old = gkey == 0xFFFFFFFFu ? 0 : key_to_k(gkey);
+        if (t == 0) dst[j] = old;
+    }
+}
+
+template <int THREADS, int PPT>
+static int launch_fps_reg(int b, int n, int m, const float *inp, int *out, cudaStream_t st) {
+    size_t smem = 64 * sizeof(unsigned long long) + (size_t)THREADS * PPT * 3 * sizeof(float);
+    auto kern = fps_reg_kernel<THREADS, PPT>;
+    if (smem > 48 * 1024) {
+        int rc = cuda_status(
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (rc) return rc;
+    }
+    kern<<<b, THREADS, smem, st>>>(n, m, inp, out);
+    return finish_launch();
+}
+
+template <int THREADS, int PPT>
+static int launch_fps_smem(int b, int n, int m, const float *inp, int *out, cudaStream_t st) {
+    size_t smem = 64 * sizeof(unsigned long long) + (size_t)THREADS * PPT * 3 * sizeof(float);
+    auto kern = fps_smem_kernel<THREADS, PPT>;
+    int rc = cuda_status(
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (rc) return rc;
+    kern<<<b, THREADS, smem, st>>>(n, m, inp, out);
+    return finish_launch();
+}
+
+// ---- gather_point / grad ---------------------------------------------------------------
+__global__ void gather_point_kernel(int n, int m, long total, const float *__restrict__ inp,
+                                    const int *__restrict__ idx, float *__restrict__ out) {
+    // one thread per output float: e = (cloud*m + j)*3 + c ; coalesced writes
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total;
+         e += (long)gridDim.x * blockDim.x) {
+        long row = e / 3;
+        int c = (int)(e - row * 3);
+        long cloud = row / m;
+        int a = __ldg(idx + row);
+        out[e] = __ldg(inp + (cloud * n + a) * 3 + c);
+    }
+}
+
+__global__ void gather_point_grad_kernel(int n, int m, long total,
+                                         const float *__restrict__ out_g,
+                                         const int *__restrict__ idx,
+                                         float *__restrict__ inp_g) {
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total;
+         e += (long)gridDim.x * blockDim.x) {
+        long row = e / 3;
+        int c = (int)(e - row * 3);
+        long cloud = row / m;
+        int a = __ldg(idx + row);
+        atomicAdd(inp_g + (cloud * n + a) * 3 + c, __ldg(out_g + e));
+    }
+}
+
+}  // namespace pn2
+
+using namespace pn2;
+
+PN2_API int pn2_fps(int b, int n, int m, const float *inp, float *temp, int *out,
+                    pn2_stream_t s) {
+    PN2_REQUIRE(b >= 0 && n > 0 && m > 0);  // tf_sampling.cpp:121-123 "expects positive npoint"
+    if (b == 0) return PN2_OK;
+    PN2_REQUIRE_PTR(inp);
+    PN2_REQUIRE_PTR(out);
+    cudaStream_t st = as_stream(s);
+    if (n <= 128) return launch_fps_reg<128, 1>(b, n, m, inp, out, st);
+    if (n <= 256) return launch_fps_reg<128, 2>(b, n, m, inp, out, st);
+    if (n <= 512) return launch_fps_reg<256, 2>(b, n, m, inp, out, st);
+    if (n <= 1024) return launch_fps_reg<256, 4>(b, n, m, inp, out, st);
+    if (n <= 2048) return launch_fps_reg<512, 4>(b, n, m, inp, out, st);
+    if (n <= 4096) return launch_fps_reg<1024, 4>(b, n, m, inp, out, st);
+    if (n <= 8192) return launch_fps_reg<1024, 8>(b, n, m, inp, out, st);
+    if (n <= 16384) return launch_fps_smem<1024, 16>(b, n, m, inp, out, st);
+    // beyond one SM's capacity: streaming kernel needs the (b,n) scratch the reference also
+    // requires (tf_sampling.cpp:143-146 allocates (32,n))
+    if (temp == nullptr) return PN2_ENULL;
+    fps_stream_kernel<<<b, 1024, 0, st>>>(n, m, inp, temp, out);
+    return finish_launch();
+}
+
+PN2_API int pn2_gather_point(int b, int n, int m, const float *inp, const int *idx, float *out,
+                             pn2_stream_t s) {
+    PN2_REQUIRE(b >= 0 && n > 0 && m >= 0);
+    long total = (long)b * m * 3;
+    if (total == 0) return PN2_OK;
+    PN2_REQUIRE_PTR(inp);
+    PN2_REQUIRE_PTR(idx);
+    PN2_REQUIRE_PTR(out);
+    int threads = 256;
+    long blocks = ceil_div<long>(total, threads);
+    if (blocks > 148L * 16) blocks = 148L * 16;
+    gather_point_kernel<<<(int)blocks, threads, 0, as_stream(s)>>>(n, m, total, inp, idx, out);
+    return finish_launch();
+}
+
+PN2_API int pn2_gather_point_grad(int b, int n, int m, const float *out_g, const int *idx,
+                                  float *inp_g, pn2_stream_t s) {
+    PN2_REQUIRE(b >= 0 && n > 0 && m >= 0);
+    if (b == 0) return PN2_OK;
+    PN2_REQUIRE_PTR(inp_g);
+    cudaStream_t st = as_stream(s);
+    int rc = cuda_status(cudaMemsetAsync(inp_g, 0, sizeof(float) * (size_t)b * n * 3, st));
+    if (rc) return rc;
+    long total = (long)b * m * 3;
+    if (total == 0) return PN2_OK;
+    PN2_REQUIRE_PTR(out_g);
+    PN2_REQUIRE_PTR(idx);
+    int threads = 256;
+    long blocks = ceil_div<long>(total, threads);
+    if (blocks > 148L * 16) blocks = 148L * 16;
+    gather_point_grad_kernel<<<(int)blocks, threads, 0, st>>>(n, m, total, out_g, idx, inp_g);
+    return finish_launch();
+}

@@ -118,6 +118,10 @@ int pn2_three_interpolate_grad_ld(int b, int n, int c, int m, const float *grad_
                                   const int *idx, const float *weight, float *grad_points,
                                   pn2_stream_t s);
 
+/* smallest float T with sqrtf(T) >= radius: the ball-query predicate max(sqrt(d2),1e-20f) < radius
+ * is evaluated as !(d2 >= T) (exported for tests). */
+float pn2_ball_threshold(float radius);
+
 /* dst[r*ldd + j] (=|+=) src[r*lds + j], j < cols */
 int pn2_copy_cols(long rows, int cols, const float *src, int lds, float *dst, int ldd,
                   int accumulate, pn2_stream_t s);
@@ -194,12 +198,13 @@ int pn2_dropout_mask(long n, float keep_prob, unsigned long long seed, unsigned 
 
 /* model.get_loss (model.py:152-161): weighted sparse softmax cross entropy with
  * SUM_BY_NONZERO_WEIGHTS.  acc[0] += sum w*ce, acc[1] += #nonzero w (fp64, caller zeroes);
- * the second call writes loss = acc0/max(acc1,1) and dlogits = gscale*w*(softmax-onehot)/max(acc1,1). */
+ * the second call writes loss = acc0/max(acc1,1) and dlogits = g*w*(softmax-onehot)/max(acc1,1)
+ * with g = gscale * (gscale_dev ? *gscale_dev : 1) (the upstream gradient, read on the device). */
 int pn2_softmax_ce_reduce(long rows, int C, const float *logits, const int *labels,
                           const float *weights, double *acc, pn2_stream_t s);
 int pn2_softmax_ce_grad(long rows, int C, const float *logits, const int *labels,
-                        const float *weights, const double *acc, float gscale, float *loss,
-                        float *dlogits, pn2_stream_t s);
+                        const float *weights, const double *acc, float gscale,
+                        const float *gscale_dev, float *loss, float *dlogits, pn2_stream_t s);
 
 /* tf.train.AdamOptimizer update on a flat buffer:
  * lr_t = lr*sqrt(1-b2^t)/(1-b1^t); m,v moments; p -= lr_t*m/(sqrt(v)+eps); gscale multiplies g */

@@ -334,11 +334,12 @@ __global__ void softmax_ce_grad_kernel(long rows, int C, const float *__restrict
                                        const int *__restrict__ labels,
                                        const float *__restrict__ weights,
                                        const double *__restrict__ acc, float gscale,
+                                       const float *__restrict__ gscale_dev,
                                        float *__restrict__ loss, float *__restrict__ dlogits) {
     const double nz = acc[1] > 0.0 ? acc[1] : 1.0;
     if (blockIdx.x == 0 && threadIdx.x == 0 && loss) *loss = (float)(acc[0] / nz);
     if (!dlogits) return;
-    const float inv = (float)((double)gscale / nz);
+    const float inv = (float)((double)gscale * (gscale_dev ? (double)*gscale_dev : 1.0) / nz);
     for (long r = blockIdx.x * (long)blockDim.x + threadIdx.x; r < rows;
          r += (long)gridDim.x * blockDim.x) {
         const float *x = logits + r * C;
@@ -656,14 +657,15 @@ PN2_API int pn2_softmax_ce_reduce(long rows, int C, const float *logits, const i
 
 PN2_API int pn2_softmax_ce_grad(long rows, int C, const float *logits, const int *labels,
                                 const float *weights, const double *acc, float gscale,
-                                float *loss, float *dlogits, pn2_stream_t s) {
+                                const float *gscale_dev, float *loss, float *dlogits,
+                                pn2_stream_t s) {
     PN2_REQUIRE(rows >= 0 && C > 0);
     if (rows == 0) return PN2_OK;
     PN2_REQUIRE_PTR(logits);
     PN2_REQUIRE_PTR(labels);
     PN2_REQUIRE_PTR(acc);
     softmax_ce_grad_kernel<<<grid_for(rows, 256), 256, 0, as_stream(s)>>>(
-        rows, C, logits, labels, weights, acc, gscale, loss, dlogits);
+        rows, C, logits, labels, weights, acc, gscale, gscale_dev, loss, dlogits);
     return finish_launch();
 }
 

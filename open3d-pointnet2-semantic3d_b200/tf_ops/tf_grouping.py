@@ -1,0 +1,102 @@
+"""Grouping ops: same names / argument order as the reference's tf_ops/tf_grouping.py.
+
+  query_ball_point(radius, nsample, xyz1, xyz2)  tf_grouping.py:13-25 (no gradient, :28)
+  group_point(points, idx)                       tf_grouping.py:46-54 (gradient :57-61)
+  select_top_k(k, dist)                          tf_grouping.py:31-40
+  knn_point(k, xyz1, xyz2)                       tf_grouping.py:64-89
+
+Validation texts follow tf_grouping.cpp:80-105, 187-200, 142-151.
+"""
+import torch
+
+from .._ffi import F32, I32, call, ptr
+
+
+def _need(cond, msg):
+    if not cond:
+        raise ValueError(msg)
+
+
+def query_ball_point(radius, nsample, xyz1, xyz2):
+    """xyz1 (B,n,3) data, xyz2 (B,m,3) queries -> idx (B,m,nsample) int32, pts_cnt (B,m) int32.
+
+    First ``nsample`` points (ascending index) with max(sqrt(d2),1e-20) < radius; shorter rows
+    are padded with the first hit; rows without any hit are zeros (reference: uninitialised)."""
+    _need(float(radius) > 0, "QueryBallPoint expects positive radius")
+    _need(int(nsample) > 0, "QueryBallPoint expects positive nsample")
+    _need(xyz1.dim() == 3 and xyz1.shape[2] == 3,
+          "QueryBallPoint expects (batch_size, ndataset, 3) xyz1 shape.")
+    _need(xyz2.dim() == 3 and xyz2.shape[2] == 3,
+          "QueryBallPoint expects (batch_size, npoint, 3) xyz2 shape.")
+    b, n, _ = xyz1.shape
+    m = xyz2.shape[1]
+    xyz1 = xyz1.detach().contiguous()
+    xyz2 = xyz2.detach().contiguous()
+    idx = torch.empty((b, m, int(nsample)), dtype=I32, device=xyz1.device)
+    cnt = torch.empty((b, m), dtype=I32, device=xyz1.device)
+    call("pn2_query_ball_point", b, n, m, float(radius), int(nsample), ptr(xyz1, F32),
+         ptr(xyz2, F32), ptr(idx, I32), ptr(cnt, I32))
+    return idx, cnt
+
+
+class _GroupPoint(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, points, idx):
+        b, n, c = points.shape
+        _, m, ns = idx.shape
+        points_c = points.contiguous()
+        out = torch.empty((b, m, ns, c), dtype=F32, device=points.device)
+        call("pn2_group_point", b, n, c, m, ns, ptr(points_c, F32), ptr(idx, I32), ptr(out, F32))
+        ctx.save_for_backward(idx)
+        ctx.dims = (b, n, c, m, ns)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (idx,) = ctx.saved_tensors
+        b, n, c, m, ns = ctx.dims
+        grad_out = grad_out.contiguous()
+        g = torch.empty((b, n, c), dtype=F32, device=grad_out.device)
+        call("pn2_group_point_grad", b, n, c, m, ns, ptr(grad_out, F32), ptr(idx, I32), ptr(g, F32))
+        return g, None
+
+
+def group_point(points, idx):
+    """points (B,n,C), idx (B,m,ns) int32 -> (B,m,ns,C); differentiable w.r.t. points."""
+    _need(points.dim() == 3, "GroupPoint expects (batch_size, num_points, channel) points shape")
+    _need(idx.dim() == 3 and idx.shape[0] == points.shape[0],
+          "GroupPoint expects (batch_size, npoints, nsample) idx shape")
+    return _GroupPoint.apply(points, idx.contiguous())
+
+
+def group_point_grad(points, idx, grad_out):
+    """Explicit gradient op (reference: grouping_module.group_point_grad)."""
+    b, n, c = points.shape
+    _, m, ns = idx.shape
+    _need(grad_out.dim() == 4 and tuple(grad_out.shape) == (b, m, ns, c),
+          "GroupPointGrad expects (batch_size, npoints, nsample, channel) grad_out shape")
+    g = torch.empty((b, n, c), dtype=F32, device=points.device)
+    call("pn2_group_point_grad", b, n, c, m, ns, ptr(grad_out.contiguous(), F32),
+         ptr(idx.contiguous(), I32), ptr(g, F32))
+    return g
+
+
+def select_top_k(k, dist):
+    """dist (B,m,n) -> (idx (B,m,n) int32, dist_out (B,m,n)); only [..., :k] is meaningful
+    (the k smallest, ascending).  Entries beyond k are NOT the reference's permutation."""
+    _need(int(k) > 0, "SelectionSort expects positive k")
+    _need(dist.dim() == 3, "SelectionSort expects (b,m,n) dist shape.")
+    b, m, n = dist.shape
+    dist = dist.detach().contiguous()
+    outi = torch.zeros((b, m, n), dtype=I32, device=dist.device)
+    out = torch.zeros((b, m, n), dtype=F32, device=dist.device)
+    call("pn2_selection_sort", b, n, m, int(k), ptr(dist, F32), ptr(outi, I32), ptr(out, F32))
+    return outi, out
+
+
+def knn_point(k, xyz1, xyz2):
+    """k nearest data points of every query (tf_grouping.py:64-89): squared-distance matrix
+    (b,m,n) followed by select_top_k.  Returns (val (B,m,k), idx (B,m,k))."""
+    d = ((xyz2.detach()[:, :, None, :] - xyz1.detach()[:, None, :, :]) ** 2).sum(-1)
+    outi, out = select_top_k(k, d)
+    return out[:, :, :k].contiguous(), outi[:, :, :k].contiguous()

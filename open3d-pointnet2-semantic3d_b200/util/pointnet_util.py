@@ -1,0 +1,236 @@
+"""PointNet++ layers: the reference's util/pointnet_util.py signatures on the sm_100a engine.
+
+  sample_and_group(npoint, radius, nsample, xyz, points, knn, use_xyz)   pointnet_util.py:18-60
+  sample_and_group_all(xyz, points, use_xyz)                             pointnet_util.py:63-95
+  pointnet_sa_module(xyz, points, npoint, radius, nsample, mlp, mlp2,
+                     group_all, is_training, bn_decay, scope, bn, pooling,
+                     knn, use_xyz, use_nchw)                             pointnet_util.py:98-216
+  pointnet_sa_module_msg(...)                                            pointnet_util.py:219-282
+  pointnet_fp_module(xyz1, xyz2, points1, points2, mlp, is_training,
+                     bn_decay, scope, bn)                                pointnet_util.py:285-326
+
+Tensors are CUDA float32, channels-last, exactly the reference's layouts.  The common
+configuration (ball query, max pooling, no mlp2) runs as: FPS -> gather -> ball query ->
+fused group+centre+concat -> shared-MLP chain with BN statistics in the GEMM epilogue ->
+fused BN+ReLU+max-pool.  Rarely used options (avg / weighted_avg / max_and_avg pooling,
+mlp2, group_all) are composed from the same kernels plus elementwise torch glue.
+"""
+import torch
+
+from .._ffi import F32, I32, call, ptr
+from ..tf_ops.tf_grouping import group_point, knn_point, query_ball_point
+from ..tf_ops.tf_interpolate import three_nn
+from ..tf_ops.tf_sampling import farthest_point_sample, gather_point
+from . import tf_util
+
+
+class _GroupConcat(torch.autograd.Function):
+    """(B,m,ns,3+C) = [xyz[idx]-new_xyz | points[idx]] (xyz_first) or [points | xyz] (MSG)."""
+
+    @staticmethod
+    def forward(ctx, xyz, new_xyz, points, idx, xyz_first, use_xyz):
+        b, n, _ = xyz.shape
+        _, m, ns = idx.shape
+        c = 0 if points is None else points.shape[2]
+        w = (3 if use_xyz else 0) + c
+        xyz_c, new_c = xyz.contiguous(), new_xyz.contiguous()
+        pts_c = None if points is None else points.contiguous()
+        out = torch.empty((b, m, ns, w), dtype=F32, device=xyz.device)
+        call("pn2_group_concat", b, n, m, ns, c, ptr(xyz_c, F32), ptr(new_c, F32),
+             ptr(pts_c, F32, True), ptr(idx, I32), 1 if xyz_first else 0, 1 if use_xyz else 0,
+             ptr(out, F32))
+        ctx.save_for_backward(idx)
+        ctx.cfg = (b, n, m, ns, c, xyz_first, use_xyz)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (idx,) = ctx.saved_tensors
+        b, n, m, ns, c, xyz_first, use_xyz = ctx.cfg
+        g = g.contiguous()
+        dev = g.device
+        need_xyz, need_new, need_pts = ctx.needs_input_grad[0], ctx.needs_input_grad[1], \
+            ctx.needs_input_grad[2] and c > 0
+        g_pts = torch.empty((b, n, c), dtype=F32, device=dev) if need_pts else None
+        g_xyz = torch.empty((b, n, 3), dtype=F32, device=dev) if (need_xyz and use_xyz) else None
+        g_new = torch.empty((b, m, 3), dtype=F32, device=dev) if (need_new and use_xyz) else None
+        if g_pts is not None or g_xyz is not None or g_new is not None:
+            call("pn2_group_concat_grad", b, n, m, ns, c, ptr(g, F32), ptr(idx, I32),
+                 1 if xyz_first else 0, 1 if use_xyz else 0, ptr(g_pts, F32, True),
+                 ptr(g_xyz, F32, True), ptr(g_new, F32, True))
+        return g_xyz, g_new, g_pts, None, None, None
+
+
+def sample_and_group(npoint, radius, nsample, xyz, points, knn=False, use_xyz=True):
+    """pointnet_util.py:18-60.  Returns new_xyz (B,npoint,3), new_points (B,npoint,nsample,3+C)
+    with channel order [xyz, features], idx (B,npoint,nsample), grouped_xyz (centred)."""
+    new_xyz = gather_point(xyz, farthest_point_sample(npoint, xyz))
+    if knn:
+        _, idx = knn_point(nsample, xyz, new_xyz)
+    else:
+        idx, _ = query_ball_point(radius, nsample, xyz, new_xyz)
+    if points is not None and use_xyz:
+        # one fused pass writes [xyz - centre | features]; grouped_xyz is its first 3 channels
+        new_points = _GroupConcat.apply(xyz, new_xyz, points, idx, True, True)
+        grouped_xyz = new_points[..., 0:3]
+    else:
+        grouped_xyz = _GroupConcat.apply(xyz, new_xyz, None, idx, True, True)
+        new_points = group_point(points, idx) if points is not None else grouped_xyz
+    return new_xyz, new_points, idx, grouped_xyz
+
+
+def sample_and_group_all(xyz, points, use_xyz=True):
+    """pointnet_util.py:63-95: one group holding every point, centroid (0,0,0)."""
+    b, n, _ = xyz.shape
+    new_xyz = torch.zeros((b, 1, 3), dtype=F32, device=xyz.device)
+    idx = torch.arange(n, dtype=I32, device=xyz.device).view(1, 1, n).repeat(b, 1, 1)
+    grouped_xyz = xyz.reshape(b, 1, n, 3)
+    if points is not None:
+        new_points = torch.cat([xyz, points], dim=2) if use_xyz else points
+        new_points = new_points.unsqueeze(1)
+    else:
+        new_points = grouped_xyz
+    return new_xyz, new_points, idx, grouped_xyz
+
+
+def _conv_layers(prefix, k, widths, bn):
+    layers = []
+    for i, n in enumerate(widths):
+        layers.append(tf_util.make_layer(prefix % i, k, n, bn, tf_util.relu))
+        k = n
+    return layers
+
+
+def pointnet_sa_module(xyz, points, npoint, radius, nsample, mlp, mlp2, group_all, is_training,
+                       bn_decay, scope, bn=True, pooling="max", knn=False, use_xyz=True,
+                       use_nchw=False):
+    """PointNet Set Abstraction module (pointnet_util.py:98-216).
+
+    Returns new_xyz (B,npoint,3), new_points (B,npoint,mlp[-1] or mlp2[-1]), idx."""
+    training = tf_util._as_bool(is_training)
+    with tf_util.variable_scope(scope):
+        if group_all:
+            nsample = xyz.shape[1]
+            new_xyz, new_points, idx, grouped_xyz = sample_and_group_all(xyz, points, use_xyz)
+        else:
+            new_xyz, new_points, idx, grouped_xyz = sample_and_group(
+                npoint, radius, nsample, xyz, points, knn, use_xyz)
+        b, m, ns, k = new_points.shape
+        layers = _conv_layers("conv%d", k, mlp, bn)
+        x2d = new_points.reshape(b * m * ns, k)
+        if pooling == "max":
+            pooled = tf_util.mlp_chain(x2d, layers, training, bn_decay, pool_ns=ns)
+            new_points = pooled.view(b, m, 1, mlp[-1])
+        else:
+            feat = tf_util.mlp_chain(x2d, layers, training, bn_decay).view(b, m, ns, mlp[-1])
+            if pooling == "avg":
+                new_points = feat.mean(dim=2, keepdim=True)
+            elif pooling == "weighted_avg":
+                dists = torch.linalg.norm(grouped_xyz, dim=-1, keepdim=True)
+                e = torch.exp(-dists * 5)
+                new_points = (feat * (e / e.sum(dim=2, keepdim=True))).sum(dim=2, keepdim=True)
+            elif pooling == "max_and_avg":
+                new_points = torch.cat([feat.mean(dim=2, keepdim=True),
+                                        feat.max(dim=2, keepdim=True)[0]], dim=-1)
+            else:
+                raise ValueError("unknown pooling %r" % (pooling,))
+        if mlp2 is not None:
+            kk = new_points.shape[-1]
+            layers2 = _conv_layers("conv_post_%d", kk, mlp2, bn)
+            new_points = tf_util.mlp_chain(new_points.reshape(b * m, kk), layers2, training,
+                                           bn_decay).view(b, m, 1, mlp2[-1])
+        return new_xyz, new_points.squeeze(2), idx
+
+
+def pointnet_sa_module_msg(xyz, points, npoint, radius_list, nsample_list, mlp_list, is_training,
+                           bn_decay, scope, bn=True, use_xyz=True, use_nchw=False):
+    """SA module with multi-scale grouping (pointnet_util.py:219-282); per scale the channel
+    order is [features, xyz] (:260), scales are concatenated in order."""
+    training = tf_util._as_bool(is_training)
+    with tf_util.variable_scope(scope):
+        new_xyz = gather_point(xyz, farthest_point_sample(npoint, xyz))
+        b, m, _ = new_xyz.shape
+        outs = []
+        for i, radius in enumerate(radius_list):
+            ns = nsample_list[i]
+            idx, _ = query_ball_point(radius, ns, xyz, new_xyz)
+            if points is not None:
+                grouped = _GroupConcat.apply(xyz, new_xyz, points, idx, False, bool(use_xyz))
+            else:
+                grouped = _GroupConcat.apply(xyz, new_xyz, None, idx, True, True)
+            k = grouped.shape[-1]
+            layers = []
+            for j, n in enumerate(mlp_list[i]):
+                layers.append(tf_util.make_layer("conv%d_%d" % (i, j), k, n, bn, tf_util.relu))
+                k = n
+            pooled = tf_util.mlp_chain(grouped.reshape(b * m * ns, grouped.shape[-1]), layers,
+                                       training, bn_decay, pool_ns=ns)
+            outs.append(pooled.view(b, m, k))
+        return new_xyz, torch.cat(outs, dim=-1)
+
+
+class _InterpConcat(torch.autograd.Function):
+    """X0 (B*n, C2+C1) = [three_interpolate(points2, idx, w) | points1], written in place."""
+
+    @staticmethod
+    def forward(ctx, points2, points1, idx, weight):
+        b, m, c2 = points2.shape
+        n = idx.shape[1]
+        c1 = 0 if points1 is None else points1.shape[2]
+        w = c2 + c1
+        p2 = points2.contiguous()
+        out = torch.empty((b * n, w), dtype=F32, device=points2.device)
+        call("pn2_three_interpolate_ld", b, m, c2, n, ptr(p2, F32), ptr(idx, I32), ptr(weight, F32),
+             ptr(out, F32), w)
+        if c1:
+            p1 = points1.contiguous()
+            call("pn2_copy_cols", b * n, c1, ptr(p1, F32), c1,
+                 _ffi_offset(out, c2), w, 0)
+        ctx.save_for_backward(idx, weight)
+        ctx.cfg = (b, m, c2, n, c1)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        idx, weight = ctx.saved_tensors
+        b, m, c2, n, c1 = ctx.cfg
+        g = g.contiguous()
+        w = c2 + c1
+        g2 = g1 = None
+        if ctx.needs_input_grad[0]:
+            g2 = torch.empty((b, m, c2), dtype=F32, device=g.device)
+            call("pn2_three_interpolate_grad_ld", b, n, c2, m, ptr(g, F32), w, ptr(idx, I32),
+                 ptr(weight, F32), ptr(g2, F32))
+        if c1 and ctx.needs_input_grad[1]:
+            g1 = torch.empty((b, n, c1), dtype=F32, device=g.device)
+            call("pn2_copy_cols", b * n, c1, _ffi_offset(g, c2), w, ptr(g1, F32), c1, 0)
+        return g2, g1, None, None
+
+
+def _ffi_offset(t, col):
+    """device address of column ``col`` of the first row of a contiguous 2-D fp32 tensor"""
+    import ctypes
+    return ctypes.c_void_p(t.data_ptr() + 4 * col)
+
+
+def fp_weights(dist):
+    """pointnet_util.py:300-303: inverse (squared) distance weights, floored at 1e-10."""
+    dist = dist.contiguous()
+    w = torch.empty_like(dist)
+    call("pn2_fp_weights", dist.numel() // 3, ptr(dist, F32), ptr(w, F32))
+    return w
+
+
+def pointnet_fp_module(xyz1, xyz2, points1, points2, mlp, is_training, bn_decay, scope, bn=True):
+    """PointNet Feature Propagation module (pointnet_util.py:285-326).
+    xyz1 (B,n1,3) dense, xyz2 (B,n2,3) sparse, points1 (B,n1,C1) or None, points2 (B,n2,C2)
+    -> (B,n1,mlp[-1]);  concat order [interpolated, points1] (:307-309)."""
+    training = tf_util._as_bool(is_training)
+    with tf_util.variable_scope(scope):
+        dist, idx = three_nn(xyz1, xyz2)
+        weight = fp_weights(dist)
+        x0 = _InterpConcat.apply(points2, points1, idx, weight)
+        b, n1, _ = xyz1.shape
+        layers = _conv_layers("conv_%d", x0.shape[1], mlp, bn)
+        out = tf_util.mlp_chain(x0, layers, training, bn_decay)
+        return out.view(b, n1, mlp[-1])

@@ -1,0 +1,410 @@
+"""Dense layer helpers: the reference's util/tf_util.py surface on the sm_100a engine.
+
+Kept names / signatures (reference file:line):
+  conv2d(inputs, num_output_channels, kernel_size, scope, ...)   tf_util.py:128-204
+  conv1d(inputs, num_output_channels, kernel_size, scope, ...)   tf_util.py:54-125
+  batch_norm_for_conv2d / _conv1d / batch_norm_template          tf_util.py:555-629
+  dropout(inputs, is_training, scope, keep_prob, noise_shape)    tf_util.py:646-665
+Only what model.py reaches is in scope (1x1 kernels, VALID/SAME are identical for 1x1);
+conv2d_transpose / conv3d / fully_connected / pools are not.
+
+TensorFlow's variable scopes become a ``VariableStore``: ``variable_scope("layer1")`` +
+``get_variable("weights", ...)`` yields the same names the reference checkpoints use
+(``layer1/conv0/weights``, ``.../bn/gamma`` ...).  Variables are plain CUDA tensors (views into
+one flat parameter buffer after ``flatten()``), NOT autograd leaves: the backward kernels
+accumulate parameter gradients straight into the flat gradient buffer, which is what the
+data-parallel all-reduce and the Adam kernel consume.
+
+All arithmetic runs in libpn2_b200.so: Y = f(A) W + b as a GEMM with the previous layer's
+BatchNorm+ReLU applied while loading A, batch statistics accumulated in the GEMM epilogue,
+BN+ReLU(+max-pool over nsample) applied by one pass over the pre-activation tensor.
+"""
+import contextlib
+import math
+
+import torch
+
+from .._ffi import F32, F64, I32, call, ptr
+
+BN_EPS = 1e-3  # tf.contrib.layers.batch_norm default epsilon (not in the reference source)
+relu = "relu"  # stands in for tf.nn.relu as activation_fn
+
+
+# ------------------------------------------------------------------------------------------
+# variables
+# ------------------------------------------------------------------------------------------
+class Variable:
+    __slots__ = ("name", "data", "grad", "trainable")
+
+    def __init__(self, name, data, trainable=True):
+        self.name, self.data, self.trainable = name, data, trainable
+        self.grad = None
+
+    def ensure_grad(self):
+        if self.grad is None:
+            self.grad = torch.zeros_like(self.data)
+        return self.grad
+
+
+class VariableStore:
+    """name -> Variable, in creation order (== the reference graph's creation order)."""
+
+    def __init__(self, device="cuda", seed=0):
+        self.device = torch.device(device)
+        self.vars = {}
+        self.scope = []
+        self.gen = torch.Generator(device="cpu")
+        self.gen.manual_seed(seed)
+        self.flat_params = self.flat_grads = None
+        # a leaf that requires grad, threaded through every layer Function so that autograd
+        # visits the Function even when its data input does not require grad
+        self.anchor = torch.zeros(1, device=self.device, requires_grad=True)
+
+    # -- creation -----------------------------------------------------------------------
+    def full_name(self, name):
+        return "/".join(self.scope + [name])
+
+    def get_variable(self, name, shape, init, trainable=True):
+        full = self.full_name(name)
+        v = self.vars.get(full)
+        if v is None:
+            if callable(init):
+                data = init(shape)
+            else:
+                data = torch.full(tuple(shape), float(init), dtype=F32)
+            v = Variable(full, data.to(self.device, F32).contiguous(), trainable)
+            self.vars[full] = v
+            self.flat_params = self.flat_grads = None  # layout changed
+        elif tuple(v.data.shape) != tuple(shape):
+            raise ValueError("variable %s exists with shape %s, requested %s"
+                             % (full, tuple(v.data.shape), tuple(shape)))
+        return v
+
+    def xavier(self, shape):
+        """tf.contrib.layers.xavier_initializer (uniform) for a [.., fan_in, fan_out] kernel."""
+        fan_in, fan_out = shape[-2], shape[-1]
+        lim = math.sqrt(6.0 / (fan_in + fan_out))
+        return (torch.rand(tuple(shape), generator=self.gen, dtype=F32) * 2 - 1) * lim
+
+    def truncated_normal(self, stddev):
+        def init(shape):
+            t = torch.empty(tuple(shape), dtype=F32)
+            torch.nn.init.trunc_normal_(t, 0.0, stddev, -2 * stddev, 2 * stddev, generator=self.gen)
+            return t
+        return init
+
+    # -- flat buffers ---------------------------------------------------------------------
+    def trainable(self):
+        return [v for v in self.vars.values() if v.trainable]
+
+    def flatten(self):
+        """Move every trainable variable into one flat fp32 buffer (+ a flat gradient buffer).
+        The flat gradient buffer is the single all-reduce message of the DP step."""
+        tv = self.trainable()
+        total = sum(v.data.numel() for v in tv)
+        flat = torch.empty(total, dtype=F32, device=self.device)
+        grads = torch.zeros(total, dtype=F32, device=self.device)
+        off = 0
+        for v in tv:
+            n = v.data.numel()
+            flat[off:off + n].copy_(v.data.reshape(-1))
+            v.data = flat[off:off + n].view(v.data.shape)
+            v.grad = grads[off:off + n].view(v.data.shape)
+            off += n
+        self.flat_params, self.flat_grads = flat, grads
+        return flat, grads
+
+    def zero_grad(self):
+        if self.flat_grads is not None:
+            self.flat_grads.zero_()
+        else:
+            for v in self.trainable():
+                if v.grad is not None:
+                    v.grad.zero_()
+
+    def state_dict(self):
+        return {k: v.data.detach().cpu().numpy().copy() for k, v in self.vars.items()}
+
+    def load_state_dict(self, sd):
+        for k, arr in sd.items():
+            t = torch.as_tensor(arr, dtype=F32)
+            if k in self.vars:
+                self.vars[k].data.copy_(t.to(self.device))
+            else:
+                trainable = not (k.endswith("moving_mean") or k.endswith("moving_variance"))
+                self.vars[k] = Variable(k, t.to(self.device).contiguous(), trainable)
+                self.flat_params = self.flat_grads = None
+
+
+_store = None
+
+
+def default_store():
+    global _store
+    if _store is None:
+        _store = VariableStore()
+    return _store
+
+
+def set_default_store(store):
+    global _store
+    _store = store
+    return store
+
+
+@contextlib.contextmanager
+def variable_scope(name):
+    st = default_store()
+    st.scope.append(name)
+    try:
+        yield name
+    finally:
+        st.scope.pop()
+
+
+def _as_bool(x):
+    if isinstance(x, torch.Tensor):
+        return bool(x.item())
+    return bool(x)
+
+
+# ------------------------------------------------------------------------------------------
+# the shared-MLP chain: [1x1 conv + bias (+BN) (+ReLU)] x L (+ max-pool over nsample)
+# ------------------------------------------------------------------------------------------
+class LayerSpec:
+    """Variables and flags of one conv layer (created by ``make_layer`` inside its scope)."""
+    __slots__ = ("w", "b", "gamma", "beta", "mm", "mv", "bn", "relu", "rank4", "k", "n")
+
+
+def make_layer(scope, k, n, bn, act, use_xavier=True, stddev=1e-3, kernel_rank=4):
+    st = default_store()
+    L = LayerSpec()
+    with variable_scope(scope):
+        init = st.xavier if use_xavier else st.truncated_normal(stddev)
+        kshape = [1, 1, k, n] if kernel_rank == 4 else [1, k, n]
+        L.w = st.get_variable("weights", kshape, init)
+        L.b = st.get_variable("biases", [n], 0.0)
+        L.bn, L.relu, L.rank4, L.k, L.n = bool(bn), act is not None, kernel_rank == 4, k, n
+        if bn:
+            with variable_scope("bn"):
+                L.gamma = st.get_variable("gamma", [n], 1.0)
+                L.beta = st.get_variable("beta", [n], 0.0)
+                L.mm = st.get_variable("moving_mean", [n], 0.0, trainable=False)
+                L.mv = st.get_variable("moving_variance", [n], 1.0, trainable=False)
+        else:
+            L.gamma = L.beta = L.mm = L.mv = None
+    return L
+
+
+class _MLPChain(torch.autograd.Function):
+    """x (M,K0) -> out (M,N_last) or, with pool_ns>0, (M/pool_ns, N_last) max-pooled.
+
+    Forward keeps only the pre-activation tensors Y_i; BatchNorm+ReLU of layer i is applied
+    on the fly when layer i+1 loads its A operand, and by the final affine(+pool) pass."""
+
+    @staticmethod
+    def forward(ctx, x, anchor, layers, is_training, bn_decay, pool_ns, gemm_mode):
+        M, K0 = x.shape
+        dev = x.device
+        x = x.contiguous()
+        decay = 0.9 if bn_decay is None else float(bn_decay)
+        a, lda, a_sc, a_sh, a_relu = x, K0, None, None, 0
+        Ys, scs, shs, saveds = [], [], [], []
+        for L in layers:
+            N = L.n
+            Y = torch.empty((M, N), dtype=F32, device=dev)
+            use_stats = L.bn and is_training
+            stats = torch.zeros(2 * N, dtype=F64, device=dev) if use_stats else None
+            call("pn2_linear_fwd", M, L.k, N, ptr(a, F32), lda, ptr(a_sc, F32, True),
+                 ptr(a_sh, F32, True), a_relu, ptr(L.w.data, F32), ptr(L.b.data, F32), ptr(Y, F32),
+                 ptr(stats, F64, True), gemm_mode)
+            sc = sh = saved = None
+            if L.bn:
+                sc = torch.empty(N, dtype=F32, device=dev)
+                sh = torch.empty(N, dtype=F32, device=dev)
+                if is_training:
+                    saved = torch.empty(2 * N, dtype=F32, device=dev)
+                    call("pn2_bn_train_finalize", N, M, ptr(stats, F64), ptr(L.gamma.data, F32),
+                         ptr(L.beta.data, F32), BN_EPS, decay, 1 if L.rank4 else 0,
+                         ptr(L.mm.data, F32), ptr(L.mv.data, F32), ptr(sc, F32), ptr(sh, F32),
+                         ptr(saved, F32))
+                else:
+                    call("pn2_bn_eval_affine", N, ptr(L.gamma.data, F32), ptr(L.beta.data, F32),
+                         ptr(L.mm.data, F32), ptr(L.mv.data, F32), BN_EPS, ptr(sc, F32),
+                         ptr(sh, F32))
+            elif L.relu:
+                sc = torch.ones(N, dtype=F32, device=dev)
+                sh = torch.zeros(N, dtype=F32, device=dev)
+            Ys.append(Y)
+            scs.append(sc)
+            shs.append(sh)
+            saveds.append(saved)
+            a, lda, a_sc, a_sh, a_relu = Y, N, sc, sh, 1 if L.relu else 0
+        L = layers[-1]
+        N = L.n
+        arg = None
+        if pool_ns:
+            G = M // pool_ns
+            out = torch.empty((G, N), dtype=F32, device=dev)
+            arg = torch.empty((G, N), dtype=I32, device=dev)
+            call("pn2_affine_act_maxpool", G, pool_ns, N, ptr(Ys[-1], F32), ptr(scs[-1], F32, True),
+                 ptr(shs[-1], F32, True), 1 if L.relu else 0, ptr(out, F32), ptr(arg, I32))
+        elif scs[-1] is None and not L.relu:
+            out = Ys[-1]
+        else:
+            out = torch.empty((M, N), dtype=F32, device=dev)
+            call("pn2_affine_act", M, N, ptr(Ys[-1], F32), ptr(scs[-1], F32, True),
+                 ptr(shs[-1], F32, True), 1 if L.relu else 0, ptr(out, F32), N)
+        ctx.layers, ctx.pool_ns, ctx.is_training, ctx.gemm_mode = layers, pool_ns, is_training, gemm_mode
+        ctx.x, ctx.Ys, ctx.scs, ctx.shs, ctx.saveds, ctx.arg = x, Ys, scs, shs, saveds, arg
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        layers, pool_ns = ctx.layers, ctx.pool_ns
+        if not ctx.is_training and any(L.bn for L in layers):
+            raise NotImplementedError("backward through inference-mode BatchNorm is not supported")
+        x, Ys, scs, shs, saveds = ctx.x, ctx.Ys, ctx.scs, ctx.shs, ctx.saveds
+        M = x.shape[0]
+        dev = x.device
+        up = d_out.contiguous()
+        for i in range(len(layers) - 1, -1, -1):
+            L = layers[i]
+            N, Y = L.n, Ys[i]
+            relu_i = 1 if L.relu else 0
+            pooled = pool_ns and i == len(layers) - 1
+            red = torch.zeros(2 * N, dtype=F64, device=dev) if L.bn else None
+            dg = ptr(L.gamma.ensure_grad(), F32) if L.bn else None
+            db_ = ptr(L.beta.ensure_grad(), F32) if L.bn else None
+            if pooled:
+                G = M // pool_ns
+                if L.bn:
+                    call("pn2_bn_bwd_reduce_pool", G, pool_ns, N, ptr(up, F32), ptr(ctx.arg, I32),
+                         ptr(Y, F32), ptr(scs[i], F32), ptr(shs[i], F32), ptr(saveds[i], F32),
+                         relu_i, ptr(red, F64))
+                dY = torch.empty((M, N), dtype=F32, device=dev)
+                call("pn2_bn_bwd_apply_pool", G, pool_ns, N, ptr(up, F32), ptr(ctx.arg, I32),
+                     ptr(Y, F32), ptr(scs[i], F32, True), ptr(shs[i], F32, True),
+                     ptr(saveds[i], F32, True), ptr(L.gamma.data, F32) if L.bn else None, relu_i,
+                     1 if L.bn else 0, ptr(red, F64, True), ptr(dY, F32), dg, db_)
+            elif L.bn or L.relu:
+                if L.bn:
+                    call("pn2_bn_bwd_reduce", M, N, ptr(up, F32), N, ptr(Y, F32), ptr(scs[i], F32),
+                         ptr(shs[i], F32), ptr(saveds[i], F32), relu_i, ptr(red, F64))
+                dY = torch.empty((M, N), dtype=F32, device=dev)
+                call("pn2_bn_bwd_apply", M, N, ptr(up, F32), N, ptr(Y, F32), ptr(scs[i], F32, True),
+                     ptr(shs[i], F32, True), ptr(saveds[i], F32, True),
+                     ptr(L.gamma.data, F32) if L.bn else None, relu_i, 1 if L.bn else 0,
+                     ptr(red, F64, True), ptr(dY, F32), dg, db_)
+            else:
+                dY = up
+            if i == 0:
+                a, lda, a_sc, a_sh, a_relu = x, x.shape[1], None, None, 0
+            else:
+                P = layers[i - 1]
+                a, lda, a_sc, a_sh, a_relu = Ys[i - 1], P.n, scs[i - 1], shs[i - 1], 1 if P.relu else 0
+            call("pn2_linear_wgrad", M, L.k, N, ptr(a, F32), lda, ptr(a_sc, F32, True),
+                 ptr(a_sh, F32, True), a_relu, ptr(dY, F32), ptr(L.w.ensure_grad(), F32),
+                 ptr(L.b.ensure_grad(), F32), ctx.gemm_mode)
+            if i > 0 or ctx.needs_input_grad[0]:
+                dX = torch.empty((M, L.k), dtype=F32, device=dev)
+                call("pn2_linear_dgrad", M, L.k, N, ptr(dY, F32), ptr(L.w.data, F32), ptr(dX, F32),
+                     L.k, ctx.gemm_mode)
+                up = dX
+            else:
+                up = None
+        ctx.Ys = ctx.x = None
+        return up, None, None, None, None, None, None
+
+
+GEMM_MODE = -1  # -1 auto, 0 exact fp32 CUDA-core kernel, 1 force tcgen05 3xTF32
+
+
+def mlp_chain(x2d, layers, is_training, bn_decay, pool_ns=0):
+    return _MLPChain.apply(x2d, default_store().anchor, layers, _as_bool(is_training), bn_decay,
+                           int(pool_ns), GEMM_MODE)
+
+
+# ------------------------------------------------------------------------------------------
+# reference-named layer functions
+# ------------------------------------------------------------------------------------------
+def _check_1x1(kernel_size, stride):
+    ks = list(kernel_size) if isinstance(kernel_size, (list, tuple)) else [kernel_size]
+    st = list(stride) if isinstance(stride, (list, tuple)) else [stride]
+    if any(k != 1 for k in ks) or any(s != 1 for s in st):
+        raise NotImplementedError("only 1x1 kernels with stride 1 are on the SA/FP hot path")
+
+
+def conv2d(inputs, num_output_channels, kernel_size, scope, stride=[1, 1], padding="SAME",
+           data_format="NHWC", use_xavier=True, stddev=1e-3, weight_decay=None,
+           activation_fn=relu, bn=False, bn_decay=None, is_training=None):
+    """1x1 2-D convolution + bias (+BN) (+ReLU) on a (B,H,W,C) tensor (tf_util.py:128-204)."""
+    _check_1x1(kernel_size, stride)
+    if data_format != "NHWC":
+        raise NotImplementedError("channels-last only (use_nchw is a layout no-op here)")
+    if weight_decay is not None:
+        raise NotImplementedError("weight_decay is never set on the SA/FP path")
+    shp = inputs.shape
+    L = make_layer(scope, shp[-1], num_output_channels, bn, activation_fn, use_xavier, stddev, 4)
+    y = mlp_chain(inputs.reshape(-1, shp[-1]), [L], True if is_training is None else is_training,
+                  bn_decay)
+    return y.view(*shp[:-1], num_output_channels)
+
+
+def conv1d(inputs, num_output_channels, kernel_size, scope, stride=1, padding="SAME",
+           data_format="NHWC", use_xavier=True, stddev=1e-3, weight_decay=None,
+           activation_fn=relu, bn=False, bn_decay=None, is_training=None):
+    """k=1 1-D convolution + bias (+BN) (+ReLU) on a (B,L,C) tensor (tf_util.py:54-125)."""
+    _check_1x1(kernel_size, stride)
+    if data_format != "NHWC":
+        raise NotImplementedError("channels-last only")
+    if weight_decay is not None:
+        raise NotImplementedError("weight_decay is never set on the SA/FP path")
+    shp = inputs.shape
+    L = make_layer(scope, shp[-1], num_output_channels, bn, activation_fn, use_xavier, stddev, 3)
+    y = mlp_chain(inputs.reshape(-1, shp[-1]), [L], True if is_training is None else is_training,
+                  bn_decay)
+    return y.view(*shp[:-1], num_output_channels)
+
+
+class _Dropout(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, keep_prob, seed):
+        x = x.contiguous()
+        out = torch.empty_like(x)
+        call("pn2_dropout", x.numel(), ptr(x, F32), float(keep_prob), int(seed), ptr(out, F32))
+        ctx.keep_prob, ctx.seed = keep_prob, seed
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        out = torch.empty_like(g)
+        call("pn2_dropout", g.numel(), ptr(g, F32), float(ctx.keep_prob), int(ctx.seed),
+             ptr(out, F32))
+        return out, None, None
+
+
+_dropout_seed = [0x5EED]
+
+
+def set_dropout_seed(seed):
+    _dropout_seed[0] = int(seed)
+
+
+def dropout_mask(numel, keep_prob, seed, device="cuda"):
+    """The 0/1 keep mask ``dropout`` uses for (seed, element index) -- test hook."""
+    m = torch.empty(numel, dtype=torch.uint8, device=device)
+    call("pn2_dropout_mask", numel, float(keep_prob), int(seed), ptr(m, torch.uint8))
+    return m
+
+
+def dropout(inputs, is_training, scope, keep_prob=0.5, noise_shape=None):
+    """tf_util.py:646-665: kept values are scaled by 1/keep_prob in training, identity else."""
+    if noise_shape is not None:
+        raise NotImplementedError("noise_shape is never set on the SA/FP path")
+    if not _as_bool(is_training):
+        return inputs
+    seed = _dropout_seed[0]
+    _dropout_seed[0] = (seed * 6364136223846793005 + 1442695040888963407) & 0xFFFFFFFFFFFFFFFF
+    return _Dropout.apply(inputs, keep_prob, seed)

@@ -1,0 +1,77 @@
+"""Shared helpers for the parity tests."""
+import ctypes
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def rng_cloud(seed, b, n, scale=(1.0, 1.0, 1.0), shift=(0.0, 0.0, 0.0)):
+    """np.random.seed(seed) legacy stream, uniform fp32 like the reference tests
+    (tf_ops/test_tf_ops.py:12-15)."""
+    rs = np.random.RandomState(seed)
+    x = rs.random_sample((b, n, 3)).astype(np.float32)
+    return (x * np.asarray(scale, np.float32) + np.asarray(shift, np.float32)).astype(np.float32)
+
+
+def to_cuda(a):
+    import torch
+    return torch.as_tensor(np.ascontiguousarray(a)).cuda()
+
+
+class RefKernels:
+    """The reference's OWN CUDA kernels (oracle/_ref/libref_tfops.so, built from
+    /root/reference/tf_ops/*.cu by oracle/Makefile).  Device pointers in, nothing copied."""
+
+    def __init__(self):
+        path = os.path.join(ROOT, "oracle", "_ref", "libref_tfops.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self.lib = ctypes.CDLL(path)
+
+    @staticmethod
+    def _p(t):
+        return ctypes.c_void_p(t.data_ptr())
+
+    def fps(self, inp, m):
+        import torch
+        b, n, _ = inp.shape
+        temp = torch.empty((32, n), dtype=torch.float32, device=inp.device)
+        out = torch.empty((b, m), dtype=torch.int32, device=inp.device)
+        torch.cuda.synchronize()
+        rc = self.lib.ref_fps(b, n, m, self._p(inp), self._p(temp), self._p(out), 1)
+        assert rc == 0, rc
+        return out
+
+    def query_ball_point(self, radius, nsample, xyz1, xyz2):
+        import torch
+        b, n, _ = xyz1.shape
+        m = xyz2.shape[1]
+        idx = torch.empty((b, m, nsample), dtype=torch.int32, device=xyz1.device)
+        cnt = torch.empty((b, m), dtype=torch.int32, device=xyz1.device)
+        torch.cuda.synchronize()
+        rc = self.lib.ref_query_ball_point(b, n, m, ctypes.c_float(radius), nsample, self._p(xyz1),
+                                           self._p(xyz2), self._p(idx), self._p(cnt), 1)
+        assert rc == 0, rc
+        return idx, cnt
+
+    def group_point(self, points, idx):
+        import torch
+        b, n, c = points.shape
+        _, m, ns = idx.shape
+        out = torch.empty((b, m, ns, c), dtype=torch.float32, device=points.device)
+        torch.cuda.synchronize()
+        rc = self.lib.ref_group_point(b, n, c, m, ns, self._p(points), self._p(idx), self._p(out), 1)
+        assert rc == 0, rc
+        return out
+
+    def gather_point(self, inp, idx):
+        import torch
+        b, n, _ = inp.shape
+        m = idx.shape[1]
+        out = torch.empty((b, m, 3), dtype=torch.float32, device=inp.device)
+        torch.cuda.synchronize()
+        rc = self.lib.ref_gather_point(b, n, m, self._p(inp), self._p(idx), self._p(out), 1)
+        assert rc == 0, rc
+        return out

@@ -1,0 +1,113 @@
+"""CPU: host-side logic -- schedules, variable store / scoping, argument validation."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+PARAMS = {"batch_size": 16, "learning_rate": 0.001, "decay_step": 200000,
+          "learning_rate_decay_rate": 0.7, "bn_init_decay": 0.5, "bn_decay_decay_rate": 0.5,
+          "bn_decay_clip": 0.99}
+
+
+def test_schedules_follow_train_py():
+    """train.py:80-119: staircase exponential decays, lr floor 1e-5, bn_decay clip 0.99."""
+    from pn2_b200.train_step import get_bn_decay, get_learning_rate
+    assert get_learning_rate(0, PARAMS) == 0.001
+    assert get_learning_rate(12499, PARAMS) == 0.001          # 12499*16 < 200000
+    assert abs(get_learning_rate(12500, PARAMS) - 0.0007) < 1e-12
+    assert get_learning_rate(10 ** 7, PARAMS) == 0.00001
+    assert get_bn_decay(0, PARAMS) == 0.5
+    assert get_bn_decay(12500, PARAMS) == 0.75
+    assert get_bn_decay(10 ** 7, PARAMS) == 0.99
+
+
+def test_variable_store_scoping_and_flatten():
+    import torch
+    from pn2_b200.util import tf_util
+    st = tf_util.set_default_store(tf_util.VariableStore(device="cpu", seed=3))
+    with tf_util.variable_scope("layer1"):
+        L = tf_util.make_layer("conv0", 6, 32, True, tf_util.relu)
+    assert L.w.name == "layer1/conv0/weights" and tuple(L.w.data.shape) == (1, 1, 6, 32)
+    assert set(st.vars) == {"layer1/conv0/weights", "layer1/conv0/biases", "layer1/conv0/bn/gamma",
+                            "layer1/conv0/bn/beta", "layer1/conv0/bn/moving_mean",
+                            "layer1/conv0/bn/moving_variance"}
+    lim = np.sqrt(6.0 / (6 + 32))
+    assert float(L.w.data.abs().max()) <= lim and float(L.b.data.abs().max()) == 0.0
+    assert float(L.gamma.data.min()) == 1.0 and float(L.mv.data.min()) == 1.0
+    # same scope again returns the same variables (reuse), shape mismatch is an error
+    with tf_util.variable_scope("layer1"):
+        L2 = tf_util.make_layer("conv0", 6, 32, True, tf_util.relu)
+        assert L2.w is L.w
+        with pytest.raises(ValueError):
+            tf_util.make_layer("conv0", 7, 32, True, tf_util.relu)
+    flat, grads = st.flatten()
+    assert flat.numel() == 6 * 32 + 32 * 3 and grads.numel() == flat.numel()
+    L.w.grad += 1.0
+    assert float(grads.sum()) == 6 * 32
+    st.zero_grad()
+    assert float(grads.abs().sum()) == 0.0
+    # data are views of the flat buffer
+    flat.fill_(2.0)
+    assert float(L.w.data.mean()) == 2.0 and not L.mm.trainable
+
+
+def test_python_validation_messages_match_reference():
+    """OP_REQUIRES texts of tf_sampling.cpp / tf_grouping.cpp / tf_interpolate.cpp."""
+    import torch
+    from pn2_b200.tf_ops import tf_grouping, tf_interpolate, tf_sampling
+    x = torch.rand(1, 8, 3)
+    with pytest.raises(ValueError, match="FarthestPointSample expects positive npoint"):
+        tf_sampling.farthest_point_sample(0, x)
+    with pytest.raises(ValueError, match=r"FarthestPointSample expects \(batch_size,num_points,3\)"):
+        tf_sampling.farthest_point_sample(4, x[..., :2])
+    with pytest.raises(ValueError, match="QueryBallPoint expects positive radius"):
+        tf_grouping.query_ball_point(-1.0, 4, x, x)
+    with pytest.raises(ValueError, match="QueryBallPoint expects positive nsample"):
+        tf_grouping.query_ball_point(1.0, 0, x, x)
+    with pytest.raises(ValueError, match="GroupPoint expects"):
+        tf_grouping.group_point(x[0], torch.zeros(1, 2, 2, dtype=torch.int32))
+    with pytest.raises(ValueError, match="ThreeNN expects"):
+        tf_interpolate.three_nn(x[..., :2], x)
+    with pytest.raises(ValueError, match="ThreeInterpolate expects"):
+        tf_interpolate.three_interpolate(x, torch.zeros(1, 4, 2, dtype=torch.int32), torch.zeros(1, 4, 3))
+    with pytest.raises(ValueError, match="SelectionSort expects positive k"):
+        tf_grouping.select_top_k(0, torch.rand(1, 2, 3))
+
+
+def test_reference_aliases():
+    import sys
+    import pn2_b200
+    pn2_b200.install_reference_aliases()
+    from tf_ops.tf_sampling import farthest_point_sample, gather_point  # noqa: F401
+    from tf_ops.tf_grouping import query_ball_point, group_point, knn_point  # noqa: F401
+    from tf_ops.tf_interpolate import three_nn, three_interpolate  # noqa: F401
+    from util.pointnet_util import (pointnet_sa_module, pointnet_sa_module_msg,  # noqa: F401
+                                    pointnet_fp_module, sample_and_group, sample_and_group_all)
+    from util import tf_util
+    assert hasattr(tf_util, "conv2d") and hasattr(tf_util, "conv1d") and hasattr(tf_util, "dropout")
+    for k in ["tf_ops", "tf_ops.tf_sampling", "util", "util.tf_util", "util.pointnet_util"]:
+        sys.modules.pop(k, None)
+
+
+def test_layer_signatures_match_reference():
+    """Positional/keyword orders of pointnet_util.py:98-116, 219-232, 285-287 and model.py."""
+    import inspect
+    from pn2_b200.util import pointnet_util as pu
+    from pn2_b200 import model
+    assert list(inspect.signature(pu.pointnet_sa_module).parameters) == [
+        "xyz", "points", "npoint", "radius", "nsample", "mlp", "mlp2", "group_all", "is_training",
+        "bn_decay", "scope", "bn", "pooling", "knn", "use_xyz", "use_nchw"]
+    assert list(inspect.signature(pu.pointnet_sa_module_msg).parameters) == [
+        "xyz", "points", "npoint", "radius_list", "nsample_list", "mlp_list", "is_training",
+        "bn_decay", "scope", "bn", "use_xyz", "use_nchw"]
+    assert list(inspect.signature(pu.pointnet_fp_module).parameters) == [
+        "xyz1", "xyz2", "points1", "points2", "mlp", "is_training", "bn_decay", "scope", "bn"]
+    assert list(inspect.signature(pu.sample_and_group).parameters) == [
+        "npoint", "radius", "nsample", "xyz", "points", "knn", "use_xyz"]
+    assert list(inspect.signature(model.get_model).parameters) == [
+        "point_cloud", "is_training", "num_class", "hyperparams", "bn_decay"]
+    ph = model.get_placeholders(8192, {"use_color": 1})
+    assert ph[0].shape == (None, 8192, 6) and ph[1].shape == (None, 8192)

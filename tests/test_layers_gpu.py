@@ -1,0 +1,291 @@
+"""GPU parity of the PointNet++ layers (pointnet_util / tf_util / model) against the fp64
+restatement in oracle/layers_ref.py.  Tolerance: 1e-5 absolute on fp32 forward outputs
+(BASELINE.json north_star); gradients are compared with 2e-5 * max(1, |expected|_max)."""
+import numpy as np
+import pytest
+
+from _util import rng_cloud, to_cuda
+
+pytestmark = pytest.mark.gpu
+
+ATOL = 1e-5
+
+
+def gtol(exp):
+    return 2e-5 * max(1.0, float(np.abs(exp).max()))
+
+
+@pytest.fixture()
+def env(cuda):
+    import pn2_b200  # noqa: F401
+    from pn2_b200.util import pointnet_util, tf_util
+    from pn2_b200 import model
+    from oracle import layers_ref as lr
+    store = tf_util.set_default_store(tf_util.VariableStore(device="cuda", seed=0))
+    return pointnet_util, tf_util, model, lr, store
+
+
+def load_params(store, params, rank3=("fc1", "fc2")):
+    sd = {}
+    for k, v in params.items():
+        if k.endswith("/weights"):
+            scope = k.split("/")[0]
+            v = v.reshape((1,) + v.shape) if scope in rank3 else v.reshape((1, 1) + v.shape)
+        sd[k] = v
+    store.load_state_dict(sd)
+
+
+def randomize_bn(params, rs):
+    for k in list(params):
+        if k.endswith("/bn/gamma"):
+            params[k] = rs.uniform(0.5, 1.5, params[k].shape).astype(np.float32)
+        if k.endswith("/bn/beta") or k.endswith("/biases"):
+            params[k] = rs.uniform(-0.3, 0.3, params[k].shape).astype(np.float32)
+
+
+def check_param_grads(store, ctx, names=None):
+    exp = ctx.grads()
+    for k, e in exp.items():
+        if names is not None and k not in names:
+            continue
+        v = store.vars[k]
+        assert v.grad is not None, k
+        got = v.grad.detach().cpu().numpy().reshape(e.shape)
+        np.testing.assert_allclose(got, e, atol=gtol(e), err_msg=k)
+
+
+def test_sa_module_config1(env):
+    """BASELINE.json configs[0]: B=2, N=1024, npoint=256, nsample=32, C=3, radius 0.2,
+    mlp [32,32,64], train-mode BN: every intermediate against the oracle."""
+    pu, tf_util, _, lr, store = env
+    import torch
+    rs = np.random.RandomState(100)
+    xyz = rs.random_sample((2, 1024, 3)).astype(np.float32)
+    pts = rs.random_sample((2, 1024, 3)).astype(np.float32)
+    params = {}
+    k = 6
+    for i, n in enumerate([32, 32, 64]):
+        lr.init_conv(params, rs, "layer1/conv%d" % i, k, n)
+        k = n
+    randomize_bn(params, rs)
+    load_params(store, params)
+    ctx = lr.Ctx(params, is_training=True, bn_decay=0.7)
+    pts_ref = torch.tensor(pts, dtype=torch.float64, requires_grad=True)
+    e_xyz, e_out, e_idx = lr.sa_module(ctx, xyz, pts_ref, 256, 0.2, 32, [32, 32, 64], "layer1")
+
+    pt = to_cuda(pts).requires_grad_(True)
+    new_xyz, out, idx = pu.pointnet_sa_module(to_cuda(xyz), pt, 256, 0.2, 32, [32, 32, 64], None,
+                                              False, True, 0.7, "layer1")
+    np.testing.assert_array_equal(idx.cpu().numpy(), e_idx)
+    np.testing.assert_array_equal(new_xyz.cpu().numpy(), e_xyz)
+    np.testing.assert_allclose(out.detach().cpu().numpy(), e_out.detach().numpy(), atol=ATOL)
+    for k2, v in ctx.new_moving.items():
+        np.testing.assert_allclose(store.vars[k2].data.cpu().numpy(), v, atol=ATOL, err_msg=k2)
+
+    g = rs.normal(size=tuple(out.shape)).astype(np.float32)
+    e_out.backward(torch.tensor(g, dtype=torch.float64))
+    out.backward(to_cuda(g))
+    check_param_grads(store, ctx)
+    eg = pts_ref.grad.numpy()
+    np.testing.assert_allclose(pt.grad.cpu().numpy(), eg, atol=gtol(eg))
+
+
+def test_sample_and_group_intermediates(env):
+    pu, _, _, lr, _ = env
+    import torch
+    rs = np.random.RandomState(3)
+    xyz = rs.random_sample((2, 512, 3)).astype(np.float32)
+    pts = rs.random_sample((2, 512, 5)).astype(np.float32)
+    e_xyz, e_np, e_idx, e_cnt, e_fps, e_gx = lr.sample_and_group(
+        64, 0.25, 16, xyz, torch.tensor(pts, dtype=torch.float64))
+    new_xyz, new_points, idx, grouped_xyz = pu.sample_and_group(64, 0.25, 16, to_cuda(xyz),
+                                                                to_cuda(pts))
+    np.testing.assert_array_equal(idx.cpu().numpy(), e_idx)
+    np.testing.assert_array_equal(new_xyz.cpu().numpy(), e_xyz)
+    # exact: the centre subtraction is one fp32 subtraction in both
+    exp = e_np.numpy()
+    np.testing.assert_allclose(new_points.cpu().numpy(), exp, atol=1e-7)
+    np.testing.assert_allclose(grouped_xyz.cpu().numpy(), e_gx.numpy(), atol=1e-7)
+    # points=None and use_xyz=False variants
+    _, np2, _, _ = pu.sample_and_group(64, 0.25, 16, to_cuda(xyz), None)
+    np.testing.assert_allclose(np2.cpu().numpy(), e_gx.numpy(), atol=1e-7)
+    _, np3, _, _ = pu.sample_and_group(64, 0.25, 16, to_cuda(xyz), to_cuda(pts), use_xyz=False)
+    np.testing.assert_array_equal(np3.cpu().numpy(), exp[..., 3:].astype(np.float32))
+
+
+@pytest.mark.parametrize("pooling,mlp2,group_all", [("avg", None, False), ("max_and_avg", None, False),
+                                                    ("weighted_avg", None, False),
+                                                    ("max", [48, 24], False), ("max", None, True)])
+def test_sa_module_options(env, pooling, mlp2, group_all):
+    pu, _, _, lr, store = env
+    import torch
+    rs = np.random.RandomState(17)
+    xyz = rs.random_sample((2, 256, 3)).astype(np.float32)
+    pts = rs.random_sample((2, 256, 4)).astype(np.float32)
+    params = {}
+    k = 7
+    for i, n in enumerate([16, 32]):
+        lr.init_conv(params, rs, "sa/conv%d" % i, k, n)
+        k = n
+    if pooling == "max_and_avg":
+        k *= 2
+    for i, n in enumerate(mlp2 or []):
+        lr.init_conv(params, rs, "sa/conv_post_%d" % i, k, n)
+        k = n
+    randomize_bn(params, rs)
+    load_params(store, params)
+    ctx = lr.Ctx(params, is_training=True, bn_decay=0.5)
+    _, e_out, _ = lr.sa_module(ctx, xyz, torch.tensor(pts, dtype=torch.float64), 32, 0.3, 16,
+                               [16, 32], "sa", mlp2=mlp2, group_all=group_all, pooling=pooling)
+    _, out, _ = pu.pointnet_sa_module(to_cuda(xyz), to_cuda(pts), 32, 0.3, 16, [16, 32], mlp2,
+                                      group_all, True, 0.5, "sa", pooling=pooling)
+    np.testing.assert_allclose(out.detach().cpu().numpy(), e_out.detach().numpy(), atol=ATOL)
+
+
+def test_sa_module_msg(env):
+    pu, _, _, lr, store = env
+    import torch
+    rs = np.random.RandomState(23)
+    xyz = rs.random_sample((2, 1024, 3)).astype(np.float32)
+    pts = rs.random_sample((2, 1024, 6)).astype(np.float32)
+    radii, nss, mlps = [0.1, 0.2, 0.4], [16, 32, 128], [[32, 32, 64], [64, 64, 128], [64, 96, 128]]
+    params = {}
+    for i, mlp in enumerate(mlps):
+        k = 9
+        for j, n in enumerate(mlp):
+            lr.init_conv(params, rs, "msg/conv%d_%d" % (i, j), k, n)
+            k = n
+    randomize_bn(params, rs)
+    load_params(store, params)
+    ctx = lr.Ctx(params, is_training=True, bn_decay=0.9)
+    pts_ref = torch.tensor(pts, dtype=torch.float64, requires_grad=True)
+    e_xyz, e_out = lr.sa_module_msg(ctx, xyz, pts_ref, 128, radii, nss, mlps, "msg")
+    pt = to_cuda(pts).requires_grad_(True)
+    new_xyz, out = pu.pointnet_sa_module_msg(to_cuda(xyz), pt, 128, radii, nss, mlps, True, 0.9,
+                                             "msg")
+    np.testing.assert_array_equal(new_xyz.cpu().numpy(), e_xyz)
+    np.testing.assert_allclose(out.detach().cpu().numpy(), e_out.detach().numpy(), atol=ATOL)
+    g = rs.normal(size=tuple(out.shape)).astype(np.float32)
+    e_out.backward(torch.tensor(g, dtype=torch.float64))
+    out.backward(to_cuda(g))
+    check_param_grads(store, ctx)
+    eg = pts_ref.grad.numpy()
+    np.testing.assert_allclose(pt.grad.cpu().numpy(), eg, atol=gtol(eg))
+
+
+def test_fp_module(env):
+    pu, _, _, lr, store = env
+    import torch
+    rs = np.random.RandomState(29)
+    xyz1 = rs.random_sample((2, 512, 3)).astype(np.float32)
+    xyz2 = np.ascontiguousarray(xyz1[:, :64])
+    p1 = rs.random_sample((2, 512, 5)).astype(np.float32)
+    p2 = rs.random_sample((2, 64, 24)).astype(np.float32)
+    params = {}
+    k = 29
+    for i, n in enumerate([64, 32]):
+        lr.init_conv(params, rs, "fa/conv_%d" % i, k, n)
+        k = n
+    randomize_bn(params, rs)
+    load_params(store, params)
+    ctx = lr.Ctx(params, is_training=True, bn_decay=0.9)
+    r1 = torch.tensor(p1, dtype=torch.float64, requires_grad=True)
+    r2 = torch.tensor(p2, dtype=torch.float64, requires_grad=True)
+    e_out = lr.fp_module(ctx, xyz1, xyz2, r1, r2, [64, 32], "fa")
+    t1, t2 = to_cuda(p1).requires_grad_(True), to_cuda(p2).requires_grad_(True)
+    out = pu.pointnet_fp_module(to_cuda(xyz1), to_cuda(xyz2), t1, t2, [64, 32], True, 0.9, "fa")
+    np.testing.assert_allclose(out.detach().cpu().numpy(), e_out.detach().numpy(), atol=ATOL)
+    g = rs.normal(size=tuple(out.shape)).astype(np.float32)
+    e_out.backward(torch.tensor(g, dtype=torch.float64))
+    out.backward(to_cuda(g))
+    check_param_grads(store, ctx)
+    np.testing.assert_allclose(t1.grad.cpu().numpy(), r1.grad.numpy(), atol=gtol(r1.grad.numpy()))
+    np.testing.assert_allclose(t2.grad.cpu().numpy(), r2.grad.numpy(), atol=gtol(r2.grad.numpy()))
+    # points1=None branch
+    store2 = env[1].set_default_store(env[1].VariableStore(device="cuda"))
+    params2 = {}
+    k = 24
+    for i, n in enumerate([16]):
+        lr.init_conv(params2, rs, "fb/conv_%d" % i, k, n)
+    load_params(store2, params2)
+    ctx2 = lr.Ctx(params2, is_training=True, bn_decay=0.9)
+    e2 = lr.fp_module(ctx2, xyz1, xyz2, None, torch.tensor(p2, dtype=torch.float64), [16], "fb")
+    o2 = pu.pointnet_fp_module(to_cuda(xyz1), to_cuda(xyz2), None, to_cuda(p2), [16], True, 0.9,
+                               "fb")
+    np.testing.assert_allclose(o2.detach().cpu().numpy(), e2.detach().numpy(), atol=ATOL)
+
+
+HP_SMALL = {"use_color": 1, "l1_npoint": 256, "l1_radius": 0.1, "l1_nsample": 32,
+            "l2_npoint": 64, "l2_radius": 0.2, "l2_nsample": 32, "l3_npoint": 16,
+            "l3_radius": 0.4, "l3_nsample": 32, "l4_npoint": 8, "l4_radius": 0.8,
+            "l4_nsample": 32}
+
+
+def run_model_parity(env, hp, b, n, scale, train=True):
+    pu, tf_util, model, lr, store = env
+    import torch
+    rs = np.random.RandomState(100)
+    pc = np.concatenate([rs.random_sample((b, n, 3)) * np.asarray(scale),
+                         rs.random_sample((b, n, 3))], -1).astype(np.float32)
+    labels = rs.randint(0, 9, (b, n)).astype(np.int32)
+    smpw = rs.uniform(0.5, 2.0, (b, n)).astype(np.float32)
+    smpw[0, :7] = 0.0
+    params = lr.init_model_params(hp, 9, seed=1)
+    randomize_bn(params, rs)
+    load_params(store, params)
+    seed = 1234
+    tf_util.set_dropout_seed(seed)
+    mask = tf_util.dropout_mask(b * n * 128, 0.5, seed).cpu().numpy().reshape(b, n, 128)
+    ctx = lr.Ctx(params, is_training=train, bn_decay=0.5,
+                 dropout_masks={"dp1": mask.astype(np.float64)})
+    e_pred = lr.get_model(ctx, pc, 9, hp)
+    pred, end_points = model.get_model(to_cuda(pc), train, 9, hp, bn_decay=0.5)
+    np.testing.assert_allclose(pred.detach().cpu().numpy(), e_pred.detach().numpy(), atol=ATOL)
+    if not train:
+        return
+    e_loss = lr.get_loss(e_pred, labels, smpw)
+    loss = model.get_loss(pred, to_cuda(labels), to_cuda(smpw), end_points)
+    assert abs(loss.item() - e_loss.item()) < ATOL
+    e_loss.backward()
+    loss.backward()
+    check_param_grads(store, ctx)
+    for k2, v in ctx.new_moving.items():
+        np.testing.assert_allclose(store.vars[k2].data.cpu().numpy(), v, atol=ATOL, err_msg=k2)
+
+
+def test_full_model_small(env):
+    run_model_parity(env, HP_SMALL, 2, 1024, (1.0, 1.0, 1.0))
+
+
+def test_full_model_eval_mode(env):
+    run_model_parity(env, HP_SMALL, 2, 1024, (1.0, 1.0, 1.0), train=False)
+
+
+def test_full_model_semantic_json_shape(env):
+    """semantic.json hyper-parameters (config 2 of BASELINE.json) at B=2: N=8192 points in a
+    10 x 10 x 5 box, radii 0.5/1/2/4, npoint 1024/256/64/16."""
+    hp = {"use_color": 1, "l1_npoint": 1024, "l1_radius": 0.5, "l1_nsample": 32,
+          "l2_npoint": 256, "l2_radius": 1.0, "l2_nsample": 32, "l3_npoint": 64,
+          "l3_radius": 2.0, "l3_nsample": 32, "l4_npoint": 16, "l4_radius": 4.0,
+          "l4_nsample": 32}
+    run_model_parity(env, hp, 2, 8192, (10.0, 10.0, 5.0))
+
+
+def test_variable_names_match_reference(env):
+    """Scopes of model.py:36-146 + tf_util.py:98-111,172-199 give the checkpoint names."""
+    _, _, model, _, store = env
+    import torch
+    pc = to_cuda(np.random.RandomState(0).random_sample((1, 512, 6)).astype(np.float32))
+    model.get_model(pc, True, 9, HP_SMALL, bn_decay=0.9)
+    names = set(store.vars)
+    for must in ["layer1/conv0/weights", "layer1/conv0/biases", "layer1/conv0/bn/gamma",
+                 "layer1/conv0/bn/beta", "layer1/conv0/bn/moving_mean",
+                 "layer1/conv0/bn/moving_variance", "layer4/conv2/weights",
+                 "fa_layer1/conv_0/weights", "fa_layer4/conv_2/bn/gamma", "fc1/weights",
+                 "fc1/bn/beta", "fc2/weights", "fc2/biases"]:
+        assert must in names, must
+    assert "fc2/bn/gamma" not in names
+    assert tuple(store.vars["layer1/conv0/weights"].data.shape) == (1, 1, 6, 32)
+    assert tuple(store.vars["fc2/weights"].data.shape) == (1, 128, 9)
+    n_train = sum(v.data.numel() for v in store.trainable())
+    assert n_train == 968425  # the all-reduce message

@@ -1,0 +1,297 @@
+"""GPU parity: every tf_ops entry point, called through the Python op surface -> ctypes ->
+C ABI -> sm_100a kernels, against the CPU oracle (bit-exact for indices and copies, 1e-5 abs
+for interpolation) and against the reference's own CUDA kernels (oracle/_ref)."""
+import numpy as np
+import pytest
+
+from _util import RefKernels, rng_cloud, to_cuda
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops(cuda):
+    import pn2_b200  # noqa: F401
+    from pn2_b200.tf_ops import tf_grouping, tf_interpolate, tf_sampling
+    from oracle import oracle as orc
+    return tf_sampling, tf_grouping, tf_interpolate, orc
+
+
+FPS_CASES = [(2, 1024, 256), (3, 64, 16), (2, 100, 100), (1, 8192, 1024), (2, 5000, 300),
+             (4, 256, 64), (1, 513, 40), (2, 2048, 128), (1, 12000, 64), (1, 20000, 32),
+             (2, 16, 20)]
+
+
+@pytest.mark.parametrize("b,n,m", FPS_CASES)
+def test_fps_matches_oracle(ops, b, n, m):
+    ts, _, _, orc = ops
+    x = rng_cloud(100 + n, b, n)
+    got = ts.farthest_point_sample(m, to_cuda(x)).cpu().numpy()
+    exp = orc.farthest_point_sample(m, x)
+    assert got.dtype == np.int32 and got.shape == (b, m)
+    np.testing.assert_array_equal(got, exp)
+
+
+@pytest.mark.parametrize("n,m", [(1500, 200), (700, 64), (4096, 128), (9000, 50)])
+def test_fps_tie_order(ops, n, m):
+    """Integer-grid clouds: many exactly equal distances and duplicate points.  The winner must
+    be the lowest (k mod 512) then lowest k, as the reference's strided scan + tree gives."""
+    ts, _, _, orc = ops
+    rs = np.random.RandomState(7)
+    x = rs.randint(0, 4, (2, n, 3)).astype(np.float32)
+    got = ts.farthest_point_sample(m, to_cuda(x)).cpu().numpy()
+    np.testing.assert_array_equal(got, orc.farthest_point_sample(m, x))
+
+
+def test_fps_properties_full_size(ops):
+    """Config-2 size: first index 0, all indices distinct and in range, min pairwise distance of
+    the prefix is non-increasing (the defining property of farthest point sampling)."""
+    ts, _, _, _ = ops
+    import torch
+    x = rng_cloud(100, 16, 8192, scale=(10, 10, 5), shift=(-5, -5, 0))
+    idx = ts.farthest_point_sample(1024, to_cuda(x)).cpu().numpy()
+    assert (idx[:, 0] == 0).all() and idx.min() >= 0 and idx.max() < 8192
+    for b in range(16):
+        assert len(set(idx[b].tolist())) == 1024
+    p = torch.as_tensor(x[0][idx[0]], dtype=torch.float64)
+    d = torch.cdist(p, p)
+    sel = []
+    for j in range(1, 64):
+        sel.append(d[j, :j].min().item())
+    assert all(sel[i] >= sel[i + 1] - 1e-9 for i in range(len(sel) - 1))
+
+
+def test_fps_matches_reference_kernel(ops):
+    ts, _, _, _ = ops
+    ref = RefKernels()
+    for b, n, m in [(2, 1024, 256), (16, 8192, 1024), (3, 5000, 333)]:
+        x = to_cuda(rng_cloud(5 + n, b, n))
+        np.testing.assert_array_equal(ts.farthest_point_sample(m, x).cpu().numpy(),
+                                      ref.fps(x, m).cpu().numpy())
+    g = to_cuda(np.random.RandomState(3).randint(0, 5, (2, 3000, 3)).astype(np.float32))
+    np.testing.assert_array_equal(ts.farthest_point_sample(400, g).cpu().numpy(),
+                                  ref.fps(g, 400).cpu().numpy())
+
+
+def test_gather_point_and_grad(ops):
+    ts, _, _, orc = ops
+    import torch
+    x = rng_cloud(1, 3, 777)
+    idx = np.random.RandomState(2).randint(0, 777, (3, 200)).astype(np.int32)
+    xt = to_cuda(x).requires_grad_(True)
+    out = ts.gather_point(xt, to_cuda(idx))
+    np.testing.assert_array_equal(out.detach().cpu().numpy(), orc.gather_point(x, idx))
+    g = np.random.RandomState(3).random_sample((3, 200, 3)).astype(np.float32)
+    out.backward(to_cuda(g))
+    np.testing.assert_allclose(xt.grad.cpu().numpy(), orc.gather_point_grad(x.shape, idx, g),
+                               atol=1e-5)
+    np.testing.assert_allclose(ts.gather_point_grad(xt.detach(), to_cuda(idx), to_cuda(g)).cpu().numpy(),
+                               orc.gather_point_grad(x.shape, idx, g), atol=1e-5)
+
+
+BALL_CASES = [  # b, n, m, radius, nsample
+    (2, 1024, 256, 0.2, 32),     # config 1: truncation and padding both occur
+    (16, 8192, 1024, 0.5, 32),   # SA1 of config 2 on the unit cube: truncation everywhere
+    (2, 333, 77, 0.15, 16),      # ragged n (no TMA path), small
+    (1, 4096, 4096, 0.05, 64),   # many queries -> streaming kernel
+    (3, 64, 16, 0.4, 32),        # tiny
+    (2, 1000, 10, 0.01, 8),      # almost no hits: zero rows
+    (1, 2050, 130, 0.3, 128),    # nsample 128, n % 4 != 0
+    (40, 2048, 512, 0.12, 24),   # enough queries for SPLIT=1 with several tiles
+]
+
+
+@pytest.mark.parametrize("b,n,m,radius,ns", BALL_CASES)
+def test_query_ball_point_matches_oracle(ops, b, n, m, radius, ns):
+    _, tg, _, orc = ops
+    x1 = rng_cloud(11 + n, b, n)
+    x2 = x1[:, :m].copy() if m <= n else rng_cloud(12, b, m)
+    if b == 2 and n == 1000:
+        x2 = rng_cloud(99, b, m)  # unrelated queries: rows with no hit at all
+    idx, cnt = tg.query_ball_point(radius, ns, to_cuda(x1), to_cuda(x2))
+    eidx, ecnt = orc.query_ball_point(radius, ns, x1, x2)
+    np.testing.assert_array_equal(cnt.cpu().numpy(), ecnt)
+    np.testing.assert_array_equal(idx.cpu().numpy(), eidx)
+
+
+def test_query_ball_boundary_radius(ops):
+    """Points at distances straddling the radius by single ulps: the d2 < T rewrite must agree
+    with the reference predicate max(sqrtf(d2),1e-20f) < radius everywhere."""
+    _, tg, _, orc = ops
+    rs = np.random.RandomState(5)
+    for radius in [0.1, 0.5, 1.0, 0.3333333, 2.0, 4.0, 1e-3]:
+        q = np.zeros((1, 1, 3), np.float32)
+        r32 = np.float32(radius)
+        # distances around the radius along x, every ulp in +-40
+        xs = [r32]
+        for _ in range(40):
+            xs.append(np.nextafter(xs[-1], np.float32(np.inf)))
+        lo = r32
+        for _ in range(40):
+            lo = np.nextafter(lo, np.float32(0))
+            xs.append(lo)
+        pts = np.zeros((1, len(xs) + 200, 3), np.float32)
+        pts[0, :len(xs), 0] = np.array(xs, np.float32)
+        rnd = rs.normal(size=(200, 3))
+        rnd = rnd / np.linalg.norm(rnd, axis=1, keepdims=True) * radius * (1 + rs.uniform(-1e-6, 1e-6, (200, 1)))
+        pts[0, len(xs):] = rnd.astype(np.float32)
+        ns = pts.shape[1]
+        idx, cnt = tg.query_ball_point(float(radius), ns, to_cuda(pts), to_cuda(q))
+        eidx, ecnt = orc.query_ball_point(float(radius), ns, pts, q)
+        np.testing.assert_array_equal(cnt.cpu().numpy(), ecnt)
+        np.testing.assert_array_equal(idx.cpu().numpy(), eidx)
+
+
+def test_query_ball_matches_reference_kernel(ops):
+    _, tg, _, _ = ops
+    ref = RefKernels()
+    for b, n, m, radius, ns in [(2, 1024, 256, 0.2, 32), (16, 8192, 1024, 0.1, 32),
+                                (4, 2048, 512, 0.25, 64)]:
+        x1 = to_cuda(rng_cloud(21 + n, b, n))
+        x2 = x1[:, :m].contiguous()
+        idx, cnt = tg.query_ball_point(radius, ns, x1, x2)
+        ridx, rcnt = ref.query_ball_point(radius, ns, x1, x2)
+        np.testing.assert_array_equal(cnt.cpu().numpy(), rcnt.cpu().numpy())
+        np.testing.assert_array_equal(idx.cpu().numpy(), ridx.cpu().numpy())
+
+
+def test_query_ball_validation(ops):
+    _, tg, _, _ = ops
+    x = to_cuda(rng_cloud(1, 1, 32))
+    with pytest.raises(ValueError, match="positive radius"):
+        tg.query_ball_point(0.0, 8, x, x)
+    with pytest.raises(ValueError, match="positive nsample"):
+        tg.query_ball_point(0.1, 0, x, x)
+    with pytest.raises(ValueError, match="xyz1 shape"):
+        tg.query_ball_point(0.1, 8, x[..., :2], x)
+
+
+@pytest.mark.parametrize("c", [3, 16, 64, 67, 128])
+def test_group_point_and_grad(ops, c):
+    _, tg, _, orc = ops
+    rs = np.random.RandomState(c)
+    pts = rs.random_sample((2, 300, c)).astype(np.float32)
+    idx = rs.randint(0, 300, (2, 40, 8)).astype(np.int32)
+    pt = to_cuda(pts).requires_grad_(True)
+    out = tg.group_point(pt, to_cuda(idx))
+    np.testing.assert_array_equal(out.detach().cpu().numpy(), orc.group_point(pts, idx))
+    g = rs.random_sample((2, 40, 8, c)).astype(np.float32)
+    out.backward(to_cuda(g))
+    np.testing.assert_allclose(pt.grad.cpu().numpy(), orc.group_point_grad(pts.shape, idx, g),
+                               atol=1e-5)
+
+
+def test_group_point_grad_check_like_reference(ops):
+    """tf_ops/test_tf_ops.py:38-56: finite-difference gradient error of group_point(points,
+    query_ball_point(0.3, 32, xyz1, xyz2)) w.r.t. points (1,128,16) below 1e-4.  group_point is
+    linear in points, so the analytic vector-Jacobian product must equal the directional
+    finite difference up to fp32 rounding."""
+    import torch
+    _, tg, _, _ = ops
+    rs = np.random.RandomState(0)
+    points = to_cuda(rs.random_sample((1, 128, 16)).astype(np.float32))
+    xyz1 = to_cuda(rs.random_sample((1, 128, 3)).astype(np.float32))
+    xyz2 = to_cuda(rs.random_sample((1, 8, 3)).astype(np.float32))
+    idx, _ = tg.query_ball_point(0.3, 32, xyz1, xyz2)
+    p = points.clone().requires_grad_(True)
+    out = tg.group_point(p, idx)
+    v = to_cuda(rs.random_sample(tuple(out.shape)).astype(np.float32))
+    out.backward(v)
+    for _ in range(4):
+        d = to_cuda(rs.normal(size=(1, 128, 16)).astype(np.float32))
+        fd = ((tg.group_point(points + 1e-2 * d, idx) - tg.group_point(points - 1e-2 * d, idx))
+              / 2e-2 * v).sum().item()
+        an = (p.grad * d).sum().item()
+        assert abs(fd - an) / max(1.0, abs(an)) < 1e-4
+
+
+def test_three_nn_golden_vector(ops):
+    """The reference's only known-answer test, tf_ops/test_interpolate.py:6-35 (seed 100,
+    (64,8192,3) targets, (64,1024,3) references)."""
+    _, _, ti, _ = ops
+    np.random.seed(100)
+    target = np.random.random((64, 8192, 3)).astype("float32")
+    reference = np.random.random((64, 1024, 3)).astype("float32")
+    dist, idx = ti.three_nn(to_cuda(target), to_cuda(reference))
+    dist, idx = dist.cpu().numpy(), idx.cpu().numpy()
+    assert dist.shape == (64, 8192, 3) and idx.dtype == np.int32 and dist.dtype == np.float32
+    exp_d = np.array([0.00175864, 0.00671887, 0.0034472, 0.00337327, 0.00191902, 0.00075543,
+                      0.00169418, 0.00473733, 0.00381071], np.float32)
+    exp_i = np.array([137, 856, 116, 76, 915, 199, 117, 659, 786])
+    np.testing.assert_allclose(dist[:3, :3, :1].flatten(), exp_d, atol=5e-9)
+    np.testing.assert_array_equal(idx[:3, :3, :1].flatten(), exp_i)
+
+
+@pytest.mark.parametrize("b,n,m", [(2, 512, 128), (1, 1000, 3), (3, 77, 1500), (16, 8192, 1024)])
+def test_three_nn_matches_oracle(ops, b, n, m):
+    _, _, ti, orc = ops
+    x1, x2 = rng_cloud(31 + n, b, n), rng_cloud(32 + m, b, m)
+    dist, idx = ti.three_nn(to_cuda(x1), to_cuda(x2))
+    ed, ei = orc.three_nn(x1, x2, threads=8)
+    np.testing.assert_array_equal(idx.cpu().numpy(), ei)
+    np.testing.assert_array_equal(dist.cpu().numpy(), ed)  # same fp64 ops, same cast: bit-exact
+
+
+def test_three_nn_ties_lowest_index(ops):
+    _, _, ti, orc = ops
+    rs = np.random.RandomState(4)
+    x2 = rs.randint(0, 3, (2, 200, 3)).astype(np.float32)
+    x1 = rs.randint(0, 3, (2, 50, 3)).astype(np.float32)
+    dist, idx = ti.three_nn(to_cuda(x1), to_cuda(x2))
+    ed, ei = orc.three_nn(x1, x2)
+    np.testing.assert_array_equal(idx.cpu().numpy(), ei)
+    np.testing.assert_array_equal(dist.cpu().numpy(), ed)
+
+
+@pytest.mark.parametrize("c", [16, 64, 131, 512])
+def test_three_interpolate_and_grad(ops, c):
+    """Forward within 1e-5 abs of the oracle (in fact bit-exact: same mul/add sequence);
+    gradient against the oracle's scatter (atomics reorder the sums: 1e-5 abs)."""
+    _, _, ti, orc = ops
+    rs = np.random.RandomState(c)
+    pts = rs.random_sample((2, 128, c)).astype(np.float32)
+    x1, x2 = rng_cloud(41, 2, 512), rng_cloud(42, 2, 128)
+    dist, idx = ti.three_nn(to_cuda(x1), to_cuda(x2))
+    w = rs.random_sample((2, 512, 3)).astype(np.float32)
+    w /= w.sum(-1, keepdims=True)
+    pt = to_cuda(pts).requires_grad_(True)
+    out = ti.three_interpolate(pt, idx, to_cuda(w))
+    exp = orc.three_interpolate(pts, idx.cpu().numpy(), w)
+    np.testing.assert_allclose(out.detach().cpu().numpy(), exp, atol=1e-5)
+    np.testing.assert_array_equal(out.detach().cpu().numpy(), exp)
+    g = rs.random_sample((2, 512, c)).astype(np.float32)
+    out.backward(to_cuda(g))
+    eg = orc.three_interpolate_grad(pts.shape, idx.cpu().numpy(), w, g)
+    np.testing.assert_allclose(pt.grad.cpu().numpy(), eg, atol=1e-5, rtol=1e-5)
+
+
+def test_three_interpolate_grad_check_like_reference(ops):
+    """tf_ops/test_tf_ops.py:80-94: weights 1/3, points (1,8,16) -> (1,128,16), error < 1e-4."""
+    _, _, ti, _ = ops
+    rs = np.random.RandomState(0)
+    points = to_cuda(rs.random_sample((1, 8, 16)).astype(np.float32))
+    xyz1 = to_cuda(rs.random_sample((1, 128, 3)).astype(np.float32))
+    xyz2 = to_cuda(rs.random_sample((1, 8, 3)).astype(np.float32))
+    dist, idx = ti.three_nn(xyz1, xyz2)
+    import torch
+    weight = torch.ones_like(dist) / 3.0
+    p = points.clone().requires_grad_(True)
+    out = ti.three_interpolate(p, idx, weight)
+    v = to_cuda(rs.random_sample(tuple(out.shape)).astype(np.float32))
+    out.backward(v)
+    for _ in range(4):
+        d = to_cuda(rs.normal(size=(1, 8, 16)).astype(np.float32))
+        fd = ((ti.three_interpolate(points + 1e-2 * d, idx, weight)
+               - ti.three_interpolate(points - 1e-2 * d, idx, weight)) / 2e-2 * v).sum().item()
+        an = (p.grad * d).sum().item()
+        assert abs(fd - an) / max(1.0, abs(an)) < 1e-4
+
+
+def test_select_top_k_and_knn(ops):
+    _, tg, _, orc = ops
+    rs = np.random.RandomState(9)
+    d = rs.random_sample((2, 20, 300)).astype(np.float32)
+    outi, out = tg.select_top_k(16, to_cuda(d))
+    ei, eo = orc.select_top_k(16, d)
+    np.testing.assert_array_equal(outi.cpu().numpy()[:, :, :16], ei[:, :, :16])
+    np.testing.assert_array_equal(out.cpu().numpy()[:, :, :16], eo[:, :, :16])

@@ -133,11 +133,16 @@ int pn2_copy_cols(long rows, int cols, const float *src, int lds, float *dst, in
  * (fp64, caller zeroes).  mode: 0 = fp32 SIMT kernel, 1 = tcgen05 3xTF32 kernel, -1 = auto. */
 int pn2_linear_fwd(long M, int K, int N, const float *A, int lda, const float *a_scale,
                    const float *a_shift, int a_relu, const float *W, const float *bias, float *Y,
-                   double *stats, int mode, pn2_stream_t s);
+                   double *stats, void *ws, long ws_bytes, int mode, pn2_stream_t s);
+
+/* bytes of caller-owned scratch the tensor-core path of pn2_linear_fwd / pn2_linear_dgrad needs
+ * for a K x N layer (the pre-split, pre-swizzled 3xTF32 weight image).  ws may be NULL: the
+ * exact fp32 CUDA-core kernel is used then. */
+long pn2_linear_workspace_bytes(int K, int N);
 
 /* dX[M,K] = dY[M,N] * W[K,N]^T */
 int pn2_linear_dgrad(long M, int K, int N, const float *dY, const float *W, float *dX, int ldx,
-                     int mode, pn2_stream_t s);
+                     void *ws, long ws_bytes, int mode, pn2_stream_t s);
 
 /* dW[K,N] += f(A)[M,K]^T * dY[M,N] ; db[N] += column sums of dY (db may be NULL).
  * Accumulates (split over M with fp32 atomics): caller zeroes dW/db once per step. */

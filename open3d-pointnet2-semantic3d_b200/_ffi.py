@@ -40,8 +40,9 @@ SIGNATURES = {
     "pn2_three_interpolate_ld": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp],
     "pn2_three_interpolate_grad_ld": [_i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp],
     "pn2_copy_cols": [_l, _i, _vp, _i, _vp, _i, _i, _vp],
-    "pn2_linear_fwd": [_l, _i, _i, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp],
-    "pn2_linear_dgrad": [_l, _i, _i, _vp, _vp, _vp, _i, _i, _vp],
+    "pn2_linear_fwd": [_l, _i, _i, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _l, _i, _vp],
+    "pn2_linear_workspace_bytes": [_i, _i],
+    "pn2_linear_dgrad": [_l, _i, _i, _vp, _vp, _vp, _i, _vp, _l, _i, _vp],
     "pn2_linear_wgrad": [_l, _i, _i, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp],
     "pn2_bn_train_finalize": [_i, _l, _vp, _vp, _vp, _f, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp],
     "pn2_bn_eval_affine": [_i, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp],
@@ -60,10 +61,11 @@ SIGNATURES = {
     "pn2_adam_step": [_l, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _i, _f, _vp],
 }
 _RESTYPE = {"pn2_strerror": ctypes.c_char_p, "pn2_last_cuda_error": ctypes.c_char_p,
-            "pn2_ball_threshold": ctypes.c_float}
+            "pn2_ball_threshold": ctypes.c_float, "pn2_linear_workspace_bytes": ctypes.c_long}
 
 _lib = None
 launches = 0  # number of native entry-point calls made (bench.py reports it)
+profile = None  # list of (name, start_event, end_event) when bench.py instruments a pass
 
 
 class Pn2Error(RuntimeError):
@@ -109,7 +111,15 @@ def ptr(t, dtype=None, allow_none=False):
 def call(name, *args):
     """Invoke an entry point on the current stream; map status codes to exceptions."""
     global launches
-    rc = getattr(lib(), name)(*args, stream())
+    if profile is not None:  # bench.py's instrumented pass: CUDA events around every call
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib(), name)(*args, stream())
+        e1.record()
+        profile.append((name, e0, e1))
+    else:
+        rc = getattr(lib(), name)(*args, stream())
     launches += 1
     if rc != PN2_OK:
         msg = lib().pn2_strerror(rc).decode()

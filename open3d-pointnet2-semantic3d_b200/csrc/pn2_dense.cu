@@ -16,9 +16,10 @@ namespace pn2 {
 // does not cover so that the caller can fall back to the exact fp32 kernel.
 int tc_linear_fwd(long M, int K, int N, const float *A, int lda, const float *a_scale,
                   const float *a_shift, int a_relu, const float *W, const float *bias, float *Y,
-                  double *stats, cudaStream_t st);
+                  double *stats, float *ws, size_t ws_bytes, cudaStream_t st);
 int tc_linear_dgrad(long M, int K, int N, const float *dY, const float *W, float *dX, int ldx,
-                    cudaStream_t st);
+                    float *ws, size_t ws_bytes, cudaStream_t st);
+size_t tc_workspace_bytes(int K, int N);
 
 // ---- SIMT GEMM dispatch ----------------------------------------------------------------------
 template <bool A_KC, bool B_NC, bool ATOMIC>
@@ -88,15 +89,15 @@ bn_bwd_reduce_kernel(long M, int N, long rpb, const float *__restrict__ dZ, int 
     for (int c = s.cx; c < N; c += s.lanes) {
         const float sc = __ldg(scale + c), sh = __ldg(shift + c);
         const float mean = __ldg(saved + c), rstd = __ldg(saved + N + c);
-        float a0 = 0.f, a1 = 0.f;
+        double a0 = 0.0, a1 = 0.0;
         for (long r = s.r0 + s.ry; r < s.r1; r += s.rpp) {
             float dzh, xh;
             bn_elem(__ldg(Y + r * N + c), __ldg(dZ + r * ldz + c), sc, sh, mean, rstd, relu, dzh, xh);
-            a0 += dzh;
-            a1 = __fmaf_rn(dzh, xh, a1);
+            a0 += (double)dzh;
+            a1 = fma((double)dzh, (double)xh, a1);
         }
-        atomicAdd(red + c, (double)a0);
-        atomicAdd(red + N + c, (double)a1);
+        atomicAdd(red + c, a0);
+        atomicAdd(red + N + c, a1);
     }
 }
 
@@ -147,17 +148,17 @@ bn_bwd_reduce_pool_kernel(long G, int ns, int N, const float *__restrict__ dOut,
     for (int c = s.cx; c < N; c += s.lanes) {
         const float sc = __ldg(scale + c), sh = __ldg(shift + c);
         const float mean = __ldg(saved + c), rstd = __ldg(saved + N + c);
-        float a0 = 0.f, a1 = 0.f;
+        double a0 = 0.0, a1 = 0.0;
         for (long g = s.r0 + s.ry; g < s.r1; g += s.rpp) {
             const int j = __ldg(arg + g * N + c);
             float dzh, xh;
             bn_elem(__ldg(Y + (g * ns + j) * N + c), __ldg(dOut + g * N + c), sc, sh, mean, rstd,
                     relu, dzh, xh);
-            a0 += dzh;
-            a1 = __fmaf_rn(dzh, xh, a1);
+            a0 += (double)dzh;
+            a1 = fma((double)dzh, (double)xh, a1);
         }
-        atomicAdd(red + c, (double)a0);
-        atomicAdd(red + N + c, (double)a1);
+        atomicAdd(red + c, a0);
+        atomicAdd(red + N + c, a1);
     }
 }
 
@@ -376,9 +377,9 @@ __global__ void colsum_kernel(long M, int N, long rpb, const float *__restrict__
     const Slab s = make_slab(M, N, rpb);
     if (!s.active) return;
     for (int c = s.cx; c < N; c += s.lanes) {
-        float a = 0.f;
-        for (long r = s.r0 + s.ry; r < s.r1; r += s.rpp) a += __ldg(X + r * N + c);
-        atomicAdd(out + c, a);
+        double a = 0.0;
+        for (long r = s.r0 + s.ry; r < s.r1; r += s.rpp) a += (double)__ldg(X + r * N + c);
+        atomicAdd(out + c, (float)a);
     }
 }
 
@@ -410,7 +411,8 @@ static bool tc_enabled() {
 
 PN2_API int pn2_linear_fwd(long M, int K, int N, const float *A, int lda, const float *a_scale,
                            const float *a_shift, int a_relu, const float *W, const float *bias,
-                           float *Y, double *stats, int mode, pn2_stream_t s) {
+                           float *Y, double *stats, void *ws, long ws_bytes, int mode,
+                           pn2_stream_t s) {
     PN2_REQUIRE(M >= 0 && K > 0 && N > 0 && lda >= K && M < (1L << 31));
     PN2_REQUIRE(mode >= -1 && mode <= 1);
     if (M == 0) return PN2_OK;
@@ -420,15 +422,21 @@ PN2_API int pn2_linear_fwd(long M, int K, int N, const float *A, int lda, const 
     PN2_REQUIRE((a_scale == nullptr) == (a_shift == nullptr));
     cudaStream_t st = as_stream(s);
     if (mode == 1 || (mode == -1 && tc_enabled())) {
-        int rc = tc_linear_fwd(M, K, N, A, lda, a_scale, a_shift, a_relu, W, bias, Y, stats, st);
+        int rc = tc_linear_fwd(M, K, N, A, lda, a_scale, a_shift, a_relu, W, bias, Y, stats,
+                               static_cast<float *>(ws), ws_bytes > 0 ? (size_t)ws_bytes : 0, st);
         if (rc != PN2_EUNSUPPORTED || mode == 1) return rc;
     }
     return launch_gemm<true, true, false>((int)M, N, K, A, lda, 1, W, N, 1, a_scale, a_shift,
                                           a_relu, bias, Y, N, stats, 1, st);
 }
 
+PN2_API long pn2_linear_workspace_bytes(int K, int N) {
+    if (K <= 0 || N <= 0) return 0;
+    return (long)tc_workspace_bytes(K, N);
+}
+
 PN2_API int pn2_linear_dgrad(long M, int K, int N, const float *dY, const float *W, float *dX,
-                             int ldx, int mode, pn2_stream_t s) {
+                             int ldx, void *ws, long ws_bytes, int mode, pn2_stream_t s) {
     PN2_REQUIRE(M >= 0 && K > 0 && N > 0 && ldx >= K && M < (1L << 31));
     PN2_REQUIRE(mode >= -1 && mode <= 1);
     if (M == 0) return PN2_OK;
@@ -437,7 +445,8 @@ PN2_API int pn2_linear_dgrad(long M, int K, int N, const float *dY, const float 
     PN2_REQUIRE_PTR(dX);
     cudaStream_t st = as_stream(s);
     if (mode == 1 || (mode == -1 && tc_enabled())) {
-        int rc = tc_linear_dgrad(M, K, N, dY, W, dX, ldx, st);
+        int rc = tc_linear_dgrad(M, K, N, dY, W, dX, ldx, static_cast<float *>(ws),
+                                 ws_bytes > 0 ? (size_t)ws_bytes : 0, st);
         if (rc != PN2_EUNSUPPORTED || mode == 1) return rc;
     }
     // C[M,K] = sum_n dY(m,n) * W(k,n):  M'=M, N'=K, K'=N ; B(k'=n, n'=k) = W + k*N + n
@@ -467,8 +476,9 @@ PN2_API int pn2_linear_wgrad(long M, int K, int N, const float *A, int lda, cons
                                             nullptr, dW, N, nullptr, splits, st);
     if (rc) return rc;
     if (db) {
-        int blocks;
-        long rpb = slab_rows(M, &blocks);
+        long rpb = ceil_div<long>(M, 64L);
+        if (rpb < 32) rpb = 32;
+        int blocks = (int)ceil_div<long>(M, rpb);
         colsum_kernel<<<blocks, 256, 0, st>>>(M, N, rpb, dY, db);
         rc = finish_launch();
     }

@@ -40,7 +40,7 @@ gemm_simt_kernel(int Mp, int Np, long Kp, const float *__restrict__ A, long a_sm
     constexpr int A_PER = BM * G_BK / G_THREADS, B_PER = BN * G_BK / G_THREADS;
     __shared__ __align__(16) float As[G_BK * LDA];
     __shared__ __align__(16) float Bs[G_BK * LDB];
-    __shared__ float red[8 * BN], red2[8 * BN];  // column-statistics staging
+    __shared__ double red[8 * BN], red2[8 * BN];  // column-statistics staging
 
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
@@ -144,9 +144,10 @@ gemm_simt_kernel(int Mp, int Np, long Kp, const float *__restrict__ A, long a_sm
     }
 
     // ---- epilogue -------------------------------------------------------------------------
-    float csum[TN], csq[TN];
+    // column statistics in fp64: E[y^2]-E[y]^2 must not lose the variance to cancellation
+    double csum[TN], csq[TN];
 #pragma unroll
-    for (int j = 0; j < TN; ++j) csum[j] = csq[j] = 0.f;
+    for (int j = 0; j < TN; ++j) csum[j] = csq[j] = 0.0;
 #pragma unroll
     for (int i = 0; i < TM; ++i) {
         const int m = m0 + RowMap<TM>::template at<BM>(ty, i);
@@ -159,8 +160,10 @@ gemm_simt_kernel(int Mp, int Np, long Kp, const float *__restrict__ A, long a_sm
             if (bias && blockIdx.z == 0) v += __ldg(bias + n);
             if (ATOMIC) atomicAdd(C + m * ldc + n, v);
             else C[m * ldc + n] = v;
-            csum[j] += v;
-            csq[j] = __fmaf_rn(v, v, csq[j]);
+            if (stats) {
+                csum[j] += (double)v;
+                csq[j] = fma((double)v, (double)v, csq[j]);
+            }
         }
     }
     if (stats) {
@@ -186,8 +189,8 @@ gemm_simt_kernel(int Mp, int Np, long Kp, const float *__restrict__ A, long a_sm
             double s = 0.0, q = 0.0;
 #pragma unroll
             for (int w = 0; w < 8; ++w) {
-                s += (double)red[w * BN + c];
-                q += (double)red2[w * BN + c];
+                s += red[w * BN + c];
+                q += red2[w * BN + c];
             }
             atomicAdd(stats + n, s);
             atomicAdd(stats + Np + n, q);

@@ -1,13 +1,497 @@
-// pn2_gemm_tc.cu -- tcgen05 (5th-gen tensor core) 3xTF32 GEMM path.  Placeholder until the
-// kernel lands: reports "unsupported" so that pn2_linear_* fall back to the exact fp32 kernel.
+// pn2_gemm_tc.cu -- shared-MLP GEMM on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a.
+//
+//   Y[M,N] = f(A)[M,K] * Bt[N,K]^T (+ bias) (+ column statistics)       (forward and dgrad)
+//
+// Precision: the reference computes these 1x1 convolutions in fp32 and the parity bar is 1e-5
+// absolute, which plain TF32 (10-bit mantissa) cannot meet.  Every product is therefore
+// evaluated as an error-compensated 3xTF32 sum with fp32 accumulation in tensor memory:
+//     a*b ~= a_hi*b_hi + a_lo*b_hi + a_hi*b_lo,   a_hi = rna_tf32(a), a_lo = a - a_hi
+// (the dropped a_lo*b_lo term is ~2^-22 relative).  Effective tensor peak = TF32 peak / 3.
+// The tensor core adds into its fp32 accumulator with truncation, a biased error that grows
+// with the number of accumulations (measured: 3.5e-5 at K=768 with one accumulator), so the
+// large hi*hi products and the small correction products go to TWO accumulators (main / corr)
+// that are summed with a round-to-nearest add in the epilogue; K is limited to 512.
+//
+// Structure (one persistent CTA per SM, 10 warps, roles as in the canonical Blackwell GEMM):
+//   warps 0-3  epilogue: tcgen05.ld accumulator (lane quadrant = warp), transpose through
+//              padded shared memory, + bias, coalesced row-major stores, fp64 column statistics
+//   warps 4-7  A producers: coalesced float4 global loads of a 128 x 32 chunk, previous layer's
+//              BatchNorm affine + ReLU applied on the fly, hi/lo split, st.shared into the
+//              128B-swizzled K-major UMMA layout, fence.proxy.async, mbarrier arrive
+//   warp 8     B loader: one cp.async.bulk per K chunk from a pre-split, pre-swizzled weight
+//              image in global memory (built by tc_prep_b_kernel, L2 resident)
+//   warp 9     TMEM allocation + single-thread tcgen05.mma issue (3 MMAs per K=8 step),
+//              tcgen05.commit onto the "stage empty" / "accumulator full" mbarriers
+// The accumulator pair is double buffered in TMEM (2 x 2 x N columns, N <= 128 per pass) so the
+// epilogue of tile i overlaps the main loop of tile i+1.
 #include "pn2_common.cuh"
 
 namespace pn2 {
-int tc_linear_fwd(long, int, int, const float *, int, const float *, const float *, int,
-                  const float *, const float *, float *, double *, cudaStream_t) {
-    return PN2_EUNSUPPORTED;
+namespace tc {
+
+constexpr int BM = 128;       // rows per tile (UMMA M)
+constexpr int BK = 32;        // fp32/tf32 elements per K chunk = one 128-byte swizzle row
+constexpr int THREADS = 320;  // 10 warps
+constexpr int MAX_STAGES = 4;
+constexpr int EPI_LD = 36;    // padded row length (floats) of the epilogue transpose buffer
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
-int tc_linear_dgrad(long, int, int, const float *, const float *, float *, int, cudaStream_t) {
-    return PN2_EUNSUPPORTED;
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LAB_DONE;\n"
+        "bra LAB_WAIT;\n"
+        "LAB_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes,
+                                         uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ float tf32_rna(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+//   [0,14) start address >> 4, [16,30) leading byte offset >> 4 (unused for swizzled K-major: 1),
+//   [32,46) stride byte offset >> 4 (8 rows x 128 B = 1024 B -> 64), [46,48) version = 1,
+//   [61,64) layout type = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) |
+           (2ull << 61);
+}
+// tcgen05 instruction descriptor (cute::UMMA::InstrDescriptor), kind::tf32, fp32 accumulate,
+// both operands K-major: c_format=F32 [4,6), a/b_format=TF32 [7,10)/[10,13), N>>3 [17,23),
+// M>>4 [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) |
+           ((uint32_t)(BM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                          uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                     smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+          "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+          "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+          "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// byte offset of element (row, k) inside one K-major SWIZZLE_128B chunk image (row = 128 B)
+__host__ __device__ __forceinline__ uint32_t sw128_offset(int row, int k) {
+    return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((((k >> 2) ^ (row & 7)) & 7) << 4) +
+                      (k & 3) * 4);
+}
+
+// Weight image: for every K chunk kc: [hi image: Npad rows x 128 B][lo image: same], elements
+// Bt(n,k) = src[n*s_n + k*s_k], zero outside (N,K).
+__global__ void tc_prep_b_kernel(int N, int K, int Npad, int KC, const float *__restrict__ src,
+                                 long s_n, long s_k, float *__restrict__ image) {
+    const long total = (long)KC * Npad * BK;
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total;
+         e += (long)gridDim.x * blockDim.x) {
+        const int kk = (int)(e % BK);
+        const long t = e / BK;
+        const int n = (int)(t % Npad);
+        const int kc = (int)(t / Npad);
+        const int k = kc * BK + kk;
+        float v = (n < N && k < K) ? __ldg(src + n * s_n + k * s_k) : 0.f;
+        const float hi = tf32_rna(v);
+        const float lo = v - hi;
+        unsigned char *base = reinterpret_cast<unsigned char *>(image) + (size_t)kc * 2 * Npad * 128;
+        const uint32_t off = sw128_offset(n, kk);
+        *reinterpret_cast<float *>(base + off) = hi;
+        *reinterpret_cast<float *>(base + (size_t)Npad * 128 + off) = lo;
+    }
+}
+
+struct Params {
+    long M;
+    int K, N, Npad, KC, stages, lda, ldy, a_relu;
+    const float *A, *a_scale, *a_shift, *bias, *image;
+    float *Y;
+    double *stats_sum, *stats_sq;  // per-column sum / sum of squares (fp64), or NULL
+};
+
+__global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const Params p) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    // carve: stages x [A_hi 16K | A_lo 16K | B_hi Npad*128 | B_lo Npad*128], epilogue staging, barriers
+    const uint32_t a_bytes = BM * 128;
+    const uint32_t b_bytes = (uint32_t)p.Npad * 128;
+    const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+    unsigned char *stage_base = smem;
+    float *epi = reinterpret_cast<float *>(smem + (size_t)p.stages * stage_bytes);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(epi + 4 * 32 * EPI_LD);
+    uint64_t *full = bars;                    // [stages]  A producers (128) + B loader (1) + tx
+    uint64_t *empty = bars + MAX_STAGES;      // [stages]  tcgen05.commit
+    uint64_t *acc_full = bars + 2 * MAX_STAGES;       // [2]
+    uint64_t *acc_empty = bars + 2 * MAX_STAGES + 2;  // [2] epilogue threads (128)
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * MAX_STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int Nacc = (p.Npad + 31) & ~31;
+    uint32_t ncols = 32;
+    while (ncols < (uint32_t)(4 * Nacc)) ncols <<= 1;  // {main, corr} x double buffer
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(&full[s], 129);
+            mbar_init(&empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&acc_full[a], 1);
+            mbar_init(&acc_empty[a], 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 9) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                         smem_u32(tmem_slot)),
+                     "r"(ncols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    const long num_tiles = (p.M + BM - 1) / BM;
+
+    if (warp >= 4 && warp < 8) {
+        // ================================ A producers ================================
+        const int t = threadIdx.x - 128;
+        const int k4 = t & 7, r0 = t >> 3;  // float4 slot inside the 32-wide chunk, base row
+        const bool vec_ok = (p.lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0);
+        uint32_t it = 0;
+        for (long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const long m0 = tile * BM;
+            for (int kc = 0; kc < p.KC; ++kc, ++it) {
+                const int s = it % p.stages;
+                const uint32_t ph = (it / p.stages) & 1;
+                const int kbase = kc * BK + k4 * 4;
+                float4 v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const long m = m0 + r0 + 16 * i;
+                    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (m < p.M) {
+                        const float *src = p.A + m * p.lda + kbase;
+                        if (vec_ok && kbase + 3 < p.K) {
+                            x = __ldg(reinterpret_cast<const float4 *>(src));
+                        } else {
+                            if (kbase + 0 < p.K) x.x = __ldg(src + 0);
+                            if (kbase + 1 < p.K) x.y = __ldg(src + 1);
+                            if (kbase + 2 < p.K) x.z = __ldg(src + 2);
+                            if (kbase + 3 < p.K) x.w = __ldg(src + 3);
+                        }
+                    }
+                    v[i] = x;
+                }
+                if (p.a_scale) {
+                    float sc[4], sh[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const bool ok = kbase + j < p.K;
+                        sc[j] = ok ? __ldg(p.a_scale + kbase + j) : 0.f;
+                        sh[j] = ok ? __ldg(p.a_shift + kbase + j) : 0.f;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const bool row_ok = (m0 + r0 + 16 * i) < p.M;
+                        float *e = reinterpret_cast<float *>(&v[i]);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            float y = __fmaf_rn(e[j], sc[j], sh[j]);
+                            if (p.a_relu) y = fmaxf(y, 0.f);
+                            e[j] = row_ok ? y : 0.f;
+                        }
+                    }
+                }
+                mbar_wait(&empty[s], ph ^ 1);
+                unsigned char *a_hi = stage_base + (size_t)s * stage_bytes;
+                unsigned char *a_lo = a_hi + a_bytes;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int r = r0 + 16 * i;
+                    const uint32_t off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 +
+                                                    (((k4 ^ (r & 7)) & 7) << 4));
+                    float4 hi, lo;
+                    hi.x = tf32_rna(v[i].x); lo.x = v[i].x - hi.x;
+                    hi.y = tf32_rna(v[i].y); lo.y = v[i].y - hi.y;
+                    hi.z = tf32_rna(v[i].z); lo.z = v[i].z - hi.z;
+                    hi.w = tf32_rna(v[i].w); lo.w = v[i].w - hi.w;
+                    *reinterpret_cast<float4 *>(a_hi + off) = hi;
+                    *reinterpret_cast<float4 *>(a_lo + off) = lo;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive(&full[s]);
+            }
+        }
+    } else if (warp == 8) {
+        // ================================ B loader ================================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                for (int kc = 0; kc < p.KC; ++kc, ++it) {
+                    const int s = it % p.stages;
+                    const uint32_t ph = (it / p.stages) & 1;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    unsigned char *b_hi = stage_base + (size_t)s * stage_bytes + 2 * a_bytes;
+                    mbar_expect_tx(&full[s], 2 * b_bytes);
+                    bulk_g2s(b_hi,
+                             reinterpret_cast<const unsigned char *>(p.image) + (size_t)kc * 2 * b_bytes,
+                             2 * b_bytes, &full[s]);
+                }
+            }
+        }
+    } else if (warp == 9) {
+        // ================================ MMA issuer ================================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(p.Npad);
+            uint32_t it = 0, tcnt = 0;
+            for (long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcnt) {
+                const uint32_t acc = tcnt & 1, aph = (tcnt >> 1) & 1;
+                mbar_wait(&acc_empty[acc], aph ^ 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d = tmem_base + acc * (uint32_t)(2 * Nacc);  // main
+                const uint32_t dc = d + (uint32_t)Nacc;                     // corrections
+                for (int kc = 0; kc < p.KC; ++kc, ++it) {
+                    const int s = it % p.stages;
+                    const uint32_t ph = (it / p.stages) & 1;
+                    mbar_wait(&full[s], ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_hi = smem_u32(stage_base + (size_t)s * stage_bytes);
+                    const uint64_t dah = make_desc(a_hi), dal = make_desc(a_hi + a_bytes);
+                    const uint64_t dbh = make_desc(a_hi + 2 * a_bytes),
+                                   dbl = make_desc(a_hi + 2 * a_bytes + b_bytes);
+#pragma unroll
+                    for (int kk = 0; kk < BK / 8; ++kk) {
+                        const uint64_t adv = (uint64_t)(kk * 2);  // 32 bytes per K=8 step, >>4
+                        const uint32_t accum = (kc > 0 || kk > 0) ? 1u : 0u;
+                        umma_tf32(d, dah + adv, dbh + adv, idesc, accum);
+                        umma_tf32(dc, dal + adv, dbh + adv, idesc, accum);
+                        umma_tf32(dc, dah + adv, dbl + adv, idesc, 1u);
+                    }
+                    umma_commit(&empty[s]);  // frees the stage once these MMAs have read it
+                }
+                umma_commit(&acc_full[acc]);  // accumulator complete -> epilogue
+            }
+        }
+    } else {
+        // ================================ epilogue (warps 0-3) ================================
+        float *stg = epi + warp * 32 * EPI_LD;
+        const int nblk = (p.N + 31) / 32;
+        double ssum[4], ssq[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ssum[i] = ssq[i] = 0.0;
+        uint32_t tcnt = 0;
+        for (long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcnt) {
+            const uint32_t acc = tcnt & 1, aph = (tcnt >> 1) & 1;
+            const long m0 = tile * BM + warp * 32;
+            mbar_wait(&acc_full[acc], aph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int cb = 0; cb < 4; ++cb) {
+                if (cb >= nblk) break;
+                uint32_t r[32], rc[32];
+                const uint32_t ta = tmem_base + ((uint32_t)(warp * 32) << 16) +
+                                    acc * (uint32_t)(2 * Nacc) + cb * 32;
+                tmem_ld32(ta, r);
+                tmem_ld32(ta + (uint32_t)Nacc, rc);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    float4 o;  // main + corrections, round-to-nearest
+                    o.x = __uint_as_float(r[q * 4]) + __uint_as_float(rc[q * 4]);
+                    o.y = __uint_as_float(r[q * 4 + 1]) + __uint_as_float(rc[q * 4 + 1]);
+                    o.z = __uint_as_float(r[q * 4 + 2]) + __uint_as_float(rc[q * 4 + 2]);
+                    o.w = __uint_as_float(r[q * 4 + 3]) + __uint_as_float(rc[q * 4 + 3]);
+                    *reinterpret_cast<float4 *>(stg + lane * EPI_LD + q * 4) = o;
+                }
+                __syncwarp();
+                const int col = cb * 32 + lane;
+                const bool col_ok = col < p.N;
+                const float bv = (p.bias && col_ok) ? __ldg(p.bias + col) : 0.f;
+                double s1 = 0.0, s2 = 0.0;
+#pragma unroll 8
+                for (int rr = 0; rr < 32; ++rr) {
+                    const long m = m0 + rr;
+                    float v = stg[rr * EPI_LD + lane] + bv;
+                    if (col_ok && m < p.M) {
+                        p.Y[m * p.ldy + col] = v;
+                        if (p.stats_sum) {
+                            s1 += (double)v;
+                            s2 = fma((double)v, (double)v, s2);
+                        }
+                    }
+                }
+                ssum[cb] += s1;
+                ssq[cb] += s2;
+                __syncwarp();
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(&acc_empty[acc]);
+        }
+        if (p.stats_sum) {
+#pragma unroll
+            for (int cb = 0; cb < 4; ++cb) {
+                const int col = cb * 32 + lane;
+                if (cb < nblk && col < p.N) {
+                    atomicAdd(p.stats_sum + col, ssum[cb]);
+                    atomicAdd(p.stats_sq + col, ssq[cb]);
+                }
+            }
+        }
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 9) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                     "r"(ncols)
+                     : "memory");
+    }
+}
+
+static size_t image_bytes(int K, int N) {
+    const int Npad = (N + 15) & ~15, KC = (K + BK - 1) / BK;
+    return (size_t)KC * 2 * Npad * 128;
+}
+
+// Y[M, n0:n0+Nc] for one chunk of at most 128 output columns (two accumulators x 2 buffers)
+static int run_chunk(long M, int K, int Nc, const float *A, int lda, const float *a_scale,
+                     const float *a_shift, int a_relu, const float *bsrc, long s_n, long s_k,
+                     const float *bias, float *Y, int ldy, double *stats_sum, double *stats_sq,
+                     float *ws, cudaStream_t st) {
+    Params p;
+    p.M = M;
+    p.K = K;
+    p.N = Nc;
+    p.Npad = (Nc + 15) & ~15;
+    p.KC = (K + BK - 1) / BK;
+    p.lda = lda;
+    p.ldy = ldy;
+    p.a_relu = a_relu;
+    p.A = A;
+    p.a_scale = a_scale;
+    p.a_shift = a_shift;
+    p.bias = bias;
+    p.image = ws;
+    p.Y = Y;
+    p.stats_sum = stats_sum;
+    p.stats_sq = stats_sq;
+    const size_t stage_bytes = 2 * (size_t)BM * 128 + 2 * (size_t)p.Npad * 128;
+    const size_t fixed = 4 * 32 * EPI_LD * sizeof(float) + (2 * MAX_STAGES + 4) * 8 + 16;
+    int stages = (int)((227 * 1024 - fixed) / stage_bytes);  // 227 KB usable shared memory per CTA
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    if (stages < 1) return PN2_EUNSUPPORTED;
+    p.stages = stages;
+    const size_t smem = (size_t)stages * stage_bytes + fixed;
+
+    const long total = (long)p.KC * p.Npad * BK;
+    int pb = (int)((total + 255) / 256);
+    if (pb > 148 * 8) pb = 148 * 8;
+    tc_prep_b_kernel<<<pb, 256, 0, st>>>(Nc, K, p.Npad, p.KC, bsrc, s_n, s_k, ws);
+    int rc = finish_launch();
+    if (rc) return rc;
+
+    rc = cuda_status(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)smem));
+    if (rc) return rc;
+    const long tiles = (M + BM - 1) / BM;
+    const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+    tc_gemm_kernel<<<grid, THREADS, smem, st>>>(p);
+    return finish_launch();
+}
+
+}  // namespace tc
+
+// Shapes worth the tensor cores: at least one full tile of rows, K and N not tiny.
+// K <= 512 keeps the truncating tensor-core accumulation inside the 1e-5 parity bar.
+static bool tc_shape_ok(long M, int K, int N) { return M >= 128 && K >= 16 && K <= 512 && N >= 16; }
+
+constexpr int TC_NCHUNK = 128;
+static size_t tc_image_bytes(int K, int N) { return tc::image_bytes(K, N > TC_NCHUNK ? TC_NCHUNK : N); }
+
+// one buffer serves both orientations of a layer: forward (K x N) and dgrad (N x K)
+size_t tc_workspace_bytes(int K, int N) {
+    const size_t a = tc_image_bytes(K, N), b = tc_image_bytes(N, K);
+    return a > b ? a : b;
+}
+
+int tc_linear_fwd(long M, int K, int N, const float *A, int lda, const float *a_scale,
+                  const float *a_shift, int a_relu, const float *W, const float *bias, float *Y,
+                  double *stats, float *ws, size_t ws_bytes, cudaStream_t st) {
+    if (!tc_shape_ok(M, K, N) || ws == nullptr || ws_bytes < tc_image_bytes(K, N))
+        return PN2_EUNSUPPORTED;
+    for (int n0 = 0; n0 < N; n0 += TC_NCHUNK) {
+        const int nc = (N - n0) < TC_NCHUNK ? (N - n0) : TC_NCHUNK;
+        // Bt(n,k) = W[k*N + n0 + n]
+        int rc = tc::run_chunk(M, K, nc, A, lda, a_scale, a_shift, a_relu, W + n0, 1, N,
+                               bias ? bias + n0 : nullptr, Y + n0, N, stats ? stats + n0 : nullptr,
+                               stats ? stats + N + n0 : nullptr, ws, st);
+        if (rc) return rc;
+    }
+    return PN2_OK;
+}
+
+int tc_linear_dgrad(long M, int K, int N, const float *dY, const float *W, float *dX, int ldx,
+                    float *ws, size_t ws_bytes, cudaStream_t st) {
+    // dX[M,K] = dY[M,N] * W[K,N]^T : contraction over N, output columns = K ; Bt(k,n) = W[k*N + n]
+    if (!tc_shape_ok(M, N, K) || ws == nullptr || ws_bytes < tc_image_bytes(N, K))
+        return PN2_EUNSUPPORTED;
+    for (int k0 = 0; k0 < K; k0 += TC_NCHUNK) {
+        const int kc = (K - k0) < TC_NCHUNK ? (K - k0) : TC_NCHUNK;
+        int rc = tc::run_chunk(M, N, kc, dY, N, nullptr, nullptr, 0, W + (long)k0 * N, N, 1, nullptr,
+                               dX + k0, ldx, nullptr, nullptr, ws, st);
+        if (rc) return rc;
+    }
+    return PN2_OK;
+}
+
 }  // namespace pn2

@@ -158,9 +158,11 @@ ball_query_stream_kernel(int n, int m, float thr, int nsample, const float *__re
     }
 }
 
-// Small-grid variant: whole cloud resident in shared memory (one TMA bulk copy), SPLIT lanes
-// per query each scanning a contiguous chunk; per-lane hit lists live in shared memory and
-// are concatenated in chunk order (== index order) at the end.
+// Small-grid variant: the whole cloud is made resident in shared memory by ONE TMA bulk copy and
+// SPLIT lanes share a query.  Per round the SPLIT lanes test SPLIT*4 consecutive points (lane s
+// takes points base+4s .. base+4s+3: three LDS.128, bank-conflict free), so lane order == index
+// order inside a round and hits can be appended to the output row in place with a SPLIT-lane
+// prefix sum.  Rounds without any hit in the warp (the common case) cost one vote instruction.
 template <int SPLIT>
 __global__ void __launch_bounds__(BQ_THREADS)
 ball_query_resident_kernel(int n, int m, float thr, int nsample, int use_tma,
@@ -168,13 +170,15 @@ ball_query_resident_kernel(int n, int m, float thr, int nsample, int use_tma,
                            int *__restrict__ idx, int *__restrict__ pts_cnt) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int QPB = BQ_THREADS / SPLIT;
-    const int npad4 = (n + 3) & ~3;
-    float *pts = reinterpret_cast<float *>(smem_raw);                    // npad4*3 floats
-    int *hits = reinterpret_cast<int *>(pts + (size_t)npad4 * 3);        // [BQ_THREADS][nsample]
+    const int npad = ((n + SPLIT * 4 - 1) / (SPLIT * 4)) * (SPLIT * 4);  // whole rounds
+    float *pts = reinterpret_cast<float *>(smem_raw);                      // npad*3 floats
     __shared__ __align__(8) uint64_t full;
 
     const int cloud = blockIdx.y;
     const float *data = xyz1 + (size_t)cloud * n * 3;
+    // padding points (never hits: coordinates NaN-free and far away is not needed, they are
+    // masked by k < n below); zero them so no uninitialised shared memory is read
+    for (int e = n * 3 + threadIdx.x; e < npad * 3; e += BQ_THREADS) pts[e] = 0.f;
     if (use_tma) {
         if (threadIdx.x == 0) {
             mbar_init(&full, 1);
@@ -182,7 +186,6 @@ ball_query_resident_kernel(int n, int m, float thr, int nsample, int use_tma,
         }
         __syncthreads();
         if (threadIdx.x == 0) {
-            // bulk copies are limited by the mbarrier tx-count (2^20-1 bytes): chunk it
             uint32_t total = (uint32_t)n * 12u;
             mbar_expect_tx(&full, total);
             for (uint32_t off = 0; off < total; off += 65536u) {
@@ -194,10 +197,12 @@ ball_query_resident_kernel(int n, int m, float thr, int nsample, int use_tma,
         mbar_wait(&full, 0);
     } else {
         for (int e = threadIdx.x; e < n * 3; e += BQ_THREADS) pts[e] = __ldg(data + e);
-        __syncthreads();
     }
+    __syncthreads();
 
     const int q = threadIdx.x / SPLIT, sub = threadIdx.x % SPLIT;
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned gbase = lane & ~(unsigned)(SPLIT - 1);
     const int j = blockIdx.x * QPB + q;
     const bool valid = j < m;
     float qx = 0.f, qy = 0.f, qz = 0.f;
@@ -207,57 +212,50 @@ ball_query_resident_kernel(int n, int m, float thr, int nsample, int use_tma,
         qy = __ldg(qp + 1);
         qz = __ldg(qp + 2);
     }
-    // chunk boundaries are multiples of 4 points so float4 reads stay aligned
-    const int chunk = ((n + SPLIT - 1) / SPLIT + 3) & ~3;
-    const int k0 = min(sub * chunk, n), k1 = min(k0 + chunk, n);
-    int *mine = hits + (size_t)threadIdx.x * nsample;
-    int cnt = 0;
-    if (valid) {
-        const float4 *b4 = reinterpret_cast<const float4 *>(pts);
-        int k = k0;
-        const int kend4 = k0 + ((k1 - k0) & ~3);
-        for (; k < kend4 && cnt < nsample; k += 4) {
-            float4 a = b4[(k >> 2) * 3 + 0], bb = b4[(k >> 2) * 3 + 1], c = b4[(k >> 2) * 3 + 2];
-            float d0 = sqdist_ref(qx - a.x, qy - a.y, qz - a.z);
-            float d1 = sqdist_ref(qx - a.w, qy - bb.x, qz - bb.y);
-            float d2 = sqdist_ref(qx - bb.z, qy - bb.w, qz - c.x);
-            float d3 = sqdist_ref(qx - c.y, qy - c.z, qz - c.w);
-            bool h0 = !(d0 >= thr), h1 = !(d1 >= thr), h2 = !(d2 >= thr), h3 = !(d3 >= thr);
-            if (h0 | h1 | h2 | h3) {
-                if (h0 && cnt < nsample) mine[cnt++] = k;
-                if (h1 && cnt < nsample) mine[cnt++] = k + 1;
-                if (h2 && cnt < nsample) mine[cnt++] = k + 2;
-                if (h3 && cnt < nsample) mine[cnt++] = k + 3;
-            }
+    int *row = idx + ((size_t)cloud * m + (valid ? j : 0)) * nsample;
+    int cnt = 0, first = 0;  // uniform inside a SPLIT-lane group
+    const float4 *b4 = reinterpret_cast<const float4 *>(pts);
+    for (int base = 0; base < npad; base += SPLIT * 4) {
+        const int k = base + sub * 4;
+        const float4 a = b4[(k >> 2) * 3 + 0], bb = b4[(k >> 2) * 3 + 1], c = b4[(k >> 2) * 3 + 2];
+        const float d0 = sqdist_ref(qx - a.x, qy - a.y, qz - a.z);
+        const float d1 = sqdist_ref(qx - a.w, qy - bb.x, qz - bb.y);
+        const float d2 = sqdist_ref(qx - bb.z, qy - bb.w, qz - c.x);
+        const float d3 = sqdist_ref(qx - c.y, qy - c.z, qz - c.w);
+        unsigned h = 0;
+        if (valid && cnt < nsample) {
+            h = (!(d0 >= thr) && k < n ? 1u : 0u) | (!(d1 >= thr) && k + 1 < n ? 2u : 0u) |
+                (!(d2 >= thr) && k + 2 < n ? 4u : 0u) | (!(d3 >= thr) && k + 3 < n ? 8u : 0u);
         }
-        for (; k < k1 && cnt < nsample; ++k) {
-            float d0 = sqdist_ref(qx - pts[k * 3], qy - pts[k * 3 + 1], qz - pts[k * 3 + 2]);
-            if (!(d0 >= thr)) mine[cnt++] = k;
-        }
-    }
-    // in-order merge inside the SPLIT-lane group (groups never straddle a warp: SPLIT | 32)
-    const unsigned lane = threadIdx.x & 31;
-    const unsigned gbase = lane & ~(unsigned)(SPLIT - 1);
-    int offset = 0, total = 0, first = 0;
-    bool have_first = false;
+        if (__any_sync(0xFFFFFFFFu, h != 0)) {  // warp-uniform slow path
+            const int cme = __popc(h);
+            int incl = cme;
 #pragma unroll
-    for (int s = 0; s < SPLIT; ++s) {
-        int c = __shfl_sync(0xFFFFFFFFu, cnt, gbase + s);
-        int f = __shfl_sync(0xFFFFFFFFu, cnt > 0 ? mine[0] : 0, gbase + s);
-        if (s < sub) offset += c;
-        if (!have_first && c > 0) {
-            first = f;
-            have_first = true;
+            for (int off = 1; off < SPLIT; off <<= 1) {
+                const int t = __shfl_up_sync(0xFFFFFFFFu, incl, off, SPLIT);
+                if (sub >= off) incl += t;
+            }
+            const int total = __shfl_sync(0xFFFFFFFFu, incl, SPLIT - 1, SPLIT);
+            // first hit of the group (only consulted while cnt == 0)
+            const unsigned gm = (__ballot_sync(0xFFFFFFFFu, cme > 0) >> gbase) &
+                                (SPLIT == 32 ? 0xFFFFFFFFu : ((1u << SPLIT) - 1u));
+            const int src = gm ? (int)gbase + __ffs(gm) - 1 : (int)lane;
+            const int f = __shfl_sync(0xFFFFFFFFu, k + __ffs(h) - 1, src);
+            if (cnt == 0 && total > 0) first = f;
+            int pos = cnt + incl - cme;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if ((h >> i) & 1u) {
+                    if (pos < nsample) row[pos] = k + i;
+                    ++pos;
+                }
+            cnt = min(cnt + total, nsample);
+            if (__all_sync(0xFFFFFFFFu, !valid || cnt >= nsample)) break;
         }
-        total += c;
     }
     if (valid) {
-        int *row = idx + ((size_t)cloud * m + j) * nsample;
-        for (int l = 0; l < cnt && offset + l < nsample; ++l) row[offset + l] = mine[l];
-        const int tot = min(total, nsample);
-        // padding slots are shared out among the group's lanes
-        for (int l = tot + sub; l < nsample; l += SPLIT) row[l] = first;
-        if (sub == 0) pts_cnt[(size_t)cloud * m + j] = tot;
+        for (int l = cnt + sub; l < nsample; l += SPLIT) row[l] = first;  // pad (0 if no hit)
+        if (sub == 0) pts_cnt[(size_t)cloud * m + j] = cnt;
     }
 }
 
@@ -426,8 +424,8 @@ PN2_API int pn2_query_ball_point(int b, int n, int m, float radius, int nsample,
     // small grids: make the cloud resident and split each query over SPLIT lanes
     const long queries = (long)b * m;
     int split = 1;
-    while (split < 8 && queries * split < 148L * 512) split *= 2;
-    const size_t res_smem = (size_t)((n + 3) & ~3) * 12 + (size_t)BQ_THREADS * nsample * 4;
+    while (split < 8 && queries * split < 148L * 1024) split *= 2;
+    const size_t res_smem = (size_t)(((n + 8 * 4 - 1) / (8 * 4)) * (8 * 4)) * 12;  // padded to whole rounds
     if (split > 1 && res_smem <= 200 * 1024) {
         dim3 grid((unsigned)ceil_div(m, BQ_THREADS / split), (unsigned)b);
         int rc = PN2_OK;

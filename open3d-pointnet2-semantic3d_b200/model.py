@@ -88,8 +88,9 @@ class _SoftmaxCE(torch.autograd.Function):
         rows, c = pred.numel() // pred.shape[-1], pred.shape[-1]
         d = torch.empty_like(pred)
         # the upstream gradient g (0-dim) is read on the device: no host synchronisation
+        gc = g.contiguous()  # named: the buffer must outlive the launch
         call("pn2_softmax_ce_grad", rows, c, ptr(pred, F32), ptr(label, I32), ptr(smpw, F32, True),
-             ptr(acc, F64), 1.0, ptr(g.contiguous(), F32), None, ptr(d, F32))
+             ptr(acc, F64), 1.0, ptr(gc, F32), None, ptr(d, F32))
         return d, None, None
 
 

@@ -76,8 +76,8 @@ def group_point_grad(points, idx, grad_out):
     _need(grad_out.dim() == 4 and tuple(grad_out.shape) == (b, m, ns, c),
           "GroupPointGrad expects (batch_size, npoints, nsample, channel) grad_out shape")
     g = torch.empty((b, n, c), dtype=F32, device=points.device)
-    call("pn2_group_point_grad", b, n, c, m, ns, ptr(grad_out.contiguous(), F32),
-         ptr(idx.contiguous(), I32), ptr(g, F32))
+    go, ii = grad_out.contiguous(), idx.contiguous()
+    call("pn2_group_point_grad", b, n, c, m, ns, ptr(go, F32), ptr(ii, I32), ptr(g, F32))
     return g
 
 

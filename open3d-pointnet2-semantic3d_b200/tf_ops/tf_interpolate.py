@@ -74,6 +74,7 @@ def three_interpolate_grad(points, idx, weight, grad_out):
     _need(grad_out.dim() == 3 and tuple(grad_out.shape) == (b, n, c),
           "ThreeInterpolateGrad expects (b,n,c) grad_out shape")
     g = torch.empty((b, m, c), dtype=F32, device=points.device)
-    call("pn2_three_interpolate_grad", b, n, c, m, ptr(grad_out.contiguous(), F32),
-         ptr(idx.contiguous(), I32), ptr(weight.contiguous(), F32), ptr(g, F32))
+    go, ii, ww = grad_out.contiguous(), idx.contiguous(), weight.contiguous()
+    call("pn2_three_interpolate_grad", b, n, c, m, ptr(go, F32), ptr(ii, I32), ptr(ww, F32),
+         ptr(g, F32))
     return g

@@ -72,6 +72,6 @@ def gather_point_grad(inp, idx, out_g):
     _need(out_g.dim() == 3 and out_g.shape[0] == b and out_g.shape[1] == m and out_g.shape[2] == 3,
           "GatherPointGradGpuOp expects (batch_size,num_result,3) out_g shape")
     inp_g = torch.empty((b, n, 3), dtype=F32, device=inp.device)
-    call("pn2_gather_point_grad", b, n, m, ptr(out_g.contiguous(), F32), ptr(idx.contiguous(), I32),
-         ptr(inp_g, F32))
+    og, ii = out_g.contiguous(), idx.contiguous()
+    call("pn2_gather_point_grad", b, n, m, ptr(og, F32), ptr(ii, I32), ptr(inp_g, F32))
     return inp_g

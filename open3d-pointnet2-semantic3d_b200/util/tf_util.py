@@ -196,6 +196,21 @@ def make_layer(scope, k, n, bn, act, use_xavier=True, stddev=1e-3, kernel_rank=4
     return L
 
 
+_ws_cache = {}
+
+
+def _workspace(L, dev):
+    """Caller-owned scratch for the tensor-core path (3xTF32 weight image), one per layer shape."""
+    key = (L.k, L.n, str(dev))
+    ws = _ws_cache.get(key)
+    if ws is None:
+        from .._ffi import lib
+        nbytes = int(lib().pn2_linear_workspace_bytes(L.k, L.n))
+        ws = torch.empty(max(nbytes // 4, 4), dtype=F32, device=dev)
+        _ws_cache[key] = ws
+    return ws
+
+
 class _MLPChain(torch.autograd.Function):
     """x (M,K0) -> out (M,N_last) or, with pool_ns>0, (M/pool_ns, N_last) max-pooled.
 
@@ -215,9 +230,11 @@ class _MLPChain(torch.autograd.Function):
             Y = torch.empty((M, N), dtype=F32, device=dev)
             use_stats = L.bn and is_training
             stats = torch.zeros(2 * N, dtype=F64, device=dev) if use_stats else None
+            ws = _workspace(L, dev) if gemm_mode != 0 else None
             call("pn2_linear_fwd", M, L.k, N, ptr(a, F32), lda, ptr(a_sc, F32, True),
                  ptr(a_sh, F32, True), a_relu, ptr(L.w.data, F32), ptr(L.b.data, F32), ptr(Y, F32),
-                 ptr(stats, F64, True), gemm_mode)
+                 ptr(stats, F64, True), ptr(ws, F32, True), 0 if ws is None else ws.numel() * 4,
+                 gemm_mode)
             sc = sh = saved = None
             if L.bn:
                 sc = torch.empty(N, dtype=F32, device=dev)
@@ -303,13 +320,19 @@ class _MLPChain(torch.autograd.Function):
             else:
                 P = layers[i - 1]
                 a, lda, a_sc, a_sh, a_relu = Ys[i - 1], P.n, scs[i - 1], shs[i - 1], 1 if P.relu else 0
+            # A bias that feeds a train-mode BatchNorm has an exactly zero gradient (BN removes the
+            # column mean, so sum_rows dY == 0); it is left at zero instead of accumulating the
+            # fp32 rounding noise of an M-term sum.
+            db = None if L.bn else ptr(L.b.ensure_grad(), F32)
+            L.b.ensure_grad()
             call("pn2_linear_wgrad", M, L.k, N, ptr(a, F32), lda, ptr(a_sc, F32, True),
                  ptr(a_sh, F32, True), a_relu, ptr(dY, F32), ptr(L.w.ensure_grad(), F32),
-                 ptr(L.b.ensure_grad(), F32), ctx.gemm_mode)
+                 db, ctx.gemm_mode)
             if i > 0 or ctx.needs_input_grad[0]:
                 dX = torch.empty((M, L.k), dtype=F32, device=dev)
+                ws = _workspace(L, dev) if ctx.gemm_mode != 0 else None
                 call("pn2_linear_dgrad", M, L.k, N, ptr(dY, F32), ptr(L.w.data, F32), ptr(dX, F32),
-                     L.k, ctx.gemm_mode)
+                     L.k, ptr(ws, F32, True), 0 if ws is None else ws.numel() * 4, ctx.gemm_mode)
                 up = dX
             else:
                 up = None
@@ -317,7 +340,11 @@ class _MLPChain(torch.autograd.Function):
         return up, None, None, None, None, None, None
 
 
-GEMM_MODE = -1  # -1 auto, 0 exact fp32 CUDA-core kernel, 1 force tcgen05 3xTF32
+import os as _os
+
+# -1 auto (tcgen05 3xTF32 where the shape allows, else fp32 CUDA cores), 0 exact fp32 CUDA-core
+# kernel only, 1 force tcgen05.  PN2_GEMM_MODE overrides the default.
+GEMM_MODE = int(_os.environ.get("PN2_GEMM_MODE", "0"))
 
 
 def mlp_chain(x2d, layers, is_training, bn_decay, pool_ns=0):

@@ -30,7 +30,13 @@ import torch
 from . import oracle as orc
 
 BN_EPS = 1e-3
-F64 = torch.float64
+F64 = torch.float64  # working dtype; bench.py's CPU-baseline leg switches it to float32
+
+
+def set_dtype(dt):
+    """fp64 for parity checks (default); fp32 when the module is TIMED as the CPU baseline."""
+    global F64
+    F64 = dt
 
 
 def _t(a):
@@ -70,7 +76,7 @@ class Ctx:
         self.acts = {}
 
     def grads(self):
-        return {k: v.grad.numpy().copy() for k, v in self.t.items() if v.grad is not None}
+        return {k: v.grad.double().numpy().copy() for k, v in self.t.items() if v.grad is not None}
 
 
 def conv_bn_relu(ctx, x, scope, bn=True, relu=True, rank4=True):

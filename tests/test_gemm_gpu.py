@@ -1,0 +1,115 @@
+"""GPU parity of the shared-MLP GEMM entry points (pn2_linear_fwd / dgrad / wgrad), called
+straight through the C ABI: the exact fp32 CUDA-core kernel (mode 0) and the tcgen05 3xTF32
+tensor-core kernel (mode 1) against an fp64 matmul.  Tolerance 1e-5 absolute on O(1) outputs."""
+import numpy as np
+import pytest
+
+from _util import to_cuda
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ffi(cuda):
+    import pn2_b200
+    return pn2_b200._ffi
+
+
+def _ws(ffi, k, n):
+    import torch
+    nb = int(ffi.lib().pn2_linear_workspace_bytes(k, n))
+    return torch.empty(max(nb // 4, 4), dtype=torch.float32, device="cuda")
+
+
+def linear_fwd(ffi, A, W, bias, scale, shift, relu, mode, lda=None, want_stats=True):
+    import torch
+    M, K = A.shape
+    N = W.shape[1]
+    Y = torch.empty((M, N), dtype=torch.float32, device="cuda")
+    stats = torch.zeros(2 * N, dtype=torch.float64, device="cuda") if want_stats else None
+    ws = _ws(ffi, K, N)
+    p = ffi.ptr
+    ffi.call("pn2_linear_fwd", M, K, N, p(A), lda or K, p(scale, None, True), p(shift, None, True),
+             1 if relu else 0, p(W), p(bias, None, True), p(Y), p(stats, None, True), p(ws),
+             ws.numel() * 4, mode)
+    return Y, stats
+
+
+SHAPES = [  # M, K, N
+    (128, 32, 32), (256, 64, 64), (1000, 67, 64), (4096, 131, 128), (640, 259, 256),
+    (512, 256, 512), (384, 128, 48), (130, 16, 16), (8192, 128, 128), (2048, 384, 256),
+    (1024, 512, 128),
+]
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("M,K,N", SHAPES)
+def test_linear_fwd(ffi, mode, M, K, N):
+    import torch
+    rs = np.random.RandomState(M + K + N)
+    A = rs.normal(size=(M, K)).astype(np.float32)
+    W = (rs.uniform(-1, 1, (K, N)) * np.sqrt(6.0 / (K + N))).astype(np.float32)
+    b = rs.uniform(-0.5, 0.5, N).astype(np.float32)
+    sc = rs.uniform(0.5, 1.5, K).astype(np.float32)
+    sh = rs.uniform(-0.5, 0.5, K).astype(np.float32)
+    At, Wt = to_cuda(A), to_cuda(W)
+    # plain
+    Y, st = linear_fwd(ffi, At, Wt, to_cuda(b), None, None, False, mode)
+    exp = A.astype(np.float64) @ W.astype(np.float64) + b
+    np.testing.assert_allclose(Y.cpu().numpy(), exp, atol=1e-5)
+    # statistics are sums over M of values that each carry ~1e-6 relative error
+    np.testing.assert_allclose(st.cpu().numpy()[:N], exp.sum(0), rtol=1e-5, atol=1e-5 * M)
+    np.testing.assert_allclose(st.cpu().numpy()[N:], (exp ** 2).sum(0), rtol=1e-5, atol=1e-5 * M)
+    # with the previous layer's BN affine + ReLU applied on the fly
+    Y2, _ = linear_fwd(ffi, At, Wt, None, to_cuda(sc), to_cuda(sh), True, mode, want_stats=False)
+    A2 = np.maximum(A.astype(np.float64) * sc + sh, 0.0)
+    np.testing.assert_allclose(Y2.cpu().numpy(), A2 @ W.astype(np.float64), atol=1e-5)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("M,K,N", [(256, 64, 64), (1000, 67, 64), (4096, 131, 128),
+                                   (512, 259, 256), (384, 512, 256), (8192, 128, 128)])
+def test_linear_dgrad(ffi, mode, M, K, N):
+    import torch
+    rs = np.random.RandomState(7 + M + K + N)
+    dY = rs.normal(size=(M, N)).astype(np.float32)
+    W = (rs.uniform(-1, 1, (K, N)) * np.sqrt(6.0 / (K + N))).astype(np.float32)
+    dX = torch.empty((M, K), dtype=torch.float32, device="cuda")
+    ws = _ws(ffi, K, N)
+    p = ffi.ptr
+    dYt, Wt = to_cuda(dY), to_cuda(W)  # keep the device buffers alive across the call
+    ffi.call("pn2_linear_dgrad", M, K, N, p(dYt), p(Wt), p(dX), K, p(ws), ws.numel() * 4, mode)
+    exp = dY.astype(np.float64) @ W.astype(np.float64).T
+    np.testing.assert_allclose(dX.cpu().numpy(), exp, atol=1e-5)
+
+
+@pytest.mark.parametrize("M,K,N", [(1000, 6, 32), (4096, 67, 64), (2048, 131, 128), (8192, 32, 32),
+                                   (300, 259, 256)])
+def test_linear_wgrad(ffi, M, K, N):
+    import torch
+    rs = np.random.RandomState(11 + M + K + N)
+    A = rs.normal(size=(M, K)).astype(np.float32)
+    dY = (rs.normal(size=(M, N)) * 0.1).astype(np.float32)
+    sc = rs.uniform(0.5, 1.5, K).astype(np.float32)
+    sh = rs.uniform(-0.5, 0.5, K).astype(np.float32)
+    dW = torch.zeros((K, N), dtype=torch.float32, device="cuda")
+    db = torch.zeros(N, dtype=torch.float32, device="cuda")
+    p = ffi.ptr
+    At, sct, sht, dYt = to_cuda(A), to_cuda(sc), to_cuda(sh), to_cuda(dY)
+    ffi.call("pn2_linear_wgrad", M, K, N, p(At), K, p(sct), p(sht), 1, p(dYt), p(dW), p(db), 0)
+    A2 = np.maximum(A.astype(np.float64) * sc + sh, 0.0)
+    exp = A2.T @ dY.astype(np.float64)
+    tol = 2e-5 * max(1.0, np.abs(exp).max())
+    np.testing.assert_allclose(dW.cpu().numpy(), exp, atol=tol)
+    np.testing.assert_allclose(db.cpu().numpy(), dY.astype(np.float64).sum(0), atol=tol)
+
+
+def test_three_tf32_beats_plain_tf32_bound(ffi):
+    """The compensated product must be far more accurate than a single TF32 pass could be:
+    with K=256 and O(1) operands a 10-bit mantissa gives ~1e-3 absolute error."""
+    rs = np.random.RandomState(0)
+    A = rs.normal(size=(1024, 256)).astype(np.float32)
+    W = rs.normal(size=(256, 128)).astype(np.float32) * 0.05
+    Y, _ = linear_fwd(ffi, to_cuda(A), to_cuda(W), None, None, None, False, 1, want_stats=False)
+    err = np.abs(Y.cpu().numpy() - A.astype(np.float64) @ W.astype(np.float64)).max()
+    assert err < 1e-5, err

@@ -67,7 +67,9 @@ def cpu_step_factory(sample_b, n):
     import torch
     from oracle import layers_ref as lr
     from oracle import oracle as orc
-    cores = os.cpu_count() or 1
+    # PyTorch-CPU ops on (65k..500k) x (6..512) matrices stop scaling (and then regress) beyond a
+    # few tens of threads; 16 was the fastest setting measured on the 128-core GPU host.
+    cores = min(os.cpu_count() or 1, int(os.environ.get("PN2_CPU_THREADS", "16")))
     torch.set_num_threads(cores)
     lr.set_dtype(torch.float32)
     threads = min(cores, orc.max_threads())

@@ -20,6 +20,8 @@ int tc_linear_fwd(long M, int K, int N, const float *A, int lda, const float *a_
 int tc_linear_dgrad(long M, int K, int N, const float *dY, const float *W, float *dX, int ldx,
                     float *ws, size_t ws_bytes, cudaStream_t st);
 size_t tc_workspace_bytes(int K, int N);
+int tc_linear_wgrad(long M, int K, int N, const float *A, int lda, const float *a_scale,
+                    const float *a_shift, int a_relu, const float *dY, float *dW, cudaStream_t st);
 
 // ---- SIMT GEMM dispatch ----------------------------------------------------------------------
 template <bool A_KC, bool B_NC, bool ATOMIC>
@@ -465,6 +467,18 @@ PN2_API int pn2_linear_wgrad(long M, int K, int N, const float *A, int lda, cons
     PN2_REQUIRE_PTR(dW);
     PN2_REQUIRE((a_scale == nullptr) == (a_shift == nullptr));
     cudaStream_t st = as_stream(s);
+    int rc = PN2_EUNSUPPORTED;
+    if (mode == 1 || (mode == -1 && tc_enabled()))
+        rc = tc_linear_wgrad(M, K, N, A, lda, a_scale, a_shift, a_relu, dY, dW, st);
+    if (rc != PN2_EUNSUPPORTED || mode == 1) {
+        if (rc == PN2_OK && db) {
+            long rpb = ceil_div<long>(M, 64L);
+            if (rpb < 32) rpb = 32;
+            colsum_kernel<<<(int)ceil_div<long>(M, rpb), 256, 0, st>>>(M, N, rpb, dY, db);
+            rc = finish_launch();
+        }
+        return rc;
+    }
     // C[K,N] += sum_m f(A)(m,k) dY(m,n): M'=K, N'=N, K'=M ; A(m'=k, k'=m) = A + m*lda + k
     const int tiles = ceil_div(K, K > 64 ? 128 : (K > 32 ? 64 : 32)) *
                       ceil_div(N, N > 64 ? 128 : (N > 32 ? 64 : 32));
@@ -472,8 +486,8 @@ PN2_API int pn2_linear_wgrad(long M, int K, int N, const float *A, int lda, cons
     const long max_splits = ceil_div<long>(M, 256);
     if (splits > max_splits) splits = (int)max_splits;
     if (splits < 1) splits = 1;
-    int rc = launch_gemm<false, true, true>(K, N, M, A, 1, lda, dY, N, 1, a_scale, a_shift, a_relu,
-                                            nullptr, dW, N, nullptr, splits, st);
+    rc = launch_gemm<false, true, true>(K, N, M, A, 1, lda, dY, N, 1, a_scale, a_shift, a_relu,
+                                        nullptr, dW, N, nullptr, splits, st);
     if (rc) return rc;
     if (db) {
         long rpb = ceil_div<long>(M, 64L);

@@ -451,6 +451,333 @@ static int run_chunk(long M, int K, int Nc, const float *A, int lda, const float
 
 }  // namespace tc
 
+// =====================================================================================================
+// wgrad on the tensor cores:  dW[K,N] += f(X)[M,K]^T * dY[M,N]   (contraction over the M rows)
+//
+// Both operands are "MN-major" for the MMA: X^T has its M' = feature index contiguous in memory
+// (a row of X), dY^T likewise.  For 32-bit operands the only MN-major shared-memory layout the
+// tensor core accepts is SWIZZLE_128B_BASE32B (cutlass sm100_common.inl: "for mn-major tf32
+// operands, SW128_32B is the only available smem layout"): atoms of 4 contraction rows x 128 B
+// (32 fp32 of the feature/column index), the four 32-byte chunks of a row XOR-permuted by the row
+// index (Swizzle<2,5,2>).  An atom is 4 consecutive rows of the row-major source, so the
+// producers copy rows (transform + hi/lo split) without any transpose.
+// The M rows are cut into segments of 512 rows; each segment accumulates into its own TMEM
+// accumulator pair (double buffered) and is flushed to dW with fp32 atomics by the epilogue warps.
+// Short segments bound the number of truncating tensor-core accumulations (64 per segment).
+// =====================================================================================================
+namespace tcw {
+using namespace tc;
+
+constexpr int W_THREADS = 416;  // warps 0-3 epilogue, 4-11 producers, 12 MMA
+constexpr int W_ROWS = 32;      // contraction rows per stage (4 MMAs of K=8)
+constexpr int W_SEG = 512;      // contraction rows per accumulator segment
+constexpr int W_FEAT = 128;     // features (rows of dW) per CTA pass = UMMA M
+
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr, uint32_t lbo_bytes,
+                                                 uint32_t sbo_bytes) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (1ull << 61);
+}
+// byte offset of float4 slot c4 (MN index 4*c4..4*c4+3) of contraction row r inside a stage
+// operand laid out as [k-group r/4][MN-group c4/8] atoms of 512 B
+__device__ __forceinline__ uint32_t mn_offset(int r, int c4, int groups) {
+    return (uint32_t)(((r >> 2) * groups + (c4 >> 3)) * 512 + (r & 3) * 128 +
+                      (((((c4 & 7) >> 1) ^ (r & 3)) & 3) << 5) + ((c4 & 1) << 4));
+}
+
+struct WParams {
+    long M;
+    int K, N, Npad, NG, lda, ldy, ldw, a_relu, k0, n0, stages;
+    const float *A, *a_scale, *a_shift, *dY;
+    float *dW;
+};
+
+__global__ void __launch_bounds__(W_THREADS, 1) tc_wgrad_kernel(const WParams p) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const uint32_t a_bytes = 8 * 4 * 512;                  // [k-group 8][mg 4] atoms of 512 B
+    const uint32_t b_bytes = 8 * (uint32_t)p.NG * 512;     // [k-group 8][ng NG] atoms
+    const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+    float *epi = reinterpret_cast<float *>(smem + (size_t)p.stages * stage_bytes);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(epi + 4 * 32 * EPI_LD);
+    uint64_t *full = bars, *empty = bars + MAX_STAGES;
+    uint64_t *acc_full = bars + 2 * MAX_STAGES, *acc_empty = bars + 2 * MAX_STAGES + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * MAX_STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int Nacc = p.Npad;  // multiple of 32
+    uint32_t ncols = 32;
+    while (ncols < (uint32_t)(4 * Nacc)) ncols <<= 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(&full[s], 256);
+            mbar_init(&empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&acc_full[a], 1);
+            mbar_init(&acc_empty[a], 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 12) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                         smem_u32(tmem_slot)),
+                     "r"(ncols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    const long num_seg = (p.M + W_SEG - 1) / W_SEG;
+
+    if (warp >= 4 && warp < 12) {
+        // ================================ producers ================================
+        const int t = threadIdx.x - 128;  // 0..255 ; 0..127 -> A (features), 128..255 -> B (dY)
+        const bool is_a = t < 128;
+        const int tt = is_a ? t : t - 128;
+        const bool a_vec = (p.lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0) &&
+                           (p.k0 % 4 == 0);
+        const bool b_vec = (p.ldy % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.dY) & 15) == 0) &&
+                           (p.n0 % 4 == 0);
+        const int bw4 = p.Npad >> 2;           // float4 per dY row
+        const int b_iters = (W_ROWS * bw4) / 128;  // Npad/4*32/128 = Npad/16
+        uint32_t it = 0;
+        for (long seg = blockIdx.x; seg < num_seg; seg += gridDim.x) {
+            const long seg0 = seg * W_SEG;
+            const int nst = (int)((min((long)W_SEG, p.M - seg0) + W_ROWS - 1) / W_ROWS);
+            for (int sidx = 0; sidx < nst; ++sidx, ++it) {
+                const int s = it % p.stages;
+                const uint32_t ph = (it / p.stages) & 1;
+                const long mbase = seg0 + (long)sidx * W_ROWS;
+                unsigned char *st_base = smem + (size_t)s * stage_bytes;
+                if (is_a) {
+                    const int c4 = tt & 31, rr = tt >> 5;
+                    const int kf = p.k0 + 4 * c4;  // first feature of this float4
+                    float sc[4] = {0.f, 0.f, 0.f, 0.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (p.a_scale) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (kf + j < p.K) {
+                                sc[j] = __ldg(p.a_scale + kf + j);
+                                sh[j] = __ldg(p.a_shift + kf + j);
+                            }
+                    }
+                    float4 v[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const long m = mbase + rr + 4 * i;
+                        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (m < p.M && kf < p.K) {
+                            const float *src = p.A + m * p.lda + kf;
+                            if (a_vec && kf + 3 < p.K) {
+                                x = __ldg(reinterpret_cast<const float4 *>(src));
+                            } else {
+                                x.x = __ldg(src);
+                                if (kf + 1 < p.K) x.y = __ldg(src + 1);
+                                if (kf + 2 < p.K) x.z = __ldg(src + 2);
+                                if (kf + 3 < p.K) x.w = __ldg(src + 3);
+                            }
+                            if (p.a_scale) {
+                                float *e = reinterpret_cast<float *>(&x);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    float y = __fmaf_rn(e[j], sc[j], sh[j]);
+                                    if (p.a_relu) y = fmaxf(y, 0.f);
+                                    e[j] = (kf + j < p.K) ? y : 0.f;
+                                }
+                            }
+                        }
+                        v[i] = x;
+                    }
+                    mbar_wait(&empty[s], ph ^ 1);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int r = rr + 4 * i;
+                        const uint32_t off = mn_offset(r, c4, 4);
+                        float4 hi, lo;
+                        hi.x = tf32_rna(v[i].x); lo.x = v[i].x - hi.x;
+                        hi.y = tf32_rna(v[i].y); lo.y = v[i].y - hi.y;
+                        hi.z = tf32_rna(v[i].z); lo.z = v[i].z - hi.z;
+                        hi.w = tf32_rna(v[i].w); lo.w = v[i].w - hi.w;
+                        *reinterpret_cast<float4 *>(st_base + off) = hi;
+                        *reinterpret_cast<float4 *>(st_base + a_bytes + off) = lo;
+                    }
+                } else {
+                    mbar_wait(&empty[s], ph ^ 1);
+                    unsigned char *b_hi = st_base + 2 * a_bytes;
+                    for (int q = 0; q < b_iters; ++q) {
+                        const int e = tt + 128 * q;
+                        const int c4 = e % bw4, r = e / bw4;
+                        const long m = mbase + r;
+                        const int nf = p.n0 + 4 * c4;
+                        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (m < p.M && nf < p.N) {
+                            const float *src = p.dY + m * p.ldy + nf;
+                            if (b_vec && nf + 3 < p.N) {
+                                x = __ldg(reinterpret_cast<const float4 *>(src));
+                            } else {
+                                x.x = __ldg(src);
+                                if (nf + 1 < p.N) x.y = __ldg(src + 1);
+                                if (nf + 2 < p.N) x.z = __ldg(src + 2);
+                                if (nf + 3 < p.N) x.w = __ldg(src + 3);
+                            }
+                        }
+                        const uint32_t off = mn_offset(r, c4, p.NG);
+                        float4 hi, lo;
+                        hi.x = tf32_rna(x.x); lo.x = x.x - hi.x;
+                        hi.y = tf32_rna(x.y); lo.y = x.y - hi.y;
+                        hi.z = tf32_rna(x.z); lo.z = x.z - hi.z;
+                        hi.w = tf32_rna(x.w); lo.w = x.w - hi.w;
+                        *reinterpret_cast<float4 *>(b_hi + off) = hi;
+                        *reinterpret_cast<float4 *>(b_hi + b_bytes + off) = lo;
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive(&full[s]);
+            }
+        }
+    } else if (warp == 12) {
+        // ================================ MMA issuer ================================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(p.Npad) | (1u << 15) | (1u << 16);  // A, B MN-major
+            uint32_t it = 0, tcnt = 0;
+            for (long seg = blockIdx.x; seg < num_seg; seg += gridDim.x, ++tcnt) {
+                const long seg0 = seg * W_SEG;
+                const int nst = (int)((min((long)W_SEG, p.M - seg0) + W_ROWS - 1) / W_ROWS);
+                const uint32_t acc = tcnt & 1, aph = (tcnt >> 1) & 1;
+                mbar_wait(&acc_empty[acc], aph ^ 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d = tmem_base + acc * (uint32_t)(2 * Nacc);
+                const uint32_t dc = d + (uint32_t)Nacc;
+                for (int sidx = 0; sidx < nst; ++sidx, ++it) {
+                    const int s = it % p.stages;
+                    const uint32_t ph = (it / p.stages) & 1;
+                    mbar_wait(&full[s], ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_hi = smem_u32(smem + (size_t)s * stage_bytes);
+                    const uint32_t b_hi = a_hi + 2 * a_bytes;
+#pragma unroll
+                    for (int kg = 0; kg < 4; ++kg) {
+                        // one K=8 MMA spans two 4-row k-groups: LBO = next MN group (512 B),
+                        // SBO = next k-group (groups * 512 B)
+                        const uint64_t dah = make_desc_mn(a_hi + kg * 4096, 512, 2048);
+                        const uint64_t dal = make_desc_mn(a_hi + a_bytes + kg * 4096, 512, 2048);
+                        const uint64_t dbh = make_desc_mn(b_hi + kg * p.NG * 1024, 512, p.NG * 512);
+                        const uint64_t dbl = make_desc_mn(b_hi + b_bytes + kg * p.NG * 1024, 512, p.NG * 512);
+                        const uint32_t accum = (sidx > 0 || kg > 0) ? 1u : 0u;
+                        umma_tf32(d, dah, dbh, idesc, accum);
+                        umma_tf32(dc, dal, dbh, idesc, accum);
+                        umma_tf32(dc, dah, dbl, idesc, 1u);
+                    }
+                    umma_commit(&empty[s]);
+                }
+                umma_commit(&acc_full[acc]);
+            }
+        }
+    } else if (warp < 4) {
+        // ================================ epilogue ================================
+        float *stg = epi + warp * 32 * EPI_LD;
+        const int nblk = p.Npad / 32;
+        uint32_t tcnt = 0;
+        for (long seg = blockIdx.x; seg < num_seg; seg += gridDim.x, ++tcnt) {
+            const uint32_t acc = tcnt & 1, aph = (tcnt >> 1) & 1;
+            mbar_wait(&acc_full[acc], aph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            for (int cb = 0; cb < nblk; ++cb) {
+                uint32_t r[32], rc[32];
+                const uint32_t ta = tmem_base + ((uint32_t)(warp * 32) << 16) +
+                                    acc * (uint32_t)(2 * Nacc) + cb * 32;
+                tmem_ld32(ta, r);
+                tmem_ld32(ta + (uint32_t)Nacc, rc);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    float4 o;
+                    o.x = __uint_as_float(r[q * 4]) + __uint_as_float(rc[q * 4]);
+                    o.y = __uint_as_float(r[q * 4 + 1]) + __uint_as_float(rc[q * 4 + 1]);
+                    o.z = __uint_as_float(r[q * 4 + 2]) + __uint_as_float(rc[q * 4 + 2]);
+                    o.w = __uint_as_float(r[q * 4 + 3]) + __uint_as_float(rc[q * 4 + 3]);
+                    *reinterpret_cast<float4 *>(stg + lane * EPI_LD + q * 4) = o;
+                }
+                __syncwarp();
+                const int n = p.n0 + cb * 32 + lane;
+                if (n < p.N) {
+#pragma unroll 8
+                    for (int rr = 0; rr < 32; ++rr) {
+                        const int k = p.k0 + warp * 32 + rr;
+                        if (k < p.K) atomicAdd(p.dW + (long)k * p.ldw + n, stg[rr * EPI_LD + lane]);
+                    }
+                }
+                __syncwarp();
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(&acc_empty[acc]);
+        }
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 12) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                     "r"(ncols)
+                     : "memory");
+    }
+}
+
+static int run(long M, int K, int N, const float *A, int lda, const float *a_scale,
+               const float *a_shift, int a_relu, const float *dY, float *dW, cudaStream_t st) {
+    for (int n0 = 0; n0 < N; n0 += 128) {
+        for (int k0 = 0; k0 < K; k0 += W_FEAT) {
+            WParams p;
+            p.M = M;
+            p.K = K;
+            p.N = N;
+            const int nc = (N - n0) < 128 ? (N - n0) : 128;
+            p.Npad = (nc + 31) & ~31;
+            p.NG = p.Npad / 32;
+            p.lda = lda;
+            p.ldy = N;
+            p.ldw = N;
+            p.a_relu = a_relu;
+            p.k0 = k0;
+            p.n0 = n0;
+            p.A = A;
+            p.a_scale = a_scale;
+            p.a_shift = a_shift;
+            p.dY = dY;
+            p.dW = dW;
+            const size_t stage_bytes = 2 * 16384 + 2 * (size_t)p.NG * 4096;
+            const size_t fixed = 4 * 32 * EPI_LD * sizeof(float) + (2 * MAX_STAGES + 4) * 8 + 16;
+            int stages = (int)((227 * 1024 - fixed) / stage_bytes);
+            if (stages > MAX_STAGES) stages = MAX_STAGES;
+            if (stages < 1) return PN2_EUNSUPPORTED;
+            p.stages = stages;
+            const size_t smem = (size_t)stages * stage_bytes + fixed;
+            int rc = cuda_status(cudaFuncSetAttribute(
+                tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (rc) return rc;
+            const long segs = (M + W_SEG - 1) / W_SEG;
+            const int grid = (int)(segs < num_sms() ? segs : num_sms());
+            tc_wgrad_kernel<<<grid, W_THREADS, smem, st>>>(p);
+            rc = finish_launch();
+            if (rc) return rc;
+        }
+    }
+    return PN2_OK;
+}
+
+}  // namespace tcw
+
+int tc_linear_wgrad(long M, int K, int N, const float *A, int lda, const float *a_scale,
+                    const float *a_shift, int a_relu, const float *dY, float *dW,
+                    cudaStream_t st) {
+    if (M < 2048 || N < 16 || K < 4) return PN2_EUNSUPPORTED;
+    return tcw::run(M, K, N, A, lda, a_scale, a_shift, a_relu, dY, dW, st);
+}
+
 // Shapes worth the tensor cores: at least one full tile of rows, K and N not tiny.
 // K <= 512 keeps the truncating tensor-core accumulation inside the 1e-5 parity bar.
 static bool tc_shape_ok(long M, int K, int N) { return M >= 128 && K >= 16 && K <= 512 && N >= 16; }

@@ -344,7 +344,7 @@ import os as _os
 
 # -1 auto (tcgen05 3xTF32 where the shape allows, else fp32 CUDA cores), 0 exact fp32 CUDA-core
 # kernel only, 1 force tcgen05.  PN2_GEMM_MODE overrides the default.
-GEMM_MODE = int(_os.environ.get("PN2_GEMM_MODE", "0"))
+GEMM_MODE = int(_os.environ.get("PN2_GEMM_MODE", "-1"))
 
 
 def mlp_chain(x2d, layers, is_training, bn_decay, pool_ns=0):

@@ -83,9 +83,13 @@ def test_linear_dgrad(ffi, mode, M, K, N):
     np.testing.assert_allclose(dX.cpu().numpy(), exp, atol=1e-5)
 
 
+@pytest.mark.parametrize("mode", [0, 1])
 @pytest.mark.parametrize("M,K,N", [(1000, 6, 32), (4096, 67, 64), (2048, 131, 128), (8192, 32, 32),
-                                   (300, 259, 256)])
-def test_linear_wgrad(ffi, M, K, N):
+                                   (300, 259, 256), (5000, 6, 32), (16384, 128, 128),
+                                   (4100, 259, 256), (3072, 320, 48), (70000, 64, 64)])
+def test_linear_wgrad(ffi, mode, M, K, N):
+    if mode == 1 and M < 2048:
+        pytest.skip("tensor-core wgrad needs M >= 2048")
     import torch
     rs = np.random.RandomState(11 + M + K + N)
     A = rs.normal(size=(M, K)).astype(np.float32)
@@ -96,7 +100,7 @@ def test_linear_wgrad(ffi, M, K, N):
     db = torch.zeros(N, dtype=torch.float32, device="cuda")
     p = ffi.ptr
     At, sct, sht, dYt = to_cuda(A), to_cuda(sc), to_cuda(sh), to_cuda(dY)
-    ffi.call("pn2_linear_wgrad", M, K, N, p(At), K, p(sct), p(sht), 1, p(dYt), p(dW), p(db), 0)
+    ffi.call("pn2_linear_wgrad", M, K, N, p(At), K, p(sct), p(sht), 1, p(dYt), p(dW), p(db), mode)
     A2 = np.maximum(A.astype(np.float64) * sc + sh, 0.0)
     exp = A2.T @ dY.astype(np.float64)
     tol = 2e-5 * max(1.0, np.abs(exp).max())

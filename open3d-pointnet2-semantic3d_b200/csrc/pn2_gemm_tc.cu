@@ -12,15 +12,17 @@
 // large hi*hi products and the small correction products go to TWO accumulators (main / corr)
 // that are summed with a round-to-nearest add in the epilogue; K is limited to 512.
 //
-// Structure (one persistent CTA per SM, 10 warps, roles as in the canonical Blackwell GEMM):
+// Structure (one persistent CTA per SM, 18 warps, roles as in the canonical Blackwell GEMM):
 //   warps 0-3  epilogue: tcgen05.ld accumulator (lane quadrant = warp), transpose through
 //              padded shared memory, + bias, coalesced row-major stores, fp64 column statistics
-//   warps 4-7  A producers: coalesced float4 global loads of a 128 x 32 chunk, previous layer's
+//   warps 4-15 A producers, three independent groups of 4 warps that take K chunks round-robin
+//              (so three chunks of global loads are in flight per SM: the kernel was load-latency
+//              bound with one): coalesced float4 loads of a 128 x 32 chunk, previous layer's
 //              BatchNorm affine + ReLU applied on the fly, hi/lo split, st.shared into the
 //              128B-swizzled K-major UMMA layout, fence.proxy.async, mbarrier arrive
-//   warp 8     B loader: one cp.async.bulk per K chunk from a pre-split, pre-swizzled weight
+//   warp 16    B loader: one cp.async.bulk per K chunk from a pre-split, pre-swizzled weight
 //              image in global memory (built by tc_prep_b_kernel, L2 resident)
-//   warp 9     TMEM allocation + single-thread tcgen05.mma issue (3 MMAs per K=8 step),
+//   warp 17    TMEM allocation + single-thread tcgen05.mma issue (3 MMAs per K=8 step),
 //              tcgen05.commit onto the "stage empty" / "accumulator full" mbarriers
 // The accumulator pair is double buffered in TMEM (2 x 2 x N columns, N <= 128 per pass) so the
 // epilogue of tile i overlaps the main loop of tile i+1.
@@ -31,7 +33,9 @@ namespace tc {
 
 constexpr int BM = 128;       // rows per tile (UMMA M)
 constexpr int BK = 32;        // fp32/tf32 elements per K chunk = one 128-byte swizzle row
-constexpr int THREADS = 320;  // 10 warps
+constexpr int NPG = 3;                    // independent A-producer groups (chunks of loads in flight)
+constexpr int THREADS = 32 * (4 + 4 * NPG + 2);  // 4 epilogue + 4*NPG producer + loader + MMA warps
+constexpr int W_LOADER = 4 + 4 * NPG, W_MMA = 5 + 4 * NPG;
 constexpr int MAX_STAGES = 4;
 constexpr int EPI_LD = 36;    // padded row length (floats) of the epilogue transpose buffer
 
@@ -188,7 +192,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const Params p) {
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 9) {
+    if (warp == W_MMA) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                          smem_u32(tmem_slot)),
                      "r"(ncols)
@@ -202,15 +206,23 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const Params p) {
 
     const long num_tiles = (p.M + BM - 1) / BM;
 
-    if (warp >= 4 && warp < 8) {
+    if (warp >= 4 && warp < W_LOADER) {
         // ================================ A producers ================================
-        const int t = threadIdx.x - 128;
+        // group g takes chunks g, g+npg, ... of this CTA's (tile, kc) sequence; npg <= stages
+        // keeps every group within one ring revolution of the consumer (phase parity is safe)
+        const int g = (warp - 4) >> 2;
+        const int npg = NPG < p.stages ? NPG : p.stages;
+        const int t = (threadIdx.x - 128) & 127;
         const int k4 = t & 7, r0 = t >> 3;  // float4 slot inside the 32-wide chunk, base row
         const bool vec_ok = (p.lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0);
-        uint32_t it = 0;
-        for (long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const long m0 = tile * BM;
-            for (int kc = 0; kc < p.KC; ++kc, ++it) {
+        const long my_tiles = blockIdx.x < num_tiles ? (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+        const long total_chunks = my_tiles * p.KC;
+        if (g < npg) {
+            for (long itl = g; itl < total_chunks; itl += npg) {
+                const uint32_t it = (uint32_t)itl;
+                const long tile = blockIdx.x + (itl / p.KC) * gridDim.x;
+                const int kc = (int)(itl % p.KC);
+                const long m0 = tile * BM;
                 const int s = it % p.stages;
                 const uint32_t ph = (it / p.stages) & 1;
                 const int kbase = kc * BK + k4 * 4;
@@ -272,7 +284,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const Params p) {
                 mbar_arrive(&full[s]);
             }
         }
-    } else if (warp == 8) {
+    } else if (warp == W_LOADER) {
         // ================================ B loader ================================
         if (lane == 0) {
             uint32_t it = 0;
@@ -289,7 +301,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const Params p) {
                 }
             }
         }
-    } else if (warp == 9) {
+    } else if (warp == W_MMA) {
         // ================================ MMA issuer ================================
         if (lane == 0) {
             const uint32_t idesc = make_idesc(p.Npad);
@@ -390,7 +402,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const Params p) {
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 9) {
+    if (warp == W_MMA) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                      "r"(ncols)
@@ -468,7 +480,9 @@ static int run_chunk(long M, int K, int Nc, const float *A, int lda, const float
 namespace tcw {
 using namespace tc;
 
-constexpr int W_THREADS = 416;  // warps 0-3 epilogue, 4-11 producers, 12 MMA
+constexpr int W_NPG = 3;                        // independent producer groups (stages of loads in flight)
+constexpr int W_WMMA = 4 + 4 * W_NPG;            // MMA / TMEM warp
+constexpr int W_THREADS = 32 * (W_WMMA + 1);  // warps 0-3 epilogue, 4.. producers, last MMA
 constexpr int W_ROWS = 32;      // contraction rows per stage (4 MMAs of K=8)
 constexpr int W_SEG = 512;      // contraction rows per accumulator segment
 constexpr int W_FEAT = 128;     // features (rows of dW) per CTA pass = UMMA M
@@ -510,7 +524,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) tc_wgrad_kernel(const WParams p)
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) {
-            mbar_init(&full[s], 256);
+            mbar_init(&full[s], 128);
             mbar_init(&empty[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
@@ -519,7 +533,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) tc_wgrad_kernel(const WParams p)
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 12) {
+    if (warp == W_WMMA) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                          smem_u32(tmem_slot)),
                      "r"(ncols)
@@ -533,39 +547,46 @@ __global__ void __launch_bounds__(W_THREADS, 1) tc_wgrad_kernel(const WParams p)
 
     const long num_seg = (p.M + W_SEG - 1) / W_SEG;
 
-    if (warp >= 4 && warp < 12) {
+    if (warp >= 4 && warp < W_WMMA) {
         // ================================ producers ================================
-        const int t = threadIdx.x - 128;  // 0..255 ; 0..127 -> A (features), 128..255 -> B (dY)
-        const bool is_a = t < 128;
-        const int tt = is_a ? t : t - 128;
+        // three independent groups of 128 threads take stages round-robin (three stages of global
+        // loads in flight); every thread issues ALL its loads of a stage (8 float4 of X rows,
+        // up to 8 float4 of dY rows) before the first use, then splits and stores
+        const int g = (warp - 4) >> 2;
+        const int npg = W_NPG < p.stages ? W_NPG : p.stages;
+        const int tt = (threadIdx.x - 128) & 127;
         const bool a_vec = (p.lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0) &&
                            (p.k0 % 4 == 0);
         const bool b_vec = (p.ldy % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.dY) & 15) == 0) &&
                            (p.n0 % 4 == 0);
-        const int bw4 = p.Npad >> 2;           // float4 per dY row
-        const int b_iters = (W_ROWS * bw4) / 128;  // Npad/4*32/128 = Npad/16
-        uint32_t it = 0;
-        for (long seg = blockIdx.x; seg < num_seg; seg += gridDim.x) {
-            const long seg0 = seg * W_SEG;
-            const int nst = (int)((min((long)W_SEG, p.M - seg0) + W_ROWS - 1) / W_ROWS);
-            for (int sidx = 0; sidx < nst; ++sidx, ++it) {
-                const int s = it % p.stages;
-                const uint32_t ph = (it / p.stages) & 1;
-                const long mbase = seg0 + (long)sidx * W_ROWS;
-                unsigned char *st_base = smem + (size_t)s * stage_bytes;
-                if (is_a) {
-                    const int c4 = tt & 31, rr = tt >> 5;
-                    const int kf = p.k0 + 4 * c4;  // first feature of this float4
-                    float sc[4] = {0.f, 0.f, 0.f, 0.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
-                    if (p.a_scale) {
+        const int bw4 = p.Npad >> 2;               // float4 per dY row (8, 16, 24 or 32)
+        const int b_iters = (W_ROWS * bw4) >> 7;   // Npad/16 <= 8
+        const int c4 = tt & 31, rr = tt >> 5;      // A part: float4 slot / base row
+        const int kf = p.k0 + 4 * c4;
+        float sc[4] = {0.f, 0.f, 0.f, 0.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
+        if (p.a_scale) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            if (kf + j < p.K) {
-                                sc[j] = __ldg(p.a_scale + kf + j);
-                                sh[j] = __ldg(p.a_shift + kf + j);
-                            }
-                    }
-                    float4 v[8];
+            for (int j = 0; j < 4; ++j)
+                if (kf + j < p.K) {
+                    sc[j] = __ldg(p.a_scale + kf + j);
+                    sh[j] = __ldg(p.a_shift + kf + j);
+                }
+        }
+        // flat stage sequence of this CTA: segment-major, 16 stages per full segment
+        const long my_segs = blockIdx.x < num_seg ? (num_seg - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+        long itl = 0;
+        if (g < npg) {
+            for (long sg = 0; sg < my_segs; ++sg) {
+                const long seg0 = (blockIdx.x + sg * gridDim.x) * (long)W_SEG;
+                const int nst = (int)((min((long)W_SEG, p.M - seg0) + W_ROWS - 1) / W_ROWS);
+                for (int sidx = 0; sidx < nst; ++sidx, ++itl) {
+                    if ((int)(itl % npg) != g) continue;
+                    const uint32_t it = (uint32_t)itl;
+                    const int s = it % p.stages;
+                    const uint32_t ph = (it / p.stages) & 1;
+                    const long mbase = seg0 + (long)sidx * W_ROWS;
+                    unsigned char *st_base = smem + (size_t)s * stage_bytes;
+                    float4 va[8], vb[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const long m = mbase + rr + 4 * i;
@@ -580,66 +601,77 @@ __global__ void __launch_bounds__(W_THREADS, 1) tc_wgrad_kernel(const WParams p)
                                 if (kf + 2 < p.K) x.z = __ldg(src + 2);
                                 if (kf + 3 < p.K) x.w = __ldg(src + 3);
                             }
-                            if (p.a_scale) {
-                                float *e = reinterpret_cast<float *>(&x);
+                        }
+                        va[i] = x;
+                    }
 #pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    float y = __fmaf_rn(e[j], sc[j], sh[j]);
-                                    if (p.a_relu) y = fmaxf(y, 0.f);
-                                    e[j] = (kf + j < p.K) ? y : 0.f;
+                    for (int q = 0; q < 8; ++q) {
+                        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (q < b_iters) {
+                            const int e = tt + 128 * q;
+                            const int bc4 = e % bw4, r = e / bw4;
+                            const long m = mbase + r;
+                            const int nf = p.n0 + 4 * bc4;
+                            if (m < p.M && nf < p.N) {
+                                const float *src = p.dY + m * p.ldy + nf;
+                                if (b_vec && nf + 3 < p.N) {
+                                    x = __ldg(reinterpret_cast<const float4 *>(src));
+                                } else {
+                                    x.x = __ldg(src);
+                                    if (nf + 1 < p.N) x.y = __ldg(src + 1);
+                                    if (nf + 2 < p.N) x.z = __ldg(src + 2);
+                                    if (nf + 3 < p.N) x.w = __ldg(src + 3);
                                 }
                             }
                         }
-                        v[i] = x;
+                        vb[q] = x;
+                    }
+                    if (p.a_scale) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const bool row_ok = (mbase + rr + 4 * i) < p.M;
+                            float *e = reinterpret_cast<float *>(&va[i]);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                float y = __fmaf_rn(e[j], sc[j], sh[j]);
+                                if (p.a_relu) y = fmaxf(y, 0.f);
+                                e[j] = (row_ok && kf + j < p.K) ? y : 0.f;
+                            }
+                        }
                     }
                     mbar_wait(&empty[s], ph ^ 1);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        const int r = rr + 4 * i;
-                        const uint32_t off = mn_offset(r, c4, 4);
+                        const uint32_t off = mn_offset(rr + 4 * i, c4, 4);
                         float4 hi, lo;
-                        hi.x = tf32_rna(v[i].x); lo.x = v[i].x - hi.x;
-                        hi.y = tf32_rna(v[i].y); lo.y = v[i].y - hi.y;
-                        hi.z = tf32_rna(v[i].z); lo.z = v[i].z - hi.z;
-                        hi.w = tf32_rna(v[i].w); lo.w = v[i].w - hi.w;
+                        hi.x = tf32_rna(va[i].x); lo.x = va[i].x - hi.x;
+                        hi.y = tf32_rna(va[i].y); lo.y = va[i].y - hi.y;
+                        hi.z = tf32_rna(va[i].z); lo.z = va[i].z - hi.z;
+                        hi.w = tf32_rna(va[i].w); lo.w = va[i].w - hi.w;
                         *reinterpret_cast<float4 *>(st_base + off) = hi;
                         *reinterpret_cast<float4 *>(st_base + a_bytes + off) = lo;
                     }
-                } else {
-                    mbar_wait(&empty[s], ph ^ 1);
                     unsigned char *b_hi = st_base + 2 * a_bytes;
-                    for (int q = 0; q < b_iters; ++q) {
-                        const int e = tt + 128 * q;
-                        const int c4 = e % bw4, r = e / bw4;
-                        const long m = mbase + r;
-                        const int nf = p.n0 + 4 * c4;
-                        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (m < p.M && nf < p.N) {
-                            const float *src = p.dY + m * p.ldy + nf;
-                            if (b_vec && nf + 3 < p.N) {
-                                x = __ldg(reinterpret_cast<const float4 *>(src));
-                            } else {
-                                x.x = __ldg(src);
-                                if (nf + 1 < p.N) x.y = __ldg(src + 1);
-                                if (nf + 2 < p.N) x.z = __ldg(src + 2);
-                                if (nf + 3 < p.N) x.w = __ldg(src + 3);
-                            }
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        if (q < b_iters) {
+                            const int e = tt + 128 * q;
+                            const uint32_t off = mn_offset(e / bw4, e % bw4, p.NG);
+                            float4 hi, lo;
+                            hi.x = tf32_rna(vb[q].x); lo.x = vb[q].x - hi.x;
+                            hi.y = tf32_rna(vb[q].y); lo.y = vb[q].y - hi.y;
+                            hi.z = tf32_rna(vb[q].z); lo.z = vb[q].z - hi.z;
+                            hi.w = tf32_rna(vb[q].w); lo.w = vb[q].w - hi.w;
+                            *reinterpret_cast<float4 *>(b_hi + off) = hi;
+                            *reinterpret_cast<float4 *>(b_hi + b_bytes + off) = lo;
                         }
-                        const uint32_t off = mn_offset(r, c4, p.NG);
-                        float4 hi, lo;
-                        hi.x = tf32_rna(x.x); lo.x = x.x - hi.x;
-                        hi.y = tf32_rna(x.y); lo.y = x.y - hi.y;
-                        hi.z = tf32_rna(x.z); lo.z = x.z - hi.z;
-                        hi.w = tf32_rna(x.w); lo.w = x.w - hi.w;
-                        *reinterpret_cast<float4 *>(b_hi + off) = hi;
-                        *reinterpret_cast<float4 *>(b_hi + b_bytes + off) = lo;
                     }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mbar_arrive(&full[s]);
                 }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                mbar_arrive(&full[s]);
             }
         }
-    } else if (warp == 12) {
+    } else if (warp == W_WMMA) {
         // ================================ MMA issuer ================================
         if (lane == 0) {
             const uint32_t idesc = make_idesc(p.Npad) | (1u << 15) | (1u << 16);  // A, B MN-major
@@ -719,7 +751,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) tc_wgrad_kernel(const WParams p)
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 12) {
+    if (warp == W_WMMA) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                      "r"(ncols)

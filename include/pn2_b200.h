@@ -195,9 +195,11 @@ int pn2_bn_bwd_apply_pool(long G, int ns, int N, const float *dOut, const int *a
 
 /* tf_util.dropout (tf_util.py:646-665): out = keep(i) ? x/keep_prob : 0 with a counter-based
  * generator keyed by (seed, element index); the same call with the same seed regenerates the
- * mask in the backward pass.  pn2_dropout_mask exports it (0/1 bytes) for tests. */
-int pn2_dropout(long n, const float *x, float keep_prob, unsigned long long seed, float *out,
-                pn2_stream_t s);
+ * mask in the backward pass.  seed_dev (optional) is a device-resident increment added to seed, so
+ * a captured CUDA graph can draw a fresh mask on every replay.  pn2_dropout_mask exports the mask
+ * (0/1 bytes) for tests. */
+int pn2_dropout(long n, const float *x, float keep_prob, unsigned long long seed,
+                const unsigned long long *seed_dev, float *out, pn2_stream_t s);
 int pn2_dropout_mask(long n, float keep_prob, unsigned long long seed, unsigned char *mask,
                      pn2_stream_t s);
 

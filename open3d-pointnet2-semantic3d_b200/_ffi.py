@@ -54,7 +54,7 @@ SIGNATURES = {
     "pn2_bn_bwd_reduce_pool": [_l, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp],
     "pn2_bn_bwd_apply_pool": [_l, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp,
                               _vp, _vp, _vp],
-    "pn2_dropout": [_l, _vp, _f, _ull, _vp, _vp],
+    "pn2_dropout": [_l, _vp, _f, _ull, _vp, _vp, _vp],
     "pn2_dropout_mask": [_l, _f, _ull, _vp, _vp],
     "pn2_softmax_ce_reduce": [_l, _i, _vp, _vp, _vp, _vp, _vp],
     "pn2_softmax_ce_grad": [_l, _i, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp],

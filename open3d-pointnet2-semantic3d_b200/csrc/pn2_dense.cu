@@ -9,6 +9,7 @@
 
 #include "pn2_common.cuh"
 #include "pn2_gemm_simt.cuh"
+#include "pn2_wgrad_rt.cuh"
 
 namespace pn2 {
 
@@ -21,7 +22,8 @@ int tc_linear_dgrad(long M, int K, int N, const float *dY, const float *W, float
                     float *ws, size_t ws_bytes, cudaStream_t st);
 size_t tc_workspace_bytes(int K, int N);
 int tc_linear_wgrad(long M, int K, int N, const float *A, int lda, const float *a_scale,
-                    const float *a_shift, int a_relu, const float *dY, float *dW, cudaStream_t st);
+                    const float *a_shift, int a_relu, const float *dY, float *dW, bool force,
+                    cudaStream_t st);
 
 // ---- SIMT GEMM dispatch ----------------------------------------------------------------------
 template <bool A_KC, bool B_NC, bool ATOMIC>
@@ -56,6 +58,21 @@ static int launch_gemm(int Mp, int Np, long Kp, const float *A, long a_sm, long 
 // ---- column-wise helpers over a row-major [M,N] matrix ------------------------------------------
 // Block = 256 threads owning a slab of rows; thread t works on columns c = cx, cx+lanes, ... and
 // rows r = ry, ry+rpp, ... so that a warp reads contiguous columns of one (or a few) rows.
+// per-block combination of fp64 column sums: shared-memory atomics, then ONE global atomic per
+// column per block (thousands of threads hammering 2N global addresses serialise in L2)
+__device__ __forceinline__ void block_zero2(double *sred, int N) {
+    for (int e = threadIdx.x; e < 2 * N; e += blockDim.x) sred[e] = 0.0;
+    __syncthreads();
+}
+__device__ __forceinline__ void block_add2(double *sred, int N, int c, double a0, double a1) {
+    atomicAdd(sred + c, a0);
+    atomicAdd(sred + N + c, a1);
+}
+__device__ __forceinline__ void block_flush2(double *sred, int N, double *__restrict__ red) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < 2 * N; e += blockDim.x) atomicAdd(red + e, sred[e]);
+}
+
 struct Slab {
     int lanes, rpp, cx, ry;
     long r0, r1;
@@ -86,9 +103,10 @@ bn_bwd_reduce_kernel(long M, int N, long rpb, const float *__restrict__ dZ, int 
                      const float *__restrict__ Y, const float *__restrict__ scale,
                      const float *__restrict__ shift, const float *__restrict__ saved, int relu,
                      double *__restrict__ red) {
+    extern __shared__ double sred[];  // [2N] per-block partial sums
     const Slab s = make_slab(M, N, rpb);
-    if (!s.active) return;
-    for (int c = s.cx; c < N; c += s.lanes) {
+    block_zero2(sred, N);
+    for (int c = s.cx; s.active && c < N; c += s.lanes) {
         const float sc = __ldg(scale + c), sh = __ldg(shift + c);
         const float mean = __ldg(saved + c), rstd = __ldg(saved + N + c);
         double a0 = 0.0, a1 = 0.0;
@@ -98,9 +116,9 @@ bn_bwd_reduce_kernel(long M, int N, long rpb, const float *__restrict__ dZ, int 
             a0 += (double)dzh;
             a1 = fma((double)dzh, (double)xh, a1);
         }
-        atomicAdd(red + c, a0);
-        atomicAdd(red + N + c, a1);
+        block_add2(sred, N, c, a0, a1);
     }
+    block_flush2(sred, N, red);
 }
 
 __global__ void __launch_bounds__(256)
@@ -134,6 +152,142 @@ bn_bwd_apply_kernel(long M, int N, long rpb, const float *__restrict__ dZ, int l
             float dzh, xh;
             bn_elem(__ldg(Y + r * N + c), __ldg(dZ + r * ldz + c), sc, sh, mean, rstd, relu, dzh, xh);
             dY[r * N + c] = bn ? gs * (dzh - m0 - xh * m1) : dzh;
+        }
+    }
+}
+
+// ---- float4-vectorised variants (N % 4 == 0, ldz % 4 == 0, 16-byte aligned bases) -----------------
+// A block owns a slab of rows; thread t works on the column quad cq = t % (N/4) and rows
+// ry, ry+rpp, ...; four rows are in flight per thread (8 independent 16-byte loads).
+struct Slab4 {
+    int nq, rpp, cq, ry;
+    long r0, r1;
+    bool active;
+};
+__device__ __forceinline__ Slab4 make_slab4(long M, int N, long rows_per_block) {
+    Slab4 s;
+    const int q = N >> 2;
+    s.nq = q < (int)blockDim.x ? q : (int)blockDim.x;
+    s.rpp = blockDim.x / s.nq;
+    s.cq = threadIdx.x % s.nq;
+    s.ry = threadIdx.x / s.nq;
+    s.active = s.ry < s.rpp;
+    s.r0 = (long)blockIdx.x * rows_per_block;
+    s.r1 = s.r0 + rows_per_block < M ? s.r0 + rows_per_block : M;
+    return s;
+}
+
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_v4_kernel(long M, int N, long rpb, const float *__restrict__ dZ, int ldz,
+                        const float *__restrict__ Y, const float *__restrict__ scale,
+                        const float *__restrict__ shift, const float *__restrict__ saved, int relu,
+                        double *__restrict__ red) {
+    extern __shared__ double sred[];  // [2N] per-block partial sums
+    const Slab4 s = make_slab4(M, N, rpb);
+    block_zero2(sred, N);
+    const int nq = N >> 2;
+    for (int cq = s.cq; s.active && cq < nq; cq += s.nq) {
+        const int c = cq * 4;
+        const float4 sc = __ldg(reinterpret_cast<const float4 *>(scale + c));
+        const float4 sh = __ldg(reinterpret_cast<const float4 *>(shift + c));
+        const float4 mean = __ldg(reinterpret_cast<const float4 *>(saved + c));
+        const float4 rstd = __ldg(reinterpret_cast<const float4 *>(saved + N + c));
+        double a0[4] = {0, 0, 0, 0}, a1[4] = {0, 0, 0, 0};
+        for (long r = s.r0 + s.ry; r < s.r1; r += 4L * s.rpp) {
+            float4 y[4], z[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const long rr = r + (long)u * s.rpp;
+                if (rr < s.r1) {
+                    y[u] = __ldg(reinterpret_cast<const float4 *>(Y + rr * N + c));
+                    z[u] = __ldg(reinterpret_cast<const float4 *>(dZ + rr * ldz + c));
+                } else {
+                    y[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    z[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                float f0[4] = {0.f, 0.f, 0.f, 0.f}, f1[4] = {0.f, 0.f, 0.f, 0.f};
+                float dzh, xh;
+                bn_elem(y[u].x, z[u].x, sc.x, sh.x, mean.x, rstd.x, relu, dzh, xh); f0[0] = dzh; f1[0] = dzh * xh;
+                bn_elem(y[u].y, z[u].y, sc.y, sh.y, mean.y, rstd.y, relu, dzh, xh); f0[1] = dzh; f1[1] = dzh * xh;
+                bn_elem(y[u].z, z[u].z, sc.z, sh.z, mean.z, rstd.z, relu, dzh, xh); f0[2] = dzh; f1[2] = dzh * xh;
+                bn_elem(y[u].w, z[u].w, sc.w, sh.w, mean.w, rstd.w, relu, dzh, xh); f0[3] = dzh; f1[3] = dzh * xh;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    a0[j] += (double)f0[j];
+                    a1[j] += (double)f1[j];
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) block_add2(sred, N, c + j, a0[j], a1[j]);
+    }
+    block_flush2(sred, N, red);
+}
+
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_v4_kernel(long M, int N, long rpb, const float *__restrict__ dZ, int ldz,
+                       const float *__restrict__ Y, const float *__restrict__ scale,
+                       const float *__restrict__ shift, const float *__restrict__ saved,
+                       const float *__restrict__ gamma, int relu, int bn,
+                       const double *__restrict__ red, float *__restrict__ dY,
+                       float *__restrict__ dgamma, float *__restrict__ dbeta) {
+    const Slab4 s = make_slab4(M, N, rpb);
+    if (!s.active) return;
+    const double invM = 1.0 / (double)M;
+    const int nq = N >> 2;
+    for (int cq = s.cq; cq < nq; cq += s.nq) {
+        const int c = cq * 4;
+        float sc[4] = {1.f, 1.f, 1.f, 1.f}, sh[4] = {0.f, 0.f, 0.f, 0.f}, mean[4] = {0.f, 0.f, 0.f, 0.f},
+              rstd[4] = {1.f, 1.f, 1.f, 1.f}, gs[4] = {1.f, 1.f, 1.f, 1.f}, m0[4] = {0.f, 0.f, 0.f, 0.f},
+              m1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (scale) {
+                sc[j] = __ldg(scale + c + j);
+                sh[j] = __ldg(shift + c + j);
+            }
+            if (bn) {
+                mean[j] = __ldg(saved + c + j);
+                rstd[j] = __ldg(saved + N + c + j);
+                gs[j] = __ldg(gamma + c + j) * rstd[j];
+                m0[j] = (float)(red[c + j] * invM);
+                m1[j] = (float)(red[N + c + j] * invM);
+                if (blockIdx.x == 0 && s.ry == 0) {
+                    if (dgamma) dgamma[c + j] += (float)red[N + c + j];
+                    if (dbeta) dbeta[c + j] += (float)red[c + j];
+                }
+            }
+        }
+        for (long r = s.r0 + s.ry; r < s.r1; r += 4L * s.rpp) {
+            float4 y[4], z[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const long rr = r + (long)u * s.rpp;
+                if (rr < s.r1) {
+                    y[u] = __ldg(reinterpret_cast<const float4 *>(Y + rr * N + c));
+                    z[u] = __ldg(reinterpret_cast<const float4 *>(dZ + rr * ldz + c));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const long rr = r + (long)u * s.rpp;
+                if (rr < s.r1) {
+                    const float *yy = reinterpret_cast<const float *>(&y[u]);
+                    const float *zz = reinterpret_cast<const float *>(&z[u]);
+                    float4 o;
+                    float *oo = reinterpret_cast<float *>(&o);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float dzh, xh;
+                        bn_elem(yy[j], zz[j], sc[j], sh[j], mean[j], rstd[j], relu, dzh, xh);
+                        oo[j] = bn ? gs[j] * (dzh - m0[j] - xh * m1[j]) : dzh;
+                    }
+                    *reinterpret_cast<float4 *>(dY + rr * N + c) = o;
+                }
+            }
         }
     }
 }
@@ -292,7 +446,10 @@ __device__ __forceinline__ bool dropout_keep(unsigned long long seed, long i, fl
     return u < keep_prob;
 }
 __global__ void dropout_kernel(long n, const float *__restrict__ x, float keep_prob, float inv,
-                               unsigned long long seed, float *__restrict__ out) {
+                               unsigned long long seed,
+                               const unsigned long long *__restrict__ seed_dev,
+                               float *__restrict__ out) {
+    if (seed_dev) seed += *seed_dev;
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n;
          i += (long)gridDim.x * blockDim.x)
         out[i] = dropout_keep(seed, i, keep_prob) ? __fmul_rn(__ldg(x + i), inv) : 0.f;
@@ -385,6 +542,11 @@ __global__ void colsum_kernel(long M, int N, long rpb, const float *__restrict__
     }
 }
 
+static inline bool vec4_ok(int N, int ldz, const void *a, const void *b) {
+    return (N % 4 == 0) && (ldz % 4 == 0) &&
+           ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0;
+}
+
 static inline int grid_for(long total, int threads) {
     long blocks = ceil_div<long>(total, threads);
     long cap = 148L * 16;
@@ -468,8 +630,10 @@ PN2_API int pn2_linear_wgrad(long M, int K, int N, const float *A, int lda, cons
     PN2_REQUIRE((a_scale == nullptr) == (a_shift == nullptr));
     cudaStream_t st = as_stream(s);
     int rc = PN2_EUNSUPPORTED;
-    if (mode == 1 || (mode == -1 && tc_enabled()))
-        rc = tc_linear_wgrad(M, K, N, A, lda, a_scale, a_shift, a_relu, dY, dW, st);
+    // narrow layers (K*N small, M huge): register-tiled streaming kernel, exact fp32
+    if (mode != 1) rc = wgrad_rt(M, K, N, A, lda, a_scale, a_shift, a_relu, dY, dW, st);
+    if (rc == PN2_EUNSUPPORTED && (mode == 1 || (mode == -1 && tc_enabled())))
+        rc = tc_linear_wgrad(M, K, N, A, lda, a_scale, a_shift, a_relu, dY, dW, mode == 1, st);
     if (rc != PN2_EUNSUPPORTED || mode == 1) {
         if (rc == PN2_OK && db) {
             long rpb = ceil_div<long>(M, 64L);
@@ -572,8 +736,12 @@ PN2_API int pn2_bn_bwd_reduce(long M, int N, const float *dZ, int ldz, const flo
     PN2_REQUIRE_PTR(red);
     int blocks;
     long rpb = slab_rows(M, &blocks);
-    bn_bwd_reduce_kernel<<<blocks, 256, 0, as_stream(s)>>>(M, N, rpb, dZ, ldz, Y, scale, shift,
-                                                           saved, relu, red);
+    if (vec4_ok(N, ldz, dZ, Y))
+        bn_bwd_reduce_v4_kernel<<<blocks, 256, 2 * N * sizeof(double), as_stream(s)>>>(
+            M, N, rpb, dZ, ldz, Y, scale, shift, saved, relu, red);
+    else
+        bn_bwd_reduce_kernel<<<blocks, 256, 2 * N * sizeof(double), as_stream(s)>>>(
+            M, N, rpb, dZ, ldz, Y, scale, shift, saved, relu, red);
     return finish_launch();
 }
 
@@ -596,8 +764,14 @@ PN2_API int pn2_bn_bwd_apply(long M, int N, const float *dZ, int ldz, const floa
     PN2_REQUIRE((scale == nullptr) == (shift == nullptr));
     int blocks;
     long rpb = slab_rows(M, &blocks);
-    bn_bwd_apply_kernel<<<blocks, 256, 0, as_stream(s)>>>(M, N, rpb, dZ, ldz, Y, scale, shift, saved,
-                                                          gamma, relu, bn, red, dY, dgamma, dbeta);
+    if (vec4_ok(N, ldz, dZ, Y) && (reinterpret_cast<uintptr_t>(dY) & 15) == 0 &&
+        (scale == nullptr || ((reinterpret_cast<uintptr_t>(scale) | reinterpret_cast<uintptr_t>(shift)) & 15) == 0))
+        bn_bwd_apply_v4_kernel<<<blocks, 256, 0, as_stream(s)>>>(M, N, rpb, dZ, ldz, Y, scale, shift,
+                                                                 saved, gamma, relu, bn, red, dY, dgamma,
+                                                                 dbeta);
+    else
+        bn_bwd_apply_kernel<<<blocks, 256, 0, as_stream(s)>>>(M, N, rpb, dZ, ldz, Y, scale, shift, saved,
+                                                              gamma, relu, bn, red, dY, dgamma, dbeta);
     return finish_launch();
 }
 
@@ -648,13 +822,13 @@ PN2_API int pn2_bn_bwd_apply_pool(long G, int ns, int N, const float *dOut, cons
 }
 
 PN2_API int pn2_dropout(long n, const float *x, float keep_prob, unsigned long long seed,
-                        float *out, pn2_stream_t s) {
+                        const unsigned long long *seed_dev, float *out, pn2_stream_t s) {
     PN2_REQUIRE(n >= 0 && keep_prob > 0.f && keep_prob <= 1.f);
     if (n == 0) return PN2_OK;
     PN2_REQUIRE_PTR(x);
     PN2_REQUIRE_PTR(out);
     dropout_kernel<<<grid_for(n, 256), 256, 0, as_stream(s)>>>(n, x, keep_prob, 1.0f / keep_prob,
-                                                               seed, out);
+                                                               seed, seed_dev, out);
     return finish_launch();
 }
 

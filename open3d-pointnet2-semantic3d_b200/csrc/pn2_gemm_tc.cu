@@ -33,7 +33,7 @@ namespace tc {
 
 constexpr int BM = 128;       // rows per tile (UMMA M)
 constexpr int BK = 32;        // fp32/tf32 elements per K chunk = one 128-byte swizzle row
-constexpr int NPG = 3;                    // independent A-producer groups (chunks of loads in flight)
+constexpr int NPG = 2;                    // independent A-producer groups (chunks of loads in flight)
 constexpr int THREADS = 32 * (4 + 4 * NPG + 2);  // 4 epilogue + 4*NPG producer + loader + MMA warps
 constexpr int W_LOADER = 4 + 4 * NPG, W_MMA = 5 + 4 * NPG;
 constexpr int MAX_STAGES = 4;
@@ -125,6 +125,31 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+          "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+          "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+          "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+          "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+          "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // byte offset of element (row, k) inside one K-major SWIZZLE_128B chunk image (row = 128 B)
 __host__ __device__ __forceinline__ uint32_t sw128_offset(int row, int k) {
     return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((((k >> 2) ^ (row & 7)) & 7) << 4) +
@@ -152,6 +177,13 @@ __global__ void tc_prep_b_kernel(int N, int K, int Npad, int KC, const float *__
         *reinterpret_cast<float *>(base + (size_t)Npad * 128 + off) = lo;
     }
 }
+
+// Cycle accounting of CTA 0 (one thread per role), read back by pn2_debug_tc_trace():
+//  [0] mma: cycles waiting for a full stage   [1] mma: cycles issuing   [2] mma: waiting acc_empty
+//  [3] producer g0: load+transform            [4] producer g0: waiting empty   [5] producer g0: store
+//  [6] epilogue w0: waiting acc_full          [7] epilogue w0: processing      [8] loader: waiting empty
+//  [9] total kernel cycles (mma thread)       [10] chunks                      [11] tiles
+__device__ long long g_tc_trace[16];
 
 struct Params {
     long M;
@@ -226,6 +258,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const Params p) {
                 const int s = it % p.stages;
                 const uint32_t ph = (it / p.stages) & 1;
                 const int kbase = kc * BK + k4 * 4;
+                const bool tr = (blockIdx.x == 0 && g == 0 && t == 0);
+                const long long c0 = tr ? clock64() : 0;
                 float4 v[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
@@ -264,7 +298,10 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const Params p) {
                         }
                     }
                 }
+                // keep the transformed values live up to here so c1 really is "data has arrived"
+                const long long c1 = tr ? (clock64() + (long long)(__float_as_int(v[7].w) & 0)) : 0;
                 mbar_wait(&empty[s], ph ^ 1);
+                const long long c2 = tr ? clock64() : 0;
                 unsigned char *a_hi = stage_base + (size_t)s * stage_bytes;
                 unsigned char *a_lo = a_hi + a_bytes;
 #pragma unroll
@@ -282,6 +319,12 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const Params p) {
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 mbar_arrive(&full[s]);
+                if (tr) {
+                    const long long c3 = clock64();
+                    g_tc_trace[3] += c1 - c0;
+                    g_tc_trace[4] += c2 - c1;
+                    g_tc_trace[5] += c3 - c2;
+                }
             }
         }
     } else if (warp == W_LOADER) {
@@ -292,7 +335,9 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const Params p) {
                 for (int kc = 0; kc < p.KC; ++kc, ++it) {
                     const int s = it % p.stages;
                     const uint32_t ph = (it / p.stages) & 1;
+                    const long long c0 = blockIdx.x == 0 ? clock64() : 0;
                     mbar_wait(&empty[s], ph ^ 1);
+                    if (blockIdx.x == 0) g_tc_trace[8] += clock64() - c0;
                     unsigned char *b_hi = stage_base + (size_t)s * stage_bytes + 2 * a_bytes;
                     mbar_expect_tx(&full[s], 2 * b_bytes);
                     bulk_g2s(b_hi,
@@ -306,16 +351,23 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const Params p) {
         if (lane == 0) {
             const uint32_t idesc = make_idesc(p.Npad);
             uint32_t it = 0, tcnt = 0;
+            const bool tr = blockIdx.x == 0;
+            const long long k0c = tr ? clock64() : 0;
+            long long w_full = 0, w_issue = 0, w_acc = 0;
             for (long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcnt) {
                 const uint32_t acc = tcnt & 1, aph = (tcnt >> 1) & 1;
+                const long long ca = tr ? clock64() : 0;
                 mbar_wait(&acc_empty[acc], aph ^ 1);
+                if (tr) w_acc += clock64() - ca;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t d = tmem_base + acc * (uint32_t)(2 * Nacc);  // main
                 const uint32_t dc = d + (uint32_t)Nacc;                     // corrections
                 for (int kc = 0; kc < p.KC; ++kc, ++it) {
                     const int s = it % p.stages;
                     const uint32_t ph = (it / p.stages) & 1;
+                    const long long cw = tr ? clock64() : 0;
                     mbar_wait(&full[s], ph);
+                    const long long ci = tr ? clock64() : 0;
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a_hi = smem_u32(stage_base + (size_t)s * stage_bytes);
                     const uint64_t dah = make_desc(a_hi), dal = make_desc(a_hi + a_bytes);
@@ -330,8 +382,20 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const Params p) {
                         umma_tf32(dc, dah + adv, dbl + adv, idesc, 1u);
                     }
                     umma_commit(&empty[s]);  // frees the stage once these MMAs have read it
+                    if (tr) {
+                        w_full += ci - cw;
+                        w_issue += clock64() - ci;
+                    }
                 }
                 umma_commit(&acc_full[acc]);  // accumulator complete -> epilogue
+            }
+            if (tr) {
+                g_tc_trace[0] += w_full;
+                g_tc_trace[1] += w_issue;
+                g_tc_trace[2] += w_acc;
+                g_tc_trace[9] += clock64() - k0c;
+                g_tc_trace[10] += it;
+                g_tc_trace[11] += tcnt;
             }
         }
     } else {
@@ -345,48 +409,77 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const Params p) {
         for (long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcnt) {
             const uint32_t acc = tcnt & 1, aph = (tcnt >> 1) & 1;
             const long m0 = tile * BM + warp * 32;
+            const bool tr = (blockIdx.x == 0 && threadIdx.x == 0);
+            const long long ce0 = tr ? clock64() : 0;
             mbar_wait(&acc_full[acc], aph);
+            const long long ce1 = tr ? clock64() : 0;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
             for (int cb = 0; cb < 4; ++cb) {
                 if (cb >= nblk) break;
-                uint32_t r[32], rc[32];
                 const uint32_t ta = tmem_base + ((uint32_t)(warp * 32) << 16) +
                                     acc * (uint32_t)(2 * Nacc) + cb * 32;
-                tmem_ld32(ta, r);
-                tmem_ld32(ta + (uint32_t)Nacc, rc);
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    float4 o;  // main + corrections, round-to-nearest
-                    o.x = __uint_as_float(r[q * 4]) + __uint_as_float(rc[q * 4]);
-                    o.y = __uint_as_float(r[q * 4 + 1]) + __uint_as_float(rc[q * 4 + 1]);
-                    o.z = __uint_as_float(r[q * 4 + 2]) + __uint_as_float(rc[q * 4 + 2]);
-                    o.w = __uint_as_float(r[q * 4 + 3]) + __uint_as_float(rc[q * 4 + 3]);
-                    *reinterpret_cast<float4 *>(stg + lane * EPI_LD + q * 4) = o;
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t r[16], rc[16];
+                    tmem_ld16_nowait(ta + half * 16, r);
+                    tmem_ld16_nowait(ta + (uint32_t)Nacc + half * 16, rc);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float4 o;  // main + corrections, round-to-nearest
+                        o.x = __uint_as_float(r[q * 4]) + __uint_as_float(rc[q * 4]);
+                        o.y = __uint_as_float(r[q * 4 + 1]) + __uint_as_float(rc[q * 4 + 1]);
+                        o.z = __uint_as_float(r[q * 4 + 2]) + __uint_as_float(rc[q * 4 + 2]);
+                        o.w = __uint_as_float(r[q * 4 + 3]) + __uint_as_float(rc[q * 4 + 3]);
+                        *reinterpret_cast<float4 *>(stg + lane * EPI_LD + half * 16 + q * 4) = o;
+                    }
                 }
                 __syncwarp();
                 const int col = cb * 32 + lane;
                 const bool col_ok = col < p.N;
                 const float bv = (p.bias && col_ok) ? __ldg(p.bias + col) : 0.f;
-                double s1 = 0.0, s2 = 0.0;
-#pragma unroll 8
-                for (int rr = 0; rr < 32; ++rr) {
-                    const long m = m0 + rr;
-                    float v = stg[rr * EPI_LD + lane] + bv;
-                    if (col_ok && m < p.M) {
-                        p.Y[m * p.ldy + col] = v;
-                        if (p.stats_sum) {
-                            s1 += (double)v;
-                            s2 = fma((double)v, (double)v, s2);
-                        }
+                // all 32 shared-memory reads are issued back to back (independent), then the stores
+                float vals[32];
+#pragma unroll
+                for (int rr = 0; rr < 32; ++rr) vals[rr] = stg[rr * EPI_LD + lane] + bv;
+                __syncwarp();
+                const long rows_left = p.M - m0;
+                if (col_ok && rows_left > 0) {
+                    float *yp = p.Y + m0 * p.ldy + col;
+                    if (rows_left >= 32) {
+#pragma unroll
+                        for (int rr = 0; rr < 32; ++rr) yp[(long)rr * p.ldy] = vals[rr];
+                    } else {
+#pragma unroll
+                        for (int rr = 0; rr < 32; ++rr)
+                            if (rr < rows_left) yp[(long)rr * p.ldy] = vals[rr];
+                    }
+                    if (p.stats_sum) {
+                        // shifted fp32 partials (deviations from the first row of the block carry
+                        // no cancellation), recombined exactly in fp64
+                        const int nv = rows_left >= 32 ? 32 : (int)rows_left;
+                        const float c0 = vals[0];
+                        float p1 = 0.f, p2 = 0.f;
+#pragma unroll
+                        for (int rr = 0; rr < 32; ++rr)
+                            if (rr < nv) {
+                                const float dv = vals[rr] - c0;
+                                p1 += dv;
+                                p2 = __fmaf_rn(dv, dv, p2);
+                            }
+                        const double dc = (double)c0, dn = (double)nv, d1 = (double)p1;
+                        ssum[cb] += d1 + dn * dc;
+                        ssq[cb] += (double)p2 + 2.0 * dc * d1 + dn * dc * dc;
                     }
                 }
-                ssum[cb] += s1;
-                ssq[cb] += s2;
-                __syncwarp();
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(&acc_empty[acc]);
+            if (tr) {
+                g_tc_trace[6] += ce1 - ce0;
+                g_tc_trace[7] += clock64() - ce1;
+            }
         }
         if (p.stats_sum) {
 #pragma unroll
@@ -480,7 +573,7 @@ static int run_chunk(long M, int K, int Nc, const float *A, int lda, const float
 namespace tcw {
 using namespace tc;
 
-constexpr int W_NPG = 3;                        // independent producer groups (stages of loads in flight)
+constexpr int W_NPG = 2;                        // independent producer groups (stages of loads in flight)
 constexpr int W_WMMA = 4 + 4 * W_NPG;            // MMA / TMEM warp
 constexpr int W_THREADS = 32 * (W_WMMA + 1);  // warps 0-3 epilogue, 4.. producers, last MMA
 constexpr int W_ROWS = 32;      // contraction rows per stage (4 MMAs of K=8)
@@ -719,28 +812,36 @@ __global__ void __launch_bounds__(W_THREADS, 1) tc_wgrad_kernel(const WParams p)
             mbar_wait(&acc_full[acc], aph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             for (int cb = 0; cb < nblk; ++cb) {
-                uint32_t r[32], rc[32];
                 const uint32_t ta = tmem_base + ((uint32_t)(warp * 32) << 16) +
                                     acc * (uint32_t)(2 * Nacc) + cb * 32;
-                tmem_ld32(ta, r);
-                tmem_ld32(ta + (uint32_t)Nacc, rc);
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    float4 o;
-                    o.x = __uint_as_float(r[q * 4]) + __uint_as_float(rc[q * 4]);
-                    o.y = __uint_as_float(r[q * 4 + 1]) + __uint_as_float(rc[q * 4 + 1]);
-                    o.z = __uint_as_float(r[q * 4 + 2]) + __uint_as_float(rc[q * 4 + 2]);
-                    o.w = __uint_as_float(r[q * 4 + 3]) + __uint_as_float(rc[q * 4 + 3]);
-                    *reinterpret_cast<float4 *>(stg + lane * EPI_LD + q * 4) = o;
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t r[16], rc[16];
+                    tmem_ld16_nowait(ta + half * 16, r);
+                    tmem_ld16_nowait(ta + (uint32_t)Nacc + half * 16, rc);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float4 o;
+                        o.x = __uint_as_float(r[q * 4]) + __uint_as_float(rc[q * 4]);
+                        o.y = __uint_as_float(r[q * 4 + 1]) + __uint_as_float(rc[q * 4 + 1]);
+                        o.z = __uint_as_float(r[q * 4 + 2]) + __uint_as_float(rc[q * 4 + 2]);
+                        o.w = __uint_as_float(r[q * 4 + 3]) + __uint_as_float(rc[q * 4 + 3]);
+                        *reinterpret_cast<float4 *>(stg + lane * EPI_LD + half * 16 + q * 4) = o;
+                    }
                 }
                 __syncwarp();
+                float vals[32];
+#pragma unroll
+                for (int rr = 0; rr < 32; ++rr) vals[rr] = stg[rr * EPI_LD + lane];
                 const int n = p.n0 + cb * 32 + lane;
-                if (n < p.N) {
-#pragma unroll 8
-                    for (int rr = 0; rr < 32; ++rr) {
-                        const int k = p.k0 + warp * 32 + rr;
-                        if (k < p.K) atomicAdd(p.dW + (long)k * p.ldw + n, stg[rr * EPI_LD + lane]);
-                    }
+                const int kb = p.k0 + warp * 32;
+                if (n < p.N && kb < p.K) {
+                    float *wp = p.dW + (long)kb * p.ldw + n;
+                    const int kv = p.K - kb;
+#pragma unroll
+                    for (int rr = 0; rr < 32; ++rr)
+                        if (rr < kv) atomicAdd(wp + (long)rr * p.ldw, vals[rr]);
                 }
                 __syncwarp();
             }
@@ -804,9 +905,12 @@ static int run(long M, int K, int N, const float *A, int lda, const float *a_sca
 }  // namespace tcw
 
 int tc_linear_wgrad(long M, int K, int N, const float *A, int lda, const float *a_scale,
-                    const float *a_shift, int a_relu, const float *dY, float *dW,
+                    const float *a_shift, int a_relu, const float *dY, float *dW, bool force,
                     cudaStream_t st) {
     if (M < 2048 || N < 16 || K < 4) return PN2_EUNSUPPORTED;
+    // measured on B200 (tests/bench_gemm.py): the 128-feature MMA tile only pays off for wide
+    // layers with many rows; narrow or short problems are faster on the split-K fp32 kernel
+    if (!force && (M < 65536 || K < 64 || N < 64)) return PN2_EUNSUPPORTED;
     return tcw::run(M, K, N, A, lda, a_scale, a_shift, a_relu, dY, dW, st);
 }
 
@@ -854,3 +958,12 @@ int tc_linear_dgrad(long M, int K, int N, const float *dY, const float *W, float
 }
 
 }  // namespace pn2
+
+// debug hook (not in the public header): read and reset the cycle accounting of CTA 0
+extern "C" __attribute__((visibility("default"))) int pn2_debug_tc_trace(long long *out16) {
+    long long zeros[16] = {0};
+    cudaDeviceSynchronize();
+    if (cudaMemcpyFromSymbol(out16, pn2::tc::g_tc_trace, sizeof(zeros)) != cudaSuccess) return -2;
+    if (cudaMemcpyToSymbol(pn2::tc::g_tc_trace, zeros, sizeof(zeros)) != cudaSuccess) return -2;
+    return 0;
+}

@@ -76,6 +76,9 @@ class Trainer:
 
     def step(self, point_cloud, labels, smpw):
         loss = self.forward_backward(point_cloud, labels, smpw)
+        return self._apply_gradients(loss)
+
+    def _apply_gradients(self, loss):
         gscale = allreduce_flat(self.grads, self.world_size)
         self.step_count += 1
         lr = get_learning_rate(self.step_count - 1, self.params)
@@ -83,3 +86,50 @@ class Trainer:
              ptr(self.m, F32), ptr(self.v, F32), float(lr), 0.9, 0.999, 1e-8, self.step_count,
              float(gscale))
         return loss
+
+    # ---- CUDA-graph mode: forward + loss + backward captured once, replayed per step -------------
+    def capture(self, point_cloud, labels, smpw):
+        """Capture forward+loss+backward of this batch shape into a CUDA graph (the ~370 launches
+        of a step are otherwise CPU-launch bound).  The dropout mask stays fresh through a
+        device-resident seed increment; schedule values that are baked in (bn_decay) trigger a
+        re-capture when they change.  Returns False (and stays in eager mode) if capture fails."""
+        from . import _ffi
+        self._graph = None
+        try:
+            self._static = [t.clone() for t in (point_cloud, labels, smpw)]
+            self._seed_dev = torch.zeros(1, dtype=torch.int64, device=point_cloud.device)
+            tf_util.set_dropout_seed_device(self._seed_dev)
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    self.forward_backward(*self._static)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            n0 = _ffi.launches
+            with torch.cuda.graph(g):
+                self._static_loss = self.forward_backward(*self._static)
+            self.launches_per_replay = _ffi.launches - n0
+            self._graph = g
+            self._graph_bn_decay = get_bn_decay(self.step_count, self.params)
+            return True
+        except Exception as e:  # noqa: BLE001 - any capture failure means eager mode
+            self._graph = None
+            self._capture_error = repr(e)
+            tf_util.set_dropout_seed_device(None)
+            torch.cuda.synchronize()
+            return False
+
+    def step_graph(self, point_cloud, labels, smpw):
+        if getattr(self, "_graph", None) is None:
+            return self.step(point_cloud, labels, smpw)
+        if get_bn_decay(self.step_count, self.params) != self._graph_bn_decay:
+            if not self.capture(point_cloud, labels, smpw):
+                return self.step(point_cloud, labels, smpw)
+        for dst, src in zip(self._static, (point_cloud, labels, smpw)):
+            if dst.data_ptr() != src.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        self._seed_dev.add_(1)
+        self._graph.replay()
+        return self._apply_gradients(self._static_loss)

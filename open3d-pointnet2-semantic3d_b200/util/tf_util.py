@@ -396,11 +396,12 @@ def conv1d(inputs, num_output_channels, kernel_size, scope, stride=1, padding="S
 
 class _Dropout(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, keep_prob, seed):
+    def forward(ctx, x, keep_prob, seed, seed_dev):
         x = x.contiguous()
         out = torch.empty_like(x)
-        call("pn2_dropout", x.numel(), ptr(x, F32), float(keep_prob), int(seed), ptr(out, F32))
-        ctx.keep_prob, ctx.seed = keep_prob, seed
+        call("pn2_dropout", x.numel(), ptr(x, F32), float(keep_prob), int(seed),
+             ptr(seed_dev, torch.int64, True), ptr(out, F32))
+        ctx.keep_prob, ctx.seed, ctx.seed_dev = keep_prob, seed, seed_dev
         return out
 
     @staticmethod
@@ -408,15 +409,21 @@ class _Dropout(torch.autograd.Function):
         g = g.contiguous()
         out = torch.empty_like(g)
         call("pn2_dropout", g.numel(), ptr(g, F32), float(ctx.keep_prob), int(ctx.seed),
-             ptr(out, F32))
-        return out, None, None
+             ptr(ctx.seed_dev, torch.int64, True), ptr(out, F32))
+        return out, None, None, None
 
 
 _dropout_seed = [0x5EED]
+_dropout_seed_dev = [None]  # optional device-resident increment (CUDA-graph replay, see train_step)
 
 
 def set_dropout_seed(seed):
     _dropout_seed[0] = int(seed)
+
+
+def set_dropout_seed_device(t):
+    """t: 1-element int64 CUDA tensor added to the host seed inside the kernel (or None)."""
+    _dropout_seed_dev[0] = t
 
 
 def dropout_mask(numel, keep_prob, seed, device="cuda"):
@@ -433,5 +440,6 @@ def dropout(inputs, is_training, scope, keep_prob=0.5, noise_shape=None):
     if not _as_bool(is_training):
         return inputs
     seed = _dropout_seed[0]
-    _dropout_seed[0] = (seed * 6364136223846793005 + 1442695040888963407) & 0xFFFFFFFFFFFFFFFF
-    return _Dropout.apply(inputs, keep_prob, seed)
+    if _dropout_seed_dev[0] is None:  # eager mode: advance the host seed every call
+        _dropout_seed[0] = (seed * 6364136223846793005 + 1442695040888963407) & 0xFFFFFFFFFFFFFFFF
+    return _Dropout.apply(inputs, keep_prob, seed, _dropout_seed_dev[0])

@@ -117,3 +117,45 @@ def test_three_tf32_beats_plain_tf32_bound(ffi):
     Y, _ = linear_fwd(ffi, to_cuda(A), to_cuda(W), None, None, None, False, 1, want_stats=False)
     err = np.abs(Y.cpu().numpy() - A.astype(np.float64) @ W.astype(np.float64)).max()
     assert err < 1e-5, err
+
+
+@pytest.mark.parametrize("M,N,ldz,relu", [(5000, 32, 32, 1), (4096, 64, 64, 1), (1000, 9, 9, 0),
+                                          (3000, 128, 160, 1), (257, 512, 512, 1), (70000, 32, 32, 1)])
+def test_bn_backward_kernels(ffi, M, N, ldz, relu):
+    """pn2_bn_train_finalize + pn2_bn_bwd_reduce + pn2_bn_bwd_apply (scalar and float4 paths) against
+    the closed-form BatchNorm(+ReLU) backward in fp64, on the same fp32 scale/shift/mean/rstd."""
+    import torch
+    rs = np.random.RandomState(M + N)
+    Y = (rs.normal(size=(M, N)) * rs.uniform(0.3, 2.0, N) + rs.uniform(-1, 1, N)).astype(np.float32)
+    dZ = np.zeros((M, ldz), np.float32)
+    dZ[:, :N] = rs.normal(size=(M, N)).astype(np.float32)
+    gamma = rs.uniform(0.5, 1.5, N).astype(np.float32)
+    beta = rs.uniform(-0.3, 0.3, N).astype(np.float32)
+    p = ffi.ptr
+    Yt, dZt, gt, bt = to_cuda(Y), to_cuda(dZ), to_cuda(gamma), to_cuda(beta)
+    stats = torch.cat([Yt.double().sum(0), (Yt.double() ** 2).sum(0)]).contiguous()
+    sc = torch.empty(N, device="cuda"); sh = torch.empty(N, device="cuda")
+    saved = torch.empty(2 * N, device="cuda")
+    mm = torch.zeros(N, device="cuda"); mv = torch.ones(N, device="cuda")
+    ffi.call("pn2_bn_train_finalize", N, M, p(stats), p(gt), p(bt), 1e-3, 0.9, 1, p(mm), p(mv), p(sc), p(sh), p(saved))
+    Y64 = Y.astype(np.float64)
+    mean, var = Y64.mean(0), Y64.var(0)
+    np.testing.assert_allclose(saved.cpu().numpy()[:N], mean, rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(saved.cpu().numpy()[N:], 1 / np.sqrt(var + 1e-3), rtol=1e-6)
+    np.testing.assert_allclose(mm.cpu().numpy(), 0.1 * mean, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(mv.cpu().numpy(), 0.9 + 0.1 * var * M / (M - 1), rtol=1e-5)
+    red = torch.zeros(2 * N, dtype=torch.float64, device="cuda")
+    dY = torch.empty((M, N), device="cuda"); dg = torch.zeros(N, device="cuda"); db = torch.zeros(N, device="cuda")
+    ffi.call("pn2_bn_bwd_reduce", M, N, p(dZt), ldz, p(Yt), p(sc), p(sh), p(saved), relu, p(red))
+    ffi.call("pn2_bn_bwd_apply", M, N, p(dZt), ldz, p(Yt), p(sc), p(sh), p(saved), p(gt), relu, 1, p(red),
+             p(dY), p(dg), p(db))
+    scn, shn, sv = sc.cpu().numpy().astype(np.float64), sh.cpu().numpy().astype(np.float64), saved.cpu().numpy().astype(np.float64)
+    z = Y64 * scn + shn
+    dzh = np.where((z > 0) | (relu == 0), dZ[:, :N].astype(np.float64), 0.0)
+    xh = (Y64 - sv[:N]) * sv[N:]
+    s1, s2 = dzh.sum(0), (dzh * xh).sum(0)
+    exp = gamma * sv[N:] * (dzh - s1 / M - xh * s2 / M)
+    np.testing.assert_allclose(red.cpu().numpy(), np.concatenate([s1, s2]), rtol=1e-6, atol=1e-4)
+    np.testing.assert_allclose(dY.cpu().numpy(), exp, atol=2e-5)
+    np.testing.assert_allclose(dg.cpu().numpy(), s2, rtol=1e-5, atol=1e-3)
+    np.testing.assert_allclose(db.cpu().numpy(), s1, rtol=1e-5, atol=1e-3)

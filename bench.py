@@ -237,6 +237,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     trainer.step(d_pc, d_lab, d_w)  # creates + flattens the variables
+    trainer.step(d_pc, d_lab, d_w)
     use_graph = (not args.no_graph) and trainer.capture(d_pc, d_lab, d_w)
     step_fn = trainer.step_graph if use_graph else trainer.step
     launches_per_step = None

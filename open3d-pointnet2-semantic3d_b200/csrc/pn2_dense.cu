@@ -23,7 +23,7 @@ int tc_linear_dgrad(long M, int K, int N, const float *dY, const float *W, float
 size_t tc_workspace_bytes(int K, int N);
 int tc_linear_wgrad(long M, int K, int N, const float *A, int lda, const float *a_scale,
                     const float *a_shift, int a_relu, const float *dY, float *dW, bool force,
-                    cudaStream_t st);
+                    int *k_done, cudaStream_t st);
 
 // ---- SIMT GEMM dispatch ----------------------------------------------------------------------
 template <bool A_KC, bool B_NC, bool ATOMIC>
@@ -630,10 +630,25 @@ PN2_API int pn2_linear_wgrad(long M, int K, int N, const float *A, int lda, cons
     PN2_REQUIRE((a_scale == nullptr) == (a_shift == nullptr));
     cudaStream_t st = as_stream(s);
     int rc = PN2_EUNSUPPORTED;
-    // narrow layers (K*N small, M huge): register-tiled streaming kernel, exact fp32
-    if (mode != 1) rc = wgrad_rt(M, K, N, A, lda, a_scale, a_shift, a_relu, dY, dW, st);
+    // (the register-tiled streaming kernel of pn2_wgrad_rt.cuh measured slower than the split-K tile
+    //  kernel on every model shape -- 174 vs 101 us at 524288x32x32 -- and is kept for PN2_WGRAD_RT=1)
+    static const bool use_rt = getenv("PN2_WGRAD_RT") && getenv("PN2_WGRAD_RT")[0] == '1';
+    if (use_rt && mode != 1) rc = wgrad_rt(M, K, N, A, lda, a_scale, a_shift, a_relu, dY, dW, st);
+    int k_done = 0;
     if (rc == PN2_EUNSUPPORTED && (mode == 1 || (mode == -1 && tc_enabled())))
-        rc = tc_linear_wgrad(M, K, N, A, lda, a_scale, a_shift, a_relu, dY, dW, mode == 1, st);
+        rc = tc_linear_wgrad(M, K, N, A, lda, a_scale, a_shift, a_relu, dY, dW, mode == 1, &k_done, st);
+    if (rc == PN2_OK && k_done > 0 && k_done < K) {
+        // feature tail [k_done, K) on the fp32 split-K kernel
+        const int kt = K - k_done;
+        int sp = (int)ceil_div<long>(148L * 4, (long)ceil_div(N, N > 64 ? 128 : (N > 32 ? 64 : 32)));
+        const long ms = ceil_div<long>(M, 256);
+        if (sp > ms) sp = (int)ms;
+        if (sp < 1) sp = 1;
+        rc = launch_gemm<false, true, true>(kt, N, M, A + k_done, 1, lda, dY, N, 1,
+                                            a_scale ? a_scale + k_done : nullptr,
+                                            a_shift ? a_shift + k_done : nullptr, a_relu, nullptr,
+                                            dW + (long)k_done * N, N, nullptr, sp, st);
+    }
     if (rc != PN2_EUNSUPPORTED || mode == 1) {
         if (rc == PN2_OK && db) {
             long rpb = ceil_div<long>(M, 64L);
@@ -646,6 +661,8 @@ PN2_API int pn2_linear_wgrad(long M, int K, int N, const float *A, int lda, cons
     // C[K,N] += sum_m f(A)(m,k) dY(m,n): M'=K, N'=N, K'=M ; A(m'=k, k'=m) = A + m*lda + k
     const int tiles = ceil_div(K, K > 64 ? 128 : (K > 32 ? 64 : 32)) *
                       ceil_div(N, N > 64 ? 128 : (N > 32 ? 64 : 32));
+    // enough CTAs to fill the machine (measured: limiting the split count to save atomics made
+    // short problems 3x slower -- parallelism over the contraction rows matters more)
     int splits = (int)ceil_div<long>(148L * 4, tiles);
     const long max_splits = ceil_div<long>(M, 256);
     if (splits > max_splits) splits = (int)max_splits;

@@ -26,6 +26,8 @@
 //              tcgen05.commit onto the "stage empty" / "accumulator full" mbarriers
 // The accumulator pair is double buffered in TMEM (2 x 2 x N columns, N <= 128 per pass) so the
 // epilogue of tile i overlaps the main loop of tile i+1.
+#include <stdlib.h>
+
 #include "pn2_common.cuh"
 
 namespace pn2 {
@@ -503,6 +505,19 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const Params p) {
     }
 }
 
+static int opt_in_smem(const void *kernel, int slot) {
+    static bool done[2][64] = {{false}};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    if (!done[slot][dev]) {
+        int rc = cuda_status(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  227 * 1024));
+        if (rc) return rc;
+        done[slot][dev] = true;
+    }
+    return PN2_OK;
+}
+
 static size_t image_bytes(int K, int N) {
     const int Npad = (N + 15) & ~15, KC = (K + BK - 1) / BK;
     return (size_t)KC * 2 * Npad * 128;
@@ -545,8 +560,9 @@ static int run_chunk(long M, int K, int Nc, const float *A, int lda, const float
     int rc = finish_launch();
     if (rc) return rc;
 
-    rc = cuda_status(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)smem));
+    // opt in to the full 227 KB once per device (not per launch: no driver call on the hot path,
+    // nothing that could disturb a stream capture)
+    rc = opt_in_smem(reinterpret_cast<const void *>(tc_gemm_kernel), 0);
     if (rc) return rc;
     const long tiles = (M + BM - 1) / BM;
     const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
@@ -595,6 +611,7 @@ __device__ __forceinline__ uint32_t mn_offset(int r, int c4, int groups) {
 struct WParams {
     long M;
     int K, N, Npad, NG, lda, ldy, ldw, a_relu, k0, n0, stages;
+    int dbg;  // PN2_DBG_WGRAD bit mask (diagnostics only): 1 skip atomics, 2 skip dY loads, 4 skip X loads
     const float *A, *a_scale, *a_shift, *dY;
     float *dW;
 };
@@ -684,7 +701,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) tc_wgrad_kernel(const WParams p)
                     for (int i = 0; i < 8; ++i) {
                         const long m = mbase + rr + 4 * i;
                         float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (m < p.M && kf < p.K) {
+                        if (m < p.M && kf < p.K && !(p.dbg & 4)) {
                             const float *src = p.A + m * p.lda + kf;
                             if (a_vec && kf + 3 < p.K) {
                                 x = __ldg(reinterpret_cast<const float4 *>(src));
@@ -705,7 +722,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) tc_wgrad_kernel(const WParams p)
                             const int bc4 = e % bw4, r = e / bw4;
                             const long m = mbase + r;
                             const int nf = p.n0 + 4 * bc4;
-                            if (m < p.M && nf < p.N) {
+                            if (m < p.M && nf < p.N && !(p.dbg & 2)) {
                                 const float *src = p.dY + m * p.ldy + nf;
                                 if (b_vec && nf + 3 < p.N) {
                                     x = __ldg(reinterpret_cast<const float4 *>(src));
@@ -769,18 +786,25 @@ __global__ void __launch_bounds__(W_THREADS, 1) tc_wgrad_kernel(const WParams p)
         if (lane == 0) {
             const uint32_t idesc = make_idesc(p.Npad) | (1u << 15) | (1u << 16);  // A, B MN-major
             uint32_t it = 0, tcnt = 0;
+            const bool tr = blockIdx.x == 0;
+            const long long k0c = tr ? clock64() : 0;
+            long long w_full = 0, w_issue = 0, w_acc = 0;
             for (long seg = blockIdx.x; seg < num_seg; seg += gridDim.x, ++tcnt) {
                 const long seg0 = seg * W_SEG;
                 const int nst = (int)((min((long)W_SEG, p.M - seg0) + W_ROWS - 1) / W_ROWS);
                 const uint32_t acc = tcnt & 1, aph = (tcnt >> 1) & 1;
+                const long long ca = tr ? clock64() : 0;
                 mbar_wait(&acc_empty[acc], aph ^ 1);
+                if (tr) w_acc += clock64() - ca;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t d = tmem_base + acc * (uint32_t)(2 * Nacc);
                 const uint32_t dc = d + (uint32_t)Nacc;
                 for (int sidx = 0; sidx < nst; ++sidx, ++it) {
                     const int s = it % p.stages;
                     const uint32_t ph = (it / p.stages) & 1;
+                    const long long cw = tr ? clock64() : 0;
                     mbar_wait(&full[s], ph);
+                    const long long ci = tr ? clock64() : 0;
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a_hi = smem_u32(smem + (size_t)s * stage_bytes);
                     const uint32_t b_hi = a_hi + 2 * a_bytes;
@@ -798,8 +822,20 @@ __global__ void __launch_bounds__(W_THREADS, 1) tc_wgrad_kernel(const WParams p)
                         umma_tf32(dc, dah, dbl, idesc, 1u);
                     }
                     umma_commit(&empty[s]);
+                    if (tr) {
+                        w_full += ci - cw;
+                        w_issue += clock64() - ci;
+                    }
                 }
                 umma_commit(&acc_full[acc]);
+            }
+            if (tr) {
+                g_tc_trace[0] += w_full;
+                g_tc_trace[1] += w_issue;
+                g_tc_trace[2] += w_acc;
+                g_tc_trace[9] += clock64() - k0c;
+                g_tc_trace[10] += it;
+                g_tc_trace[11] += tcnt;
             }
         }
     } else if (warp < 4) {
@@ -836,7 +872,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) tc_wgrad_kernel(const WParams p)
                 for (int rr = 0; rr < 32; ++rr) vals[rr] = stg[rr * EPI_LD + lane];
                 const int n = p.n0 + cb * 32 + lane;
                 const int kb = p.k0 + warp * 32;
-                if (n < p.N && kb < p.K) {
+                if (n < p.N && kb < p.K && !(p.dbg & 1)) {
                     float *wp = p.dW + (long)kb * p.ldw + n;
                     const int kv = p.K - kb;
 #pragma unroll
@@ -860,10 +896,10 @@ __global__ void __launch_bounds__(W_THREADS, 1) tc_wgrad_kernel(const WParams p)
     }
 }
 
-static int run(long M, int K, int N, const float *A, int lda, const float *a_scale,
+static int run(long M, int K, int Kdo, int N, const float *A, int lda, const float *a_scale,
                const float *a_shift, int a_relu, const float *dY, float *dW, cudaStream_t st) {
     for (int n0 = 0; n0 < N; n0 += 128) {
-        for (int k0 = 0; k0 < K; k0 += W_FEAT) {
+        for (int k0 = 0; k0 < Kdo; k0 += W_FEAT) {
             WParams p;
             p.M = M;
             p.K = K;
@@ -882,6 +918,10 @@ static int run(long M, int K, int N, const float *A, int lda, const float *a_sca
             p.a_shift = a_shift;
             p.dY = dY;
             p.dW = dW;
+            {
+                const char *e = getenv("PN2_DBG_WGRAD");
+                p.dbg = e ? atoi(e) : 0;
+            }
             const size_t stage_bytes = 2 * 16384 + 2 * (size_t)p.NG * 4096;
             const size_t fixed = 4 * 32 * EPI_LD * sizeof(float) + (2 * MAX_STAGES + 4) * 8 + 16;
             int stages = (int)((227 * 1024 - fixed) / stage_bytes);
@@ -889,8 +929,7 @@ static int run(long M, int K, int N, const float *A, int lda, const float *a_sca
             if (stages < 1) return PN2_EUNSUPPORTED;
             p.stages = stages;
             const size_t smem = (size_t)stages * stage_bytes + fixed;
-            int rc = cuda_status(cudaFuncSetAttribute(
-                tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int rc = tc::opt_in_smem(reinterpret_cast<const void *>(tc_wgrad_kernel), 1);
             if (rc) return rc;
             const long segs = (M + W_SEG - 1) / W_SEG;
             const int grid = (int)(segs < num_sms() ? segs : num_sms());
@@ -906,12 +945,18 @@ static int run(long M, int K, int N, const float *A, int lda, const float *a_sca
 
 int tc_linear_wgrad(long M, int K, int N, const float *A, int lda, const float *a_scale,
                     const float *a_shift, int a_relu, const float *dY, float *dW, bool force,
-                    cudaStream_t st) {
+                    int *k_done, cudaStream_t st) {
+    *k_done = 0;
     if (M < 2048 || N < 16 || K < 4) return PN2_EUNSUPPORTED;
     // measured on B200 (tests/bench_gemm.py): the 128-feature MMA tile only pays off for wide
     // layers with many rows; narrow or short problems are faster on the split-K fp32 kernel
     if (!force && (M < 65536 || K < 64 || N < 64)) return PN2_EUNSUPPORTED;
-    return tcw::run(M, K, N, A, lda, a_scale, a_shift, a_relu, dY, dW, st);
+    // a narrow tail of features (K = 131 -> 3) would cost a full extra pass over dY on the
+    // 128-feature MMA tile; it is left to the caller's fp32 kernel (k_done tells where it starts)
+    int Kdo = K;
+    if (!force && K > tcw::W_FEAT && (K % tcw::W_FEAT) < 32) Kdo = K - (K % tcw::W_FEAT);
+    *k_done = Kdo;
+    return tcw::run(M, K, Kdo, N, A, lda, a_scale, a_shift, a_relu, dY, dW, st);
 }
 
 // Shapes worth the tensor cores: at least one full tile of rows, K and N not tiny.

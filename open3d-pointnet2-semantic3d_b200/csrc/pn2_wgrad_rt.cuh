@@ -15,13 +15,15 @@
 namespace pn2 {
 
 constexpr int WRT_THREADS = 256;
-constexpr int WRT_UNROLL = 2;  // rows in flight per thread
+// rows in flight per thread: the kernel is bound by bytes in flight, so 32/TK rows are loaded
+// before the first FMA (8 rows for TK=4, 4 rows for TK=8)
 
 template <int TK>
 __global__ void __launch_bounds__(WRT_THREADS)
 wgrad_rt_kernel(long M, int K, int N, const float *__restrict__ A, int lda,
                 const float *__restrict__ a_scale, const float *__restrict__ a_shift, int a_relu,
                 const float *__restrict__ dY, float *__restrict__ dW, long rows_per_cta, int tk, int tn) {
+    constexpr int WRT_UNROLL = 32 / TK;
     extern __shared__ float tile[];  // [tk*TK][tn*4]
     const int G = tk * tn;
     const int RG = WRT_THREADS / G;

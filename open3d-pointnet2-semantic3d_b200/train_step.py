@@ -95,31 +95,50 @@ class Trainer:
         re-capture when they change.  Returns False (and stays in eager mode) if capture fails."""
         from . import _ffi
         self._graph = None
-        try:
-            self._static = [t.clone() for t in (point_cloud, labels, smpw)]
-            self._seed_dev = torch.zeros(1, dtype=torch.int64, device=point_cloud.device)
-            tf_util.set_dropout_seed_device(self._seed_dev)
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                for _ in range(2):
+        for mode in ("global", "thread_local"):
+            try:
+                self._static = [t.clone() for t in (point_cloud, labels, smpw)]
+                self._seed_dev = torch.zeros(1, dtype=torch.int64, device=point_cloud.device)
+                tf_util.set_dropout_seed_device(self._seed_dev)
+                for _ in range(2):  # eager passes: every kernel / workspace / gradient buffer exists
                     self.forward_backward(*self._static)
-            torch.cuda.current_stream().wait_stream(side)
-            torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            n0 = _ffi.launches
-            with torch.cuda.graph(g):
-                self._static_loss = self.forward_backward(*self._static)
-            self.launches_per_replay = _ffi.launches - n0
-            self._graph = g
-            self._graph_bn_decay = get_bn_decay(self.step_count, self.params)
-            return True
-        except Exception as e:  # noqa: BLE001 - any capture failure means eager mode
-            self._graph = None
-            self._capture_error = repr(e)
-            tf_util.set_dropout_seed_device(None)
-            torch.cuda.synchronize()
-            return False
+                torch.cuda.synchronize()
+                static = self._static
+
+                def fb():
+                    return self.forward_backward(*static)
+
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    fb()
+                    fb()
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                n0 = _ffi.launches
+                with torch.cuda.graph(g, capture_error_mode=mode):
+                    loss = fb()
+                self._static_loss = loss
+                self.launches_per_replay = _ffi.launches - n0
+                g.replay()
+                torch.cuda.synchronize()
+                self._graph = g
+                self._graph_bn_decay = get_bn_decay(self.step_count, self.params)
+                self._capture_error = None
+                return True
+            except Exception as e:  # noqa: BLE001 - any capture failure means eager mode
+                import traceback
+                self._graph = None
+                self._capture_error = "[%s] " % mode + repr(e)[:160] + " | " + " <- ".join(
+                    l.strip() for l in traceback.format_exc().splitlines()
+                    if l.strip().startswith("File"))[-700:]
+                try:
+                    torch.cuda.synchronize()
+                except Exception:  # noqa: BLE001
+                    pass
+        tf_util.set_dropout_seed_device(None)
+        return False
 
     def step_graph(self, point_cloud, labels, smpw):
         if getattr(self, "_graph", None) is None:

@@ -27,3 +27,17 @@ for (M, K, N, pro) in [(131072, 128, 128, 1), (131072, 128, 128, 0), (524288, 32
     ch = max(v[10], 1)
     for i, nme in enumerate(names):
         print("   %-20s %10d cycles  (%8.1f per chunk)" % (nme, v[i], v[i] / ch))
+
+print("######## wgrad")
+for (M, K, N) in [(131072, 128, 128), (131072, 64, 64), (524288, 32, 32)]:
+    A = torch.randn(M, K, device="cuda"); dY = torch.randn(M, N, device="cuda"); dW = torch.zeros(K, N, device="cuda")
+    sc = torch.ones(K, device="cuda"); sh = torch.zeros(K, device="cuda")
+    def run():
+        ffi.call("pn2_linear_wgrad", M, K, N, p(A), K, p(sc), p(sh), 1, p(dY), p(dW), None, 1)
+    for _ in range(3): run()
+    buf = (ctypes.c_longlong * 16)()
+    lib.pn2_debug_tc_trace(buf); run(); lib.pn2_debug_tc_trace(buf)
+    v = list(buf); ch = max(v[10], 1)
+    print("== wgrad M,K,N=%s" % ((M, K, N),))
+    for i in (0, 1, 2, 9, 10, 11):
+        print("   %-20s %10d cycles  (%8.1f per stage)" % (names[i], v[i], v[i] / ch))

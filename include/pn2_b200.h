@@ -101,6 +101,12 @@ int pn2_selection_sort(int b, int n, int m, int k, const float *dist, int *outi,
 int pn2_group_concat(int b, int n, int m, int nsample, int c, const float *xyz,
                      const float *new_xyz, const float *points, const int *idx, int xyz_first,
                      int use_xyz, float *out, pn2_stream_t s);
+/* same with a padded row pitch: row r of the output starts at out + r*ld (ld >= 3+c floats; the
+ * padding is not written).  ld % 4 == 0 makes the rows 16-byte aligned for the TMA tensor maps
+ * of pn2_linear_fwd / pn2_linear_wgrad. */
+int pn2_group_concat_ld(int b, int n, int m, int nsample, int c, const float *xyz,
+                        const float *new_xyz, const float *points, const int *idx, int xyz_first,
+                        int use_xyz, float *out, int ld, pn2_stream_t s);
 /* gradient of the above w.r.t. points (b,n,c) (zeroed here).  grad_xyz (b,n,3) and
  * grad_new_xyz (b,m,3) are optional (NULL = not needed); when given they are zeroed here. */
 int pn2_group_concat_grad(int b, int n, int m, int nsample, int c, const float *grad_out,

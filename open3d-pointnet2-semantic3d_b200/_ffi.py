@@ -35,6 +35,7 @@ SIGNATURES = {
     "pn2_three_interpolate_grad": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "pn2_selection_sort": [_i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "pn2_group_concat": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp],
+    "pn2_group_concat_ld": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _i, _vp],
     "pn2_group_concat_grad": [_i, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp],
     "pn2_fp_weights": [_i, _vp, _vp, _vp],
     "pn2_three_interpolate_ld": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp],
@@ -106,6 +107,18 @@ def ptr(t, dtype=None, allow_none=False):
     if dtype is not None and t.dtype != dtype:
         raise Pn2Error("expected dtype %s, got %s" % (dtype, t.dtype))
     return ctypes.c_void_p(t.data_ptr())
+
+
+def ptr_rows(t, dtype=None):
+    """(address, row pitch in elements) of a 2-D CUDA tensor whose rows are dense but may be padded
+    (stride(1) == 1, stride(0) >= shape[1]), e.g. a column slice of a wider buffer."""
+    if not isinstance(t, torch.Tensor) or not t.is_cuda or t.dim() != 2:
+        raise Pn2Error("pn2 ops need 2-D CUDA tensors here; got %r" % (type(t),))
+    if t.shape[1] > 1 and t.stride(1) != 1 or t.stride(0) < t.shape[1]:
+        raise Pn2Error("rows must be dense (unit column stride)")
+    if dtype is not None and t.dtype != dtype:
+        raise Pn2Error("expected dtype %s, got %s" % (dtype, t.dtype))
+    return ctypes.c_void_p(t.data_ptr()), int(t.stride(0))
 
 
 def call(name, *args):

@@ -26,7 +26,9 @@
 //              tcgen05.commit onto the "stage empty" / "accumulator full" mbarriers
 // The accumulator pair is double buffered in TMEM (2 x 2 x N columns, N <= 128 per pass) so the
 // epilogue of tile i overlaps the main loop of tile i+1.
+#include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "pn2_common.cuh"
 
@@ -35,10 +37,14 @@ namespace tc {
 
 constexpr int BM = 128;       // rows per tile (UMMA M)
 constexpr int BK = 32;        // fp32/tf32 elements per K chunk = one 128-byte swizzle row
-constexpr int NPG = 2;                    // independent A-producer groups (chunks of loads in flight)
-constexpr int THREADS = 32 * (4 + 4 * NPG + 2);  // 4 epilogue + 4*NPG producer + loader + MMA warps
-constexpr int W_LOADER = 4 + 4 * NPG, W_MMA = 5 + 4 * NPG;
+constexpr int NPG = 2;                    // A-transform groups of 4 warps, taking K chunks round-robin
+constexpr int THREADS = 32 * (4 + 4 * NPG + 3);  // 4 epilogue + 4*NPG transform + A loader + B loader + MMA
+constexpr int W_ALOAD = 4 + 4 * NPG, W_BLOAD = 5 + 4 * NPG, W_MMA = 6 + 4 * NPG;
+constexpr int MAX_RAW = 4;                // raw A ring slots (16 KB each) filled by TMA tensor loads
+constexpr int RAW_BYTES = BM * BK * 4;
+constexpr int EPI_BYTES = 32 * 1024;      // epilogue staging
 constexpr int MAX_STAGES = 4;
+constexpr int MAX_KC = 16;    // K <= 512
 constexpr int EPI_LD = 36;    // padded row length (floats) of the epilogue transpose buffer
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
@@ -182,33 +188,60 @@ __global__ void tc_prep_b_kernel(int N, int K, int Npad, int KC, const float *__
 
 // Cycle accounting of CTA 0 (one thread per role), read back by pn2_debug_tc_trace():
 //  [0] mma: cycles waiting for a full stage   [1] mma: cycles issuing   [2] mma: waiting acc_empty
-//  [3] producer g0: load+transform            [4] producer g0: waiting empty   [5] producer g0: store
-//  [6] epilogue w0: waiting acc_full          [7] epilogue w0: processing      [8] loader: waiting empty
+//  [3] transform g0: wait raw + load          [4] transform g0: waiting empty  [5] transform g0: store
+//  [6] epilogue w0: waiting acc_full          [7] epilogue w0: processing      [8] B loader: waiting empty
 //  [9] total kernel cycles (mma thread)       [10] chunks                      [11] tiles
 __device__ long long g_tc_trace[16];
 
 struct Params {
     long M;
-    int K, N, Npad, KC, stages, lda, ldy, a_relu;
+    int K, N, Npad, KC, stages, b_res, raw_slots, a_tma, y_tma, lda, ldy, a_relu;
     const float *A, *a_scale, *a_shift, *bias, *image;
     float *Y;
     double *stats_sum, *stats_sq;  // per-column sum / sum of squares (fp64), or NULL
 };
 
-__global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const Params p) {
+__device__ __forceinline__ void tma_load_2d(void *dst_smem, const CUtensorMap *tm, int c0, int c1,
+                                            uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, "
+        "%3}], [%4];" ::"r"(smem_u32(dst_smem)),
+        "l"(tm), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *tm, int c0, int c1,
+                                             const void *src_smem) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tm),
+                 "r"(c0), "r"(c1), "r"(smem_u32(src_smem))
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+    tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmY,
+                   const Params p) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    // carve: stages x [A_hi 16K | A_lo 16K | B_hi Npad*128 | B_lo Npad*128], epilogue staging, barriers
+    // carve:  [resident B: KC x (B_hi | B_lo)]            (p.b_res: weights loaded once per CTA)
+    //         stages x [A_hi 16K | A_lo 16K (| B_hi | B_lo when B is streamed per chunk)]
+    //         raw_slots x 16K   raw fp32 A chunks as written by the TMA tensor loads
+    //         32K epilogue staging (4 warps x 2 buffers x 32 rows x 128 B, 128B-swizzled)
+    //         bias (128 floats), mbarriers
     const uint32_t a_bytes = BM * 128;
     const uint32_t b_bytes = (uint32_t)p.Npad * 128;
-    const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
-    unsigned char *stage_base = smem;
-    float *epi = reinterpret_cast<float *>(smem + (size_t)p.stages * stage_bytes);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(epi + 4 * 32 * EPI_LD);
-    uint64_t *full = bars;                    // [stages]  A producers (128) + B loader (1) + tx
+    const uint32_t stage_bytes = p.b_res ? 2 * a_bytes : 2 * a_bytes + 2 * b_bytes;
+    unsigned char *bres = smem;
+    unsigned char *stage_base = smem + (p.b_res ? (size_t)p.KC * 2 * b_bytes : 0);
+    unsigned char *raw = stage_base + (size_t)p.stages * stage_bytes;
+    unsigned char *epi_b = raw + (size_t)p.raw_slots * RAW_BYTES;
+    float *sbias = reinterpret_cast<float *>(epi_b + EPI_BYTES);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sbias + 128);
+    uint64_t *full = bars;                    // [stages]  transform threads (128) (+ B loader + tx)
     uint64_t *empty = bars + MAX_STAGES;      // [stages]  tcgen05.commit
     uint64_t *acc_full = bars + 2 * MAX_STAGES;       // [2]
     uint64_t *acc_empty = bars + 2 * MAX_STAGES + 2;  // [2] epilogue threads (128)
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * MAX_STAGES + 4);
+    uint64_t *bfull = bars + 2 * MAX_STAGES + 4;      // [MAX_KC] resident-B chunk landed (tx)
+    uint64_t *raw_full = bfull + MAX_KC;              // [MAX_RAW] TMA tx
+    uint64_t *raw_empty = raw_full + MAX_RAW;         // [MAX_RAW] transform threads (128)
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(raw_empty + MAX_RAW);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int Nacc = (p.Npad + 31) & ~31;
@@ -217,15 +250,22 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const Params p) {
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) {
-            mbar_init(&full[s], 129);
+            mbar_init(&full[s], p.b_res ? 128 : 129);
             mbar_init(&empty[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&acc_full[a], 1);
             mbar_init(&acc_empty[a], 128);
         }
+        for (int kc = 0; kc < MAX_KC; ++kc) mbar_init(&bfull[kc], 1);
+        for (int r = 0; r < MAX_RAW; ++r) {
+            mbar_init(&raw_full[r], 1);
+            mbar_init(&raw_empty[r], 128);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (threadIdx.x < 128)
+        sbias[threadIdx.x] = (p.bias && (int)threadIdx.x < p.N) ? __ldg(p.bias + threadIdx.x) : 0.f;
     if (warp == W_MMA) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                          smem_u32(tmem_slot)),
@@ -240,10 +280,13 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const Params p) {
 
     const long num_tiles = (p.M + BM - 1) / BM;
 
-    if (warp >= 4 && warp < W_LOADER) {
-        // ================================ A producers ================================
+    if (warp >= 4 && warp < W_ALOAD) {
+        // ================================ A transform ================================
         // group g takes chunks g, g+npg, ... of this CTA's (tile, kc) sequence; npg <= stages
-        // keeps every group within one ring revolution of the consumer (phase parity is safe)
+        // keeps every group within one ring revolution of the consumer (phase parity is safe).
+        // The raw chunk comes from the TMA ring (or, when A cannot be described by a tensor map,
+        // from float4 global loads); BatchNorm affine + ReLU of the previous layer, hi/lo split,
+        // st.shared into the 128B-swizzled K-major UMMA layout, proxy fence, mbarrier arrive.
         const int g = (warp - 4) >> 2;
         const int npg = NPG < p.stages ? NPG : p.stages;
         const int t = (threadIdx.x - 128) & 127;
@@ -262,32 +305,44 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const Params p) {
                 const int kbase = kc * BK + k4 * 4;
                 const bool tr = (blockIdx.x == 0 && g == 0 && t == 0);
                 const long long c0 = tr ? clock64() : 0;
-                float4 v[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const long m = m0 + r0 + 16 * i;
-                    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (m < p.M) {
-                        const float *src = p.A + m * p.lda + kbase;
-                        if (vec_ok && kbase + 3 < p.K) {
-                            x = __ldg(reinterpret_cast<const float4 *>(src));
-                        } else {
-                            if (kbase + 0 < p.K) x.x = __ldg(src + 0);
-                            if (kbase + 1 < p.K) x.y = __ldg(src + 1);
-                            if (kbase + 2 < p.K) x.z = __ldg(src + 2);
-                            if (kbase + 3 < p.K) x.w = __ldg(src + 3);
-                        }
-                    }
-                    v[i] = x;
-                }
+                float sc[4], sh[4];
                 if (p.a_scale) {
-                    float sc[4], sh[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const bool ok = kbase + j < p.K;
                         sc[j] = ok ? __ldg(p.a_scale + kbase + j) : 0.f;
                         sh[j] = ok ? __ldg(p.a_shift + kbase + j) : 0.f;
                     }
+                }
+                float4 v[8];
+                if (p.a_tma) {
+                    const int rs = it % p.raw_slots;
+                    const uint32_t rph = (it / p.raw_slots) & 1;
+                    mbar_wait(&raw_full[rs], rph);
+                    const unsigned char *slot = raw + (size_t)rs * RAW_BYTES;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        v[i] = *reinterpret_cast<const float4 *>(slot + (r0 + 16 * i) * 128 + k4 * 16);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const long m = m0 + r0 + 16 * i;
+                        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (m < p.M) {
+                            const float *src = p.A + m * p.lda + kbase;
+                            if (vec_ok && kbase + 3 < p.K) {
+                                x = __ldg(reinterpret_cast<const float4 *>(src));
+                            } else {
+                                if (kbase + 0 < p.K) x.x = __ldg(src + 0);
+                                if (kbase + 1 < p.K) x.y = __ldg(src + 1);
+                                if (kbase + 2 < p.K) x.z = __ldg(src + 2);
+                                if (kbase + 3 < p.K) x.w = __ldg(src + 3);
+                            }
+                        }
+                        v[i] = x;
+                    }
+                }
+                if (p.a_scale) {
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const bool row_ok = (m0 + r0 + 16 * i) < p.M;
@@ -300,8 +355,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const Params p) {
                         }
                     }
                 }
-                // keep the transformed values live up to here so c1 really is "data has arrived"
-                const long long c1 = tr ? (clock64() + (long long)(__float_as_int(v[7].w) & 0)) : 0;
+                const long long c1 = tr ? clock64() : 0;
                 mbar_wait(&empty[s], ph ^ 1);
                 const long long c2 = tr ? clock64() : 0;
                 unsigned char *a_hi = stage_base + (size_t)s * stage_bytes;
@@ -321,6 +375,12 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const Params p) {
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 mbar_arrive(&full[s]);
+                // The raw slot goes back to the TMA loader only here: every value read from it has
+                // been consumed (the stores above depend on them) and the proxy fence orders this
+                // thread's generic-proxy reads of the slot before the async-proxy refill.  Releasing
+                // it right after issuing the ld.shared let the refill overtake the reads (rare,
+                // timing dependent: rows of the NEXT tile showed up in the accumulator).
+                if (p.a_tma) mbar_arrive(&raw_empty[it % p.raw_slots]);
                 if (tr) {
                     const long long c3 = clock64();
                     g_tc_trace[3] += c1 - c0;
@@ -329,9 +389,32 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const Params p) {
                 }
             }
         }
-    } else if (warp == W_LOADER) {
+    } else if (warp == W_ALOAD) {
+        // ================================ A loader (TMA) ================================
+        // one 2-D tensor load per 128 x 32 chunk into the raw ring, running raw_slots chunks ahead
+        if (lane == 0 && p.a_tma) {
+            uint32_t it = 0;
+            for (long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                for (int kc = 0; kc < p.KC; ++kc, ++it) {
+                    const int rs = it % p.raw_slots;
+                    const uint32_t rph = (it / p.raw_slots) & 1;
+                    mbar_wait(&raw_empty[rs], rph ^ 1);
+                    mbar_expect_tx(&raw_full[rs], RAW_BYTES);
+                    tma_load_2d(raw + (size_t)rs * RAW_BYTES, &tmA, kc * BK, (int)(tile * BM),
+                                &raw_full[rs]);
+                }
+            }
+        }
+    } else if (warp == W_BLOAD) {
         // ================================ B loader ================================
-        if (lane == 0) {
+        if (lane == 0 && p.b_res) {
+            for (int kc = 0; kc < p.KC; ++kc) {
+                mbar_expect_tx(&bfull[kc], 2 * b_bytes);
+                bulk_g2s(bres + (size_t)kc * 2 * b_bytes,
+                         reinterpret_cast<const unsigned char *>(p.image) + (size_t)kc * 2 * b_bytes,
+                         2 * b_bytes, &bfull[kc]);
+            }
+        } else if (lane == 0) {
             uint32_t it = 0;
             for (long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 for (int kc = 0; kc < p.KC; ++kc, ++it) {
@@ -369,12 +452,14 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const Params p) {
                     const uint32_t ph = (it / p.stages) & 1;
                     const long long cw = tr ? clock64() : 0;
                     mbar_wait(&full[s], ph);
+                    if (p.b_res && tcnt == 0) mbar_wait(&bfull[kc], 0);
                     const long long ci = tr ? clock64() : 0;
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a_hi = smem_u32(stage_base + (size_t)s * stage_bytes);
+                    const uint32_t b_hi = p.b_res ? smem_u32(bres + (size_t)kc * 2 * b_bytes)
+                                                  : a_hi + 2 * a_bytes;
                     const uint64_t dah = make_desc(a_hi), dal = make_desc(a_hi + a_bytes);
-                    const uint64_t dbh = make_desc(a_hi + 2 * a_bytes),
-                                   dbl = make_desc(a_hi + 2 * a_bytes + b_bytes);
+                    const uint64_t dbh = make_desc(b_hi), dbl = make_desc(b_hi + b_bytes);
 #pragma unroll
                     for (int kk = 0; kk < BK / 8; ++kk) {
                         const uint64_t adv = (uint64_t)(kk * 2);  // 32 bytes per K=8 step, >>4
@@ -400,14 +485,27 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const Params p) {
                 g_tc_trace[11] += tcnt;
             }
         }
-    } else {
+    } else if (warp < 4) {
         // ================================ epilogue (warps 0-3) ================================
-        float *stg = epi + warp * 32 * EPI_LD;
+        // tcgen05.ld (lane = row) -> main + corr + bias -> 128B-swizzled staging tile (32 rows x
+        // 32 columns per warp) -> one TMA tensor store per tile; the BatchNorm column statistics
+        // read the same staging tile column-wise.  Fallback without a Y tensor map: padded
+        // staging + coalesced st.global.
+        float *stg = reinterpret_cast<float *>(epi_b) + warp * 32 * EPI_LD;
+        unsigned char *wbuf = epi_b + warp * 8192;
         const int nblk = (p.N + 31) / 32;
+        // BatchNorm statistics: per lane-column fp64 sums of (y - c) and (y - c)^2 with a constant
+        // shift c (the first value this lane sees in the column) so that neither the fp32 partial
+        // sums over 32 rows nor the final variance suffer cancellation; un-shifted once at the end.
         double ssum[4], ssq[4];
+        float cshift[4];
+        long nrows = 0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) ssum[i] = ssq[i] = 0.0;
-        uint32_t tcnt = 0;
+        for (int i = 0; i < 4; ++i) {
+            ssum[i] = ssq[i] = 0.0;
+            cshift[i] = 0.f;
+        }
+        uint32_t tcnt = 0, cbi = 0;
         for (long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcnt) {
             const uint32_t acc = tcnt & 1, aph = (tcnt >> 1) & 1;
             const long m0 = tile * BM + warp * 32;
@@ -416,80 +514,144 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const Params p) {
             mbar_wait(&acc_full[acc], aph);
             const long long ce1 = tr ? clock64() : 0;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const long rows_left = p.M - m0;
+            long long tA = 0, tB = 0, tC = 0, tD = 0;
 #pragma unroll
             for (int cb = 0; cb < 4; ++cb) {
                 if (cb >= nblk) break;
                 const uint32_t ta = tmem_base + ((uint32_t)(warp * 32) << 16) +
                                     acc * (uint32_t)(2 * Nacc) + cb * 32;
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    uint32_t r[16], rc[16];
-                    tmem_ld16_nowait(ta + half * 16, r);
-                    tmem_ld16_nowait(ta + (uint32_t)Nacc + half * 16, rc);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        float4 o;  // main + corrections, round-to-nearest
-                        o.x = __uint_as_float(r[q * 4]) + __uint_as_float(rc[q * 4]);
-                        o.y = __uint_as_float(r[q * 4 + 1]) + __uint_as_float(rc[q * 4 + 1]);
-                        o.z = __uint_as_float(r[q * 4 + 2]) + __uint_as_float(rc[q * 4 + 2]);
-                        o.w = __uint_as_float(r[q * 4 + 3]) + __uint_as_float(rc[q * 4 + 3]);
-                        *reinterpret_cast<float4 *>(stg + lane * EPI_LD + half * 16 + q * 4) = o;
-                    }
-                }
-                __syncwarp();
                 const int col = cb * 32 + lane;
                 const bool col_ok = col < p.N;
-                const float bv = (p.bias && col_ok) ? __ldg(p.bias + col) : 0.f;
-                // all 32 shared-memory reads are issued back to back (independent), then the stores
-                float vals[32];
+                const bool do_stats = p.stats_sum && col_ok && rows_left > 0;
+                const int nv = rows_left >= 32 ? 32 : (int)rows_left;
+                if (p.y_tma) {
+                    unsigned char *buf = wbuf + (cbi & 1) * 4096;
+                    ++cbi;
+                    const long long q0 = tr ? clock64() : 0;
+                    // the tensor store issued from this buffer two blocks ago has read it
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    __syncwarp();
+                    const long long q1 = tr ? clock64() : 0;
 #pragma unroll
-                for (int rr = 0; rr < 32; ++rr) vals[rr] = stg[rr * EPI_LD + lane] + bv;
-                __syncwarp();
-                const long rows_left = p.M - m0;
-                if (col_ok && rows_left > 0) {
-                    float *yp = p.Y + m0 * p.ldy + col;
-                    if (rows_left >= 32) {
+                    for (int half = 0; half < 2; ++half) {
+                        uint32_t r[16], rc[16];
+                        tmem_ld16_nowait(ta + half * 16, r);
+                        tmem_ld16_nowait(ta + (uint32_t)Nacc + half * 16, rc);
+                        tmem_ld_wait();
 #pragma unroll
-                        for (int rr = 0; rr < 32; ++rr) yp[(long)rr * p.ldy] = vals[rr];
-                    } else {
-#pragma unroll
-                        for (int rr = 0; rr < 32; ++rr)
-                            if (rr < rows_left) yp[(long)rr * p.ldy] = vals[rr];
+                        for (int q = 0; q < 4; ++q) {
+                            const float4 b4 =
+                                *reinterpret_cast<const float4 *>(sbias + cb * 32 + half * 16 + q * 4);
+                            float4 o;  // main + corrections (round-to-nearest) + bias
+                            o.x = (__uint_as_float(r[q * 4]) + __uint_as_float(rc[q * 4])) + b4.x;
+                            o.y = (__uint_as_float(r[q * 4 + 1]) + __uint_as_float(rc[q * 4 + 1])) + b4.y;
+                            o.z = (__uint_as_float(r[q * 4 + 2]) + __uint_as_float(rc[q * 4 + 2])) + b4.z;
+                            o.w = (__uint_as_float(r[q * 4 + 3]) + __uint_as_float(rc[q * 4 + 3])) + b4.w;
+                            const int c16 = half * 4 + q;
+                            *reinterpret_cast<float4 *>(buf + lane * 128 + ((c16 ^ (lane & 7)) << 4)) = o;
+                        }
                     }
-                    if (p.stats_sum) {
-                        // shifted fp32 partials (deviations from the first row of the block carry
-                        // no cancellation), recombined exactly in fp64
-                        const int nv = rows_left >= 32 ? 32 : (int)rows_left;
-                        const float c0 = vals[0];
-                        float p1 = 0.f, p2 = 0.f;
+                    const long long q2 = tr ? clock64() : 0;
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    const long long q3 = tr ? clock64() : 0;
+                    if (lane == 0) {
+                        // one bulk group per block even when there is nothing to store: the
+                        // wait_group.read 1 above counts groups to tell which buffer is free
+                        if (rows_left > 0) tma_store_2d(&tmY, cb * 32, (int)m0, buf);  // rows >= M, cols >= N clipped
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    const long long q4 = tr ? clock64() : 0;
+                    tA += q1 - q0; tB += q2 - q1; tC += q3 - q2; tD += q4 - q3;
+                    if (do_stats) {
+                        const unsigned char *colp = buf + (lane & 3) * 4;
+                        const int c16 = lane >> 2;
+                        if (tcnt == 0) cshift[cb] = *reinterpret_cast<const float *>(colp + (c16 << 4));
+                        const float c0 = cshift[cb];
+                        float p1[4] = {0.f, 0.f, 0.f, 0.f}, p2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                        for (int rr = 0; rr < 32; ++rr)
-                            if (rr < nv) {
-                                const float dv = vals[rr] - c0;
-                                p1 += dv;
-                                p2 = __fmaf_rn(dv, dv, p2);
-                            }
-                        const double dc = (double)c0, dn = (double)nv, d1 = (double)p1;
-                        ssum[cb] += d1 + dn * dc;
-                        ssq[cb] += (double)p2 + 2.0 * dc * d1 + dn * dc * dc;
+                        for (int rr = 0; rr < 32; ++rr) {
+                            const float y = *reinterpret_cast<const float *>(
+                                colp + rr * 128 + (((c16 ^ (rr & 7)) & 7) << 4));
+                            const float dv = rr < nv ? y - c0 : 0.f;
+                            p1[rr & 3] += dv;
+                            p2[rr & 3] = __fmaf_rn(dv, dv, p2[rr & 3]);
+                        }
+                        ssum[cb] += (double)((p1[0] + p1[1]) + (p1[2] + p1[3]));
+                        ssq[cb] += (double)((p2[0] + p2[1]) + (p2[2] + p2[3]));
+                    }
+                } else {
+                    float vals[32];
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        uint32_t r[16], rc[16];
+                        tmem_ld16_nowait(ta + half * 16, r);
+                        tmem_ld16_nowait(ta + (uint32_t)Nacc + half * 16, rc);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            float4 o;  // main + corrections, round-to-nearest
+                            o.x = __uint_as_float(r[q * 4]) + __uint_as_float(rc[q * 4]);
+                            o.y = __uint_as_float(r[q * 4 + 1]) + __uint_as_float(rc[q * 4 + 1]);
+                            o.z = __uint_as_float(r[q * 4 + 2]) + __uint_as_float(rc[q * 4 + 2]);
+                            o.w = __uint_as_float(r[q * 4 + 3]) + __uint_as_float(rc[q * 4 + 3]);
+                            *reinterpret_cast<float4 *>(stg + lane * EPI_LD + half * 16 + q * 4) = o;
+                        }
+                    }
+                    __syncwarp();
+                    const float bv = sbias[col & 127];
+                    // all 32 shared-memory reads are issued back to back (independent), then the stores
+#pragma unroll
+                    for (int rr = 0; rr < 32; ++rr) vals[rr] = stg[rr * EPI_LD + lane] + bv;
+                    __syncwarp();
+                    if (col_ok && rows_left > 0) {
+                        float *yp = p.Y + m0 * p.ldy + col;
+                        if (rows_left >= 32) {
+#pragma unroll
+                            for (int rr = 0; rr < 32; ++rr) yp[(long)rr * p.ldy] = vals[rr];
+                        } else {
+#pragma unroll
+                            for (int rr = 0; rr < 32; ++rr)
+                                if (rr < rows_left) yp[(long)rr * p.ldy] = vals[rr];
+                        }
+                    }
+                    if (do_stats) {
+                        if (tcnt == 0) cshift[cb] = vals[0];
+                        const float c0 = cshift[cb];
+                        float p1[4] = {0.f, 0.f, 0.f, 0.f}, p2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                        for (int rr = 0; rr < 32; ++rr) {
+                            const float dv = rr < nv ? vals[rr] - c0 : 0.f;
+                            p1[rr & 3] += dv;
+                            p2[rr & 3] = __fmaf_rn(dv, dv, p2[rr & 3]);
+                        }
+                        ssum[cb] += (double)((p1[0] + p1[1]) + (p1[2] + p1[3]));
+                        ssq[cb] += (double)((p2[0] + p2[1]) + (p2[2] + p2[3]));
                     }
                 }
             }
+            nrows += rows_left >= 32 ? 32 : (rows_left > 0 ? rows_left : 0);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(&acc_empty[acc]);
             if (tr) {
                 g_tc_trace[6] += ce1 - ce0;
                 g_tc_trace[7] += clock64() - ce1;
+                g_tc_trace[12] += tA;
+                g_tc_trace[13] += tB;
+                g_tc_trace[14] += tC;
+                g_tc_trace[15] += tD;
             }
         }
+        if (p.y_tma && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         if (p.stats_sum) {
 #pragma unroll
             for (int cb = 0; cb < 4; ++cb) {
                 const int col = cb * 32 + lane;
-                if (cb < nblk && col < p.N) {
-                    atomicAdd(p.stats_sum + col, ssum[cb]);
-                    atomicAdd(p.stats_sq + col, ssq[cb]);
+                if (cb < nblk && col < p.N && nrows > 0) {
+                    const double c = (double)cshift[cb], n = (double)nrows;
+                    atomicAdd(p.stats_sum + col, ssum[cb] + n * c);
+                    atomicAdd(p.stats_sq + col, ssq[cb] + 2.0 * c * ssum[cb] + n * c * c);
                 }
             }
         }
@@ -516,6 +678,39 @@ static int opt_in_smem(const void *kernel, int slot) {
         done[slot][dev] = true;
     }
     return PN2_OK;
+}
+
+// cuTensorMapEncodeTiled is reached through the runtime's driver entry point query: the library
+// does not link libcuda (it must load on machines without a driver for the ABI tests).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                  const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void *f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return reinterpret_cast<EncodeTiledFn>(f);
+    }();
+    return fn;
+}
+// row-major fp32 matrix [rows x cols], leading dimension ld (floats): box = box_rows x 32 columns
+static bool make_tensor_map(CUtensorMap *tm, const float *base, long rows, int cols, int ld,
+                            int box_rows, bool swizzle128) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn || (ld % 4) != 0 || (reinterpret_cast<uintptr_t>(base) & 15) != 0 || rows <= 0 || cols <= 0)
+        return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    const cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+    const cuuint32_t es[2] = {1u, 1u};
+    return fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, es,
+              CU_TENSOR_MAP_INTERLEAVE_NONE,
+              swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 static size_t image_bytes(int K, int N) {
@@ -545,13 +740,50 @@ static int run_chunk(long M, int K, int Nc, const float *A, int lda, const float
     p.Y = Y;
     p.stats_sum = stats_sum;
     p.stats_sq = stats_sq;
-    const size_t stage_bytes = 2 * (size_t)BM * 128 + 2 * (size_t)p.Npad * 128;
-    const size_t fixed = 4 * 32 * EPI_LD * sizeof(float) + (2 * MAX_STAGES + 4) * 8 + 16;
-    int stages = (int)((227 * 1024 - fixed) / stage_bytes);  // 227 KB usable shared memory per CTA
+    if (p.KC > MAX_KC || Nc > 128) return PN2_EUNSUPPORTED;
+
+    // PN2_TC_TMA bit mask (diagnostics): 1 = tensor loads for A, 2 = tensor stores for Y; default 3
+    static const int tma_mask = getenv("PN2_TC_TMA") ? atoi(getenv("PN2_TC_TMA")) : 3;
+    CUtensorMap tmA, tmY;
+    memset(&tmA, 0, sizeof(tmA));
+    memset(&tmY, 0, sizeof(tmY));
+    p.a_tma = ((tma_mask & 1) && M < (1l << 31) && make_tensor_map(&tmA, A, M, K, lda, BM, false)) ? 1 : 0;
+    p.y_tma = ((tma_mask & 2) && M < (1l << 31) && make_tensor_map(&tmY, Y, M, Nc, ldy, 32, true)) ? 1 : 0;
+
+    // shared memory plan (227 KB usable per CTA): raw ring (4 slots if possible), >= 2 MMA stages,
+    // weights resident when they fit next to that
+    const size_t a_stage = 2 * (size_t)BM * 128, b_chunk = 2 * (size_t)p.Npad * 128;
+    const size_t fixed = EPI_BYTES + 512 + (2 * MAX_STAGES + 4 + MAX_KC + 2 * MAX_RAW) * 8 + 16;
+    const size_t budget = 227 * 1024 - fixed;
+    static const int force_stream = getenv("PN2_TC_STREAM_B") ? atoi(getenv("PN2_TC_STREAM_B")) : 0;
+    const size_t bres = (size_t)p.KC * b_chunk;
+    // (an even number of raw slots: the two transform groups must each own fixed slots, otherwise
+    //  a group could test a slot's mbarrier one phase early)
+    int raw_slots = p.a_tma ? MAX_RAW : 0, stages = 0;
+    p.b_res = 0;
+    for (;; raw_slots -= 2) {
+        const size_t rawb = (size_t)raw_slots * RAW_BYTES;
+        if (!force_stream && bres + 2 * a_stage + rawb <= budget) {
+            p.b_res = 1;
+            stages = (int)((budget - bres - rawb) / a_stage);
+            break;
+        }
+        if (2 * (a_stage + b_chunk) + rawb <= budget) {
+            stages = (int)((budget - rawb) / (a_stage + b_chunk));
+            break;
+        }
+        if (raw_slots <= (p.a_tma ? 2 : 0)) {  // last resort: a single stage
+            stages = (int)((budget - rawb) / (a_stage + b_chunk));
+            break;
+        }
+    }
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     if (stages < 1) return PN2_EUNSUPPORTED;
     p.stages = stages;
-    const size_t smem = (size_t)stages * stage_bytes + fixed;
+    p.raw_slots = raw_slots;
+    const size_t stage_bytes = p.b_res ? a_stage : a_stage + b_chunk;
+    const size_t smem = (p.b_res ? bres : 0) + (size_t)stages * stage_bytes +
+                        (size_t)raw_slots * RAW_BYTES + fixed;
 
     const long total = (long)p.KC * p.Npad * BK;
     int pb = (int)((total + 255) / 256);
@@ -566,7 +798,7 @@ static int run_chunk(long M, int K, int Nc, const float *A, int lda, const float
     if (rc) return rc;
     const long tiles = (M + BM - 1) / BM;
     const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-    tc_gemm_kernel<<<grid, THREADS, smem, st>>>(p);
+    tc_gemm_kernel<<<grid, THREADS, smem, st>>>(tmA, tmY, p);
     return finish_launch();
 }
 
@@ -581,20 +813,32 @@ static int run_chunk(long M, int K, int Nc, const float *A, int lda, const float
 // operands, SW128_32B is the only available smem layout"): atoms of 4 contraction rows x 128 B
 // (32 fp32 of the feature/column index), the four 32-byte chunks of a row XOR-permuted by the row
 // index (Swizzle<2,5,2>).  An atom is 4 consecutive rows of the row-major source, so the
-// producers copy rows (transform + hi/lo split) without any transpose.
-// The M rows are cut into segments of 512 rows; each segment accumulates into its own TMEM
-// accumulator pair (double buffered) and is flushed to dW with fp32 atomics by the epilogue warps.
-// Short segments bound the number of truncating tensor-core accumulations (64 per segment).
+// transform warps copy rows (BN affine + ReLU, hi/lo split) without any transpose.
+//
+// Work decomposition: one launch, persistent CTAs over units (row segment, 128-feature block,
+// 128-column block).  The row segments are sized so that the units fill the machine (short
+// problems get 128-row segments, long ones up to 512 rows); each unit accumulates in its own TMEM
+// accumulator pair (double buffered) and is flushed to dW with vectorised fp32 reductions
+// (red.global.add.v4.f32) straight from the TMEM registers.  Segments of at most 512 rows bound
+// the number of truncating tensor-core accumulations (64 per accumulator).
+// Data path: TMA tensor loads of raw X / dY row blocks into a 2-slot ring (the loads run ahead
+// of the math, nothing is staged through registers) -> two transform groups of 4 warps -> 2 MMA
+// stages.  A stage holds 32 / 64 / 128 contraction rows depending on the operand widths so that
+// every transform thread always moves 8 + 8 float4.
 // =====================================================================================================
 namespace tcw {
 using namespace tc;
 
-constexpr int W_NPG = 2;                        // independent producer groups (stages of loads in flight)
-constexpr int W_WMMA = 4 + 4 * W_NPG;            // MMA / TMEM warp
-constexpr int W_THREADS = 32 * (W_WMMA + 1);  // warps 0-3 epilogue, 4.. producers, last MMA
-constexpr int W_ROWS = 32;      // contraction rows per stage (4 MMAs of K=8)
-constexpr int W_SEG = 512;      // contraction rows per accumulator segment
-constexpr int W_FEAT = 128;     // features (rows of dW) per CTA pass = UMMA M
+constexpr int W_NPG = 2;                        // transform groups (stages in flight)
+constexpr int W_LOAD = 4 + 4 * W_NPG;           // TMA loader warp
+constexpr int W_WMMA = W_LOAD + 1;              // MMA / TMEM warp
+constexpr int W_THREADS = 32 * (W_WMMA + 1);    // warps 0-3 epilogue, 4-11 transform, loader, MMA
+constexpr int W_MAXSEG = 512;   // contraction rows per accumulator segment (accuracy bound)
+constexpr int W_FEAT = 128;     // features (rows of dW) per unit = UMMA M
+constexpr int W_RAW = 2;        // raw ring slots: one per transform group (an even count is required:
+                                // with slots shared between the groups a group could test a slot's
+                                // mbarrier one phase early)
+constexpr int W_STAGES = 2;     // MMA stages
 
 __device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr, uint32_t lbo_bytes,
                                                  uint32_t sbo_bytes) {
@@ -607,35 +851,52 @@ __device__ __forceinline__ uint32_t mn_offset(int r, int c4, int groups) {
     return (uint32_t)(((r >> 2) * groups + (c4 >> 3)) * 512 + (r & 3) * 128 +
                       (((((c4 & 7) >> 1) ^ (r & 3)) & 3) << 5) + ((c4 & 1) << 4));
 }
+__device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c),
+                 "f"(d)
+                 : "memory");
+}
 
 struct WParams {
-    long M;
-    int K, N, Npad, NG, lda, ldy, ldw, a_relu, k0, n0, stages;
-    int dbg;  // PN2_DBG_WGRAD bit mask (diagnostics only): 1 skip atomics, 2 skip dY loads, 4 skip X loads
-    const float *A, *a_scale, *a_shift, *dY;
+    long M, nseg, units;
+    int K, N, Kdo, ldw, a_relu;
+    int MG, NG;      // 32-feature groups of X / 32-column groups of dY held per stage (1..4)
+    int rows;        // contraction rows per stage: 128 / max(MG,NG) rounded to 32, 64, 128
+    int seg_rows;    // rows per unit (multiple of rows, <= W_MAXSEG)
+    int KB, NB;      // feature blocks / column blocks
+    const float *a_scale, *a_shift;
     float *dW;
 };
 
-__global__ void __launch_bounds__(W_THREADS, 1) tc_wgrad_kernel(const WParams p) {
+__global__ void __launch_bounds__(W_THREADS, 1)
+    tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG,
+                    const WParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    const uint32_t a_bytes = 8 * 4 * 512;                  // [k-group 8][mg 4] atoms of 512 B
-    const uint32_t b_bytes = 8 * (uint32_t)p.NG * 512;     // [k-group 8][ng NG] atoms
-    const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
-    float *epi = reinterpret_cast<float *>(smem + (size_t)p.stages * stage_bytes);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(epi + 4 * 32 * EPI_LD);
-    uint64_t *full = bars, *empty = bars + MAX_STAGES;
-    uint64_t *acc_full = bars + 2 * MAX_STAGES, *acc_empty = bars + 2 * MAX_STAGES + 2;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * MAX_STAGES + 4);
+    // carve: W_STAGES x [X_hi | X_lo | G_hi | G_lo], W_RAW x [X raw | G raw], barriers
+    const uint32_t a_bytes = (uint32_t)p.rows * p.MG * 128;
+    const uint32_t b_bytes = (uint32_t)p.rows * p.NG * 128;
+    const uint32_t raw_bytes = a_bytes + b_bytes;
+    const uint32_t stage_bytes = 2 * raw_bytes;
+    unsigned char *raw = smem + (size_t)W_STAGES * stage_bytes;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(raw + (size_t)W_RAW * raw_bytes);
+    uint64_t *full = bars, *empty = bars + W_STAGES;           // MMA stages
+    uint64_t *raw_full = bars + 2 * W_STAGES, *raw_empty = raw_full + W_RAW;
+    uint64_t *acc_full = raw_empty + W_RAW, *acc_empty = acc_full + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int Nacc = p.Npad;  // multiple of 32
+    const int Nacc = 32 * p.NG;
     uint32_t ncols = 32;
     while (ncols < (uint32_t)(4 * Nacc)) ncols <<= 1;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < p.stages; ++s) {
+        for (int s = 0; s < W_STAGES; ++s) {
             mbar_init(&full[s], 128);
             mbar_init(&empty[s], 1);
+        }
+        for (int r = 0; r < W_RAW; ++r) {
+            mbar_init(&raw_full[r], 1);
+            mbar_init(&raw_empty[r], 128);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&acc_full[a], 1);
@@ -655,104 +916,77 @@ __global__ void __launch_bounds__(W_THREADS, 1) tc_wgrad_kernel(const WParams p)
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
-    const long num_seg = (p.M + W_SEG - 1) / W_SEG;
+    const int upb = p.KB * p.NB;  // units per row segment; consecutive units share their rows (L2)
+    // stages of unit u: rows [seg*seg_rows, min(M, (seg+1)*seg_rows)) in steps of p.rows
+    auto unit_stages = [&](long u) -> int {
+        const long seg0 = (u / upb) * (long)p.seg_rows;
+        const long len = min((long)p.seg_rows, p.M - seg0);
+        return (int)((len + p.rows - 1) / p.rows);
+    };
 
-    if (warp >= 4 && warp < W_WMMA) {
-        // ================================ producers ================================
-        // three independent groups of 128 threads take stages round-robin (three stages of global
-        // loads in flight); every thread issues ALL its loads of a stage (8 float4 of X rows,
-        // up to 8 float4 of dY rows) before the first use, then splits and stores
+    if (warp >= 4 && warp < W_LOAD) {
+        // ================================ transform ================================
         const int g = (warp - 4) >> 2;
-        const int npg = W_NPG < p.stages ? W_NPG : p.stages;
         const int tt = (threadIdx.x - 128) & 127;
-        const bool a_vec = (p.lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0) &&
-                           (p.k0 % 4 == 0);
-        const bool b_vec = (p.ldy % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.dY) & 15) == 0) &&
-                           (p.n0 % 4 == 0);
-        const int bw4 = p.Npad >> 2;               // float4 per dY row (8, 16, 24 or 32)
-        const int b_iters = (W_ROWS * bw4) >> 7;   // Npad/16 <= 8
-        const int c4 = tt & 31, rr = tt >> 5;      // A part: float4 slot / base row
-        const int kf = p.k0 + 4 * c4;
-        float sc[4] = {0.f, 0.f, 0.f, 0.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
-        if (p.a_scale) {
+        const int aw4 = 8 * p.MG, bw4 = 8 * p.NG;         // float4 per raw row
+        const int a_iters = (p.rows * p.MG) >> 4;          // <= 8
+        const int b_iters = (p.rows * p.NG) >> 4;          // <= 8
+        const int ac4 = tt % aw4, ar0 = tt / aw4, ar_step = 128 / aw4;  // 128 % aw4 == 0
+        uint32_t it = 0;
+        for (long u = blockIdx.x; u < p.units; u += gridDim.x) {
+            const long seg0 = (u / upb) * (long)p.seg_rows;
+            const int k0 = (int)((u % upb) / p.NB) * W_FEAT;
+            const int nst = unit_stages(u);
+            const int kf = k0 + 4 * ac4;
+            float sc[4] = {0.f, 0.f, 0.f, 0.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
+            if (p.a_scale) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (kf + j < p.K) {
-                    sc[j] = __ldg(p.a_scale + kf + j);
-                    sh[j] = __ldg(p.a_shift + kf + j);
-                }
-        }
-        // flat stage sequence of this CTA: segment-major, 16 stages per full segment
-        const long my_segs = blockIdx.x < num_seg ? (num_seg - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-        long itl = 0;
-        if (g < npg) {
-            for (long sg = 0; sg < my_segs; ++sg) {
-                const long seg0 = (blockIdx.x + sg * gridDim.x) * (long)W_SEG;
-                const int nst = (int)((min((long)W_SEG, p.M - seg0) + W_ROWS - 1) / W_ROWS);
-                for (int sidx = 0; sidx < nst; ++sidx, ++itl) {
-                    if ((int)(itl % npg) != g) continue;
-                    const uint32_t it = (uint32_t)itl;
-                    const int s = it % p.stages;
-                    const uint32_t ph = (it / p.stages) & 1;
-                    const long mbase = seg0 + (long)sidx * W_ROWS;
-                    unsigned char *st_base = smem + (size_t)s * stage_bytes;
-                    float4 va[8], vb[8];
+                for (int j = 0; j < 4; ++j)
+                    if (kf + j < p.Kdo) {
+                        sc[j] = __ldg(p.a_scale + kf + j);
+                        sh[j] = __ldg(p.a_shift + kf + j);
+                    }
+            }
+            for (int sidx = 0; sidx < nst; ++sidx, ++it) {
+                if ((int)(it % W_NPG) != g) continue;
+                const int s = it % W_STAGES;
+                const uint32_t ph = (it / W_STAGES) & 1;
+                const int rs = it % W_RAW;
+                const uint32_t rph = (it / W_RAW) & 1;
+                const long mbase = seg0 + (long)sidx * p.rows;
+                const unsigned char *rx = raw + (size_t)rs * raw_bytes;
+                const unsigned char *rg = rx + a_bytes;
+                float4 va[8], vb[8];
+                mbar_wait(&raw_full[rs], rph);
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if (i < a_iters)
+                        va[i] = *reinterpret_cast<const float4 *>(rx + (size_t)(tt + 128 * i) * 16);
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    if (q < b_iters)
+                        vb[q] = *reinterpret_cast<const float4 *>(rg + (size_t)(tt + 128 * q) * 16);
+                if (p.a_scale) {
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        const long m = mbase + rr + 4 * i;
-                        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (m < p.M && kf < p.K && !(p.dbg & 4)) {
-                            const float *src = p.A + m * p.lda + kf;
-                            if (a_vec && kf + 3 < p.K) {
-                                x = __ldg(reinterpret_cast<const float4 *>(src));
-                            } else {
-                                x.x = __ldg(src);
-                                if (kf + 1 < p.K) x.y = __ldg(src + 1);
-                                if (kf + 2 < p.K) x.z = __ldg(src + 2);
-                                if (kf + 3 < p.K) x.w = __ldg(src + 3);
-                            }
-                        }
-                        va[i] = x;
-                    }
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (q < b_iters) {
-                            const int e = tt + 128 * q;
-                            const int bc4 = e % bw4, r = e / bw4;
-                            const long m = mbase + r;
-                            const int nf = p.n0 + 4 * bc4;
-                            if (m < p.M && nf < p.N && !(p.dbg & 2)) {
-                                const float *src = p.dY + m * p.ldy + nf;
-                                if (b_vec && nf + 3 < p.N) {
-                                    x = __ldg(reinterpret_cast<const float4 *>(src));
-                                } else {
-                                    x.x = __ldg(src);
-                                    if (nf + 1 < p.N) x.y = __ldg(src + 1);
-                                    if (nf + 2 < p.N) x.z = __ldg(src + 2);
-                                    if (nf + 3 < p.N) x.w = __ldg(src + 3);
-                                }
-                            }
-                        }
-                        vb[q] = x;
-                    }
-                    if (p.a_scale) {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const bool row_ok = (mbase + rr + 4 * i) < p.M;
+                        if (i < a_iters) {
+                            const bool row_ok = (mbase + ar0 + ar_step * i) < p.M;
                             float *e = reinterpret_cast<float *>(&va[i]);
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
                                 float y = __fmaf_rn(e[j], sc[j], sh[j]);
                                 if (p.a_relu) y = fmaxf(y, 0.f);
-                                e[j] = (row_ok && kf + j < p.K) ? y : 0.f;
+                                e[j] = (row_ok && kf + j < p.Kdo) ? y : 0.f;
                             }
                         }
                     }
-                    mbar_wait(&empty[s], ph ^ 1);
+                }
+                unsigned char *st_base = smem + (size_t)s * stage_bytes;
+                mbar_wait(&empty[s], ph ^ 1);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const uint32_t off = mn_offset(rr + 4 * i, c4, 4);
+                for (int i = 0; i < 8; ++i) {
+                    if (i < a_iters) {
+                        const uint32_t off = mn_offset(ar0 + ar_step * i, ac4, p.MG);
                         float4 hi, lo;
                         hi.x = tf32_rna(va[i].x); lo.x = va[i].x - hi.x;
                         hi.y = tf32_rna(va[i].y); lo.y = va[i].y - hi.y;
@@ -761,38 +995,62 @@ __global__ void __launch_bounds__(W_THREADS, 1) tc_wgrad_kernel(const WParams p)
                         *reinterpret_cast<float4 *>(st_base + off) = hi;
                         *reinterpret_cast<float4 *>(st_base + a_bytes + off) = lo;
                     }
-                    unsigned char *b_hi = st_base + 2 * a_bytes;
+                }
+                unsigned char *b_hi = st_base + 2 * a_bytes;
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        if (q < b_iters) {
-                            const int e = tt + 128 * q;
-                            const uint32_t off = mn_offset(e / bw4, e % bw4, p.NG);
-                            float4 hi, lo;
-                            hi.x = tf32_rna(vb[q].x); lo.x = vb[q].x - hi.x;
-                            hi.y = tf32_rna(vb[q].y); lo.y = vb[q].y - hi.y;
-                            hi.z = tf32_rna(vb[q].z); lo.z = vb[q].z - hi.z;
-                            hi.w = tf32_rna(vb[q].w); lo.w = vb[q].w - hi.w;
-                            *reinterpret_cast<float4 *>(b_hi + off) = hi;
-                            *reinterpret_cast<float4 *>(b_hi + b_bytes + off) = lo;
-                        }
+                for (int q = 0; q < 8; ++q) {
+                    if (q < b_iters) {
+                        const int e = tt + 128 * q;
+                        const uint32_t off = mn_offset(e / bw4, e % bw4, p.NG);
+                        float4 hi, lo;
+                        hi.x = tf32_rna(vb[q].x); lo.x = vb[q].x - hi.x;
+                        hi.y = tf32_rna(vb[q].y); lo.y = vb[q].y - hi.y;
+                        hi.z = tf32_rna(vb[q].z); lo.z = vb[q].z - hi.z;
+                        hi.w = tf32_rna(vb[q].w); lo.w = vb[q].w - hi.w;
+                        *reinterpret_cast<float4 *>(b_hi + off) = hi;
+                        *reinterpret_cast<float4 *>(b_hi + b_bytes + off) = lo;
                     }
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    mbar_arrive(&full[s]);
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive(&full[s]);
+                mbar_arrive(&raw_empty[rs]);  // after the fence: see the forward kernel
+            }
+        }
+    } else if (warp == W_LOAD) {
+        // ================================ TMA loader ================================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (long u = blockIdx.x; u < p.units; u += gridDim.x) {
+                const long seg0 = (u / upb) * (long)p.seg_rows;
+                const int k0 = (int)((u % upb) / p.NB) * W_FEAT;
+                const int n0 = (int)(u % p.NB) * 128;
+                const int nst = unit_stages(u);
+                for (int sidx = 0; sidx < nst; ++sidx, ++it) {
+                    const int rs = it % W_RAW;
+                    const uint32_t rph = (it / W_RAW) & 1;
+                    const int m = (int)(seg0 + (long)sidx * p.rows);
+                    mbar_wait(&raw_empty[rs], rph ^ 1);
+                    mbar_expect_tx(&raw_full[rs], raw_bytes);
+                    unsigned char *dst = raw + (size_t)rs * raw_bytes;
+                    tma_load_2d(dst, &tmX, k0, m, &raw_full[rs]);          // rows/features out of range: 0
+                    tma_load_2d(dst + a_bytes, &tmG, n0, m, &raw_full[rs]);
                 }
             }
         }
     } else if (warp == W_WMMA) {
         // ================================ MMA issuer ================================
         if (lane == 0) {
-            const uint32_t idesc = make_idesc(p.Npad) | (1u << 15) | (1u << 16);  // A, B MN-major
-            uint32_t it = 0, tcnt = 0;
+            // UMMA M is always 128: feature groups >= MG read shared memory of the neighbouring
+            // atoms and produce accumulator rows that nobody reads
+            const uint32_t idesc = make_idesc(Nacc) | (1u << 15) | (1u << 16);  // A, B MN-major
+            uint32_t it = 0, ucnt = 0;
             const bool tr = blockIdx.x == 0;
             const long long k0c = tr ? clock64() : 0;
             long long w_full = 0, w_issue = 0, w_acc = 0;
-            for (long seg = blockIdx.x; seg < num_seg; seg += gridDim.x, ++tcnt) {
-                const long seg0 = seg * W_SEG;
-                const int nst = (int)((min((long)W_SEG, p.M - seg0) + W_ROWS - 1) / W_ROWS);
-                const uint32_t acc = tcnt & 1, aph = (tcnt >> 1) & 1;
+            const int ksteps = p.rows / 8;
+            for (long u = blockIdx.x; u < p.units; u += gridDim.x, ++ucnt) {
+                const int nst = unit_stages(u);
+                const uint32_t acc = ucnt & 1, aph = (ucnt >> 1) & 1;
                 const long long ca = tr ? clock64() : 0;
                 mbar_wait(&acc_empty[acc], aph ^ 1);
                 if (tr) w_acc += clock64() - ca;
@@ -800,23 +1058,23 @@ __global__ void __launch_bounds__(W_THREADS, 1) tc_wgrad_kernel(const WParams p)
                 const uint32_t d = tmem_base + acc * (uint32_t)(2 * Nacc);
                 const uint32_t dc = d + (uint32_t)Nacc;
                 for (int sidx = 0; sidx < nst; ++sidx, ++it) {
-                    const int s = it % p.stages;
-                    const uint32_t ph = (it / p.stages) & 1;
+                    const int s = it % W_STAGES;
+                    const uint32_t ph = (it / W_STAGES) & 1;
                     const long long cw = tr ? clock64() : 0;
                     mbar_wait(&full[s], ph);
                     const long long ci = tr ? clock64() : 0;
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a_hi = smem_u32(smem + (size_t)s * stage_bytes);
                     const uint32_t b_hi = a_hi + 2 * a_bytes;
-#pragma unroll
-                    for (int kg = 0; kg < 4; ++kg) {
+                    for (int ks = 0; ks < ksteps; ++ks) {
                         // one K=8 MMA spans two 4-row k-groups: LBO = next MN group (512 B),
                         // SBO = next k-group (groups * 512 B)
-                        const uint64_t dah = make_desc_mn(a_hi + kg * 4096, 512, 2048);
-                        const uint64_t dal = make_desc_mn(a_hi + a_bytes + kg * 4096, 512, 2048);
-                        const uint64_t dbh = make_desc_mn(b_hi + kg * p.NG * 1024, 512, p.NG * 512);
-                        const uint64_t dbl = make_desc_mn(b_hi + b_bytes + kg * p.NG * 1024, 512, p.NG * 512);
-                        const uint32_t accum = (sidx > 0 || kg > 0) ? 1u : 0u;
+                        const uint32_t ao = ks * p.MG * 1024, bo = ks * p.NG * 1024;
+                        const uint64_t dah = make_desc_mn(a_hi + ao, 512, p.MG * 512);
+                        const uint64_t dal = make_desc_mn(a_hi + a_bytes + ao, 512, p.MG * 512);
+                        const uint64_t dbh = make_desc_mn(b_hi + bo, 512, p.NG * 512);
+                        const uint64_t dbl = make_desc_mn(b_hi + b_bytes + bo, 512, p.NG * 512);
+                        const uint32_t accum = (sidx > 0 || ks > 0) ? 1u : 0u;
                         umma_tf32(d, dah, dbh, idesc, accum);
                         umma_tf32(dc, dal, dbh, idesc, accum);
                         umma_tf32(dc, dah, dbl, idesc, 1u);
@@ -835,51 +1093,50 @@ __global__ void __launch_bounds__(W_THREADS, 1) tc_wgrad_kernel(const WParams p)
                 g_tc_trace[2] += w_acc;
                 g_tc_trace[9] += clock64() - k0c;
                 g_tc_trace[10] += it;
-                g_tc_trace[11] += tcnt;
+                g_tc_trace[11] += ucnt;
             }
         }
     } else if (warp < 4) {
         // ================================ epilogue ================================
-        float *stg = epi + warp * 32 * EPI_LD;
-        const int nblk = p.Npad / 32;
-        uint32_t tcnt = 0;
-        for (long seg = blockIdx.x; seg < num_seg; seg += gridDim.x, ++tcnt) {
-            const uint32_t acc = tcnt & 1, aph = (tcnt >> 1) & 1;
+        // lane = feature row of dW; 16 consecutive columns per tcgen05.ld -> 4 vector reductions
+        uint32_t ucnt = 0;
+        for (long u = blockIdx.x; u < p.units; u += gridDim.x, ++ucnt) {
+            const int k0 = (int)((u % upb) / p.NB) * W_FEAT;
+            const int n0 = (int)(u % p.NB) * 128;
+            const uint32_t acc = ucnt & 1, aph = (ucnt >> 1) & 1;
             mbar_wait(&acc_full[acc], aph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            for (int cb = 0; cb < nblk; ++cb) {
-                const uint32_t ta = tmem_base + ((uint32_t)(warp * 32) << 16) +
-                                    acc * (uint32_t)(2 * Nacc) + cb * 32;
+            const int k = k0 + warp * 32 + lane;
+            if (warp < p.MG) {
+                float *wrow = p.dW + (long)k * p.ldw;
+                for (int cb = 0; cb < p.NG; ++cb) {
+                    const uint32_t ta = tmem_base + ((uint32_t)(warp * 32) << 16) +
+                                        acc * (uint32_t)(2 * Nacc) + cb * 32;
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    uint32_t r[16], rc[16];
-                    tmem_ld16_nowait(ta + half * 16, r);
-                    tmem_ld16_nowait(ta + (uint32_t)Nacc + half * 16, rc);
-                    tmem_ld_wait();
+                    for (int half = 0; half < 2; ++half) {
+                        uint32_t r[16], rc[16];
+                        tmem_ld16_nowait(ta + half * 16, r);
+                        tmem_ld16_nowait(ta + (uint32_t)Nacc + half * 16, rc);
+                        tmem_ld_wait();
+                        if (k < p.Kdo) {
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        float4 o;
-                        o.x = __uint_as_float(r[q * 4]) + __uint_as_float(rc[q * 4]);
-                        o.y = __uint_as_float(r[q * 4 + 1]) + __uint_as_float(rc[q * 4 + 1]);
-                        o.z = __uint_as_float(r[q * 4 + 2]) + __uint_as_float(rc[q * 4 + 2]);
-                        o.w = __uint_as_float(r[q * 4 + 3]) + __uint_as_float(rc[q * 4 + 3]);
-                        *reinterpret_cast<float4 *>(stg + lane * EPI_LD + half * 16 + q * 4) = o;
+                            for (int q = 0; q < 4; ++q) {
+                                const int n = n0 + cb * 32 + half * 16 + q * 4;
+                                const float o0 = __uint_as_float(r[q * 4]) + __uint_as_float(rc[q * 4]);
+                                const float o1 = __uint_as_float(r[q * 4 + 1]) + __uint_as_float(rc[q * 4 + 1]);
+                                const float o2 = __uint_as_float(r[q * 4 + 2]) + __uint_as_float(rc[q * 4 + 2]);
+                                const float o3 = __uint_as_float(r[q * 4 + 3]) + __uint_as_float(rc[q * 4 + 3]);
+                                if (n + 3 < p.N) {
+                                    red_add_v4(wrow + n, o0, o1, o2, o3);  // N % 4 == 0: 16-byte aligned
+                                } else {
+                                    if (n < p.N) atomicAdd(wrow + n, o0);
+                                    if (n + 1 < p.N) atomicAdd(wrow + n + 1, o1);
+                                    if (n + 2 < p.N) atomicAdd(wrow + n + 2, o2);
+                                }
+                            }
+                        }
                     }
                 }
-                __syncwarp();
-                float vals[32];
-#pragma unroll
-                for (int rr = 0; rr < 32; ++rr) vals[rr] = stg[rr * EPI_LD + lane];
-                const int n = p.n0 + cb * 32 + lane;
-                const int kb = p.k0 + warp * 32;
-                if (n < p.N && kb < p.K && !(p.dbg & 1)) {
-                    float *wp = p.dW + (long)kb * p.ldw + n;
-                    const int kv = p.K - kb;
-#pragma unroll
-                    for (int rr = 0; rr < 32; ++rr)
-                        if (rr < kv) atomicAdd(wp + (long)rr * p.ldw, vals[rr]);
-                }
-                __syncwarp();
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(&acc_empty[acc]);
@@ -896,49 +1153,70 @@ __global__ void __launch_bounds__(W_THREADS, 1) tc_wgrad_kernel(const WParams p)
     }
 }
 
+// row-major fp32 matrix [rows x cols] (leading dimension ld): box = box_rows x box_cols, no swizzle
+static bool make_map(CUtensorMap *tm, const float *base, long rows, int cols, int ld, int box_rows,
+                     int box_cols) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn || (ld % 4) != 0 || (reinterpret_cast<uintptr_t>(base) & 15) != 0 || rows <= 0 || cols <= 0)
+        return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    const cuuint32_t es[2] = {1u, 1u};
+    return fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, es,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 static int run(long M, int K, int Kdo, int N, const float *A, int lda, const float *a_scale,
                const float *a_shift, int a_relu, const float *dY, float *dW, cudaStream_t st) {
-    for (int n0 = 0; n0 < N; n0 += 128) {
-        for (int k0 = 0; k0 < Kdo; k0 += W_FEAT) {
-            WParams p;
-            p.M = M;
-            p.K = K;
-            p.N = N;
-            const int nc = (N - n0) < 128 ? (N - n0) : 128;
-            p.Npad = (nc + 31) & ~31;
-            p.NG = p.Npad / 32;
-            p.lda = lda;
-            p.ldy = N;
-            p.ldw = N;
-            p.a_relu = a_relu;
-            p.k0 = k0;
-            p.n0 = n0;
-            p.A = A;
-            p.a_scale = a_scale;
-            p.a_shift = a_shift;
-            p.dY = dY;
-            p.dW = dW;
-            {
-                const char *e = getenv("PN2_DBG_WGRAD");
-                p.dbg = e ? atoi(e) : 0;
-            }
-            const size_t stage_bytes = 2 * 16384 + 2 * (size_t)p.NG * 4096;
-            const size_t fixed = 4 * 32 * EPI_LD * sizeof(float) + (2 * MAX_STAGES + 4) * 8 + 16;
-            int stages = (int)((227 * 1024 - fixed) / stage_bytes);
-            if (stages > MAX_STAGES) stages = MAX_STAGES;
-            if (stages < 1) return PN2_EUNSUPPORTED;
-            p.stages = stages;
-            const size_t smem = (size_t)stages * stage_bytes + fixed;
-            int rc = tc::opt_in_smem(reinterpret_cast<const void *>(tc_wgrad_kernel), 1);
-            if (rc) return rc;
-            const long segs = (M + W_SEG - 1) / W_SEG;
-            const int grid = (int)(segs < num_sms() ? segs : num_sms());
-            tc_wgrad_kernel<<<grid, W_THREADS, smem, st>>>(p);
-            rc = finish_launch();
-            if (rc) return rc;
+    WParams p;
+    p.M = M;
+    p.K = K;
+    p.N = N;
+    p.Kdo = Kdo;
+    p.ldw = N;
+    p.a_relu = a_relu;
+    p.a_scale = a_scale;
+    p.a_shift = a_shift;
+    p.dW = dW;
+    p.KB = (Kdo + W_FEAT - 1) / W_FEAT;
+    p.NB = (N + 127) / 128;
+    p.MG = Kdo >= W_FEAT ? 4 : (Kdo + 31) / 32;
+    if (p.MG == 3) p.MG = 4;  // transform threads keep fixed feature columns: 128 % (8*MG) == 0
+    p.NG = N >= 128 ? 4 : (N + 31) / 32;
+    const int mx = p.MG > p.NG ? p.MG : p.NG;
+    p.rows = mx == 1 ? 128 : (mx == 2 ? 64 : 32);
+    // row segments: as long as allowed (<= 512 rows) while the units still fill the machine twice
+    const int upb = p.KB * p.NB;
+    const int min_seg = p.rows > 128 ? p.rows : 128;
+    int seg = W_MAXSEG;
+    for (int r = 2; r <= 64; r += 2) {
+        long S = (long)num_sms() * r / upb;
+        if (S < 1) S = 1;
+        long sr = ((M + S - 1) / S + p.rows - 1) / p.rows * p.rows;
+        if (sr < min_seg) sr = min_seg;
+        if (sr <= W_MAXSEG) {
+            seg = (int)sr;
+            break;
         }
     }
-    return PN2_OK;
+    p.seg_rows = seg;
+    p.nseg = (M + seg - 1) / seg;
+    p.units = p.nseg * upb;
+
+    CUtensorMap tmX, tmG;
+    if (!make_map(&tmX, A, M, Kdo, lda, p.rows, 32 * p.MG) ||
+        !make_map(&tmG, dY, M, N, N, p.rows, 32 * p.NG))
+        return PN2_EUNSUPPORTED;
+
+    const size_t raw_bytes = (size_t)p.rows * (p.MG + p.NG) * 128;
+    const size_t smem = (size_t)(2 * W_STAGES + W_RAW) * raw_bytes + (2 * W_STAGES + 2 * W_RAW + 4) * 8 + 16;
+    int rc = tc::opt_in_smem(reinterpret_cast<const void *>(tc_wgrad_kernel), 1);
+    if (rc) return rc;
+    const int grid = (int)(p.units < num_sms() ? p.units : num_sms());
+    tc_wgrad_kernel<<<grid, W_THREADS, smem, st>>>(tmX, tmG, p);
+    return finish_launch();
 }
 
 }  // namespace tcw
@@ -947,16 +1225,16 @@ int tc_linear_wgrad(long M, int K, int N, const float *A, int lda, const float *
                     const float *a_shift, int a_relu, const float *dY, float *dW, bool force,
                     int *k_done, cudaStream_t st) {
     *k_done = 0;
-    if (M < 2048 || N < 16 || K < 4) return PN2_EUNSUPPORTED;
-    // measured on B200 (tests/bench_gemm.py): the 128-feature MMA tile only pays off for wide
-    // layers with many rows; narrow or short problems are faster on the split-K fp32 kernel
-    if (!force && (M < 65536 || K < 64 || N < 64)) return PN2_EUNSUPPORTED;
+    // tensor maps need 16-byte aligned rows (lda % 4, N % 4) and 16-byte aligned bases
+    if (M < 512 || N < 16 || K < 4 || (N % 4) != 0 || (lda % 4) != 0 || M >= (1l << 31))
+        return PN2_EUNSUPPORTED;
     // a narrow tail of features (K = 131 -> 3) would cost a full extra pass over dY on the
     // 128-feature MMA tile; it is left to the caller's fp32 kernel (k_done tells where it starts)
     int Kdo = K;
     if (!force && K > tcw::W_FEAT && (K % tcw::W_FEAT) < 32) Kdo = K - (K % tcw::W_FEAT);
-    *k_done = Kdo;
-    return tcw::run(M, K, Kdo, N, A, lda, a_scale, a_shift, a_relu, dY, dW, st);
+    int rc = tcw::run(M, K, Kdo, N, A, lda, a_scale, a_shift, a_relu, dY, dW, st);
+    if (rc == PN2_OK) *k_done = Kdo;
+    return rc;
 }
 
 // Shapes worth the tensor cores: at least one full tile of rows, K and N not tiny.

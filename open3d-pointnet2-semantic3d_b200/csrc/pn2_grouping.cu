@@ -290,7 +290,7 @@ __global__ void group_point_grad_kernel(int n, int c, long rows_per_cloud, long 
 }
 
 // out[row, :] = [xyz[idx]-new_xyz | points[idx]]  (or [points | xyz] when !xyz_first)
-__global__ void group_concat_kernel(int n, int m, int ns, int c, int w, int xoff, int poff,
+__global__ void group_concat_kernel(int n, int m, int ns, int c, int w, int ld, int xoff, int poff,
                                     int use_xyz, long total, const float *__restrict__ xyz,
                                     const float *__restrict__ new_xyz,
                                     const float *__restrict__ points,
@@ -309,7 +309,7 @@ __global__ void group_concat_kernel(int n, int m, int ns, int c, int w, int xoff
         } else {
             v = __ldg(points + (cloud * n + ii) * c + (col - poff));
         }
-        out[e] = v;
+        out[row * ld + col] = v;
     }
 }
 
@@ -495,12 +495,13 @@ PN2_API int pn2_group_point_grad(int b, int n, int c, int m, int nsample, const 
     return finish_launch();
 }
 
-PN2_API int pn2_group_concat(int b, int n, int m, int nsample, int c, const float *xyz,
-                             const float *new_xyz, const float *points, const int *idx,
-                             int xyz_first, int use_xyz, float *out, pn2_stream_t s) {
+PN2_API int pn2_group_concat_ld(int b, int n, int m, int nsample, int c, const float *xyz,
+                                const float *new_xyz, const float *points, const int *idx,
+                                int xyz_first, int use_xyz, float *out, int ld, pn2_stream_t s) {
     PN2_REQUIRE(b >= 0 && n > 0 && m >= 0 && nsample >= 0 && c >= 0);
     PN2_REQUIRE(use_xyz || c > 0);
     const int w = (use_xyz ? 3 : 0) + c;
+    PN2_REQUIRE(ld >= w);
     long total = (long)b * m * nsample * w;
     if (total == 0) return PN2_OK;
     PN2_REQUIRE_PTR(idx);
@@ -512,8 +513,15 @@ PN2_API int pn2_group_concat(int b, int n, int m, int nsample, int c, const floa
     if (c > 0) PN2_REQUIRE_PTR(points);
     const int xoff = xyz_first ? 0 : c, poff = (use_xyz && xyz_first) ? 3 : 0;
     group_concat_kernel<<<grid_for(total, 256), 256, 0, as_stream(s)>>>(
-        n, m, nsample, c, w, xoff, poff, use_xyz, total, xyz, new_xyz, points, idx, out);
+        n, m, nsample, c, w, ld, xoff, poff, use_xyz, total, xyz, new_xyz, points, idx, out);
     return finish_launch();
+}
+
+PN2_API int pn2_group_concat(int b, int n, int m, int nsample, int c, const float *xyz,
+                             const float *new_xyz, const float *points, const int *idx,
+                             int xyz_first, int use_xyz, float *out, pn2_stream_t s) {
+    return pn2_group_concat_ld(b, n, m, nsample, c, xyz, new_xyz, points, idx, xyz_first, use_xyz,
+                               out, (use_xyz ? 3 : 0) + c, s);
 }
 
 PN2_API int pn2_group_concat_grad(int b, int n, int m, int nsample, int c, const float *grad_out,

@@ -24,6 +24,10 @@ from ..tf_ops.tf_sampling import farthest_point_sample, gather_point
 from . import tf_util
 
 
+def _pad4(w):
+    return (w + 3) // 4 * 4
+
+
 class _GroupConcat(torch.autograd.Function):
     """(B,m,ns,3+C) = [xyz[idx]-new_xyz | points[idx]] (xyz_first) or [points | xyz] (MSG)."""
 
@@ -35,13 +39,16 @@ class _GroupConcat(torch.autograd.Function):
         w = (3 if use_xyz else 0) + c
         xyz_c, new_c = xyz.contiguous(), new_xyz.contiguous()
         pts_c = None if points is None else points.contiguous()
-        out = torch.empty((b, m, ns, w), dtype=F32, device=xyz.device)
-        call("pn2_group_concat", b, n, m, ns, c, ptr(xyz_c, F32), ptr(new_c, F32),
+        # rows padded to a multiple of 4 floats: 16-byte aligned rows are what the GEMM's TMA
+        # tensor maps need (3+C is odd for every SA layer); the result is the (.., :w) view
+        ld = _pad4(w)
+        buf = torch.empty((b, m, ns, ld), dtype=F32, device=xyz.device)
+        call("pn2_group_concat_ld", b, n, m, ns, c, ptr(xyz_c, F32), ptr(new_c, F32),
              ptr(pts_c, F32, True), ptr(idx, I32), 1 if xyz_first else 0, 1 if use_xyz else 0,
-             ptr(out, F32))
+             ptr(buf, F32), ld)
         ctx.save_for_backward(idx)
         ctx.cfg = (b, n, m, ns, c, xyz_first, use_xyz)
-        return out
+        return buf[..., :w] if ld != w else buf
 
     @staticmethod
     def backward(ctx, g):
@@ -179,16 +186,17 @@ class _InterpConcat(torch.autograd.Function):
         c1 = 0 if points1 is None else points1.shape[2]
         w = c2 + c1
         p2 = points2.contiguous()
-        out = torch.empty((b * n, w), dtype=F32, device=points2.device)
+        ld = _pad4(w)  # 16-byte aligned rows for the GEMM's TMA tensor maps
+        buf = torch.empty((b * n, ld), dtype=F32, device=points2.device)
         call("pn2_three_interpolate_ld", b, m, c2, n, ptr(p2, F32), ptr(idx, I32), ptr(weight, F32),
-             ptr(out, F32), w)
+             ptr(buf, F32), ld)
         if c1:
             p1 = points1.contiguous()
             call("pn2_copy_cols", b * n, c1, ptr(p1, F32), c1,
-                 _ffi_offset(out, c2), w, 0)
+                 _ffi_offset(buf, c2), ld, 0)
         ctx.save_for_backward(idx, weight)
         ctx.cfg = (b, m, c2, n, c1)
-        return out
+        return buf[:, :w] if ld != w else buf
 
     @staticmethod
     def backward(ctx, g):

@@ -24,7 +24,7 @@ import math
 
 import torch
 
-from .._ffi import F32, F64, I32, call, ptr
+from .._ffi import F32, F64, I32, call, ptr, ptr_rows
 
 BN_EPS = 1e-3  # tf.contrib.layers.batch_norm default epsilon (not in the reference source)
 relu = "relu"  # stands in for tf.nn.relu as activation_fn
@@ -221,9 +221,13 @@ class _MLPChain(torch.autograd.Function):
     def forward(ctx, x, anchor, layers, is_training, bn_decay, pool_ns, gemm_mode):
         M, K0 = x.shape
         dev = x.device
-        x = x.contiguous()
+        # rows may be padded (a column slice of a wider buffer: the SA/FP concat buffers are
+        # allocated with a 16-byte aligned row pitch for the TMA tensor maps)
+        if not (x.stride(1) == 1 and x.stride(0) >= K0):
+            x = x.contiguous()
+        a_ptr, lda = ptr_rows(x, F32)
         decay = 0.9 if bn_decay is None else float(bn_decay)
-        a, lda, a_sc, a_sh, a_relu = x, K0, None, None, 0
+        a_sc, a_sh, a_relu = None, None, 0
         Ys, scs, shs, saveds = [], [], [], []
         for L in layers:
             N = L.n
@@ -231,7 +235,7 @@ class _MLPChain(torch.autograd.Function):
             use_stats = L.bn and is_training
             stats = torch.zeros(2 * N, dtype=F64, device=dev) if use_stats else None
             ws = _workspace(L, dev) if gemm_mode != 0 else None
-            call("pn2_linear_fwd", M, L.k, N, ptr(a, F32), lda, ptr(a_sc, F32, True),
+            call("pn2_linear_fwd", M, L.k, N, a_ptr, lda, ptr(a_sc, F32, True),
                  ptr(a_sh, F32, True), a_relu, ptr(L.w.data, F32), ptr(L.b.data, F32), ptr(Y, F32),
                  ptr(stats, F64, True), ptr(ws, F32, True), 0 if ws is None else ws.numel() * 4,
                  gemm_mode)
@@ -256,7 +260,7 @@ class _MLPChain(torch.autograd.Function):
             scs.append(sc)
             shs.append(sh)
             saveds.append(saved)
-            a, lda, a_sc, a_sh, a_relu = Y, N, sc, sh, 1 if L.relu else 0
+            a_ptr, lda, a_sc, a_sh, a_relu = ptr(Y, F32), N, sc, sh, 1 if L.relu else 0
         L = layers[-1]
         N = L.n
         arg = None
@@ -316,16 +320,17 @@ class _MLPChain(torch.autograd.Function):
             else:
                 dY = up
             if i == 0:
-                a, lda, a_sc, a_sh, a_relu = x, x.shape[1], None, None, 0
+                (a_ptr, lda), a_sc, a_sh, a_relu = ptr_rows(x, F32), None, None, 0
             else:
                 P = layers[i - 1]
-                a, lda, a_sc, a_sh, a_relu = Ys[i - 1], P.n, scs[i - 1], shs[i - 1], 1 if P.relu else 0
+                a_ptr, lda, a_sc, a_sh, a_relu = ptr(Ys[i - 1], F32), P.n, scs[i - 1], shs[i - 1], \
+                    1 if P.relu else 0
             # A bias that feeds a train-mode BatchNorm has an exactly zero gradient (BN removes the
             # column mean, so sum_rows dY == 0); it is left at zero instead of accumulating the
             # fp32 rounding noise of an M-term sum.
             db = None if L.bn else ptr(L.b.ensure_grad(), F32)
             L.b.ensure_grad()
-            call("pn2_linear_wgrad", M, L.k, N, ptr(a, F32), lda, ptr(a_sc, F32, True),
+            call("pn2_linear_wgrad", M, L.k, N, a_ptr, lda, ptr(a_sc, F32, True),
                  ptr(a_sh, F32, True), a_relu, ptr(dY, F32), ptr(L.w.ensure_grad(), F32),
                  db, ctx.gemm_mode)
             if i > 0 or ctx.needs_input_grad[0]:

@@ -25,6 +25,14 @@ def err(a, b):
     return float(np.abs(a - b).max()), float(np.abs(b).max())
 
 
+def poison():
+    """fill the caching allocator's free blocks with NaN so that reads of never-written padding show"""
+    if os.environ.get("PN2_POISON") == "1":
+        t = [torch.full((1 << 24,), float("nan"), device="cuda") for _ in range(8)]
+        torch.cuda.synchronize()
+        del t
+
+
 def main(hp, b, n, scale):
     rs = np.random.RandomState(100)
     pc = np.concatenate([rs.random_sample((b, n, 3)) * np.asarray(scale), rs.random_sample((b, n, 3))],
@@ -49,6 +57,7 @@ def main(hp, b, n, scale):
     for l in (1, 2, 3, 4):
         args = (hp["l%d_npoint" % l], hp["l%d_radius" % l], hp["l%d_nsample" % l], list(lr.SA_MLPS[l]),
                 None, False, True, 0.5, "layer%d" % l)
+        poison()
         _, iso, _ = pu.pointnet_sa_module(cu(xyz[l - 1]), cu(pts[l - 1].detach().numpy()), *args)
         my_xyz[l], my_pts[l], _ = pu.pointnet_sa_module(my_xyz[l - 1], my_pts[l - 1], *args)
         print("SA%d  isolated %.3g  chained %.3g  (|ref|max %.3g)  M=%d" % (
@@ -62,6 +71,7 @@ def main(hp, b, n, scale):
                 key, flat.mean(0).min(), flat.mean(0).max(), flat.std(0).min(), flat.std(0).max()))
     my_up = my_pts[4]
     for l, (lo, hi) in zip((1, 2, 3, 4), ((3, 4), (2, 3), (1, 2), (0, 1))):
+        poison()
         iso = pu.pointnet_fp_module(cu(xyz[lo]), cu(xyz[hi]), cu(pts[lo].detach().numpy()),
                                     cu(ups[l - 1].detach().numpy()), list(lr.FP_MLPS[l]), True, 0.5,
                                     "fa_layer%d" % l)

@@ -8,7 +8,8 @@ ffi = pn2_b200._ffi
 p = ffi.ptr
 lib = ffi.lib()
 names = ["mma wait full", "mma issue", "mma wait acc_empty", "prod load+xform", "prod wait empty", "prod store",
-         "epi wait acc_full", "epi process", "loader wait empty", "mma total", "chunks", "tiles"]
+         "epi wait acc_full", "epi process", "loader wait empty", "mma total", "chunks", "tiles",
+         "epi wait store", "epi tmem->smem", "epi fence", "epi store issue"]
 for (M, K, N, pro) in [(131072, 128, 128, 1), (131072, 128, 128, 0), (524288, 32, 32, 1), (8192, 256, 256, 1)]:
     A = torch.randn(M, K, device="cuda"); W = torch.randn(K, N, device="cuda") * 0.1
     Y = torch.empty(M, N, device="cuda"); sc = torch.ones(K, device="cuda"); sh = torch.zeros(K, device="cuda")
@@ -29,7 +30,7 @@ for (M, K, N, pro) in [(131072, 128, 128, 1), (131072, 128, 128, 0), (524288, 32
         print("   %-20s %10d cycles  (%8.1f per chunk)" % (nme, v[i], v[i] / ch))
 
 print("######## wgrad")
-for (M, K, N) in [(131072, 128, 128), (131072, 64, 64), (524288, 32, 32)]:
+for (M, K, N) in [(131072, 128, 128), (131072, 64, 64), (524288, 32, 32), (4096, 256, 256)]:
     A = torch.randn(M, K, device="cuda"); dY = torch.randn(M, N, device="cuda"); dW = torch.zeros(K, N, device="cuda")
     sc = torch.ones(K, device="cuda"); sh = torch.zeros(K, device="cuda")
     def run():
@@ -39,5 +40,6 @@ for (M, K, N) in [(131072, 128, 128), (131072, 64, 64), (524288, 32, 32)]:
     lib.pn2_debug_tc_trace(buf); run(); lib.pn2_debug_tc_trace(buf)
     v = list(buf); ch = max(v[10], 1)
     print("== wgrad M,K,N=%s" % ((M, K, N),))
+    names[6] = 'prod fence+arrive'
     for i in (0, 1, 2, 9, 10, 11):
         print("   %-20s %10d cycles  (%8.1f per stage)" % (names[i], v[i], v[i] / ch))

@@ -23,8 +23,8 @@ def _ws(ffi, k, n):
 
 def linear_fwd(ffi, A, W, bias, scale, shift, relu, mode, lda=None, want_stats=True):
     import torch
-    M, K = A.shape
-    N = W.shape[1]
+    M = A.shape[0]
+    K, N = W.shape
     Y = torch.empty((M, N), dtype=torch.float32, device="cuda")
     stats = torch.zeros(2 * N, dtype=torch.float64, device="cuda") if want_stats else None
     ws = _ws(ffi, K, N)
@@ -67,8 +67,36 @@ def test_linear_fwd(ffi, mode, M, K, N):
 
 
 @pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("M,K,N", [(65536, 32, 32), (65536, 32, 64), (16384, 67, 64), (4096, 131, 128),
+                                   (1024, 259, 256), (128, 256, 256), (2048, 320, 256),
+                                   (40000, 131, 128), (40000, 128, 128), (30000, 6, 32)])
+def test_linear_fwd_padded_rows_many_tiles(ffi, mode, M, K, N):
+    """The layers' shapes: A in a row-padded buffer (lda = K rounded up to 4, NaN in the padding),
+    more row tiles than SMs (persistent CTAs loop), BN prologue + bias + statistics together."""
+    if mode == 1 and K < 16:
+        pytest.skip("tensor-core forward needs K >= 16")
+    rs = np.random.RandomState(M + K + N)
+    A = rs.normal(size=(M, K)).astype(np.float32)
+    W = (rs.uniform(-1, 1, (K, N)) * np.sqrt(6.0 / (K + N))).astype(np.float32)
+    b = rs.uniform(-0.5, 0.5, N).astype(np.float32)
+    sc = rs.uniform(0.5, 1.5, K).astype(np.float32)
+    sh = rs.uniform(-0.5, 0.5, K).astype(np.float32)
+    lda = (K + 3) // 4 * 4
+    Apad = np.full((M, lda), np.nan, np.float32)
+    Apad[:, :K] = A
+    Y, st = linear_fwd(ffi, to_cuda(Apad), to_cuda(W), to_cuda(b), to_cuda(sc), to_cuda(sh), True,
+                       mode, lda=lda)
+    A2 = np.maximum(A.astype(np.float64) * sc + sh, 0.0)
+    exp = A2 @ W.astype(np.float64) + b
+    np.testing.assert_allclose(Y.cpu().numpy(), exp, atol=1e-5)
+    np.testing.assert_allclose(st.cpu().numpy()[:N], exp.sum(0), rtol=1e-5, atol=1e-5 * M)
+    np.testing.assert_allclose(st.cpu().numpy()[N:], (exp ** 2).sum(0), rtol=1e-5, atol=1e-5 * M)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
 @pytest.mark.parametrize("M,K,N", [(256, 64, 64), (1000, 67, 64), (4096, 131, 128),
-                                   (512, 259, 256), (384, 512, 256), (8192, 128, 128)])
+                                   (512, 259, 256), (384, 512, 256), (8192, 128, 128),
+                                   (40000, 128, 128), (50000, 64, 32)])
 def test_linear_dgrad(ffi, mode, M, K, N):
     import torch
     rs = np.random.RandomState(7 + M + K + N)
@@ -86,10 +114,14 @@ def test_linear_dgrad(ffi, mode, M, K, N):
 @pytest.mark.parametrize("mode", [0, 1])
 @pytest.mark.parametrize("M,K,N", [(1000, 6, 32), (4096, 67, 64), (2048, 131, 128), (8192, 32, 32),
                                    (300, 259, 256), (5000, 6, 32), (16384, 128, 128),
-                                   (4100, 259, 256), (3072, 320, 48), (70000, 64, 64)])
+                                   (4100, 259, 256), (3072, 320, 48), (70000, 64, 64),
+                                   (600, 768, 256), (33000, 64, 128), (20000, 32, 64),
+                                   (9000, 96, 96), (1024, 256, 512), (40000, 6, 32)])
 def test_linear_wgrad(ffi, mode, M, K, N):
-    if mode == 1 and M < 2048:
-        pytest.skip("tensor-core wgrad needs M >= 2048")
+    """A lives in a row-padded buffer (lda = K rounded up to 4, NaN in the padding) the way the
+    layers allocate it, so that the TMA tensor-map path is taken for odd K as well."""
+    if mode == 1 and M < 512:
+        pytest.skip("tensor-core wgrad needs M >= 512")
     import torch
     rs = np.random.RandomState(11 + M + K + N)
     A = rs.normal(size=(M, K)).astype(np.float32)
@@ -99,13 +131,34 @@ def test_linear_wgrad(ffi, mode, M, K, N):
     dW = torch.zeros((K, N), dtype=torch.float32, device="cuda")
     db = torch.zeros(N, dtype=torch.float32, device="cuda")
     p = ffi.ptr
-    At, sct, sht, dYt = to_cuda(A), to_cuda(sc), to_cuda(sh), to_cuda(dY)
-    ffi.call("pn2_linear_wgrad", M, K, N, p(At), K, p(sct), p(sht), 1, p(dYt), p(dW), p(db), mode)
+    lda = (K + 3) // 4 * 4
+    Apad = np.full((M, lda), np.nan, np.float32)
+    Apad[:, :K] = A
+    At, sct, sht, dYt = to_cuda(Apad), to_cuda(sc), to_cuda(sh), to_cuda(dY)
+    ffi.call("pn2_linear_wgrad", M, K, N, p(At), lda, p(sct), p(sht), 1, p(dYt), p(dW), p(db), mode)
     A2 = np.maximum(A.astype(np.float64) * sc + sh, 0.0)
     exp = A2.T @ dY.astype(np.float64)
     tol = 2e-5 * max(1.0, np.abs(exp).max())
     np.testing.assert_allclose(dW.cpu().numpy(), exp, atol=tol)
     np.testing.assert_allclose(db.cpu().numpy(), dY.astype(np.float64).sum(0), atol=tol)
+
+
+def test_linear_wgrad_unpadded_rows_fall_back(ffi):
+    """Rows that are not 16-byte aligned (lda = 67) cannot be described by a tensor map: auto mode
+    must silently use the fp32 kernel, forced tensor-core mode must say so."""
+    import torch
+    M, K, N = 2048, 67, 64
+    rs = np.random.RandomState(5)
+    A = rs.normal(size=(M, K)).astype(np.float32)
+    dY = (rs.normal(size=(M, N)) * 0.1).astype(np.float32)
+    p = ffi.ptr
+    At, dYt = to_cuda(A), to_cuda(dY)
+    dW = torch.zeros((K, N), dtype=torch.float32, device="cuda")
+    ffi.call("pn2_linear_wgrad", M, K, N, p(At), K, None, None, 0, p(dYt), p(dW), None, -1)
+    exp = A.astype(np.float64).T @ dY.astype(np.float64)
+    np.testing.assert_allclose(dW.cpu().numpy(), exp, atol=2e-5 * max(1.0, np.abs(exp).max()))
+    with pytest.raises(Exception):
+        ffi.call("pn2_linear_wgrad", M, K, N, p(At), K, None, None, 0, p(dYt), p(dW), None, 1)
 
 
 def test_three_tf32_beats_plain_tf32_bound(ffi):

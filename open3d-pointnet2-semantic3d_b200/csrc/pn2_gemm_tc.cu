@@ -44,7 +44,7 @@ constexpr int MAX_RAW = 4;                // raw A ring slots (16 KB each) fille
 constexpr int RAW_BYTES = BM * BK * 4;
 constexpr int EPI_BYTES = 32 * 1024;      // epilogue staging
 constexpr int MAX_STAGES = 4;
-constexpr int MAX_KC = 16;    // K <= 512
+constexpr int MAX_KC = 32;    // K <= 1024 (K > 512 runs as two K halves with their own accumulators)
 constexpr int EPI_LD = 36;    // padded row length (floats) of the epilogue transpose buffer
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
@@ -164,23 +164,28 @@ __host__ __device__ __forceinline__ uint32_t sw128_offset(int row, int k) {
                       (k & 3) * 4);
 }
 
-// Weight image: for every K chunk kc: [hi image: Npad rows x 128 B][lo image: same], elements
-// Bt(n,k) = src[n*s_n + k*s_k], zero outside (N,K).
-__global__ void tc_prep_b_kernel(int N, int K, int Npad, int KC, const float *__restrict__ src,
-                                 long s_n, long s_k, float *__restrict__ image) {
-    const long total = (long)KC * Npad * BK;
+// Weight image: for every column block (128 columns, or all N <= 128) and every K chunk kc:
+// [hi image: Npad rows x 128 B][lo image: same], elements Bt(n,k) = src[n*s_n + k*s_k], zero outside (N,K).
+__global__ void tc_prep_b_kernel(int N, int K, int Npad, int KC, int nchunks,
+                                 const float *__restrict__ src, long s_n, long s_k,
+                                 float *__restrict__ image) {
+    const long total = (long)nchunks * KC * Npad * BK;
     for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total;
          e += (long)gridDim.x * blockDim.x) {
         const int kk = (int)(e % BK);
         const long t = e / BK;
-        const int n = (int)(t % Npad);
-        const int kc = (int)(t / Npad);
+        const int nl = (int)(t % Npad);
+        const long t2 = t / Npad;
+        const int kc = (int)(t2 % KC);
+        const int ch = (int)(t2 / KC);
         const int k = kc * BK + kk;
-        float v = (n < N && k < K) ? __ldg(src + n * s_n + k * s_k) : 0.f;
+        const long n = (long)ch * 128 + nl;  // N = columns per block when nchunks > 1
+        float v = (nl < N && k < K) ? __ldg(src + n * s_n + k * s_k) : 0.f;
         const float hi = tf32_rna(v);
         const float lo = v - hi;
-        unsigned char *base = reinterpret_cast<unsigned char *>(image) + (size_t)kc * 2 * Npad * 128;
-        const uint32_t off = sw128_offset(n, kk);
+        unsigned char *base = reinterpret_cast<unsigned char *>(image) + ((size_t)ch * KC + kc) * 2 * Npad * 128;
+        const int n_ = nl;
+        const uint32_t off = sw128_offset(n_, kk);
         *reinterpret_cast<float *>(base + off) = hi;
         *reinterpret_cast<float *>(base + (size_t)Npad * 128 + off) = lo;
     }
@@ -196,6 +201,8 @@ __device__ long long g_tc_trace[16];
 struct Params {
     long M;
     int K, N, Npad, KC, stages, b_res, raw_slots, a_tma, y_tma, lda, ldy, a_relu;
+    int nchunks;  // column blocks of 128 handled by this launch (CTA c works on block c % nchunks)
+    int ksplit;   // K > 512: chunks [0,KC/2) and [KC/2,KC) accumulate separately (no double buffering)
     const float *A, *a_scale, *a_shift, *bias, *image;
     float *Y;
     double *stats_sum, *stats_sq;  // per-column sum / sum of squares (fp64), or NULL
@@ -246,7 +253,12 @@ __global__ void __launch_bounds__(THREADS, 1)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int Nacc = (p.Npad + 31) & ~31;
     uint32_t ncols = 32;
-    while (ncols < (uint32_t)(4 * Nacc)) ncols <<= 1;  // {main, corr} x double buffer
+    while (ncols < (uint32_t)(4 * Nacc)) ncols <<= 1;  // {main, corr} x (double buffer | K halves)
+    // column block of this CTA and its row-tile sequence
+    const int nc = blockIdx.x % p.nchunks, n0 = nc * 128;
+    const long mt0 = blockIdx.x / p.nchunks, mstride = gridDim.x / p.nchunks;
+    const unsigned char *image = reinterpret_cast<const unsigned char *>(p.image) +
+                                 (size_t)nc * p.KC * 2 * ((size_t)p.Npad * 128);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) {
@@ -265,7 +277,7 @@ __global__ void __launch_bounds__(THREADS, 1)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (threadIdx.x < 128)
-        sbias[threadIdx.x] = (p.bias && (int)threadIdx.x < p.N) ? __ldg(p.bias + threadIdx.x) : 0.f;
+        sbias[threadIdx.x] = (p.bias && (int)threadIdx.x < p.N) ? __ldg(p.bias + n0 + threadIdx.x) : 0.f;
     if (warp == W_MMA) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                          smem_u32(tmem_slot)),
@@ -292,12 +304,12 @@ __global__ void __launch_bounds__(THREADS, 1)
         const int t = (threadIdx.x - 128) & 127;
         const int k4 = t & 7, r0 = t >> 3;  // float4 slot inside the 32-wide chunk, base row
         const bool vec_ok = (p.lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0);
-        const long my_tiles = blockIdx.x < num_tiles ? (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+        const long my_tiles = mt0 < num_tiles ? (num_tiles - mt0 + mstride - 1) / mstride : 0;
         const long total_chunks = my_tiles * p.KC;
         if (g < npg) {
             for (long itl = g; itl < total_chunks; itl += npg) {
                 const uint32_t it = (uint32_t)itl;
-                const long tile = blockIdx.x + (itl / p.KC) * gridDim.x;
+                const long tile = mt0 + (itl / p.KC) * mstride;
                 const int kc = (int)(itl % p.KC);
                 const long m0 = tile * BM;
                 const int s = it % p.stages;
@@ -394,7 +406,7 @@ __global__ void __launch_bounds__(THREADS, 1)
         // one 2-D tensor load per 128 x 32 chunk into the raw ring, running raw_slots chunks ahead
         if (lane == 0 && p.a_tma) {
             uint32_t it = 0;
-            for (long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (long tile = mt0; tile < num_tiles; tile += mstride) {
                 for (int kc = 0; kc < p.KC; ++kc, ++it) {
                     const int rs = it % p.raw_slots;
                     const uint32_t rph = (it / p.raw_slots) & 1;
@@ -411,12 +423,12 @@ __global__ void __launch_bounds__(THREADS, 1)
             for (int kc = 0; kc < p.KC; ++kc) {
                 mbar_expect_tx(&bfull[kc], 2 * b_bytes);
                 bulk_g2s(bres + (size_t)kc * 2 * b_bytes,
-                         reinterpret_cast<const unsigned char *>(p.image) + (size_t)kc * 2 * b_bytes,
+                         image + (size_t)kc * 2 * b_bytes,
                          2 * b_bytes, &bfull[kc]);
             }
         } else if (lane == 0) {
             uint32_t it = 0;
-            for (long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (long tile = mt0; tile < num_tiles; tile += mstride) {
                 for (int kc = 0; kc < p.KC; ++kc, ++it) {
                     const int s = it % p.stages;
                     const uint32_t ph = (it / p.stages) & 1;
@@ -426,7 +438,7 @@ __global__ void __launch_bounds__(THREADS, 1)
                     unsigned char *b_hi = stage_base + (size_t)s * stage_bytes + 2 * a_bytes;
                     mbar_expect_tx(&full[s], 2 * b_bytes);
                     bulk_g2s(b_hi,
-                             reinterpret_cast<const unsigned char *>(p.image) + (size_t)kc * 2 * b_bytes,
+                             image + (size_t)kc * 2 * b_bytes,
                              2 * b_bytes, &full[s]);
                 }
             }
@@ -439,15 +451,19 @@ __global__ void __launch_bounds__(THREADS, 1)
             const bool tr = blockIdx.x == 0;
             const long long k0c = tr ? clock64() : 0;
             long long w_full = 0, w_issue = 0, w_acc = 0;
-            for (long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcnt) {
-                const uint32_t acc = tcnt & 1, aph = (tcnt >> 1) & 1;
+            const int kh = p.ksplit ? p.KC / 2 : p.KC;  // chunks per accumulator set
+            for (long tile = mt0; tile < num_tiles; tile += mstride, ++tcnt) {
+                // two accumulator sets: ping-pong over tiles, or (ksplit) the two K halves of one tile
+                const uint32_t acc = p.ksplit ? 0 : (tcnt & 1), aph = p.ksplit ? (tcnt & 1) : ((tcnt >> 1) & 1);
                 const long long ca = tr ? clock64() : 0;
                 mbar_wait(&acc_empty[acc], aph ^ 1);
                 if (tr) w_acc += clock64() - ca;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t d = tmem_base + acc * (uint32_t)(2 * Nacc);  // main
-                const uint32_t dc = d + (uint32_t)Nacc;                     // corrections
                 for (int kc = 0; kc < p.KC; ++kc, ++it) {
+                    const uint32_t set = p.ksplit ? (kc >= kh ? 1u : 0u) : acc;
+                    const int kcl = kc >= kh ? kc - kh : kc;
+                    const uint32_t d = tmem_base + set * (uint32_t)(2 * Nacc);  // main
+                    const uint32_t dc = d + (uint32_t)Nacc;                     // corrections
                     const int s = it % p.stages;
                     const uint32_t ph = (it / p.stages) & 1;
                     const long long cw = tr ? clock64() : 0;
@@ -463,7 +479,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 #pragma unroll
                     for (int kk = 0; kk < BK / 8; ++kk) {
                         const uint64_t adv = (uint64_t)(kk * 2);  // 32 bytes per K=8 step, >>4
-                        const uint32_t accum = (kc > 0 || kk > 0) ? 1u : 0u;
+                        const uint32_t accum = (kcl > 0 || kk > 0) ? 1u : 0u;
                         umma_tf32(d, dah + adv, dbh + adv, idesc, accum);
                         umma_tf32(dc, dal + adv, dbh + adv, idesc, accum);
                         umma_tf32(dc, dah + adv, dbl + adv, idesc, 1u);
@@ -505,9 +521,26 @@ __global__ void __launch_bounds__(THREADS, 1)
             ssum[i] = ssq[i] = 0.0;
             cshift[i] = 0.f;
         }
+        // 16 accumulator columns of this lane's row: main + corrections (round-to-nearest), summed
+        // over both K halves when the contraction was split
+        auto load_sum16 = [&](uint32_t taddr, float (&o)[16]) {
+            uint32_t r[16], rc[16];
+            tmem_ld16_nowait(taddr, r);
+            tmem_ld16_nowait(taddr + (uint32_t)Nacc, rc);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o[j] = __uint_as_float(r[j]) + __uint_as_float(rc[j]);
+            if (p.ksplit) {
+                tmem_ld16_nowait(taddr + (uint32_t)(2 * Nacc), r);
+                tmem_ld16_nowait(taddr + (uint32_t)(3 * Nacc), rc);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) o[j] += __uint_as_float(r[j]) + __uint_as_float(rc[j]);
+            }
+        };
         uint32_t tcnt = 0, cbi = 0;
-        for (long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcnt) {
-            const uint32_t acc = tcnt & 1, aph = (tcnt >> 1) & 1;
+        for (long tile = mt0; tile < num_tiles; tile += mstride, ++tcnt) {
+            const uint32_t acc = p.ksplit ? 0 : (tcnt & 1), aph = p.ksplit ? (tcnt & 1) : ((tcnt >> 1) & 1);
             const long m0 = tile * BM + warp * 32;
             const bool tr = (blockIdx.x == 0 && threadIdx.x == 0);
             const long long ce0 = tr ? clock64() : 0;
@@ -515,7 +548,6 @@ __global__ void __launch_bounds__(THREADS, 1)
             const long long ce1 = tr ? clock64() : 0;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const long rows_left = p.M - m0;
-            long long tA = 0, tB = 0, tC = 0, tD = 0;
 #pragma unroll
             for (int cb = 0; cb < 4; ++cb) {
                 if (cb >= nblk) break;
@@ -528,42 +560,34 @@ __global__ void __launch_bounds__(THREADS, 1)
                 if (p.y_tma) {
                     unsigned char *buf = wbuf + (cbi & 1) * 4096;
                     ++cbi;
-                    const long long q0 = tr ? clock64() : 0;
                     // the tensor store issued from this buffer two blocks ago has read it
                     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                     __syncwarp();
-                    const long long q1 = tr ? clock64() : 0;
 #pragma unroll
                     for (int half = 0; half < 2; ++half) {
-                        uint32_t r[16], rc[16];
-                        tmem_ld16_nowait(ta + half * 16, r);
-                        tmem_ld16_nowait(ta + (uint32_t)Nacc + half * 16, rc);
-                        tmem_ld_wait();
+                        float a16[16];
+                        load_sum16(ta + half * 16, a16);
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             const float4 b4 =
                                 *reinterpret_cast<const float4 *>(sbias + cb * 32 + half * 16 + q * 4);
-                            float4 o;  // main + corrections (round-to-nearest) + bias
-                            o.x = (__uint_as_float(r[q * 4]) + __uint_as_float(rc[q * 4])) + b4.x;
-                            o.y = (__uint_as_float(r[q * 4 + 1]) + __uint_as_float(rc[q * 4 + 1])) + b4.y;
-                            o.z = (__uint_as_float(r[q * 4 + 2]) + __uint_as_float(rc[q * 4 + 2])) + b4.z;
-                            o.w = (__uint_as_float(r[q * 4 + 3]) + __uint_as_float(rc[q * 4 + 3])) + b4.w;
+                            float4 o;  // accumulators + bias
+                            o.x = a16[q * 4] + b4.x;
+                            o.y = a16[q * 4 + 1] + b4.y;
+                            o.z = a16[q * 4 + 2] + b4.z;
+                            o.w = a16[q * 4 + 3] + b4.w;
                             const int c16 = half * 4 + q;
                             *reinterpret_cast<float4 *>(buf + lane * 128 + ((c16 ^ (lane & 7)) << 4)) = o;
                         }
                     }
-                    const long long q2 = tr ? clock64() : 0;
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
-                    const long long q3 = tr ? clock64() : 0;
                     if (lane == 0) {
                         // one bulk group per block even when there is nothing to store: the
                         // wait_group.read 1 above counts groups to tell which buffer is free
-                        if (rows_left > 0) tma_store_2d(&tmY, cb * 32, (int)m0, buf);  // rows >= M, cols >= N clipped
+                        if (rows_left > 0) tma_store_2d(&tmY, n0 + cb * 32, (int)m0, buf);  // rows >= M, cols >= N clipped
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
-                    const long long q4 = tr ? clock64() : 0;
-                    tA += q1 - q0; tB += q2 - q1; tC += q3 - q2; tD += q4 - q3;
                     if (do_stats) {
                         const unsigned char *colp = buf + (lane & 3) * 4;
                         const int c16 = lane >> 2;
@@ -585,17 +609,11 @@ __global__ void __launch_bounds__(THREADS, 1)
                     float vals[32];
 #pragma unroll
                     for (int half = 0; half < 2; ++half) {
-                        uint32_t r[16], rc[16];
-                        tmem_ld16_nowait(ta + half * 16, r);
-                        tmem_ld16_nowait(ta + (uint32_t)Nacc + half * 16, rc);
-                        tmem_ld_wait();
+                        float a16[16];
+                        load_sum16(ta + half * 16, a16);
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            float4 o;  // main + corrections, round-to-nearest
-                            o.x = __uint_as_float(r[q * 4]) + __uint_as_float(rc[q * 4]);
-                            o.y = __uint_as_float(r[q * 4 + 1]) + __uint_as_float(rc[q * 4 + 1]);
-                            o.z = __uint_as_float(r[q * 4 + 2]) + __uint_as_float(rc[q * 4 + 2]);
-                            o.w = __uint_as_float(r[q * 4 + 3]) + __uint_as_float(rc[q * 4 + 3]);
+                            const float4 o = make_float4(a16[q * 4], a16[q * 4 + 1], a16[q * 4 + 2], a16[q * 4 + 3]);
                             *reinterpret_cast<float4 *>(stg + lane * EPI_LD + half * 16 + q * 4) = o;
                         }
                     }
@@ -606,7 +624,7 @@ __global__ void __launch_bounds__(THREADS, 1)
                     for (int rr = 0; rr < 32; ++rr) vals[rr] = stg[rr * EPI_LD + lane] + bv;
                     __syncwarp();
                     if (col_ok && rows_left > 0) {
-                        float *yp = p.Y + m0 * p.ldy + col;
+                        float *yp = p.Y + m0 * p.ldy + n0 + col;
                         if (rows_left >= 32) {
 #pragma unroll
                             for (int rr = 0; rr < 32; ++rr) yp[(long)rr * p.ldy] = vals[rr];
@@ -637,10 +655,6 @@ __global__ void __launch_bounds__(THREADS, 1)
             if (tr) {
                 g_tc_trace[6] += ce1 - ce0;
                 g_tc_trace[7] += clock64() - ce1;
-                g_tc_trace[12] += tA;
-                g_tc_trace[13] += tB;
-                g_tc_trace[14] += tC;
-                g_tc_trace[15] += tD;
             }
         }
         if (p.y_tma && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -650,8 +664,8 @@ __global__ void __launch_bounds__(THREADS, 1)
                 const int col = cb * 32 + lane;
                 if (cb < nblk && col < p.N && nrows > 0) {
                     const double c = (double)cshift[cb], n = (double)nrows;
-                    atomicAdd(p.stats_sum + col, ssum[cb] + n * c);
-                    atomicAdd(p.stats_sq + col, ssq[cb] + 2.0 * c * ssum[cb] + n * c * c);
+                    atomicAdd(p.stats_sum + n0 + col, ssum[cb] + n * c);
+                    atomicAdd(p.stats_sq + n0 + col, ssq[cb] + 2.0 * c * ssum[cb] + n * c * c);
                 }
             }
         }
@@ -714,12 +728,14 @@ static bool make_tensor_map(CUtensorMap *tm, const float *base, long rows, int c
 }
 
 static size_t image_bytes(int K, int N) {
-    const int Npad = (N + 15) & ~15, KC = (K + BK - 1) / BK;
+    const int KC = (K + BK - 1) / BK;
+    if (N > 128) return (size_t)(N / 128 > 0 ? N / 128 : 1) * KC * 2 * 128 * 128;
+    const int Npad = (N + 15) & ~15;
     return (size_t)KC * 2 * Npad * 128;
 }
 
-// Y[M, n0:n0+Nc] for one chunk of at most 128 output columns (two accumulators x 2 buffers)
-static int run_chunk(long M, int K, int Nc, const float *A, int lda, const float *a_scale,
+// Y[M, 0:nchunks*Nc]: nchunks column blocks of Nc columns (Nc == 128 when nchunks > 1, else <= 128)
+static int run_chunk(long M, int K, int Nc, int nchunks, const float *A, int lda, const float *a_scale,
                      const float *a_shift, int a_relu, const float *bsrc, long s_n, long s_k,
                      const float *bias, float *Y, int ldy, double *stats_sum, double *stats_sq,
                      float *ws, cudaStream_t st) {
@@ -740,7 +756,9 @@ static int run_chunk(long M, int K, int Nc, const float *A, int lda, const float
     p.Y = Y;
     p.stats_sum = stats_sum;
     p.stats_sq = stats_sq;
-    if (p.KC > MAX_KC || Nc > 128) return PN2_EUNSUPPORTED;
+    if (p.KC > MAX_KC || Nc > 128 || nchunks < 1 || (nchunks > 1 && Nc != 128)) return PN2_EUNSUPPORTED;
+    p.nchunks = nchunks;
+    p.ksplit = p.KC > 16 ? 1 : 0;  // K > 512: two accumulator sets bound the truncating accumulation
 
     // PN2_TC_TMA bit mask (diagnostics): 1 = tensor loads for A, 2 = tensor stores for Y; default 3
     static const int tma_mask = getenv("PN2_TC_TMA") ? atoi(getenv("PN2_TC_TMA")) : 3;
@@ -748,7 +766,7 @@ static int run_chunk(long M, int K, int Nc, const float *A, int lda, const float
     memset(&tmA, 0, sizeof(tmA));
     memset(&tmY, 0, sizeof(tmY));
     p.a_tma = ((tma_mask & 1) && M < (1l << 31) && make_tensor_map(&tmA, A, M, K, lda, BM, false)) ? 1 : 0;
-    p.y_tma = ((tma_mask & 2) && M < (1l << 31) && make_tensor_map(&tmY, Y, M, Nc, ldy, 32, true)) ? 1 : 0;
+    p.y_tma = ((tma_mask & 2) && M < (1l << 31) && make_tensor_map(&tmY, Y, M, Nc * nchunks, ldy, 32, true)) ? 1 : 0;
 
     // shared memory plan (227 KB usable per CTA): raw ring (4 slots if possible), >= 2 MMA stages,
     // weights resident when they fit next to that
@@ -785,10 +803,10 @@ static int run_chunk(long M, int K, int Nc, const float *A, int lda, const float
     const size_t smem = (p.b_res ? bres : 0) + (size_t)stages * stage_bytes +
                         (size_t)raw_slots * RAW_BYTES + fixed;
 
-    const long total = (long)p.KC * p.Npad * BK;
+    const long total = (long)nchunks * p.KC * p.Npad * BK;
     int pb = (int)((total + 255) / 256);
     if (pb > 148 * 8) pb = 148 * 8;
-    tc_prep_b_kernel<<<pb, 256, 0, st>>>(Nc, K, p.Npad, p.KC, bsrc, s_n, s_k, ws);
+    tc_prep_b_kernel<<<pb, 256, 0, st>>>(Nc, K, p.Npad, p.KC, nchunks, bsrc, s_n, s_k, ws);
     int rc = finish_launch();
     if (rc) return rc;
 
@@ -797,7 +815,10 @@ static int run_chunk(long M, int K, int Nc, const float *A, int lda, const float
     rc = opt_in_smem(reinterpret_cast<const void *>(tc_gemm_kernel), 0);
     if (rc) return rc;
     const long tiles = (M + BM - 1) / BM;
-    const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+    long per_chunk = num_sms() / nchunks;  // persistent CTAs per column block
+    if (per_chunk < 1) per_chunk = 1;
+    if (per_chunk > tiles) per_chunk = tiles;
+    const int grid = (int)per_chunk * nchunks;
     tc_gemm_kernel<<<grid, THREADS, smem, st>>>(tmA, tmY, p);
     return finish_launch();
 }
@@ -1238,11 +1259,14 @@ int tc_linear_wgrad(long M, int K, int N, const float *A, int lda, const float *
 }
 
 // Shapes worth the tensor cores: at least one full tile of rows, K and N not tiny.
-// K <= 512 keeps the truncating tensor-core accumulation inside the 1e-5 parity bar.
-static bool tc_shape_ok(long M, int K, int N) { return M >= 128 && K >= 16 && K <= 512 && N >= 16; }
+// Each accumulator set sees at most 512 contraction terms (K > 512 is split in two halves), which
+// keeps the truncating tensor-core accumulation inside the 1e-5 parity bar.
+static bool tc_shape_ok(long M, int K, int N) { return M >= 128 && K >= 16 && K <= 1024 && N >= 16; }
 
 constexpr int TC_NCHUNK = 128;
-static size_t tc_image_bytes(int K, int N) { return tc::image_bytes(K, N > TC_NCHUNK ? TC_NCHUNK : N); }
+static size_t tc_image_bytes(int K, int N) {
+    return tc::image_bytes(K, (N > TC_NCHUNK && N % TC_NCHUNK != 0) ? TC_NCHUNK : N);
+}
 
 // one buffer serves both orientations of a layer: forward (K x N) and dgrad (N x K)
 size_t tc_workspace_bytes(int K, int N) {
@@ -1255,10 +1279,14 @@ int tc_linear_fwd(long M, int K, int N, const float *A, int lda, const float *a_
                   double *stats, float *ws, size_t ws_bytes, cudaStream_t st) {
     if (!tc_shape_ok(M, K, N) || ws == nullptr || ws_bytes < tc_image_bytes(K, N))
         return PN2_EUNSUPPORTED;
+    if (N <= TC_NCHUNK || N % TC_NCHUNK == 0)  // all column blocks in one launch; Bt(n,k) = W[k*N + n]
+        return tc::run_chunk(M, K, N <= TC_NCHUNK ? N : TC_NCHUNK, N <= TC_NCHUNK ? 1 : N / TC_NCHUNK, A,
+                             lda, a_scale, a_shift, a_relu, W, 1, N, bias, Y, N, stats,
+                             stats ? stats + N : nullptr, ws, st);
     for (int n0 = 0; n0 < N; n0 += TC_NCHUNK) {
         const int nc = (N - n0) < TC_NCHUNK ? (N - n0) : TC_NCHUNK;
         // Bt(n,k) = W[k*N + n0 + n]
-        int rc = tc::run_chunk(M, K, nc, A, lda, a_scale, a_shift, a_relu, W + n0, 1, N,
+        int rc = tc::run_chunk(M, K, nc, 1, A, lda, a_scale, a_shift, a_relu, W + n0, 1, N,
                                bias ? bias + n0 : nullptr, Y + n0, N, stats ? stats + n0 : nullptr,
                                stats ? stats + N + n0 : nullptr, ws, st);
         if (rc) return rc;
@@ -1271,9 +1299,12 @@ int tc_linear_dgrad(long M, int K, int N, const float *dY, const float *W, float
     // dX[M,K] = dY[M,N] * W[K,N]^T : contraction over N, output columns = K ; Bt(k,n) = W[k*N + n]
     if (!tc_shape_ok(M, N, K) || ws == nullptr || ws_bytes < tc_image_bytes(N, K))
         return PN2_EUNSUPPORTED;
+    if (K <= TC_NCHUNK || K % TC_NCHUNK == 0)
+        return tc::run_chunk(M, N, K <= TC_NCHUNK ? K : TC_NCHUNK, K <= TC_NCHUNK ? 1 : K / TC_NCHUNK, dY, N,
+                             nullptr, nullptr, 0, W, N, 1, nullptr, dX, ldx, nullptr, nullptr, ws, st);
     for (int k0 = 0; k0 < K; k0 += TC_NCHUNK) {
         const int kc = (K - k0) < TC_NCHUNK ? (K - k0) : TC_NCHUNK;
-        int rc = tc::run_chunk(M, N, kc, dY, N, nullptr, nullptr, 0, W + (long)k0 * N, N, 1, nullptr,
+        int rc = tc::run_chunk(M, N, kc, 1, dY, N, nullptr, nullptr, 0, W + (long)k0 * N, N, 1, nullptr,
                                dX + k0, ldx, nullptr, nullptr, ws, st);
         if (rc) return rc;
     }

@@ -38,7 +38,8 @@ def linear_fwd(ffi, A, W, bias, scale, shift, relu, mode, lda=None, want_stats=T
 SHAPES = [  # M, K, N
     (128, 32, 32), (256, 64, 64), (1000, 67, 64), (4096, 131, 128), (640, 259, 256),
     (512, 256, 512), (384, 128, 48), (130, 16, 16), (8192, 128, 128), (2048, 384, 256),
-    (1024, 512, 128),
+    (1024, 512, 128), (1024, 768, 256), (2000, 640, 384), (20000, 1024, 128), (3000, 544, 192),
+    (30000, 96, 256),
 ]
 
 
@@ -96,7 +97,8 @@ def test_linear_fwd_padded_rows_many_tiles(ffi, mode, M, K, N):
 @pytest.mark.parametrize("mode", [0, 1])
 @pytest.mark.parametrize("M,K,N", [(256, 64, 64), (1000, 67, 64), (4096, 131, 128),
                                    (512, 259, 256), (384, 512, 256), (8192, 128, 128),
-                                   (40000, 128, 128), (50000, 64, 32)])
+                                   (40000, 128, 128), (50000, 64, 32), (1024, 768, 256),
+                                   (2048, 384, 1024), (30000, 256, 128)])
 def test_linear_dgrad(ffi, mode, M, K, N):
     import torch
     rs = np.random.RandomState(7 + M + K + N)

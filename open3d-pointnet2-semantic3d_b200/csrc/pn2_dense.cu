@@ -206,19 +206,20 @@ bn_bwd_reduce_v4_kernel(long M, int N, long rpb, const float *__restrict__ dZ, i
                     z[u] = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             }
+            // fp32 partial sums over the four rows in flight, fp64 across batches
+            float f0[4] = {0.f, 0.f, 0.f, 0.f}, f1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                float f0[4] = {0.f, 0.f, 0.f, 0.f}, f1[4] = {0.f, 0.f, 0.f, 0.f};
                 float dzh, xh;
-                bn_elem(y[u].x, z[u].x, sc.x, sh.x, mean.x, rstd.x, relu, dzh, xh); f0[0] = dzh; f1[0] = dzh * xh;
-                bn_elem(y[u].y, z[u].y, sc.y, sh.y, mean.y, rstd.y, relu, dzh, xh); f0[1] = dzh; f1[1] = dzh * xh;
-                bn_elem(y[u].z, z[u].z, sc.z, sh.z, mean.z, rstd.z, relu, dzh, xh); f0[2] = dzh; f1[2] = dzh * xh;
-                bn_elem(y[u].w, z[u].w, sc.w, sh.w, mean.w, rstd.w, relu, dzh, xh); f0[3] = dzh; f1[3] = dzh * xh;
+                bn_elem(y[u].x, z[u].x, sc.x, sh.x, mean.x, rstd.x, relu, dzh, xh); f0[0] += dzh; f1[0] = __fmaf_rn(dzh, xh, f1[0]);
+                bn_elem(y[u].y, z[u].y, sc.y, sh.y, mean.y, rstd.y, relu, dzh, xh); f0[1] += dzh; f1[1] = __fmaf_rn(dzh, xh, f1[1]);
+                bn_elem(y[u].z, z[u].z, sc.z, sh.z, mean.z, rstd.z, relu, dzh, xh); f0[2] += dzh; f1[2] = __fmaf_rn(dzh, xh, f1[2]);
+                bn_elem(y[u].w, z[u].w, sc.w, sh.w, mean.w, rstd.w, relu, dzh, xh); f0[3] += dzh; f1[3] = __fmaf_rn(dzh, xh, f1[3]);
+            }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    a0[j] += (double)f0[j];
-                    a1[j] += (double)f1[j];
-                }
+            for (int j = 0; j < 4; ++j) {
+                a0[j] += (double)f0[j];
+                a1[j] += (double)f1[j];
             }
         }
 #pragma unroll
@@ -298,10 +299,11 @@ bn_bwd_reduce_pool_kernel(long G, int ns, int N, const float *__restrict__ dOut,
                           const int *__restrict__ arg, const float *__restrict__ Y,
                           const float *__restrict__ scale, const float *__restrict__ shift,
                           const float *__restrict__ saved, int relu, double *__restrict__ red) {
+    extern __shared__ double sred[];  // [2N] per-block partial sums
     const long rpb = ceil_div<long>(G, (long)gridDim.x);
     const Slab s = make_slab(G, N, rpb);
-    if (!s.active) return;
-    for (int c = s.cx; c < N; c += s.lanes) {
+    block_zero2(sred, N);
+    for (int c = s.cx; s.active && c < N; c += s.lanes) {
         const float sc = __ldg(scale + c), sh = __ldg(shift + c);
         const float mean = __ldg(saved + c), rstd = __ldg(saved + N + c);
         double a0 = 0.0, a1 = 0.0;
@@ -313,8 +315,71 @@ bn_bwd_reduce_pool_kernel(long G, int ns, int N, const float *__restrict__ dOut,
             a0 += (double)dzh;
             a1 = fma((double)dzh, (double)xh, a1);
         }
-        atomicAdd(red + c, a0);
-        atomicAdd(red + N + c, a1);
+        block_add2(sred, N, c, a0, a1);
+    }
+    block_flush2(sred, N, red);
+}
+
+// float4 variant of the kernel below (N % 4 == 0, 16-byte aligned bases): a block owns a slab of
+// groups; thread t works on column quad cq = t % (N/4) and sample rows j = ry, ry+rpp, ...; the
+// group's arg / dOut quads are loaded once per group
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_pool_v4_kernel(long G, int ns, int N, long gpb, const float *__restrict__ dOut,
+                            const int *__restrict__ arg, const float *__restrict__ Y,
+                            const float *__restrict__ scale, const float *__restrict__ shift,
+                            const float *__restrict__ saved, const float *__restrict__ gamma,
+                            int relu, int bn, const double *__restrict__ red,
+                            float *__restrict__ dY, float *__restrict__ dgamma,
+                            float *__restrict__ dbeta) {
+    const Slab4 s = make_slab4(G, N, gpb);
+    if (!s.active) return;
+    const double invM = 1.0 / (double)(G * ns);
+    const int nq = N >> 2;
+    for (int cq = s.cq; cq < nq; cq += s.nq) {
+        const int c = cq * 4;
+        float sc[4] = {1.f, 1.f, 1.f, 1.f}, sh[4] = {0.f, 0.f, 0.f, 0.f}, mean[4] = {0.f, 0.f, 0.f, 0.f},
+              rstd[4] = {1.f, 1.f, 1.f, 1.f}, gs[4] = {1.f, 1.f, 1.f, 1.f}, m0[4] = {0.f, 0.f, 0.f, 0.f},
+              m1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (scale) {
+                sc[j] = __ldg(scale + c + j);
+                sh[j] = __ldg(shift + c + j);
+            }
+            if (bn) {
+                mean[j] = __ldg(saved + c + j);
+                rstd[j] = __ldg(saved + N + c + j);
+                gs[j] = __ldg(gamma + c + j) * rstd[j];
+                m0[j] = (float)(red[c + j] * invM);
+                m1[j] = (float)(red[N + c + j] * invM);
+                if (blockIdx.x == 0 && s.ry == 0) {
+                    if (dgamma) dgamma[c + j] += (float)red[N + c + j];
+                    if (dbeta) dbeta[c + j] += (float)red[c + j];
+                }
+            }
+        }
+        for (long g = s.r0; g < s.r1; ++g) {
+            const int4 a4 = __ldg(reinterpret_cast<const int4 *>(arg + g * N + c));
+            const float4 d4 = __ldg(reinterpret_cast<const float4 *>(dOut + g * N + c));
+            const int aa[4] = {a4.x, a4.y, a4.z, a4.w};
+            const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
+            const float *yg = Y + g * ns * N + c;
+            float *og = dY + g * ns * N + c;
+#pragma unroll 4
+            for (int j = s.ry; j < ns; j += s.rpp) {
+                const float4 y4 = __ldg(reinterpret_cast<const float4 *>(yg + (long)j * N));
+                const float yy[4] = {y4.x, y4.y, y4.z, y4.w};
+                float4 o;
+                float *oo = reinterpret_cast<float *>(&o);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float dzh, xh;
+                    bn_elem(yy[q], aa[q] == j ? dd[q] : 0.f, sc[q], sh[q], mean[q], rstd[q], relu, dzh, xh);
+                    oo[q] = bn ? gs[q] * (dzh - m0[q] - xh * m1[q]) : dzh;
+                }
+                *reinterpret_cast<float4 *>(og + (long)j * N) = o;
+            }
+        }
     }
 }
 
@@ -407,6 +472,72 @@ __global__ void affine_act_kernel(long total, int N, const float *__restrict__ Y
         if (scale) v = __fmaf_rn(v, __ldg(scale + c), __ldg(shift + c));
         if (relu) v = fmaxf(v, 0.f);
         Z[r * ldz + c] = v;
+    }
+}
+
+// float4 variants (N % 4 == 0, ldz % 4 == 0, 16-byte aligned bases)
+__global__ void affine_act_v4_kernel(long total4, int nq, const float *__restrict__ Y,
+                                     const float *__restrict__ scale,
+                                     const float *__restrict__ shift, int relu,
+                                     float *__restrict__ Z, int ldz) {
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total4;
+         e += (long)gridDim.x * blockDim.x) {
+        const long r = e / nq;
+        const int c = (int)(e - r * nq) * 4;
+        float4 v = __ldg(reinterpret_cast<const float4 *>(Y) + e);
+        if (scale) {
+            const float4 sc = __ldg(reinterpret_cast<const float4 *>(scale + c));
+            const float4 sh = __ldg(reinterpret_cast<const float4 *>(shift + c));
+            v.x = __fmaf_rn(v.x, sc.x, sh.x);
+            v.y = __fmaf_rn(v.y, sc.y, sh.y);
+            v.z = __fmaf_rn(v.z, sc.z, sh.z);
+            v.w = __fmaf_rn(v.w, sc.w, sh.w);
+        }
+        if (relu) {
+            v.x = fmaxf(v.x, 0.f);
+            v.y = fmaxf(v.y, 0.f);
+            v.z = fmaxf(v.z, 0.f);
+            v.w = fmaxf(v.w, 0.f);
+        }
+        *reinterpret_cast<float4 *>(Z + r * ldz + c) = v;
+    }
+}
+
+__global__ void __launch_bounds__(128)
+affine_act_maxpool_v4_kernel(long total4, int ns, int N, const float *__restrict__ Y,
+                             const float *__restrict__ scale, const float *__restrict__ shift,
+                             int relu, float *__restrict__ out, int *__restrict__ arg) {
+    const int nq = N >> 2;
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total4;
+         e += (long)gridDim.x * blockDim.x) {
+        const long g = e / nq;
+        const int c = (int)(e - g * nq) * 4;
+        float sc[4] = {1.f, 1.f, 1.f, 1.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
+        if (scale) {
+            const float4 s4 = __ldg(reinterpret_cast<const float4 *>(scale + c));
+            const float4 h4 = __ldg(reinterpret_cast<const float4 *>(shift + c));
+            sc[0] = s4.x; sc[1] = s4.y; sc[2] = s4.z; sc[3] = s4.w;
+            sh[0] = h4.x; sh[1] = h4.y; sh[2] = h4.z; sh[3] = h4.w;
+        }
+        const float *y = Y + g * ns * N + c;
+        float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        int bj[4] = {0, 0, 0, 0};
+#pragma unroll 8
+        for (int j = 0; j < ns; ++j) {
+            const float4 y4 = __ldg(reinterpret_cast<const float4 *>(y + (long)j * N));
+            const float yy[4] = {y4.x, y4.y, y4.z, y4.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float v = __fmaf_rn(yy[q], sc[q], sh[q]);
+                if (relu) v = fmaxf(v, 0.f);
+                if (v > best[q]) {
+                    best[q] = v;
+                    bj[q] = j;
+                }
+            }
+        }
+        *reinterpret_cast<float4 *>(out + g * N + c) = make_float4(best[0], best[1], best[2], best[3]);
+        if (arg) *reinterpret_cast<int4 *>(arg + g * N + c) = make_int4(bj[0], bj[1], bj[2], bj[3]);
     }
 }
 
@@ -721,8 +852,15 @@ PN2_API int pn2_affine_act(long M, int N, const float *Y, const float *scale, co
     PN2_REQUIRE_PTR(Y);
     PN2_REQUIRE_PTR(Z);
     const long total = M * N;
-    affine_act_kernel<<<grid_for(total, 256), 256, 0, as_stream(s)>>>(total, N, Y, scale, shift,
-                                                                      relu, Z, ldz);
+    const bool v4 = vec4_ok(N, ldz, Y, Z) &&
+                    (scale == nullptr ||
+                     ((reinterpret_cast<uintptr_t>(scale) | reinterpret_cast<uintptr_t>(shift)) & 15) == 0);
+    if (v4)
+        affine_act_v4_kernel<<<grid_for(total / 4, 256), 256, 0, as_stream(s)>>>(total / 4, N / 4, Y, scale,
+                                                                               shift, relu, Z, ldz);
+    else
+        affine_act_kernel<<<grid_for(total, 256), 256, 0, as_stream(s)>>>(total, N, Y, scale, shift,
+                                                                          relu, Z, ldz);
     return finish_launch();
 }
 
@@ -735,8 +873,15 @@ PN2_API int pn2_affine_act_maxpool(long G, int ns, int N, const float *Y, const 
     PN2_REQUIRE_PTR(Y);
     PN2_REQUIRE_PTR(out);
     const long total = G * N;
-    affine_act_maxpool_kernel<<<grid_for(total, 128), 128, 0, as_stream(s)>>>(
-        total, ns, N, Y, scale, shift, relu, out, arg);
+    const bool v4 = vec4_ok(N, N, Y, out) && (arg == nullptr || (reinterpret_cast<uintptr_t>(arg) & 15) == 0) &&
+                    (scale == nullptr ||
+                     ((reinterpret_cast<uintptr_t>(scale) | reinterpret_cast<uintptr_t>(shift)) & 15) == 0);
+    if (v4)
+        affine_act_maxpool_v4_kernel<<<grid_for(total / 4, 128), 128, 0, as_stream(s)>>>(
+            total / 4, ns, N, Y, scale, shift, relu, out, arg);
+    else
+        affine_act_maxpool_kernel<<<grid_for(total, 128), 128, 0, as_stream(s)>>>(
+            total, ns, N, Y, scale, shift, relu, out, arg);
     return finish_launch();
 }
 
@@ -753,9 +898,14 @@ PN2_API int pn2_bn_bwd_reduce(long M, int N, const float *dZ, int ldz, const flo
     PN2_REQUIRE_PTR(red);
     int blocks;
     long rpb = slab_rows(M, &blocks);
-    if (vec4_ok(N, ldz, dZ, Y))
-        bn_bwd_reduce_v4_kernel<<<blocks, 256, 2 * N * sizeof(double), as_stream(s)>>>(
-            M, N, rpb, dZ, ldz, Y, scale, shift, saved, relu, red);
+    if (vec4_ok(N, ldz, dZ, Y)) {
+        // two resident blocks of work per SM: every block ends with 2N global fp64 atomics
+        long rpb4 = ceil_div<long>(M, 148L * 2);
+        if (rpb4 < 32) rpb4 = 32;
+        const int blocks4 = (int)ceil_div<long>(M, rpb4);
+        bn_bwd_reduce_v4_kernel<<<blocks4, 256, 2 * N * sizeof(double), as_stream(s)>>>(
+            M, N, rpb4, dZ, ldz, Y, scale, shift, saved, relu, red);
+    }
     else
         bn_bwd_reduce_kernel<<<blocks, 256, 2 * N * sizeof(double), as_stream(s)>>>(
             M, N, rpb, dZ, ldz, Y, scale, shift, saved, relu, red);
@@ -804,10 +954,13 @@ PN2_API int pn2_bn_bwd_reduce_pool(long G, int ns, int N, const float *dOut, con
     PN2_REQUIRE_PTR(shift);
     PN2_REQUIRE_PTR(saved);
     PN2_REQUIRE_PTR(red);
-    int blocks;
-    (void)slab_rows(G, &blocks);
-    bn_bwd_reduce_pool_kernel<<<blocks, 256, 0, as_stream(s)>>>(G, ns, N, dOut, arg, Y, scale, shift,
-                                                                saved, relu, red);
+    // ~2048 (group, column) elements per block, at most four blocks per SM
+    long blocks = ceil_div<long>(G * (long)N, 2048L);
+    if (blocks > 148L * 4) blocks = 148L * 4;
+    if (blocks > G) blocks = G;
+    if (blocks < 1) blocks = 1;
+    bn_bwd_reduce_pool_kernel<<<(int)blocks, 256, 2 * N * sizeof(double), as_stream(s)>>>(
+        G, ns, N, dOut, arg, Y, scale, shift, saved, relu, red);
     return finish_launch();
 }
 
@@ -830,6 +983,16 @@ PN2_API int pn2_bn_bwd_apply_pool(long G, int ns, int N, const float *dOut, cons
         PN2_REQUIRE_PTR(red);
     }
     PN2_REQUIRE((scale == nullptr) == (shift == nullptr));
+    const bool v4 = (N % 4 == 0) &&
+                    ((reinterpret_cast<uintptr_t>(dOut) | reinterpret_cast<uintptr_t>(arg) |
+                      reinterpret_cast<uintptr_t>(Y) | reinterpret_cast<uintptr_t>(dY)) & 15) == 0;
+    if (v4) {
+        long gpb = ceil_div<long>(G, 148L * 8);
+        if (gpb < 1) gpb = 1;
+        bn_bwd_apply_pool_v4_kernel<<<(int)ceil_div<long>(G, gpb), 256, 0, as_stream(s)>>>(
+            G, ns, N, gpb, dOut, arg, Y, scale, shift, saved, gamma, relu, bn, red, dY, dgamma, dbeta);
+        return finish_launch();
+    }
     int blocks;
     long rpb = slab_rows(G * ns, &blocks);
     bn_bwd_apply_pool_kernel<<<blocks, 256, 0, as_stream(s)>>>(G, ns, N, rpb, dOut, arg, Y, scale,

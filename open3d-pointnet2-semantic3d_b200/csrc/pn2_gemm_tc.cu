@@ -166,7 +166,7 @@ __host__ __device__ __forceinline__ uint32_t sw128_offset(int row, int k) {
 
 // Weight image: for every column block (128 columns, or all N <= 128) and every K chunk kc:
 // [hi image: Npad rows x 128 B][lo image: same], elements Bt(n,k) = src[n*s_n + k*s_k], zero outside (N,K).
-__global__ void tc_prep_b_kernel(int N, int K, int Npad, int KC, int nchunks,
+__global__ void tc_prep_b_kernel(int N, int Ntot, int K, int Npad, int KC, int nchunks,
                                  const float *__restrict__ src, long s_n, long s_k,
                                  float *__restrict__ image) {
     const long total = (long)nchunks * KC * Npad * BK;
@@ -180,7 +180,7 @@ __global__ void tc_prep_b_kernel(int N, int K, int Npad, int KC, int nchunks,
         const int ch = (int)(t2 / KC);
         const int k = kc * BK + kk;
         const long n = (long)ch * 128 + nl;  // N = columns per block when nchunks > 1
-        float v = (nl < N && k < K) ? __ldg(src + n * s_n + k * s_k) : 0.f;
+        float v = (nl < N && n < Ntot && k < K) ? __ldg(src + n * s_n + k * s_k) : 0.f;
         const float hi = tf32_rna(v);
         const float lo = v - hi;
         unsigned char *base = reinterpret_cast<unsigned char *>(image) + ((size_t)ch * KC + kc) * 2 * Npad * 128;
@@ -202,6 +202,7 @@ struct Params {
     long M;
     int K, N, Npad, KC, stages, b_res, raw_slots, a_tma, y_tma, lda, ldy, a_relu;
     int nchunks;  // column blocks of 128 handled by this launch (CTA c works on block c % nchunks)
+    int Ntot;     // output columns of the launch; the last block may be narrower than N
     int ksplit;   // K > 512: chunks [0,KC/2) and [KC/2,KC) accumulate separately (no double buffering)
     const float *A, *a_scale, *a_shift, *bias, *image;
     float *Y;
@@ -256,6 +257,7 @@ __global__ void __launch_bounds__(THREADS, 1)
     while (ncols < (uint32_t)(4 * Nacc)) ncols <<= 1;  // {main, corr} x (double buffer | K halves)
     // column block of this CTA and its row-tile sequence
     const int nc = blockIdx.x % p.nchunks, n0 = nc * 128;
+    const int Nv = (p.Ntot - n0) < p.N ? (p.Ntot - n0) : p.N;  // valid columns of this block
     const long mt0 = blockIdx.x / p.nchunks, mstride = gridDim.x / p.nchunks;
     const unsigned char *image = reinterpret_cast<const unsigned char *>(p.image) +
                                  (size_t)nc * p.KC * 2 * ((size_t)p.Npad * 128);
@@ -277,7 +279,7 @@ __global__ void __launch_bounds__(THREADS, 1)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (threadIdx.x < 128)
-        sbias[threadIdx.x] = (p.bias && (int)threadIdx.x < p.N) ? __ldg(p.bias + n0 + threadIdx.x) : 0.f;
+        sbias[threadIdx.x] = (p.bias && (int)threadIdx.x < Nv) ? __ldg(p.bias + n0 + threadIdx.x) : 0.f;
     if (warp == W_MMA) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                          smem_u32(tmem_slot)),
@@ -509,7 +511,7 @@ __global__ void __launch_bounds__(THREADS, 1)
         // staging + coalesced st.global.
         float *stg = reinterpret_cast<float *>(epi_b) + warp * 32 * EPI_LD;
         unsigned char *wbuf = epi_b + warp * 8192;
-        const int nblk = (p.N + 31) / 32;
+        const int nblk = (Nv + 31) / 32;
         // BatchNorm statistics: per lane-column fp64 sums of (y - c) and (y - c)^2 with a constant
         // shift c (the first value this lane sees in the column) so that neither the fp32 partial
         // sums over 32 rows nor the final variance suffer cancellation; un-shifted once at the end.
@@ -554,7 +556,7 @@ __global__ void __launch_bounds__(THREADS, 1)
                 const uint32_t ta = tmem_base + ((uint32_t)(warp * 32) << 16) +
                                     acc * (uint32_t)(2 * Nacc) + cb * 32;
                 const int col = cb * 32 + lane;
-                const bool col_ok = col < p.N;
+                const bool col_ok = col < Nv;
                 const bool do_stats = p.stats_sum && col_ok && rows_left > 0;
                 const int nv = rows_left >= 32 ? 32 : (int)rows_left;
                 if (p.y_tma) {
@@ -662,7 +664,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 #pragma unroll
             for (int cb = 0; cb < 4; ++cb) {
                 const int col = cb * 32 + lane;
-                if (cb < nblk && col < p.N && nrows > 0) {
+                if (cb < nblk && col < Nv && nrows > 0) {
                     const double c = (double)cshift[cb], n = (double)nrows;
                     atomicAdd(p.stats_sum + n0 + col, ssum[cb] + n * c);
                     atomicAdd(p.stats_sq + n0 + col, ssq[cb] + 2.0 * c * ssum[cb] + n * c * c);
@@ -729,13 +731,14 @@ static bool make_tensor_map(CUtensorMap *tm, const float *base, long rows, int c
 
 static size_t image_bytes(int K, int N) {
     const int KC = (K + BK - 1) / BK;
-    if (N > 128) return (size_t)(N / 128 > 0 ? N / 128 : 1) * KC * 2 * 128 * 128;
+    if (N > 128) return (size_t)((N + 127) / 128) * KC * 2 * 128 * 128;
     const int Npad = (N + 15) & ~15;
     return (size_t)KC * 2 * Npad * 128;
 }
 
-// Y[M, 0:nchunks*Nc]: nchunks column blocks of Nc columns (Nc == 128 when nchunks > 1, else <= 128)
-static int run_chunk(long M, int K, int Nc, int nchunks, const float *A, int lda, const float *a_scale,
+// Y[M, 0:Ntot]: nchunks column blocks of Nc columns (Nc == 128 when nchunks > 1, the last one may be
+// narrower; a single block has Nc = Ntot <= 128)
+static int run_chunk(long M, int K, int Nc, int nchunks, int Ntot, const float *A, int lda, const float *a_scale,
                      const float *a_shift, int a_relu, const float *bsrc, long s_n, long s_k,
                      const float *bias, float *Y, int ldy, double *stats_sum, double *stats_sq,
                      float *ws, cudaStream_t st) {
@@ -758,6 +761,7 @@ static int run_chunk(long M, int K, int Nc, int nchunks, const float *A, int lda
     p.stats_sq = stats_sq;
     if (p.KC > MAX_KC || Nc > 128 || nchunks < 1 || (nchunks > 1 && Nc != 128)) return PN2_EUNSUPPORTED;
     p.nchunks = nchunks;
+    p.Ntot = Ntot;
     p.ksplit = p.KC > 16 ? 1 : 0;  // K > 512: two accumulator sets bound the truncating accumulation
 
     // PN2_TC_TMA bit mask (diagnostics): 1 = tensor loads for A, 2 = tensor stores for Y; default 3
@@ -766,7 +770,7 @@ static int run_chunk(long M, int K, int Nc, int nchunks, const float *A, int lda
     memset(&tmA, 0, sizeof(tmA));
     memset(&tmY, 0, sizeof(tmY));
     p.a_tma = ((tma_mask & 1) && M < (1l << 31) && make_tensor_map(&tmA, A, M, K, lda, BM, false)) ? 1 : 0;
-    p.y_tma = ((tma_mask & 2) && M < (1l << 31) && make_tensor_map(&tmY, Y, M, Nc * nchunks, ldy, 32, true)) ? 1 : 0;
+    p.y_tma = ((tma_mask & 2) && M < (1l << 31) && make_tensor_map(&tmY, Y, M, Ntot, ldy, 32, true)) ? 1 : 0;
 
     // shared memory plan (227 KB usable per CTA): raw ring (4 slots if possible), >= 2 MMA stages,
     // weights resident when they fit next to that
@@ -806,7 +810,7 @@ static int run_chunk(long M, int K, int Nc, int nchunks, const float *A, int lda
     const long total = (long)nchunks * p.KC * p.Npad * BK;
     int pb = (int)((total + 255) / 256);
     if (pb > 148 * 8) pb = 148 * 8;
-    tc_prep_b_kernel<<<pb, 256, 0, st>>>(Nc, K, p.Npad, p.KC, nchunks, bsrc, s_n, s_k, ws);
+    tc_prep_b_kernel<<<pb, 256, 0, st>>>(Nc, Ntot, K, p.Npad, p.KC, nchunks, bsrc, s_n, s_k, ws);
     int rc = finish_launch();
     if (rc) return rc;
 
@@ -1264,9 +1268,7 @@ int tc_linear_wgrad(long M, int K, int N, const float *A, int lda, const float *
 static bool tc_shape_ok(long M, int K, int N) { return M >= 128 && K >= 16 && K <= 1024 && N >= 16; }
 
 constexpr int TC_NCHUNK = 128;
-static size_t tc_image_bytes(int K, int N) {
-    return tc::image_bytes(K, (N > TC_NCHUNK && N % TC_NCHUNK != 0) ? TC_NCHUNK : N);
-}
+static size_t tc_image_bytes(int K, int N) { return tc::image_bytes(K, N); }
 
 // one buffer serves both orientations of a layer: forward (K x N) and dgrad (N x K)
 size_t tc_workspace_bytes(int K, int N) {
@@ -1279,19 +1281,10 @@ int tc_linear_fwd(long M, int K, int N, const float *A, int lda, const float *a_
                   double *stats, float *ws, size_t ws_bytes, cudaStream_t st) {
     if (!tc_shape_ok(M, K, N) || ws == nullptr || ws_bytes < tc_image_bytes(K, N))
         return PN2_EUNSUPPORTED;
-    if (N <= TC_NCHUNK || N % TC_NCHUNK == 0)  // all column blocks in one launch; Bt(n,k) = W[k*N + n]
-        return tc::run_chunk(M, K, N <= TC_NCHUNK ? N : TC_NCHUNK, N <= TC_NCHUNK ? 1 : N / TC_NCHUNK, A,
-                             lda, a_scale, a_shift, a_relu, W, 1, N, bias, Y, N, stats,
-                             stats ? stats + N : nullptr, ws, st);
-    for (int n0 = 0; n0 < N; n0 += TC_NCHUNK) {
-        const int nc = (N - n0) < TC_NCHUNK ? (N - n0) : TC_NCHUNK;
-        // Bt(n,k) = W[k*N + n0 + n]
-        int rc = tc::run_chunk(M, K, nc, 1, A, lda, a_scale, a_shift, a_relu, W + n0, 1, N,
-                               bias ? bias + n0 : nullptr, Y + n0, N, stats ? stats + n0 : nullptr,
-                               stats ? stats + N + n0 : nullptr, ws, st);
-        if (rc) return rc;
-    }
-    return PN2_OK;
+    // all column blocks in one launch; Bt(n,k) = W[k*N + n]
+    const int nch = (N + TC_NCHUNK - 1) / TC_NCHUNK;
+    return tc::run_chunk(M, K, nch == 1 ? N : TC_NCHUNK, nch, N, A, lda, a_scale, a_shift, a_relu, W, 1, N,
+                         bias, Y, N, stats, stats ? stats + N : nullptr, ws, st);
 }
 
 int tc_linear_dgrad(long M, int K, int N, const float *dY, const float *W, float *dX, int ldx,
@@ -1299,16 +1292,9 @@ int tc_linear_dgrad(long M, int K, int N, const float *dY, const float *W, float
     // dX[M,K] = dY[M,N] * W[K,N]^T : contraction over N, output columns = K ; Bt(k,n) = W[k*N + n]
     if (!tc_shape_ok(M, N, K) || ws == nullptr || ws_bytes < tc_image_bytes(N, K))
         return PN2_EUNSUPPORTED;
-    if (K <= TC_NCHUNK || K % TC_NCHUNK == 0)
-        return tc::run_chunk(M, N, K <= TC_NCHUNK ? K : TC_NCHUNK, K <= TC_NCHUNK ? 1 : K / TC_NCHUNK, dY, N,
-                             nullptr, nullptr, 0, W, N, 1, nullptr, dX, ldx, nullptr, nullptr, ws, st);
-    for (int k0 = 0; k0 < K; k0 += TC_NCHUNK) {
-        const int kc = (K - k0) < TC_NCHUNK ? (K - k0) : TC_NCHUNK;
-        int rc = tc::run_chunk(M, N, kc, 1, dY, N, nullptr, nullptr, 0, W + (long)k0 * N, N, 1, nullptr,
-                               dX + k0, ldx, nullptr, nullptr, ws, st);
-        if (rc) return rc;
-    }
-    return PN2_OK;
+    const int nch = (K + TC_NCHUNK - 1) / TC_NCHUNK;
+    return tc::run_chunk(M, N, nch == 1 ? K : TC_NCHUNK, nch, K, dY, N, nullptr, nullptr, 0, W, N, 1, nullptr,
+                         dX, ldx, nullptr, nullptr, ws, st);
 }
 
 }  // namespace pn2

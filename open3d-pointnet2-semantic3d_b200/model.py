@@ -73,7 +73,7 @@ class _SoftmaxCE(torch.autograd.Function):
     def forward(ctx, pred, label, smpw):
         rows, c = pred.numel() // pred.shape[-1], pred.shape[-1]
         pred = pred.contiguous()
-        acc = torch.zeros(2, dtype=F64, device=pred.device)
+        acc = tf_util.zero_arena.take(2, pred.device)
         loss = torch.empty((), dtype=F32, device=pred.device)
         call("pn2_softmax_ce_reduce", rows, c, ptr(pred, F32), ptr(label, I32),
              ptr(smpw, F32, True), ptr(acc, F64))

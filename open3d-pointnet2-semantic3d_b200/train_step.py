@@ -64,14 +64,19 @@ class Trainer:
     def forward_backward(self, point_cloud, labels, smpw):
         bn_decay = get_bn_decay(self.step_count, self.params)
         tf_util.set_default_store(self.store)
-        pred, _ = model.get_model(point_cloud, True, self.num_class, self.params, bn_decay=bn_decay)
-        if self.store.flat_params is None:   # first call created the variables: flatten, redo
-            self._ensure_flat()
-            pred, _ = model.get_model(point_cloud, True, self.num_class, self.params,
-                                      bn_decay=bn_decay)
-        self.store.zero_grad()
-        loss = model.get_loss(pred, labels, smpw)
-        loss.backward()
+        tf_util.zero_arena.reset(point_cloud.device)  # one memset for every layer's fp64 accumulators
+        try:
+            pred, _ = model.get_model(point_cloud, True, self.num_class, self.params, bn_decay=bn_decay)
+            if self.store.flat_params is None:   # first call created the variables: flatten, redo
+                self._ensure_flat()
+                tf_util.zero_arena.reset(point_cloud.device)
+                pred, _ = model.get_model(point_cloud, True, self.num_class, self.params,
+                                          bn_decay=bn_decay)
+            self.store.zero_grad()
+            loss = model.get_loss(pred, labels, smpw)
+            loss.backward()
+        finally:
+            tf_util.zero_arena.disarm()
         return loss
 
     def step(self, point_cloud, labels, smpw):

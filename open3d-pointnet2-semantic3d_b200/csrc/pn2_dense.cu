@@ -662,6 +662,50 @@ __global__ void adam_kernel(long n, float *__restrict__ p, const float *__restri
     }
 }
 
+// dW[K,N] += f(A)^T dY for narrow outputs (N <= 16: the 9-class head).  Thread = feature k with N
+// accumulators in registers; the dY rows of a 64-row tile are broadcast from shared memory, the A
+// column reads are coalesced across the block.  One fp32 atomic per (k, n) per block.
+template <int NMAX>
+__global__ void __launch_bounds__(128)
+wgrad_skinny_kernel(long M, int K, int N, long rpb, const float *__restrict__ A, int lda,
+                    const float *__restrict__ a_scale, const float *__restrict__ a_shift, int a_relu,
+                    const float *__restrict__ dY, float *__restrict__ dW) {
+    __shared__ float sdy[64 * NMAX];
+    const int k = blockIdx.y * 128 + threadIdx.x;
+    const bool kok = k < K;
+    const float sc = (a_scale && kok) ? __ldg(a_scale + k) : 1.f;
+    const float sh = (a_scale && kok) ? __ldg(a_shift + k) : 0.f;
+    float acc[NMAX];
+#pragma unroll
+    for (int n = 0; n < NMAX; ++n) acc[n] = 0.f;
+    for (int e = threadIdx.x; e < 64 * NMAX; e += 128) sdy[e] = 0.f;
+    const long r0 = (long)blockIdx.x * rpb;
+    const long r1 = r0 + rpb < M ? r0 + rpb : M;
+    for (long rt = r0; rt < r1; rt += 64) {
+        const int nr = (int)((r1 - rt) < 64 ? (r1 - rt) : 64);
+        __syncthreads();
+        for (int e = threadIdx.x; e < nr * N; e += 128)
+            sdy[(e / N) * NMAX + (e % N)] = __ldg(dY + rt * N + e);
+        __syncthreads();
+        const float *ap = A + rt * lda + k;
+#pragma unroll 8
+        for (int r = 0; r < nr; ++r) {
+            float a = kok ? __ldg(ap + (long)r * lda) : 0.f;
+            if (a_scale) {
+                a = __fmaf_rn(a, sc, sh);
+                if (a_relu) a = fmaxf(a, 0.f);
+            }
+#pragma unroll
+            for (int n = 0; n < NMAX; ++n) acc[n] = __fmaf_rn(a, sdy[r * NMAX + n], acc[n]);
+        }
+    }
+    if (kok) {
+#pragma unroll
+        for (int n = 0; n < NMAX; ++n)
+            if (n < N) atomicAdd(dW + (long)k * N + n, acc[n]);
+    }
+}
+
 __global__ void colsum_kernel(long M, int N, long rpb, const float *__restrict__ X,
                               float *__restrict__ out) {
     const Slab s = make_slab(M, N, rpb);
@@ -766,6 +810,15 @@ PN2_API int pn2_linear_wgrad(long M, int K, int N, const float *A, int lda, cons
     static const bool use_rt = getenv("PN2_WGRAD_RT") && getenv("PN2_WGRAD_RT")[0] == '1';
     if (use_rt && mode != 1) rc = wgrad_rt(M, K, N, A, lda, a_scale, a_shift, a_relu, dY, dW, st);
     int k_done = 0;
+    if (rc == PN2_EUNSUPPORTED && mode != 1 && N <= 16) {  // narrow output: feature-per-thread kernel
+        long rpb = ceil_div<long>(M, 148L * 4);
+        if (rpb < 64) rpb = 64;
+        dim3 grid((unsigned)ceil_div<long>(M, rpb), (unsigned)ceil_div(K, 128));
+        wgrad_skinny_kernel<16><<<grid, 128, 0, st>>>(M, K, N, rpb, A, lda, a_scale, a_shift, a_relu, dY, dW);
+        rc = finish_launch();
+        if (rc) return rc;
+        k_done = K;
+    }
     if (rc == PN2_EUNSUPPORTED && (mode == 1 || (mode == -1 && tc_enabled())))
         rc = tc_linear_wgrad(M, K, N, A, lda, a_scale, a_shift, a_relu, dY, dW, mode == 1, &k_done, st);
     if (rc == PN2_OK && k_done > 0 && k_done < K) {

@@ -1256,7 +1256,8 @@ int tc_linear_wgrad(long M, int K, int N, const float *A, int lda, const float *
     // a narrow tail of features (K = 131 -> 3) would cost a full extra pass over dY on the
     // 128-feature MMA tile; it is left to the caller's fp32 kernel (k_done tells where it starts)
     int Kdo = K;
-    if (!force && K > tcw::W_FEAT && (K % tcw::W_FEAT) < 32) Kdo = K - (K % tcw::W_FEAT);
+    static const bool tail_simt = getenv("PN2_WGRAD_TAIL") && getenv("PN2_WGRAD_TAIL")[0] == '1';
+    if (tail_simt && !force && K > tcw::W_FEAT && (K % tcw::W_FEAT) < 32) Kdo = K - (K % tcw::W_FEAT);
     int rc = tcw::run(M, K, Kdo, N, A, lda, a_scale, a_shift, a_relu, dY, dW, st);
     if (rc == PN2_OK) *k_done = Kdo;
     return rc;
@@ -1265,7 +1266,9 @@ int tc_linear_wgrad(long M, int K, int N, const float *A, int lda, const float *
 // Shapes worth the tensor cores: at least one full tile of rows, K and N not tiny.
 // Each accumulator set sees at most 512 contraction terms (K > 512 is split in two halves), which
 // keeps the truncating tensor-core accumulation inside the 1e-5 parity bar.
-static bool tc_shape_ok(long M, int K, int N) { return M >= 128 && K >= 16 && K <= 1024 && N >= 16; }
+// Narrow layers run too (the 6-channel input layer, the 9-class head): a partial K chunk and the
+// columns past N are zero-filled in shared memory.
+static bool tc_shape_ok(long M, int K, int N) { return M >= 128 && K >= 1 && K <= 1024 && N >= 1; }
 
 constexpr int TC_NCHUNK = 128;
 static size_t tc_image_bytes(int K, int N) { return tc::image_bytes(K, N); }

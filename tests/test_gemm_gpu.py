@@ -74,8 +74,6 @@ def test_linear_fwd(ffi, mode, M, K, N):
 def test_linear_fwd_padded_rows_many_tiles(ffi, mode, M, K, N):
     """The layers' shapes: A in a row-padded buffer (lda = K rounded up to 4, NaN in the padding),
     more row tiles than SMs (persistent CTAs loop), BN prologue + bias + statistics together."""
-    if mode == 1 and K < 16:
-        pytest.skip("tensor-core forward needs K >= 16")
     rs = np.random.RandomState(M + K + N)
     A = rs.normal(size=(M, K)).astype(np.float32)
     W = (rs.uniform(-1, 1, (K, N)) * np.sqrt(6.0 / (K + N))).astype(np.float32)
@@ -214,3 +212,32 @@ def test_bn_backward_kernels(ffi, M, N, ldz, relu):
     np.testing.assert_allclose(dY.cpu().numpy(), exp, atol=2e-5)
     np.testing.assert_allclose(dg.cpu().numpy(), s2, rtol=1e-5, atol=1e-3)
     np.testing.assert_allclose(db.cpu().numpy(), s1, rtol=1e-5, atol=1e-3)
+
+
+@pytest.mark.parametrize("M,K,N", [(20000, 128, 9), (30000, 6, 32), (3000, 3, 16), (70000, 64, 9)])
+def test_narrow_layers_auto_mode(ffi, M, K, N):
+    """The 6-channel input layer and the 9-class head in auto mode (-1): forward / dgrad on the
+    tensor cores with zero-filled partial chunks, wgrad on the feature-per-thread kernel."""
+    import torch
+    rs = np.random.RandomState(M + K + N)
+    A = rs.normal(size=(M, K)).astype(np.float32)
+    W = (rs.uniform(-1, 1, (K, N)) * np.sqrt(6.0 / (K + N))).astype(np.float32)
+    b = rs.uniform(-0.5, 0.5, N).astype(np.float32)
+    dY = (rs.normal(size=(M, N)) * 0.1).astype(np.float32)
+    p = ffi.ptr
+    At, Wt, dYt = to_cuda(A), to_cuda(W), to_cuda(dY)
+    Y, st = linear_fwd(ffi, At, Wt, to_cuda(b), None, None, False, -1)
+    exp = A.astype(np.float64) @ W.astype(np.float64) + b
+    np.testing.assert_allclose(Y.cpu().numpy(), exp, atol=1e-5)
+    np.testing.assert_allclose(st.cpu().numpy()[:N], exp.sum(0), rtol=1e-5, atol=1e-5 * M)
+    ws = _ws(ffi, K, N)
+    dX = torch.empty((M, K), dtype=torch.float32, device="cuda")
+    ffi.call("pn2_linear_dgrad", M, K, N, p(dYt), p(Wt), p(dX), K, p(ws), ws.numel() * 4, -1)
+    np.testing.assert_allclose(dX.cpu().numpy(), dY.astype(np.float64) @ W.astype(np.float64).T, atol=1e-5)
+    dW = torch.zeros((K, N), dtype=torch.float32, device="cuda")
+    db = torch.zeros(N, dtype=torch.float32, device="cuda")
+    ffi.call("pn2_linear_wgrad", M, K, N, p(At), K, None, None, 0, p(dYt), p(dW), p(db), -1)
+    expw = A.astype(np.float64).T @ dY.astype(np.float64)
+    tol = 2e-5 * max(1.0, np.abs(expw).max())
+    np.testing.assert_allclose(dW.cpu().numpy(), expw, atol=tol)
+    np.testing.assert_allclose(db.cpu().numpy(), dY.astype(np.float64).sum(0), atol=tol)

@@ -12,20 +12,21 @@
 // large hi*hi products and the small correction products go to TWO accumulators (main / corr)
 // that are summed with a round-to-nearest add in the epilogue; K is limited to 512.
 //
-// Structure (one persistent CTA per SM, 18 warps, roles as in the canonical Blackwell GEMM):
-//   warps 0-3  epilogue: tcgen05.ld accumulator (lane quadrant = warp), transpose through
-//              padded shared memory, + bias, coalesced row-major stores, fp64 column statistics
-//   warps 4-15 A producers, three independent groups of 4 warps that take K chunks round-robin
-//              (so three chunks of global loads are in flight per SM: the kernel was load-latency
-//              bound with one): coalesced float4 loads of a 128 x 32 chunk, previous layer's
-//              BatchNorm affine + ReLU applied on the fly, hi/lo split, st.shared into the
-//              128B-swizzled K-major UMMA layout, fence.proxy.async, mbarrier arrive
-//   warp 16    B loader: one cp.async.bulk per K chunk from a pre-split, pre-swizzled weight
-//              image in global memory (built by tc_prep_b_kernel, L2 resident)
-//   warp 17    TMEM allocation + single-thread tcgen05.mma issue (3 MMAs per K=8 step),
-//              tcgen05.commit onto the "stage empty" / "accumulator full" mbarriers
-// The accumulator pair is double buffered in TMEM (2 x 2 x N columns, N <= 128 per pass) so the
-// epilogue of tile i overlaps the main loop of tile i+1.
+// Structure (one persistent CTA per SM, 15 warps, roles as in the canonical Blackwell GEMM):
+//   warps 0-7   epilogue: tcgen05.ld (lane quadrant = warp & 3, column blocks split between the two
+//               warps of a quadrant) + bias -> 128B-swizzled staging tile -> TMA tensor store;
+//               BatchNorm column statistics from the staging tile (fp32 partials, fp64 totals)
+//   warps 8-11  A transform: raw 128 x 32 chunk from the TMA ring -> previous layer's BatchNorm
+//               affine + ReLU -> hi/lo split -> st.shared into the 128B-swizzled K-major UMMA
+//               layout -> fence.proxy.async -> mbarrier arrive
+//   warp 12     A loader: 2-D TMA tensor loads into a 4-slot raw ring (zero fill out of range)
+//   warp 13     B loader: cp.async.bulk of a pre-split, pre-swizzled weight image in global memory
+//               (built by tc_prep_b_kernel, L2 resident); resident in shared memory when it fits
+//   warp 14     TMEM allocation + single-thread tcgen05.mma issue (3 MMAs per K=8 step),
+//               tcgen05.commit onto the "stage empty" / "accumulator full" mbarriers
+// The accumulator pair is double buffered in TMEM (2 x 2 x N columns, N <= 128 per column block) so
+// the epilogue of tile i overlaps the main loop of tile i+1; all column blocks of a layer run in one
+// launch (CTA c owns block c mod nblocks).
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
@@ -37,15 +38,15 @@ namespace tc {
 
 constexpr int BM = 128;       // rows per tile (UMMA M)
 constexpr int BK = 32;        // fp32/tf32 elements per K chunk = one 128-byte swizzle row
-constexpr int NPG = 2;                    // A-transform groups of 4 warps, taking K chunks round-robin
-constexpr int THREADS = 32 * (4 + 4 * NPG + 3);  // 4 epilogue + 4*NPG transform + A loader + B loader + MMA
-constexpr int W_ALOAD = 4 + 4 * NPG, W_BLOAD = 5 + 4 * NPG, W_MMA = 6 + 4 * NPG;
+constexpr int W_EPI = 8;                  // epilogue warps 0-7: two per TMEM lane quadrant, column blocks split
+constexpr int W_XF = 4;                   // A-transform warps 8-11
+constexpr int THREADS = 32 * (W_EPI + W_XF + 3);  // + A loader + B loader + MMA
+constexpr int W_ALOAD = W_EPI + W_XF, W_BLOAD = W_ALOAD + 1, W_MMA = W_ALOAD + 2;
 constexpr int MAX_RAW = 4;                // raw A ring slots (16 KB each) filled by TMA tensor loads
 constexpr int RAW_BYTES = BM * BK * 4;
 constexpr int EPI_BYTES = 32 * 1024;      // epilogue staging
 constexpr int MAX_STAGES = 4;
 constexpr int MAX_KC = 32;    // K <= 1024 (K > 512 runs as two K halves with their own accumulators)
-constexpr int EPI_LD = 36;    // padded row length (floats) of the epilogue transpose buffer
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -269,7 +270,7 @@ __global__ void __launch_bounds__(THREADS, 1)
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&acc_full[a], 1);
-            mbar_init(&acc_empty[a], 128);
+            mbar_init(&acc_empty[a], 32 * W_EPI);
         }
         for (int kc = 0; kc < MAX_KC; ++kc) mbar_init(&bfull[kc], 1);
         for (int r = 0; r < MAX_RAW; ++r) {
@@ -294,22 +295,18 @@ __global__ void __launch_bounds__(THREADS, 1)
 
     const long num_tiles = (p.M + BM - 1) / BM;
 
-    if (warp >= 4 && warp < W_ALOAD) {
+    if (warp >= W_EPI && warp < W_ALOAD) {
         // ================================ A transform ================================
-        // group g takes chunks g, g+npg, ... of this CTA's (tile, kc) sequence; npg <= stages
-        // keeps every group within one ring revolution of the consumer (phase parity is safe).
         // The raw chunk comes from the TMA ring (or, when A cannot be described by a tensor map,
         // from float4 global loads); BatchNorm affine + ReLU of the previous layer, hi/lo split,
         // st.shared into the 128B-swizzled K-major UMMA layout, proxy fence, mbarrier arrive.
-        const int g = (warp - 4) >> 2;
-        const int npg = NPG < p.stages ? NPG : p.stages;
-        const int t = (threadIdx.x - 128) & 127;
+        const int t = threadIdx.x - 32 * W_EPI;
         const int k4 = t & 7, r0 = t >> 3;  // float4 slot inside the 32-wide chunk, base row
         const bool vec_ok = (p.lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0);
         const long my_tiles = mt0 < num_tiles ? (num_tiles - mt0 + mstride - 1) / mstride : 0;
         const long total_chunks = my_tiles * p.KC;
-        if (g < npg) {
-            for (long itl = g; itl < total_chunks; itl += npg) {
+        {
+            for (long itl = 0; itl < total_chunks; ++itl) {
                 const uint32_t it = (uint32_t)itl;
                 const long tile = mt0 + (itl / p.KC) * mstride;
                 const int kc = (int)(itl % p.KC);
@@ -317,7 +314,7 @@ __global__ void __launch_bounds__(THREADS, 1)
                 const int s = it % p.stages;
                 const uint32_t ph = (it / p.stages) & 1;
                 const int kbase = kc * BK + k4 * 4;
-                const bool tr = (blockIdx.x == 0 && g == 0 && t == 0);
+                const bool tr = (blockIdx.x == 0 && t == 0);
                 const long long c0 = tr ? clock64() : 0;
                 float sc[4], sh[4];
                 if (p.a_scale) {
@@ -503,23 +500,24 @@ __global__ void __launch_bounds__(THREADS, 1)
                 g_tc_trace[11] += tcnt;
             }
         }
-    } else if (warp < 4) {
-        // ================================ epilogue (warps 0-3) ================================
-        // tcgen05.ld (lane = row) -> main + corr + bias -> 128B-swizzled staging tile (32 rows x
-        // 32 columns per warp) -> one TMA tensor store per tile; the BatchNorm column statistics
-        // read the same staging tile column-wise.  Fallback without a Y tensor map: padded
-        // staging + coalesced st.global.
-        float *stg = reinterpret_cast<float *>(epi_b) + warp * 32 * EPI_LD;
-        unsigned char *wbuf = epi_b + warp * 8192;
+    } else if (warp < W_EPI) {
+        // ================================ epilogue (warps 0-7) ================================
+        // Warp w reads the TMEM lane quadrant w & 3 (rows) and the 32-column blocks cb with
+        // cb & 1 == w >> 2.  tcgen05.ld (lane = row) -> accumulators + bias -> 128B-swizzled staging
+        // tile (32 rows x 32 columns) -> one TMA tensor store per block (or, without a Y tensor map,
+        // coalesced st.global of the columns read back from the tile); the BatchNorm column
+        // statistics read the same staging tile column-wise.
+        const int q4 = warp & 3, wg = warp >> 2;
+        unsigned char *buf = epi_b + warp * 4096;
         const int nblk = (Nv + 31) / 32;
         // BatchNorm statistics: per lane-column fp64 sums of (y - c) and (y - c)^2 with a constant
         // shift c (the first value this lane sees in the column) so that neither the fp32 partial
         // sums over 32 rows nor the final variance suffer cancellation; un-shifted once at the end.
-        double ssum[4], ssq[4];
-        float cshift[4];
+        double ssum[2], ssq[2];
+        float cshift[2];
         long nrows = 0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 2; ++i) {
             ssum[i] = ssq[i] = 0.0;
             cshift[i] = 0.f;
         }
@@ -540,105 +538,73 @@ __global__ void __launch_bounds__(THREADS, 1)
                 for (int j = 0; j < 16; ++j) o[j] += __uint_as_float(r[j]) + __uint_as_float(rc[j]);
             }
         };
-        uint32_t tcnt = 0, cbi = 0;
+        uint32_t tcnt = 0;
         for (long tile = mt0; tile < num_tiles; tile += mstride, ++tcnt) {
             const uint32_t acc = p.ksplit ? 0 : (tcnt & 1), aph = p.ksplit ? (tcnt & 1) : ((tcnt >> 1) & 1);
-            const long m0 = tile * BM + warp * 32;
+            const long m0 = tile * BM + q4 * 32;
             const bool tr = (blockIdx.x == 0 && threadIdx.x == 0);
             const long long ce0 = tr ? clock64() : 0;
             mbar_wait(&acc_full[acc], aph);
             const long long ce1 = tr ? clock64() : 0;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const long rows_left = p.M - m0;
+            const int nv = rows_left >= 32 ? 32 : (int)rows_left;
 #pragma unroll
-            for (int cb = 0; cb < 4; ++cb) {
+            for (int ci = 0; ci < 2; ++ci) {
+                const int cb = 2 * ci + wg;
                 if (cb >= nblk) break;
-                const uint32_t ta = tmem_base + ((uint32_t)(warp * 32) << 16) +
+                const uint32_t ta = tmem_base + ((uint32_t)(q4 * 32) << 16) +
                                     acc * (uint32_t)(2 * Nacc) + cb * 32;
                 const int col = cb * 32 + lane;
                 const bool col_ok = col < Nv;
                 const bool do_stats = p.stats_sum && col_ok && rows_left > 0;
-                const int nv = rows_left >= 32 ? 32 : (int)rows_left;
-                if (p.y_tma) {
-                    unsigned char *buf = wbuf + (cbi & 1) * 4096;
-                    ++cbi;
-                    // the tensor store issued from this buffer two blocks ago has read it
-                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                    __syncwarp();
+                // the tensor store issued from the staging tile one block ago has read it
+                if (p.y_tma && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncwarp();
 #pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        float a16[16];
-                        load_sum16(ta + half * 16, a16);
+                for (int half = 0; half < 2; ++half) {
+                    float a16[16];
+                    load_sum16(ta + half * 16, a16);
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const float4 b4 =
-                                *reinterpret_cast<const float4 *>(sbias + cb * 32 + half * 16 + q * 4);
-                            float4 o;  // accumulators + bias
-                            o.x = a16[q * 4] + b4.x;
-                            o.y = a16[q * 4 + 1] + b4.y;
-                            o.z = a16[q * 4 + 2] + b4.z;
-                            o.w = a16[q * 4 + 3] + b4.w;
-                            const int c16 = half * 4 + q;
-                            *reinterpret_cast<float4 *>(buf + lane * 128 + ((c16 ^ (lane & 7)) << 4)) = o;
-                        }
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 b4 =
+                            *reinterpret_cast<const float4 *>(sbias + cb * 32 + half * 16 + q * 4);
+                        float4 o;  // accumulators + bias
+                        o.x = a16[q * 4] + b4.x;
+                        o.y = a16[q * 4 + 1] + b4.y;
+                        o.z = a16[q * 4 + 2] + b4.z;
+                        o.w = a16[q * 4 + 3] + b4.w;
+                        const int c16 = half * 4 + q;
+                        *reinterpret_cast<float4 *>(buf + lane * 128 + ((c16 ^ (lane & 7)) << 4)) = o;
                     }
+                }
+                if (p.y_tma) {
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
-                    if (lane == 0) {
-                        // one bulk group per block even when there is nothing to store: the
-                        // wait_group.read 1 above counts groups to tell which buffer is free
-                        if (rows_left > 0) tma_store_2d(&tmY, n0 + cb * 32, (int)m0, buf);  // rows >= M, cols >= N clipped
+                    if (lane == 0 && rows_left > 0) {
+                        tma_store_2d(&tmY, n0 + cb * 32, (int)m0, buf);  // rows >= M, cols >= N clipped
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
-                    if (do_stats) {
-                        const unsigned char *colp = buf + (lane & 3) * 4;
-                        const int c16 = lane >> 2;
-                        if (tcnt == 0) cshift[cb] = *reinterpret_cast<const float *>(colp + (c16 << 4));
-                        const float c0 = cshift[cb];
-                        float p1[4] = {0.f, 0.f, 0.f, 0.f}, p2[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                        for (int rr = 0; rr < 32; ++rr) {
-                            const float y = *reinterpret_cast<const float *>(
-                                colp + rr * 128 + (((c16 ^ (rr & 7)) & 7) << 4));
-                            const float dv = rr < nv ? y - c0 : 0.f;
-                            p1[rr & 3] += dv;
-                            p2[rr & 3] = __fmaf_rn(dv, dv, p2[rr & 3]);
-                        }
-                        ssum[cb] += (double)((p1[0] + p1[1]) + (p1[2] + p1[3]));
-                        ssq[cb] += (double)((p2[0] + p2[1]) + (p2[2] + p2[3]));
-                    }
                 } else {
+                    __syncwarp();
+                }
+                if (do_stats || !p.y_tma) {
+                    // column `lane` of the tile, rows 0..31 (conflict-free: a row is one 128-byte line)
+                    const unsigned char *colp = buf + (lane & 3) * 4;
+                    const int c16 = lane >> 2;
                     float vals[32];
 #pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        float a16[16];
-                        load_sum16(ta + half * 16, a16);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const float4 o = make_float4(a16[q * 4], a16[q * 4 + 1], a16[q * 4 + 2], a16[q * 4 + 3]);
-                            *reinterpret_cast<float4 *>(stg + lane * EPI_LD + half * 16 + q * 4) = o;
-                        }
-                    }
-                    __syncwarp();
-                    const float bv = sbias[col & 127];
-                    // all 32 shared-memory reads are issued back to back (independent), then the stores
-#pragma unroll
-                    for (int rr = 0; rr < 32; ++rr) vals[rr] = stg[rr * EPI_LD + lane] + bv;
-                    __syncwarp();
-                    if (col_ok && rows_left > 0) {
+                    for (int rr = 0; rr < 32; ++rr)
+                        vals[rr] = *reinterpret_cast<const float *>(colp + rr * 128 + (((c16 ^ (rr & 7)) & 7) << 4));
+                    if (!p.y_tma && col_ok && rows_left > 0) {
                         float *yp = p.Y + m0 * p.ldy + n0 + col;
-                        if (rows_left >= 32) {
 #pragma unroll
-                            for (int rr = 0; rr < 32; ++rr) yp[(long)rr * p.ldy] = vals[rr];
-                        } else {
-#pragma unroll
-                            for (int rr = 0; rr < 32; ++rr)
-                                if (rr < rows_left) yp[(long)rr * p.ldy] = vals[rr];
-                        }
+                        for (int rr = 0; rr < 32; ++rr)
+                            if (rr < nv) yp[(long)rr * p.ldy] = vals[rr];
                     }
                     if (do_stats) {
-                        if (tcnt == 0) cshift[cb] = vals[0];
-                        const float c0 = cshift[cb];
+                        if (tcnt == 0) cshift[ci] = vals[0];
+                        const float c0 = cshift[ci];
                         float p1[4] = {0.f, 0.f, 0.f, 0.f}, p2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                         for (int rr = 0; rr < 32; ++rr) {
@@ -646,9 +612,10 @@ __global__ void __launch_bounds__(THREADS, 1)
                             p1[rr & 3] += dv;
                             p2[rr & 3] = __fmaf_rn(dv, dv, p2[rr & 3]);
                         }
-                        ssum[cb] += (double)((p1[0] + p1[1]) + (p1[2] + p1[3]));
-                        ssq[cb] += (double)((p2[0] + p2[1]) + (p2[2] + p2[3]));
+                        ssum[ci] += (double)((p1[0] + p1[1]) + (p1[2] + p1[3]));
+                        ssq[ci] += (double)((p2[0] + p2[1]) + (p2[2] + p2[3]));
                     }
+                    if (!p.y_tma) __syncwarp();  // all column reads done before the tile is rewritten
                 }
             }
             nrows += rows_left >= 32 ? 32 : (rows_left > 0 ? rows_left : 0);
@@ -662,12 +629,13 @@ __global__ void __launch_bounds__(THREADS, 1)
         if (p.y_tma && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         if (p.stats_sum) {
 #pragma unroll
-            for (int cb = 0; cb < 4; ++cb) {
+            for (int ci = 0; ci < 2; ++ci) {
+                const int cb = 2 * ci + wg;
                 const int col = cb * 32 + lane;
                 if (cb < nblk && col < Nv && nrows > 0) {
-                    const double c = (double)cshift[cb], n = (double)nrows;
-                    atomicAdd(p.stats_sum + n0 + col, ssum[cb] + n * c);
-                    atomicAdd(p.stats_sq + n0 + col, ssq[cb] + 2.0 * c * ssum[cb] + n * c * c);
+                    const double c = (double)cshift[ci], n = (double)nrows;
+                    atomicAdd(p.stats_sum + n0 + col, ssum[ci] + n * c);
+                    atomicAdd(p.stats_sq + n0 + col, ssq[ci] + 2.0 * c * ssum[ci] + n * c * c);
                 }
             }
         }

@@ -238,8 +238,10 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        import datetime
         dist.init_process_group("nccl", rank=rank, world_size=world,
-                                device_id=torch.device("cuda", local))
+                                device_id=torch.device("cuda", local),
+                                timeout=datetime.timedelta(seconds=180))
     dev = torch.device("cuda", local)
     b, n = args.batch, args.npoint
     pc, labels, smpw = make_batch(b, n, 100 + rank)
@@ -307,17 +309,19 @@ def run_ours(args):
 
     # ---- per-entry-point breakdown (separate instrumented pass) + roofline ------------------
     roofline, breakdown = None, None
+    # every rank takes the instrumented steps (they contain the gradient all-reduce); rank 0 records
+    _ffi.profile = [] if rank == 0 else None
+    torch.cuda.synchronize()
+    psteps = min(args.steps, 3)
+    for _ in range(psteps):
+        flush.zero_()
+        # keep the launch queue backlogged (a ~25 ms spin kernel first): the events around every
+        # entry point then time GPU execution only, not the gaps of the eager Python launches
+        torch.cuda._sleep(50_000_000)
+        trainer.step(d_pc, d_lab, d_w)
+    torch.cuda.synchronize()
+    barrier()
     if rank == 0:
-        _ffi.profile = []
-        torch.cuda.synchronize()
-        psteps = min(args.steps, 3)
-        for _ in range(psteps):
-            flush.zero_()
-            # keep the launch queue backlogged (a ~25 ms spin kernel first): the events around every
-            # entry point then time GPU execution only, not the gaps of the eager Python launches
-            torch.cuda._sleep(50_000_000)
-            trainer.step(d_pc, d_lab, d_w)
-        torch.cuda.synchronize()
         agg = {}
         for name, a, bb in _ffi.profile:
             d = agg.setdefault(name, [0.0, 0])

@@ -127,51 +127,77 @@ def run_reference(args):
 # our arm
 # ---------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons DURING the timed region: an in-process NVML polling thread (a step
+    takes ~5 ms, so the whole timed region is shorter than one `nvidia-smi -lms` period)."""
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"),
+               (0x4, "sw_power_cap"))
 
     def __init__(self, gpu_index):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
+        import threading
+        self.sm, self.mx, self.reasons, self.h = [], None, set(), None
+        self._stop = threading.Event()
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "100"],
-                                      stdout=self.f, stderr=subprocess.DEVNULL)
-        except OSError:
-            self.p = None
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            # LOCAL_RANK indexes the visible devices; map through CUDA_VISIBLE_DEVICES if it is set
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = gpu_index
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if gpu_index < len(ids) and ids[gpu_index].isdigit():
+                    phys = int(ids[gpu_index])
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.h = None
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+
+    def _sample(self):
+        try:
+            self.sm.append(float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+            try:
+                r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            except Exception:
+                r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            for bit, name in self.REASONS:
+                if r & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def _run(self):
+        if self.h is None:
+            return
+        while not self._stop.is_set():
+            self._sample()
+            time.sleep(0.002)
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        if self.p is None:
-            return out
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.p.kill()
-        self.f.flush()
-        self.f.seek(0)
-        sm, mx, reasons = [], [], set()
-        for ln in self.f.read().splitlines():
-            c = [x.strip() for x in ln.split(",")]
-            if len(c) < 9:
-                continue
+        self._stop.set()
+        self.t.join(timeout=2)
+        if self.h is not None:
+            self._sample()
+        out = {"sm_mhz": None, "sm_max_mhz": self.mx, "reasons": sorted(self.reasons)}
+        if self.sm:
+            out["sm_mhz"] = float(np.median(self.sm))
+            out["samples"] = len(self.sm)
+            out["source"] = "nvml, polled every 2 ms inside the timed region"
+        else:  # NVML unavailable: one nvidia-smi query right after the timed region
             try:
-                sm.append(float(c[1]))
-                mx.append(float(c[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
-                                "sw_power_cap"), c[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if sm:
-            out["sm_mhz"] = float(np.median(sm))
-            out["sm_max_mhz"] = float(max(mx))
-            out["samples"] = len(sm)
-        out["reasons"] = sorted(reasons)
-        os.unlink(self.f.name)
+                q = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm,"
+                                    "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                                    "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap",
+                                    "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                                   timeout=10).stdout.splitlines()[0].split(",")
+                out["sm_mhz"], out["sm_max_mhz"] = float(q[0]), float(q[1])
+                out["reasons"] = [n for n, v in zip(("hw_slowdown", "hw_thermal_slowdown",
+                                                     "sw_thermal_slowdown", "sw_power_cap"), q[2:6])
+                                  if v.strip().lower().startswith("active")]
+                out["source"] = "nvidia-smi, one query right after the timed region"
+            except Exception:
+                pass
         return out
 
 

@@ -811,8 +811,9 @@ PN2_API int pn2_linear_wgrad(long M, int K, int N, const float *A, int lda, cons
     if (use_rt && mode != 1) rc = wgrad_rt(M, K, N, A, lda, a_scale, a_shift, a_relu, dY, dW, st);
     int k_done = 0;
     if (rc == PN2_EUNSUPPORTED && mode != 1 && N <= 16) {  // narrow output: feature-per-thread kernel
-        long rpb = ceil_div<long>(M, 148L * 4);
-        if (rpb < 64) rpb = 64;
+        // ~7 blocks of 128 threads per SM, 8 independent row loads in flight per thread
+        long rpb = ceil_div<long>(M, 148L * 7);
+        rpb = ceil_div<long>(rpb, 64L) * 64;
         dim3 grid((unsigned)ceil_div<long>(M, rpb), (unsigned)ceil_div(K, 128));
         wgrad_skinny_kernel<16><<<grid, 128, 0, st>>>(M, K, N, rpb, A, lda, a_scale, a_shift, a_relu, dY, dW);
         rc = finish_launch();

@@ -48,6 +48,18 @@ const char *pn2_last_cuda_error(void);
  * NULL: the running minimum distances live in registers, not in global memory. */
 int pn2_fps(int b, int n, int m, const float *inp, float *temp, int *out, pn2_stream_t s);
 
+/* replaces cumsumLauncher                  tf_ops/tf_sampling.cu:208-210
+ * inp (b,n) -> out (b,n): row-wise inclusive prefix sum, bit-identical to the reference's
+ * blocked scan (same fp32 addition order, see oracle/pn2_oracle.c cumsum_row_ref). */
+int pn2_cumsum(int b, int n, const float *inp, float *out, pn2_stream_t s);
+
+/* replaces probsampleLauncher              tf_ops/tf_sampling.cu:212-216
+ * inp_p (b,n) weights, inp_r (b,m) uniform numbers in [0,1) -> out (b,m) int32 category
+ * indices (inverse CDF).  temp: (b,n) floats of scratch, receives the CDF
+ * (tf_sampling.cpp:104-108 allocates the same). */
+int pn2_prob_sample(int b, int n, int m, const float *inp_p, const float *inp_r, float *temp,
+                    int *out, pn2_stream_t s);
+
 /* replaces gatherpointLauncher             tf_ops/tf_sampling.cu:222-225 */
 int pn2_gather_point(int b, int n, int m, const float *inp, const int *idx, float *out,
                      pn2_stream_t s);

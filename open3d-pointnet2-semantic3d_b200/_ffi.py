@@ -25,6 +25,8 @@ SIGNATURES = {
     "pn2_last_cuda_error": [],
     "pn2_ball_threshold": [_f],
     "pn2_fps": [_i, _i, _i, _vp, _vp, _vp, _vp],
+    "pn2_cumsum": [_i, _i, _vp, _vp, _vp],
+    "pn2_prob_sample": [_i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "pn2_gather_point": [_i, _i, _i, _vp, _vp, _vp, _vp],
     "pn2_gather_point_grad": [_i, _i, _i, _vp, _vp, _vp, _vp],
     "pn2_query_ball_point": [_i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp],

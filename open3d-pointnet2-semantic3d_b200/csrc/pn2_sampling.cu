@@ -454,6 +454,137 @@ __global__ void gather_point_grad_kernel(int n, int m, long total,
     }
 }
 
+// ---- prob_sample: prefix sum in the reference's rounding order + inverse-CDF search ------
+// fp32 addition is not associative, so bit-exact parity with tf_sampling.cu:7-92 fixes the
+// addition DAG (see oracle/pn2_oracle.c cumsum_row_ref): chunks of 8192 elements; local quad
+// prefixes; balanced tree sums S over the quad totals; inclusive prefixes
+// P(p) = S(p) + P(p - lowbit(p+1)); a compensated carry between chunks.  The DAG is evaluated
+// here without any shared-memory tree: one CTA per row, 1024 threads, thread t owns the quad
+// pair (2t, 2t+1); the first tree level is a register add, levels 1-5 are warp shuffles, levels
+// 6-10 are shuffles of one warp over the 32 warp totals, and the down-sweep runs the same
+// ladder backwards.  Positions beyond the end of a ragged chunk hold zeros; in-range positions
+// never read them (every read goes to a lower position), so no bounds test is needed.
+constexpr int kScanThreads = 1024;
+constexpr int kScanChunk = 8192;  // part of the rounding sequence (tf_sampling.cu:9,15), not a tuning knob
+
+__global__ void __launch_bounds__(kScanThreads)
+prob_cdf_kernel(int n, const float *__restrict__ inp, float *__restrict__ out) {
+    __shared__ float warp_tot[32];
+    __shared__ float chunk_total;
+    const unsigned full = 0xffffffffu;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const float *row = inp + (size_t)blockIdx.x * n;
+    float *orow = out + (size_t)blockIdx.x * n;
+    float run = 0.0f, comp = 0.0f;
+
+    for (int j = 0; j < n; j += kScanChunk) {
+        const int len = min(n - j, kScanChunk);
+        const int nq = (len + 3) >> 2;
+        float e[2][4];
+        float qt[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int k = 4 * (2 * t + h);
+            if (k + 3 < len) {
+                const float a = __ldg(row + j + k), b = __ldg(row + j + k + 1);
+                const float c = __ldg(row + j + k + 2), d = __ldg(row + j + k + 3);
+                const float ba = __fadd_rn(b, a), dc = __fadd_rn(d, c);
+                e[h][0] = a;
+                e[h][1] = ba;
+                e[h][2] = __fadd_rn(c, ba);
+                e[h][3] = __fadd_rn(dc, ba);
+                qt[h] = e[h][3];
+            } else {  // ragged last quad: left to right from zero; beyond the chunk: zeros
+                float acc = 0.0f;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (k + i < len) acc = __fadd_rn(acc, __ldg(row + j + k + i));
+                    e[h][i] = acc;
+                }
+                qt[h] = acc;
+            }
+        }
+        // up-sweep: a = S(block of lowbit(lane+1) pairs ending at this pair)
+        float a = __fadd_rn(qt[1], qt[0]);
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const float o = __shfl_up_sync(full, a, d);
+            if (((lane + 1) & (2 * d - 1)) == 0) a = __fadd_rn(a, o);
+        }
+        if (lane == 31) warp_tot[w] = a;
+        __syncthreads();
+        if (w == 0) {  // tree over the 32 warp totals, then their inclusive prefixes
+            float x = warp_tot[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const float o = __shfl_up_sync(full, x, d);
+                if (((lane + 1) & (2 * d - 1)) == 0) x = __fadd_rn(x, o);
+            }
+#pragma unroll
+            for (int d = 8; d >= 1; d >>= 1) {
+                const float o = __shfl_up_sync(full, x, d);
+                if (((lane + 1) & (2 * d - 1)) == d && lane + 1 > d) x = __fadd_rn(x, o);
+            }
+            warp_tot[lane] = x;
+        }
+        __syncthreads();
+        // down-sweep inside the warp: P(p) = S(p) + P(p - lowbit(p+1)); the pair in front of the
+        // warp's first block is the last pair of the previous warp (its prefix is warp_tot[w-1])
+        const float before = w > 0 ? warp_tot[w - 1] : 0.0f;
+        if (lane == 31) a = warp_tot[w];
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+            const float o = __shfl_up_sync(full, a, d);
+            if (((lane + 1) & (2 * d - 1)) == d) {
+                if (lane + 1 > d) a = __fadd_rn(a, o);
+                else if (w > 0) a = __fadd_rn(a, before);
+            }
+        }
+        float pprev = __shfl_up_sync(full, a, 1);  // inclusive prefix of pair t-1
+        if (lane == 0) pprev = before;
+        const bool has_prev = t > 0;
+        const float pre0 = has_prev ? __fadd_rn(qt[0], pprev) : qt[0];  // prefix of quad 2t
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int k = 4 * (2 * t + h);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (k + i < len) {
+                    float v = e[h][i];
+                    if (h == 1) v = __fadd_rn(v, pre0);
+                    else if (has_prev) v = __fadd_rn(v, pprev);
+                    orow[j + k + i] = __fadd_rn(v, run);
+                }
+            }
+        }
+        if (t == ((nq - 1) >> 1)) chunk_total = ((nq - 1) & 1) ? a : pre0;
+        __syncthreads();
+        const float tt = __fadd_rn(chunk_total, comp);
+        const float r2 = __fadd_rn(run, tt);
+        comp = __fsub_rn(tt, __fsub_rn(r2, run));
+        run = r2;
+    }
+}
+
+// tf_sampling.cu:94-110: r = n-1; for k = base, base/2, .. 1: if (r >= k && cdf[r-k] >= q) r -= k.
+// The CDF need not be monotone in fp32 (tree-ordered sum), so this exact search -- not a generic
+// lower bound -- is what defines the result.  One thread per draw; the top levels of the search
+// hit the same few CDF entries for every thread and stay in L1.
+__global__ void prob_search_kernel(int b, int n, int m, int base, const float *__restrict__ cdf,
+                                   const float *__restrict__ query, int *__restrict__ result) {
+    for (int i = blockIdx.y; i < b; i += gridDim.y) {
+        const float *c = cdf + (size_t)i * n;
+        const float total = __ldg(c + n - 1);
+        for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < m; j += gridDim.x * blockDim.x) {
+            const float q = __fmul_rn(__ldg(query + (size_t)i * m + j), total);
+            int r = n - 1;
+            for (int k = base; k >= 1; k >>= 1)
+                if (r >= k && __ldg(c + r - k) >= q) r -= k;
+            result[(size_t)i * m + j] = r;
+        }
+    }
+}
+
 }  // namespace pn2
 
 using namespace pn2;
@@ -516,5 +647,34 @@ PN2_API int pn2_gather_point_grad(int b, int n, int m, const float *out_g, const
     long blocks = ceil_div<long>(total, threads);
     if (blocks > 148L * 16) blocks = 148L * 16;
     gather_point_grad_kernel<<<(int)blocks, threads, 0, st>>>(n, m, total, out_g, idx, inp_g);
+    return finish_launch();
+}
+
+PN2_API int pn2_cumsum(int b, int n, const float *inp, float *out, pn2_stream_t s) {
+    PN2_REQUIRE(b >= 0 && n > 0);
+    if (b == 0) return PN2_OK;
+    PN2_REQUIRE_PTR(inp);
+    PN2_REQUIRE_PTR(out);
+    prob_cdf_kernel<<<b, kScanThreads, 0, as_stream(s)>>>(n, inp, out);
+    return finish_launch();
+}
+
+PN2_API int pn2_prob_sample(int b, int n, int m, const float *inp_p, const float *inp_r,
+                            float *temp, int *out, pn2_stream_t s) {
+    PN2_REQUIRE(b >= 0 && n > 0 && m >= 0);
+    if (b == 0 || m == 0) return PN2_OK;
+    PN2_REQUIRE_PTR(inp_p);
+    PN2_REQUIRE_PTR(inp_r);
+    PN2_REQUIRE_PTR(temp);  // (b,n) floats: the CDF, as in the reference (tf_sampling.cpp:104-108)
+    PN2_REQUIRE_PTR(out);
+    cudaStream_t st = as_stream(s);
+    prob_cdf_kernel<<<b, kScanThreads, 0, st>>>(n, inp_p, temp);
+    int rc = finish_launch();
+    if (rc) return rc;
+    int base = 1;
+    while (base < n) base <<= 1;
+    const int threads = 256;
+    dim3 grid((unsigned)min(ceil_div(m, threads), 148 * 8), (unsigned)min(b, 65535));
+    prob_search_kernel<<<grid, threads, 0, st>>>(b, n, m, base, temp, inp_r, out);
     return finish_launch();
 }

@@ -1,11 +1,12 @@
 """Sampling ops: same names / argument order as the reference's tf_ops/tf_sampling.py.
 
+  prob_sample(inp, inpr)               tf_sampling.py:18-26  (no gradient, :29)
   farthest_point_sample(npoint, inp)   tf_sampling.py:61-69  (no gradient, :72)
   gather_point(inp, idx)               tf_sampling.py:38-46  (gradient :54-58)
 
 Inputs and outputs are contiguous CUDA torch tensors (float32 / int32); the work is done by
 the sm_100a kernels behind the C ABI (csrc/pn2_sampling.cu).  Shape errors raise ValueError
-with the reference's InvalidArgument texts (tf_sampling.cpp:121-132, 166-178).
+with the reference's InvalidArgument texts (tf_sampling.cpp:86-96, 121-132, 166-178).
 """
 import torch
 
@@ -16,6 +17,23 @@ from .._ffi import F32, I32, call, ptr
 def _need(cond, msg):
     if not cond:
         raise ValueError(msg)
+
+
+def prob_sample(inp, inpr):
+    """inp (B,ncategory) float32 weights, inpr (B,npoints) float32 uniform numbers in [0,1) ->
+    (B,npoints) int32: category drawn by inverting the cumulative weights.  The prefix sum follows
+    the reference's fp32 addition order, so the result is bit-identical (csrc/pn2_sampling.cu)."""
+    _need(inp.dim() == 2, "ProbSample expects (batch_size,num_choices) inp shape")
+    _need(inpr.dim() == 2 and inpr.shape[0] == inp.shape[0],
+          "ProbSample expects (batch_size,num_points) inpr shape")
+    b, n = inp.shape
+    m = inpr.shape[1]
+    _need(n > 0, "ProbSample expects (batch_size,num_choices) inp shape")
+    inp, inpr = inp.detach().contiguous(), inpr.detach().contiguous()
+    out = torch.empty((b, m), dtype=I32, device=inp.device)
+    temp = torch.empty((b, n), dtype=F32, device=inp.device)
+    call("pn2_prob_sample", b, n, m, ptr(inp, F32), ptr(inpr, F32), ptr(temp, F32), ptr(out, I32))
+    return out
 
 
 def farthest_point_sample(npoint, inp):

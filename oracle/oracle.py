@@ -155,6 +155,15 @@ def select_top_k(k, dist):
     return outi, out
 
 
+def cumsum(inp):
+    """Row-wise inclusive prefix sum in the reference's rounding order (tf_sampling.cu:7-92)."""
+    inp = _f32(inp)
+    b, n = inp.shape
+    out = np.empty((b, n), np.float32)
+    lib().orc_cumsum(_ci(b), _ci(n), _p(inp), _p(out))
+    return out
+
+
 def prob_sample(inp, inpr):
     inp, inpr = _f32(inp), _f32(inpr)
     b, n = inp.shape

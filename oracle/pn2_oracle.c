@@ -20,6 +20,7 @@
  *   orc_three_interpolate      tf_ops/tf_interpolate.cpp:307-330
  *   orc_three_interpolate_grad tf_ops/tf_interpolate.cpp:397-421 (+memset :477)
  *   orc_selection_sort         tf_ops/tf_grouping.cu:95-136
+ *   orc_cumsum                 tf_ops/tf_sampling.cu:7-92 (prefix sum, reference rounding order)
  *   orc_prob_sample            tf_ops/tf_sampling.cu:7-110 (cumsum + binary search)
  *
  * Pinning status:
@@ -301,21 +302,88 @@ ORC_API void orc_selection_sort(int b, int n, int m, int k, const float *dist,
     }
 }
 
-/* tf_sampling.cu:94-110 applied to an inclusive prefix sum of inp_p
- * (tf_sampling.cu:7-92 computes that sum blockwise with a compensated carry;
- * the cumulative sum is restated in fp64 and rounded, so results can differ
- * from the device in the last ulp of the CDF -- documented as "next" scope). */
+/* ------------------------------------------------------------------------- */
+/* Inclusive prefix sum with the reference's rounding sequence.
+ * tf_sampling.cu:7-92 (cumsumKernel).  fp32 addition is not associative, so
+ * the ORDER of the additions is part of the result.  The reference fixes it
+ * as follows (restated here as a recurrence, not as its shared-memory scan):
+ *   - a row is cut into chunks of 8192 elements (:9 BlockSize*4, :15);
+ *   - inside a chunk, elements form quads.  A full quad (a,b,c,d) gets the
+ *     local prefixes a, b+a, c+(b+a), (d+c)+(b+a) (:21-33); the ragged last
+ *     quad is summed left to right starting from 0 (:35-44);
+ *   - over the quad totals q[0..nq) the up-sweep (:47-58) builds balanced
+ *     tree sums  S(p) = sum of the block of lowbit(p+1) quads ending at p,
+ *     S over 2^(u+1) quads = S(right half) + S(left half);
+ *   - the down-sweep (:59-70) turns them into inclusive prefixes
+ *     P(p) = S(p) + P(p - lowbit(p+1))      (P(p) = S(p) when p+1 is a power of two);
+ *   - element value = local prefix (+ P(quad-1) unless quad 0, :72-80), then
+ *     + the carry of the previous chunks (:82-84);
+ *   - the carry over chunk totals is a compensated (Kahan-style) sum (:85-89).
+ */
+#define ORC_SCAN_CHUNK 8192
+static void cumsum_row_ref(int n, const float *in, float *out) {
+    float loc[ORC_SCAN_CHUNK + 4];
+    float S[ORC_SCAN_CHUNK / 4], P[ORC_SCAN_CHUNK / 4];
+    float run = 0.0f, comp = 0.0f;
+    for (int j = 0; j < n; j += ORC_SCAN_CHUNK) {
+        const int len = n - j < ORC_SCAN_CHUNK ? n - j : ORC_SCAN_CHUNK;
+        const int nq = (len + 3) >> 2;
+        for (int q = 0; q < nq; ++q) {
+            const float *v = in + j + 4 * q;
+            float *e = loc + 4 * q;
+            if (4 * q + 3 < len) {
+                float ba = v[1] + v[0];
+                float dc = v[3] + v[2];
+                e[0] = v[0];
+                e[1] = ba;
+                e[2] = v[2] + ba;
+                e[3] = dc + ba;
+                S[q] = e[3];
+            } else {
+                float acc = 0.0f;
+                for (int k = 4 * q; k < len; ++k) {
+                    acc += in[j + k];
+                    loc[k] = acc;
+                }
+                S[q] = acc;
+            }
+        }
+        /* balanced tree sums, level by level (blocks of 2, 4, 8, ... quads) */
+        for (int half = 1; 2 * half <= nq; half <<= 1)
+            for (int p = 2 * half - 1; p < nq; p += 2 * half) S[p] = S[p] + S[p - half];
+        /* inclusive prefixes in ascending order: P(p - lowbit) is final by then */
+        for (int p = 0; p < nq; ++p) {
+            int low = (p + 1) & -(p + 1);
+            P[p] = (p + 1 == low) ? S[p] : S[p] + P[p - low];
+        }
+        for (int k = 0; k < len; ++k) {
+            int q = k >> 2;
+            float v = loc[k];
+            if (q > 0) v = v + P[q - 1];
+            out[j + k] = v + run;
+        }
+        {
+            float t = P[nq - 1] + comp;
+            float r2 = run + t;
+            comp = t - (r2 - run);
+            run = r2;
+        }
+    }
+}
+
+ORC_API void orc_cumsum(int b, int n, const float *inp, float *out) {
+    for (int i = 0; i < b; ++i) cumsum_row_ref(n, inp + (size_t)i * n, out + (size_t)i * n);
+}
+
+/* tf_sampling.cu:94-110 (binarysearchKernel) over the prefix sum above:
+ * q = r * cdf[n-1]; descending power-of-two steps, r -= k while cdf[r-k] >= q. */
 ORC_API void orc_prob_sample(int b, int n, int m, const float *inp_p,
                              const float *inp_r, int *out) {
     float *cdf = (float *)malloc(sizeof(float) * (size_t)(n > 0 ? n : 1));
     int base = 1;
     while (base < n) base <<= 1;
     for (int i = 0; i < b; ++i) {
-        double acc = 0.0;
-        for (int j = 0; j < n; ++j) {
-            acc += inp_p[(size_t)i * n + j];
-            cdf[j] = (float)acc;
-        }
+        cumsum_row_ref(n, inp_p + (size_t)i * n, cdf);
         for (int j = 0; j < m; ++j) {
             float q = inp_r[(size_t)i * m + j] * cdf[n - 1];
             int r = n - 1;

@@ -5,7 +5,7 @@
  * tf_ops/tf_sampling.cu and tf_ops/tf_grouping.cu where they lie under
  * /root/reference (never copied into this repo) and links them with this shim
  * into oracle/_ref/libref_tfops.so.  The shim only forwards to the launchers the
- * reference defines (tf_sampling.cu:218-229, tf_grouping.cu:138-162) and adds the
+ * reference defines (tf_sampling.cu:208-229, tf_grouping.cu:138-162) and adds the
  * memsets the reference's TF glue performs (tf_sampling.cpp:236,
  * tf_grouping.cpp:271) plus a device synchronise + error code, because the
  * reference launchers use the legacy default stream and never check errors.
@@ -13,6 +13,9 @@
  */
 #include <cuda_runtime.h>
 
+void cumsumLauncher(int b, int n, const float* inp, float* out);
+void probsampleLauncher(int b, int n, int m, const float* inp_p, const float* inp_r, float* temp,
+                        int* out);
 void farthestpointsamplingLauncher(int b, int n, int m, const float* inp, float* temp, int* out);
 void gatherpointLauncher(int b, int n, int m, const float* inp, const int* idx, float* out);
 void scatteraddpointLauncher(int b, int n, int m, const float* out_g, const int* idx, float* inp_g);
@@ -30,6 +33,16 @@ static int finish(int sync) {
 }
 
 extern "C" {
+int ref_cumsum(int b, int n, const float* inp, float* out, int sync) {
+    cumsumLauncher(b, n, inp, out);
+    return finish(sync);
+}
+/* temp: b*n floats of device scratch (tf_sampling.cpp:104-108) */
+int ref_prob_sample(int b, int n, int m, const float* inp_p, const float* inp_r, float* temp,
+                    int* out, int sync) {
+    probsampleLauncher(b, n, m, inp_p, inp_r, temp, out);
+    return finish(sync);
+}
 /* temp: 32*n floats of device scratch (tf_sampling.cpp:143-146) */
 int ref_fps(int b, int n, int m, const float* inp, float* temp, int* out, int sync) {
     farthestpointsamplingLauncher(b, n, m, inp, temp, out);

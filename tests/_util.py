@@ -34,6 +34,19 @@ class RefKernels:
     def _p(t):
         return ctypes.c_void_p(t.data_ptr())
 
+    def prob_sample(self, inp, inpr):
+        """-> (indices, cdf): tf_sampling.cu:212-216 (cumsumKernel + binarysearchKernel)."""
+        import torch
+        b, n = inp.shape
+        m = inpr.shape[1]
+        temp = torch.empty((b, n), dtype=torch.float32, device=inp.device)
+        out = torch.empty((b, m), dtype=torch.int32, device=inp.device)
+        torch.cuda.synchronize()
+        rc = self.lib.ref_prob_sample(b, n, m, self._p(inp), self._p(inpr), self._p(temp),
+                                      self._p(out), 1)
+        assert rc == 0, rc
+        return out, temp
+
     def fps(self, inp, m):
         import torch
         b, n, _ = inp.shape

@@ -295,3 +295,90 @@ def test_select_top_k_and_knn(ops):
     ei, eo = orc.select_top_k(16, d)
     np.testing.assert_array_equal(outi.cpu().numpy()[:, :, :16], ei[:, :, :16])
     np.testing.assert_array_equal(out.cpu().numpy()[:, :, :16], eo[:, :, :16])
+
+
+# ---------------------------------------------------------------- prob_sample
+PROB_CASES = [(1, 5, 8192), (2, 1, 16), (3, 33, 100), (2, 1024, 1000), (2, 4099, 300),
+              (2, 8192, 500), (2, 8193, 500), (1, 20000, 3000), (4, 16389, 64), (40, 257, 33)]
+
+
+def _prob_inputs(b, n, m):
+    rs = np.random.RandomState(100 + n)
+    p = (rs.random_sample((b, n)) * rs.choice([1e-3, 1.0, 37.0], size=(b, n))).astype(np.float32)
+    p[:, rs.randint(0, n, max(1, n // 7))] = 0  # zero-weight categories: flat CDF steps
+    r = rs.random_sample((b, m)).astype(np.float32)
+    r[:, 0] = 0.0
+    if m > 1:
+        r[:, 1] = np.nextafter(np.float32(1), np.float32(0))
+    return p, r
+
+
+@pytest.mark.parametrize("b,n,m", PROB_CASES)
+def test_prob_sample_matches_oracle(ops, b, n, m):
+    """Indices bit-exact; the CDF itself (pn2_cumsum) bit-exact: the kernel reproduces the
+    reference's fp32 addition order (tf_sampling.cu:7-92) with warp shuffles."""
+    import torch
+    from pn2_b200._ffi import F32, call, ptr
+    ts, _, _, orc = ops
+    p, r = _prob_inputs(b, n, m)
+    got = ts.prob_sample(to_cuda(p), to_cuda(r)).cpu().numpy()
+    assert got.dtype == np.int32 and got.shape == (b, m)
+    np.testing.assert_array_equal(got, orc.prob_sample(p, r))
+    pc = to_cuda(p)
+    cdf = torch.empty_like(pc)
+    call("pn2_cumsum", b, n, ptr(pc, F32), ptr(cdf, F32))
+    np.testing.assert_array_equal(cdf.cpu().numpy().view(np.uint32), orc.cumsum(p).view(np.uint32))
+
+
+def test_prob_sample_matches_reference_kernel(ops):
+    """Against the reference's own cumsumKernel + binarysearchKernel running on this GPU."""
+    import torch
+    from pn2_b200._ffi import F32, call, ptr
+    ts, _, _, _ = ops
+    ref = RefKernels()
+    for b, n, m in [(1, 5, 8192), (2, 8193, 500), (3, 20000, 2000), (32, 1000, 100)]:
+        p, r = _prob_inputs(b, n, m)
+        pc, rc = to_cuda(p), to_cuda(r)
+        exp_idx, exp_cdf = ref.prob_sample(pc, rc)
+        got = ts.prob_sample(pc, rc)
+        np.testing.assert_array_equal(got.cpu().numpy(), exp_idx.cpu().numpy())
+        cdf = torch.empty_like(pc)
+        call("pn2_cumsum", b, n, ptr(pc, F32), ptr(cdf, F32))
+        np.testing.assert_array_equal(cdf.cpu().numpy().view(np.uint32),
+                                      exp_cdf.cpu().numpy().view(np.uint32))
+
+
+def test_prob_sample_like_reference_test(ops):
+    """tf_ops/test_tf_ops.py:96-128 (TestSampling): triangle areas -> prob_sample -> gather_point
+    -> barycentric points -> farthest_point_sample(1024) -> gather_point, checked op by op."""
+    import torch
+    ts, _, _, orc = ops
+    np.random.seed(100)
+    tri = np.random.rand(1, 5, 3, 3).astype("float32")
+    a, b, c = (np.ascontiguousarray(tri[:, :, i]) for i in range(3))
+    areas = np.sqrt((np.cross(b - a, c - a) ** 2).sum(2) + 1e-9).astype(np.float32)
+    r = np.random.rand(1, 8192).astype(np.float32)
+    ids = ts.prob_sample(to_cuda(areas), to_cuda(r))
+    np.testing.assert_array_equal(ids.cpu().numpy(), orc.prob_sample(areas, r))
+    us, vs = (torch.as_tensor(np.random.rand(1, 8192).astype(np.float32)).cuda() for _ in range(2))
+    upv, umv = 1 - (us + vs - 1).abs(), us - vs
+    us, vs = (upv + umv) * 0.5, (upv - umv) * 0.5
+    ta, tb, tc = (ts.gather_point(to_cuda(t), ids) for t in (a, b, c))
+    np.testing.assert_array_equal(ta.cpu().numpy(), orc.gather_point(a, ids.cpu().numpy()))
+    pts = (ta + (tb - ta) * us[..., None] + (tc - ta) * vs[..., None]).contiguous()
+    fps = ts.farthest_point_sample(1024, pts)
+    np.testing.assert_array_equal(fps.cpu().numpy(),
+                                  orc.farthest_point_sample(1024, pts.cpu().numpy()))
+    red = ts.gather_point(pts, fps)
+    assert red.shape == (1, 1024, 3) and bool(torch.isfinite(red).all())
+
+
+def test_prob_sample_validation(ops):
+    import torch
+    ts, _, _, _ = ops
+    p = torch.ones((2, 5), device="cuda")
+    with pytest.raises(ValueError, match="num_choices"):
+        ts.prob_sample(torch.ones((2, 5, 1), device="cuda"), torch.ones((2, 3), device="cuda"))
+    with pytest.raises(ValueError, match="num_points"):
+        ts.prob_sample(p, torch.ones((3, 3), device="cuda"))
+    assert ts.prob_sample(p, torch.zeros((2, 0), device="cuda")).shape == (2, 0)

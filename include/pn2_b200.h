@@ -87,6 +87,17 @@ int pn2_group_point_grad(int b, int n, int c, int m, int nsample, const float *g
 int pn2_three_nn(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist, int *idx,
                  pn2_stream_t s);
 
+/* replaces interpolate_label_with_color_cpu tf_ops/tf_interpolate.cpp:71-115
+ * sparse_points (num_sparse,3), sparse_labels (num_sparse), dense_points (num_dense,3) ->
+ * dense_labels (num_dense) int32, dense_colors (num_dense,3) uint8: label vote among the knn
+ * nearest sparse points (exact fp64 distances, nearest first; the label whose running count
+ * first becomes the largest wins) and its colour from the reference's 9-entry table.
+ * knn <= 32 (PN2_EUNSUPPORTED beyond).  No sparse point at all -> label -1, colour 0. */
+int pn2_interpolate_label_with_color(int num_sparse, int num_dense, const float *sparse_points,
+                                     const int *sparse_labels, const float *dense_points,
+                                     int *dense_labels, unsigned char *dense_colors, int knn,
+                                     pn2_stream_t s);
+
 /* replaces threeinterpolate_cpu            tf_ops/tf_interpolate.cpp:307-330 */
 int pn2_three_interpolate(int b, int m, int c, int n, const float *points, const int *idx,
                           const float *weight, float *out, pn2_stream_t s);

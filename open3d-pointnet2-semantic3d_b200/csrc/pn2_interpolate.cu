@@ -165,6 +165,108 @@ __global__ void copy_cols_kernel(long rows, int cols, long total, const float *_
     }
 }
 
+// ---- interpolate_label_with_color: kNN label vote (tf_interpolate.cpp:71-115) -------------
+// The step right after the network at inference: every point of the full-resolution cloud takes
+// the label that wins among its knn nearest predicted (sparse) points.  The reference builds an
+// Open3D KD-tree on the CPU and searches it per dense point; here it is the same brute-force
+// fp64 scan as three_nn (same staging, same non-contracted distance expression, strict '<' so
+// equal distances keep the lowest index), with the k best candidates of a thread in a register
+// array (KMAX is a compile-time bound, all indexing is unrolled) and the vote done in place:
+// walking the neighbours from nearest to farthest, the label whose running count first exceeds
+// the best count so far wins (:97-106) -- O(k^2) comparisons instead of a hash map.
+constexpr int KV_THREADS = 256;
+
+__constant__ unsigned char kLabelColors[9][3] = {
+    {255, 255, 255}, {0, 0, 255}, {128, 0, 0}, {255, 0, 255}, {0, 128, 0},
+    {255, 0, 0},     {128, 0, 128}, {0, 0, 128}, {128, 128, 0}};  // tf_interpolate.cpp:46-48
+
+template <int KMAX>
+__global__ void __launch_bounds__(KV_THREADS)
+knn_vote_kernel(int ns, int nd, int k, const float *__restrict__ sparse,
+                const int *__restrict__ labels, const float *__restrict__ dense,
+                int *__restrict__ out_labels, unsigned char *__restrict__ out_colors) {
+    __shared__ __align__(16) double kx[NN_TILE], ky[NN_TILE], kz[NN_TILE];
+    const long j = (long)blockIdx.x * KV_THREADS + threadIdx.x;
+    const bool valid = j < nd;
+    double qx = 0, qy = 0, qz = 0;
+    if (valid) {
+        const float *q = dense + (size_t)j * 3;
+        qx = (double)__ldg(q);
+        qy = (double)__ldg(q + 1);
+        qz = (double)__ldg(q + 2);
+    }
+    const double INF = __longlong_as_double(0x7FF0000000000000LL);
+    double bd[KMAX];
+    int bi[KMAX];
+#pragma unroll
+    for (int s = 0; s < KMAX; ++s) {
+        bd[s] = INF;
+        bi[s] = -1;
+    }
+    double worst = INF;  // bd[k-1]: a candidate must beat it to enter the list
+    for (int base = 0; base < ns; base += NN_TILE) {
+        const int cnt = min(NN_TILE, ns - base);
+        __syncthreads();
+        for (int e = threadIdx.x; e < cnt * 3; e += KV_THREADS) {
+            int p = e / 3, c = e - p * 3;
+            double v = (double)__ldg(sparse + (size_t)base * 3 + e);
+            (c == 0 ? kx : (c == 1 ? ky : kz))[p] = v;
+        }
+        __syncthreads();
+        if (valid) {
+#pragma unroll 2
+            for (int p = 0; p < cnt; ++p) {
+                double dx = __dsub_rn(qx, kx[p]);
+                double dy = __dsub_rn(qy, ky[p]);
+                double dz = __dsub_rn(qz, kz[p]);
+                double d = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)),
+                                     __dmul_rn(dz, dz));
+                if (d < worst) {
+                    // replace the current k-th, then bubble towards the front (strict '<':
+                    // an equal distance stays behind the earlier index)
+#pragma unroll
+                    for (int s = 0; s < KMAX; ++s)
+                        if (s == k - 1) {
+                            bd[s] = d;
+                            bi[s] = base + p;
+                        }
+#pragma unroll
+                    for (int s = KMAX - 1; s > 0; --s)
+                        if (s < k && bd[s] < bd[s - 1]) {
+                            double td = bd[s]; bd[s] = bd[s - 1]; bd[s - 1] = td;
+                            int ti = bi[s]; bi[s] = bi[s - 1]; bi[s - 1] = ti;
+                        }
+#pragma unroll
+                    for (int s = 0; s < KMAX; ++s)
+                        if (s == k - 1) worst = bd[s];
+                }
+            }
+        }
+    }
+    if (!valid) return;
+    int lab[KMAX];
+#pragma unroll
+    for (int s = 0; s < KMAX; ++s) lab[s] = (s < k && bi[s] >= 0) ? __ldg(labels + bi[s]) : 0;
+    int best = -1, best_count = 0;
+#pragma unroll
+    for (int s = 0; s < KMAX; ++s) {
+        if (s < k && bi[s] >= 0) {
+            int cnt = 0;
+#pragma unroll
+            for (int u = 0; u <= s; ++u) cnt += (lab[u] == lab[s]) ? 1 : 0;
+            if (cnt > best_count) {
+                best = lab[s];
+                best_count = cnt;
+            }
+        }
+    }
+    out_labels[j] = best;
+    const bool known = best >= 0 && best < 9;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+        out_colors[(size_t)j * 3 + c] = known ? kLabelColors[best][c] : (unsigned char)0;
+}
+
 static inline int grid_for(long total, int threads) {
     long blocks = ceil_div<long>(total, threads);
     long cap = 148L * 32;
@@ -261,5 +363,34 @@ PN2_API int pn2_copy_cols(long rows, int cols, const float *src, int lds, float 
     PN2_REQUIRE_PTR(dst);
     copy_cols_kernel<<<grid_for(total, 256), 256, 0, as_stream(s)>>>(rows, cols, total, src, lds,
                                                                      dst, ldd, accumulate);
+    return finish_launch();
+}
+
+PN2_API int pn2_interpolate_label_with_color(int num_sparse, int num_dense,
+                                             const float *sparse_points, const int *sparse_labels,
+                                             const float *dense_points, int *dense_labels,
+                                             unsigned char *dense_colors, int knn,
+                                             pn2_stream_t s) {
+    PN2_REQUIRE(num_sparse >= 0 && num_dense >= 0 && knn > 0);
+    if (knn > 32) return PN2_EUNSUPPORTED;  // the candidate list lives in registers
+    if (num_dense == 0) return PN2_OK;
+    PN2_REQUIRE_PTR(dense_points);
+    PN2_REQUIRE_PTR(dense_labels);
+    PN2_REQUIRE_PTR(dense_colors);
+    if (num_sparse > 0) {
+        PN2_REQUIRE_PTR(sparse_points);
+        PN2_REQUIRE_PTR(sparse_labels);
+    }
+    cudaStream_t st = as_stream(s);
+    const unsigned grid = (unsigned)ceil_div<long>(num_dense, KV_THREADS);
+#define PN2_LAUNCH_VOTE(KM)                                                                    \
+    knn_vote_kernel<KM><<<grid, KV_THREADS, 0, st>>>(num_sparse, num_dense, knn, sparse_points, \
+                                                     sparse_labels, dense_points, dense_labels, \
+                                                     dense_colors)
+    if (knn <= 4) PN2_LAUNCH_VOTE(4);
+    else if (knn <= 8) PN2_LAUNCH_VOTE(8);
+    else if (knn <= 16) PN2_LAUNCH_VOTE(16);
+    else PN2_LAUNCH_VOTE(32);
+#undef PN2_LAUNCH_VOTE
     return finish_launch();
 }

@@ -1,5 +1,7 @@
 """Interpolation ops: same names / argument order as the reference's tf_ops/tf_interpolate.py.
 
+  interpolate_label_with_color(sparse_points, sparse_labels, dense_points, knn)
+                                          tf_interpolate.py:26-43 (inference post-processing)
   three_nn(xyz1, xyz2)                    tf_interpolate.py:13-22 (no gradient, :25)
   three_interpolate(points, idx, weight)  tf_interpolate.py:50-59 (gradient :62-71)
 
@@ -15,6 +17,35 @@ from .._ffi import F32, I32, call, ptr
 def _need(cond, msg):
     if not cond:
         raise ValueError(msg)
+
+
+def interpolate_label_with_color(sparse_points, sparse_labels, dense_points, knn):
+    """sparse_points (Ns,3) float32, sparse_labels (Ns,) int32, dense_points (Nd,3) float32,
+    knn int -> (dense_labels (Nd,) int32, dense_colors (Nd,3) uint8).
+
+    Label vote among the knn nearest sparse points of every dense point (nearest first; the
+    label whose running count first becomes the largest wins) plus the reference's colour table
+    (tf_interpolate.cpp:46-48, 71-115).  Validation texts: tf_interpolate.cpp:125-160."""
+    _need(sparse_points.dim() == 2 and sparse_points.shape[1] == 3,
+          "sparse_points must be: (num_sparse_points, 3)")
+    ns = sparse_points.shape[0]
+    _need(sparse_labels.dim() == 1 and sparse_labels.shape[0] == ns,
+          "sparse_labels must be: (num_sparse_points, 3)")  # sic: the reference's message
+    _need(dense_points.dim() == 2 and dense_points.shape[1] == 3,
+          "dense_points must be: (num_dense_points, 3)")
+    _need(isinstance(knn, int) or (isinstance(knn, torch.Tensor) and knn.dim() == 0),
+          "knn must be an int scalar")
+    knn = int(knn)
+    _need(knn > 0, "knn must be an int scalar")
+    nd = dense_points.shape[0]
+    sp = sparse_points.detach().contiguous()
+    sl = sparse_labels.contiguous()
+    dp = dense_points.detach().contiguous()
+    labels = torch.empty((nd,), dtype=I32, device=dp.device)
+    colors = torch.empty((nd, 3), dtype=torch.uint8, device=dp.device)
+    call("pn2_interpolate_label_with_color", ns, nd, ptr(sp, F32), ptr(sl, I32), ptr(dp, F32),
+         ptr(labels, I32), ptr(colors, torch.uint8), knn)
+    return labels, colors
 
 
 def three_nn(xyz1, xyz2):

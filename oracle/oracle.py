@@ -146,6 +146,18 @@ def three_interpolate_grad(points_shape, idx, weight, grad_out):
     return g
 
 
+def interpolate_label_with_color(sparse_points, sparse_labels, dense_points, knn, threads=0):
+    """tf_interpolate.cpp:71-115 -> (dense_labels (N,) int32, dense_colors (N,3) uint8)."""
+    sp, sl, dp = _f32(sparse_points), _i32(sparse_labels), _f32(dense_points)
+    ns, nd = sp.shape[0], dp.shape[0]
+    labels = np.empty((nd,), np.int32)
+    colors = np.empty((nd, 3), np.uint8)
+    lib().orc_interpolate_label_with_color(
+        _ci(ns), _ci(nd), _p(sp), _p(sl), _p(dp), _p(labels),
+        colors.ctypes.data_as(ctypes.POINTER(ctypes.c_ubyte)), _ci(int(knn)), _ci(threads))
+    return labels, colors
+
+
 def select_top_k(k, dist):
     dist = _f32(dist)
     b, m, n = dist.shape

@@ -20,6 +20,7 @@
  *   orc_three_interpolate      tf_ops/tf_interpolate.cpp:307-330
  *   orc_three_interpolate_grad tf_ops/tf_interpolate.cpp:397-421 (+memset :477)
  *   orc_selection_sort         tf_ops/tf_grouping.cu:95-136
+ *   orc_interpolate_label_with_color  tf_ops/tf_interpolate.cpp:71-115 (kNN label vote)
  *   orc_cumsum                 tf_ops/tf_sampling.cu:7-92 (prefix sum, reference rounding order)
  *   orc_prob_sample            tf_ops/tf_sampling.cu:7-110 (cumsum + binary search)
  *
@@ -393,6 +394,73 @@ ORC_API void orc_prob_sample(int b, int n, int m, const float *inp_p,
         }
     }
     free(cdf);
+}
+
+/* ------------------------------------------------------------------------- */
+/* InterpolateLabelWithColor.  tf_interpolate.cpp:71-115: per dense point the
+ * knn nearest sparse points (Open3D KDTreeFlann::SearchKNN on fp64 copies of
+ * the fp32 coordinates == the knn smallest fp64 squared distances, ascending),
+ * then the label that first reaches the highest count while walking the
+ * neighbours from nearest to farthest (:97-106), then the colour table (:46-48).
+ * Brute force; equal distances resolve to the lowest index (FLANN's tie order
+ * is unspecified).  Labels outside the 9-entry table are undefined behaviour in
+ * the reference (vector index out of range); here they get colour (0,0,0). */
+static const unsigned char orc_label_colors[9][3] = {
+    {255, 255, 255}, {0, 0, 255}, {128, 0, 0}, {255, 0, 255}, {0, 128, 0},
+    {255, 0, 0},     {128, 0, 128}, {0, 0, 128}, {128, 128, 0}};
+
+ORC_API void orc_interpolate_label_with_color(int num_sparse, int num_dense,
+                                              const float *sparse_points,
+                                              const int *sparse_labels,
+                                              const float *dense_points,
+                                              int *dense_labels,
+                                              unsigned char *dense_colors, int knn,
+                                              int threads) {
+    if (knn < 0) knn = 0;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) num_threads(threads > 0 ? threads : 1)
+#endif
+    for (int j = 0; j < num_dense; ++j) {
+        double *bd = (double *)malloc(sizeof(double) * (size_t)(knn + 1));
+        int *bi = (int *)malloc(sizeof(int) * (size_t)(knn + 1));
+        int found = 0;
+        double qx = dense_points[(size_t)j * 3 + 0], qy = dense_points[(size_t)j * 3 + 1],
+               qz = dense_points[(size_t)j * 3 + 2];
+        for (int s = 0; s < num_sparse; ++s) {
+            double dx = qx - (double)sparse_points[(size_t)s * 3 + 0];
+            double dy = qy - (double)sparse_points[(size_t)s * 3 + 1];
+            double dz = qz - (double)sparse_points[(size_t)s * 3 + 2];
+            double d = (dx * dx + dy * dy) + dz * dz;
+            if (found < knn) {
+                bd[found] = d;
+                bi[found] = s;
+                ++found;
+            } else if (knn > 0 && d < bd[knn - 1]) {
+                bd[knn - 1] = d;
+                bi[knn - 1] = s;
+            } else {
+                continue;
+            }
+            for (int t = (found < knn ? found : knn) - 1; t > 0 && bd[t] < bd[t - 1]; --t) {
+                double td = bd[t]; bd[t] = bd[t - 1]; bd[t - 1] = td;
+                int ti = bi[t]; bi[t] = bi[t - 1]; bi[t - 1] = ti;
+            }
+        }
+        int best = -1, best_count = 0;
+        for (int t = 0; t < found; ++t) {
+            int lab = sparse_labels[bi[t]], cnt = 0;
+            for (int u = 0; u <= t; ++u) cnt += sparse_labels[bi[u]] == lab;
+            if (cnt > best_count) {
+                best = lab;
+                best_count = cnt;
+            }
+        }
+        dense_labels[j] = best;
+        for (int c = 0; c < 3; ++c)
+            dense_colors[(size_t)j * 3 + c] = (best >= 0 && best < 9) ? orc_label_colors[best][c] : 0;
+        free(bd);
+        free(bi);
+    }
 }
 
 ORC_API int orc_max_threads(void) {

@@ -382,3 +382,75 @@ def test_prob_sample_validation(ops):
     with pytest.raises(ValueError, match="num_points"):
         ts.prob_sample(p, torch.ones((3, 3), device="cuda"))
     assert ts.prob_sample(p, torch.zeros((2, 0), device="cuda")).shape == (2, 0)
+
+
+# ------------------------------------------- interpolate_label_with_color
+def _vote_inputs(seed, ns, nd, nlabels=9, grid=False):
+    rs = np.random.RandomState(seed)
+    if grid:  # integer lattice: many exactly equal distances and duplicate points
+        sp = rs.randint(0, 5, (ns, 3)).astype(np.float32)
+        dp = rs.randint(0, 5, (nd, 3)).astype(np.float32)
+    else:
+        sp = rs.random_sample((ns, 3)).astype(np.float32)
+        dp = rs.random_sample((nd, 3)).astype(np.float32)
+    sl = rs.randint(0, nlabels, (ns,)).astype(np.int32)
+    return sp, sl, dp
+
+
+@pytest.mark.parametrize("ns,nd,knn", [(500, 3000, 3), (1024, 777, 1), (1025, 1000, 5), (3000, 2049, 4),
+                                       (5000, 513, 8), (2500, 300, 9), (2100, 256, 16), (1500, 200, 17),
+                                       (1200, 100, 32), (2, 100, 3), (1, 10, 3)])
+def test_interpolate_label_with_color_matches_oracle(ops, ns, nd, knn):
+    _, _, ti, orc = ops
+    sp, sl, dp = _vote_inputs(ns + knn, ns, nd)
+    lab, col = ti.interpolate_label_with_color(to_cuda(sp), to_cuda(sl), to_cuda(dp), knn)
+    assert lab.dtype.is_floating_point is False and tuple(lab.shape) == (nd,)
+    assert str(col.dtype) == "torch.uint8" and tuple(col.shape) == (nd, 3)
+    elab, ecol = orc.interpolate_label_with_color(sp, sl, dp, knn)
+    np.testing.assert_array_equal(lab.cpu().numpy(), elab)
+    np.testing.assert_array_equal(col.cpu().numpy(), ecol)
+
+
+@pytest.mark.parametrize("knn", [1, 3, 6])
+def test_interpolate_label_ties_lowest_index(ops, knn):
+    """Equal distances resolve to the lowest sparse index, and the vote keeps the label that first
+    reaches the top count in nearest-first order (tf_interpolate.cpp:97-106)."""
+    _, _, ti, orc = ops
+    sp, sl, dp = _vote_inputs(11, 900, 700, nlabels=4, grid=True)
+    lab, col = ti.interpolate_label_with_color(to_cuda(sp), to_cuda(sl), to_cuda(dp), knn)
+    elab, ecol = orc.interpolate_label_with_color(sp, sl, dp, knn)
+    np.testing.assert_array_equal(lab.cpu().numpy(), elab)
+    np.testing.assert_array_equal(col.cpu().numpy(), ecol)
+
+
+def test_interpolate_label_knn1_is_nearest_label_and_color_table(ops):
+    """knn=1 must return the label of the nearest sparse point (checked with three_nn) and the
+    colours of tf_interpolate.cpp:46-48; labels outside the table get (0,0,0)."""
+    import torch
+    _, _, ti, _ = ops
+    sp, sl, dp = _vote_inputs(5, 4000, 6000, nlabels=11)
+    lab, col = ti.interpolate_label_with_color(to_cuda(sp), to_cuda(sl), to_cuda(dp), 1)
+    _, i3 = ti.three_nn(to_cuda(dp[None]), to_cuda(sp[None]))
+    np.testing.assert_array_equal(lab.cpu().numpy(), sl[i3[0, :, 0].cpu().numpy()])
+    table = np.array([[255, 255, 255], [0, 0, 255], [128, 0, 0], [255, 0, 255], [0, 128, 0],
+                      [255, 0, 0], [128, 0, 128], [0, 0, 128], [128, 128, 0], [0, 0, 0], [0, 0, 0]],
+                     np.uint8)
+    np.testing.assert_array_equal(col.cpu().numpy(), table[lab.cpu().numpy()])
+
+
+def test_interpolate_label_validation(ops):
+    import torch
+    _, _, ti, _ = ops
+    sp = torch.zeros((4, 3), device="cuda")
+    sl = torch.zeros((4,), dtype=torch.int32, device="cuda")
+    dp = torch.zeros((5, 3), device="cuda")
+    with pytest.raises(ValueError, match="sparse_points must be"):
+        ti.interpolate_label_with_color(torch.zeros((4, 2), device="cuda"), sl, dp, 3)
+    with pytest.raises(ValueError, match="sparse_labels must be"):
+        ti.interpolate_label_with_color(sp, sl[:3], dp, 3)
+    with pytest.raises(ValueError, match="dense_points must be"):
+        ti.interpolate_label_with_color(sp, sl, torch.zeros((5,), device="cuda"), 3)
+    with pytest.raises(ValueError, match="knn must be"):
+        ti.interpolate_label_with_color(sp, sl, dp, 0)
+    lab, col = ti.interpolate_label_with_color(sp, sl, dp[:0], 3)
+    assert tuple(lab.shape) == (0,) and tuple(col.shape) == (0, 3)

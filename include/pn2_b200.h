@@ -48,6 +48,13 @@ const char *pn2_last_cuda_error(void);
  * NULL: the running minimum distances live in registers, not in global memory. */
 int pn2_fps(int b, int n, int m, const float *inp, float *temp, int *out, pn2_stream_t s);
 
+/* Same result as pn2_fps, always through the thread-block-cluster kernel (one cluster of up to
+ * 16 CTAs per cloud, the cloud resident in their shared memories, candidates exchanged through
+ * distributed shared memory).  pn2_fps selects it by itself for large clouds; this entry point
+ * exists for tests and benchmarks.  PN2_EUNSUPPORTED when n > 262144 or the device cannot
+ * co-schedule the cluster. */
+int pn2_fps_cluster(int b, int n, int m, const float *inp, int *out, pn2_stream_t s);
+
 /* replaces cumsumLauncher                  tf_ops/tf_sampling.cu:208-210
  * inp (b,n) -> out (b,n): row-wise inclusive prefix sum, bit-identical to the reference's
  * blocked scan (same fp32 addition order, see oracle/pn2_oracle.c cumsum_row_ref). */

@@ -15,6 +15,7 @@
 // k -- exactly the order the reference's 512-thread strided scan + left-biased tree gives.
 #include <stdlib.h>
 
+#include <cooperative_groups.h>
 #include <cub/block/block_radix_sort.cuh>
 #include <cub/block/block_reduce.cuh>
 
@@ -339,6 +340,116 @@ fps_smem_kernel(int n, int m, const float *__restrict__ inp, int *__restrict__ o
     }
 }
 
+// Clouds larger than one SM can hold: a thread-block CLUSTER per cloud.  CTA `rank` of the
+// cluster keeps the contiguous slice [rank*1024*PPT, (rank+1)*1024*PPT) of the cloud in its shared
+// memory (SoA) and the running minima of its slice in registers, for all rounds -- nothing is
+// re-read from L2/HBM.  A round is: local update + arg-max (as in fps_smem_kernel), ONE
+// __syncthreads, warp 0 reduces the 32 warp candidates and pushes the CTA's candidate
+// {distance bits | tie key, x, y, z} into the exchange slot [round parity][rank] of EVERY CTA of the
+// cluster through distributed shared memory, ONE cluster barrier, then every warp picks the winner
+// among the <= 16 candidates it finds in its own shared memory (max distance, then min tie key:
+// the same total order as inside a CTA, so the result is bit-identical) and takes the winner's
+// coordinates from the record -- no global or remote read on the critical path.
+// Slices are multiples of 1024 points, so a thread's points t + 1024*i all share (k mod 512) and are
+// visited in ascending k: the strict '>' keeps the lowest tie key, as in the other kernels.
+struct __align__(16) FpsCand {
+    unsigned long long dk;  // (distance bits << 32) | tie key ; key 0xFFFFFFFF = no candidate
+    float x, y, z, pad;
+};
+constexpr int kFpsMaxCluster = 16;
+constexpr bool kFpsClusterDefault = true;  // verified on the B200: bit-identical at every config-5 size, 1.1-14x faster
+
+template <int PPT>
+__global__ void __launch_bounds__(1024, 1)
+fps_cluster_kernel(int n, int m, const float *__restrict__ inp, int *__restrict__ out) {
+    namespace cg = cooperative_groups;
+    constexpr int THREADS = 1024, NW = 32, SLICE = THREADS * PPT;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned long long *slots = reinterpret_cast<unsigned long long *>(smem_raw);      // [2][32]
+    FpsCand *exch = reinterpret_cast<FpsCand *>(slots + 64);                            // [2][16]
+    float *xs = reinterpret_cast<float *>(exch + 2 * kFpsMaxCluster);
+    float *ys = xs + SLICE;
+    float *zs = ys + SLICE;
+
+    cg::cluster_group cluster = cg::this_cluster();
+    const int cs = (int)cluster.num_blocks();
+    const int rank = (int)cluster.block_rank();
+    const int cloud = blockIdx.x / cs;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const float *src = inp + (size_t)cloud * n * 3;
+    int *dst = out + (size_t)cloud * m;
+    const int k0 = rank * SLICE;                       // first point of this CTA's slice
+    const int cnt = max(0, min(SLICE, n - k0));        // points it really holds
+
+    // stage the slice: coalesced AoS global read -> SoA shared memory (tail padded with zeros)
+    for (int e = t; e < SLICE * 3; e += THREADS) {
+        int k = e / 3, c = e - k * 3;
+        float v = k < cnt ? __ldg(src + (size_t)k0 * 3 + e) : 0.f;
+        (c == 0 ? xs : (c == 1 ? ys : zs))[k] = v;
+    }
+    float pd[PPT];
+#pragma unroll
+    for (int i = 0; i < PPT; ++i) pd[i] = (t + i * THREADS) < cnt ? 1e38f : -1.f;
+    float x1 = __ldg(src), y1 = __ldg(src + 1), z1 = __ldg(src + 2);  // round 0 selects point 0
+    if (rank == 0 && t == 0) dst[0] = 0;
+    __syncthreads();
+    cluster.sync();  // every CTA of the cluster is running: its shared memory may be written
+
+    for (int j = 1; j < m; ++j) {
+        float best = -1.f;
+        int besti = 0;
+#pragma unroll
+        for (int i = 0; i < PPT; ++i) {
+            const int k = t + i * THREADS;
+            float d = sqdist_ref(xs[k] - x1, ys[k] - y1, zs[k] - z1);
+            float d2 = fminf(d, pd[i]);
+            pd[i] = d2;
+            if (d2 > best) {
+                best = d2;
+                besti = i;
+            }
+        }
+        const bool has = best >= 0.f;
+        unsigned db = has ? __float_as_uint(best) : 0u;
+        unsigned key = has ? tie_key(k0 + t + besti * THREADS) : 0xFFFFFFFFu;
+        unsigned wmax = __reduce_max_sync(0xFFFFFFFFu, db);
+        unsigned wkey = __reduce_min_sync(0xFFFFFFFFu, db == wmax ? key : 0xFFFFFFFFu);
+        const int par = j & 1;
+        if (lane == 0) slots[par * 32 + warp] = ((unsigned long long)wmax << 32) | wkey;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long v = slots[par * 32 + lane];  // NW == 32: one slot per lane
+            unsigned d2 = (unsigned)(v >> 32), k2 = (unsigned)v;
+            unsigned cmax = __reduce_max_sync(0xFFFFFFFFu, d2);
+            unsigned ckey = __reduce_min_sync(0xFFFFFFFFu, d2 == cmax ? k2 : 0xFFFFFFFFu);
+            if (lane < cs) {
+                FpsCand c;
+                c.dk = ((unsigned long long)cmax << 32) | ckey;
+                const int kl = ckey == 0xFFFFFFFFu ? 0 : key_to_k(ckey) - k0;  // local index
+                c.x = xs[kl];
+                c.y = ys[kl];
+                c.z = zs[kl];
+                c.pad = 0.f;
+                FpsCand *peer = cluster.map_shared_rank(exch, lane);  // CTA `lane`'s exchange area
+                peer[par * kFpsMaxCluster + rank] = c;
+            }
+            __syncwarp();
+        }
+        cluster.sync();  // release the pushes / acquire everybody's
+        // winner among the cs candidates (same order: max distance bits, then min tie key)
+        unsigned long long v = lane < cs ? exch[par * kFpsMaxCluster + lane].dk : 0x00000000FFFFFFFFull;
+        unsigned d2 = (unsigned)(v >> 32), k2 = (unsigned)v;
+        unsigned gmax = __reduce_max_sync(0xFFFFFFFFu, d2);
+        unsigned gkey = __reduce_min_sync(0xFFFFFFFFu, d2 == gmax ? k2 : 0xFFFFFFFFu);
+        const unsigned who = __ballot_sync(0xFFFFFFFFu, lane < cs && d2 == gmax && k2 == gkey);
+        const FpsCand *w = exch + par * kFpsMaxCluster + (who ? __ffs(who) - 1 : 0);
+        x1 = w->x;
+        y1 = w->y;
+        z1 = w->z;
+        if (rank == 0 && t == 0) dst[j] = gkey == 0xFFFFFFFFu ? 0 : key_to_k(gkey);
+    }
+}
+
 // Fallback for clouds larger than one SM can hold: one CTA per cloud, coordinates read
 // through L1/L2 each round, running minimum in a caller-provided (b,n) global scratch.
 // Same arithmetic and tie order; used only beyond 16384 points (sweep sizes of config 5).
@@ -424,6 +535,60 @@ static int launch_fps_smem(int b, int n, int m, const float *inp, int *out, cuda
     if (rc) return rc;
     kern<<<b, THREADS, smem, st>>>(n, m, inp, out);
     return finish_launch();
+}
+
+template <int PPT>
+static int launch_fps_cluster(int b, int cs, int n, int m, const float *inp, int *out,
+                              cudaStream_t st) {
+    size_t smem = 64 * sizeof(unsigned long long) + 2 * kFpsMaxCluster * sizeof(FpsCand) +
+                  (size_t)1024 * PPT * 3 * sizeof(float);
+    auto kern = fps_cluster_kernel<PPT>;
+    int rc = cuda_status(
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (rc) return rc;
+    if (cs > 8) {
+        rc = cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        if (rc) return rc;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(b * cs), 1, 1);
+    cfg.blockDim = dim3(1024, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&clusters, kern, &cfg) != cudaSuccess || clusters < 1) {
+        cudaGetLastError();
+        return PN2_EUNSUPPORTED;  // this cluster shape cannot be co-scheduled on the device
+    }
+    rc = cuda_status(cudaLaunchKernelEx(&cfg, kern, n, m, inp, out));
+    if (rc) return rc;
+    return finish_launch();
+}
+
+// Cluster shape: the fewest points per thread (shortest round) whose cluster fits the limit of 16
+// CTAs and, when possible, lets all b clusters run in one wave; a shape the device cannot
+// co-schedule (e.g. no GPC with 16 free SMs) falls through to the next larger slice per CTA.
+// PN2_EUNSUPPORTED when no shape works (n > 262144, or clusters unavailable).
+static int dispatch_fps_cluster(int b, int n, int m, const float *inp, int *out, cudaStream_t st) {
+    for (int p = 2; p <= 16; p *= 2) {
+        int need = ceil_div(n, 1024 * p), cs = 2;
+        while (cs < need) cs *= 2;
+        if (cs > kFpsMaxCluster) continue;
+        if ((long)b * cs > num_sms() && p < 16) continue;
+        int rc = p == 2   ? launch_fps_cluster<2>(b, cs, n, m, inp, out, st)
+                 : p == 4 ? launch_fps_cluster<4>(b, cs, n, m, inp, out, st)
+                 : p == 8 ? launch_fps_cluster<8>(b, cs, n, m, inp, out, st)
+                          : launch_fps_cluster<16>(b, cs, n, m, inp, out, st);
+        if (rc != PN2_EUNSUPPORTED) return rc;
+    }
+    return PN2_EUNSUPPORTED;
 }
 
 // ---- gather_point / grad ---------------------------------------------------------------
@@ -608,12 +773,28 @@ PN2_API int pn2_fps(int b, int n, int m, const float *inp, float *temp, int *out
                                                       : launch_fps_reg<1024, 4>(b, n, m, inp, out, st);
     if (n <= 8192) return prune && m > 64 ? launch_fps_pruned<1024, 8>(b, n, m, inp, out, st)
                                           : launch_fps_reg<1024, 8>(b, n, m, inp, out, st);
+    // more than 8192 points: a thread-block cluster per cloud keeps the whole cloud on chip
+    // (PN2_FPS_CLUSTER=0/1 overrides the default)
+    static const char *cl_env = getenv("PN2_FPS_CLUSTER");
+    static const bool use_cluster = cl_env ? cl_env[0] != '0' : kFpsClusterDefault;
+    if (use_cluster) {
+        int rc = dispatch_fps_cluster(b, n, m, inp, out, st);
+        if (rc != PN2_EUNSUPPORTED) return rc;
+    }
     if (n <= 16384) return launch_fps_smem<1024, 16>(b, n, m, inp, out, st);
-    // beyond one SM's capacity: streaming kernel needs the (b,n) scratch the reference also
-    // requires (tf_sampling.cpp:143-146 allocates (32,n))
+    // beyond what a cluster holds (or no cluster available): streaming kernel; it needs the
+    // (b,n) scratch the reference also requires (tf_sampling.cpp:143-146 allocates (32,n))
     if (temp == nullptr) return PN2_ENULL;
     fps_stream_kernel<<<b, 1024, 0, st>>>(n, m, inp, temp, out);
     return finish_launch();
+}
+
+PN2_API int pn2_fps_cluster(int b, int n, int m, const float *inp, int *out, pn2_stream_t s) {
+    PN2_REQUIRE(b >= 0 && n > 0 && m > 0);
+    if (b == 0) return PN2_OK;
+    PN2_REQUIRE_PTR(inp);
+    PN2_REQUIRE_PTR(out);
+    return dispatch_fps_cluster(b, n, m, inp, out, as_stream(s));
 }
 
 PN2_API int pn2_gather_point(int b, int n, int m, const float *inp, const int *idx, float *out,

@@ -3,7 +3,7 @@
 N in {4096, 16384, 65536, 262144}, npoint = N/4, nsample = 64) plus the standalone index/gather
 ops at their config-2 sizes, each against the roofline SURVEY.md 8(d) assigns to it.
 
-    python profiles/op_sweep.py [--budget SECONDS] [--only cfg2|msg] [--no-ref] [--out FILE]
+    python profiles/op_sweep.py [--budget SECONDS] [--only cfg2|msg|fps_cluster] [--no-ref] [--out FILE]
 
 Inputs are resident in HBM, every op is called through the public Python op surface (ctypes ->
 C ABI -> sm_100a kernel), timed with CUDA events on the launching stream after one warm-up, a
@@ -165,6 +165,33 @@ def main():
                gemm_gflop_fwd=flops / 1e9, gemm_tflops_fwd_plus_bwd=3 * flops / ms / 1e9,
                note="FPS + 3x(ball query, group+concat, 3-layer shared MLP with train-mode BN, max pool) and "
                     "the backward pass; 3xTF32 tensor-core GEMMs")
+        print("wrote", args.out)
+        return
+
+    # ------------------------------------------- config 5 FPS: cluster kernel vs one CTA per cloud
+    if args.only == "fps_cluster":
+        from pn2_b200._ffi import F32, I32, call, ptr
+
+        def cluster_fps(x, m):
+            out = torch.empty((x.shape[0], m), dtype=I32, device=x.device)
+            call("pn2_fps_cluster", x.shape[0], x.shape[1], m, ptr(x, F32), ptr(out, I32))
+            return out
+
+        for n in (16384, 65536, 262144):
+            for b in (16, 1):
+                m = n // 4
+                x = cloud(100 + n, b, n)
+                ms = timed(lambda: cluster_fps(x, m))
+                same = None
+                if not out_of_time():  # full-size parity: the single-CTA kernels are bit-exact vs the oracle
+                    same = bool((cluster_fps(x, m) == tf_sampling.farthest_point_sample(m, x)).all())
+                stream_bytes = b * (m - 1) * n * 20.0
+                record(op="farthest_point_sample (cluster kernel)", case="sweep N=%d B=%d" % (n, b), B=b, N=n,
+                       npoint=m, ms=ms, us_per_round=ms * 1e3 / (m - 1),
+                       streaming_model_GBps=stream_bytes / ms / 1e6,
+                       streaming_model_frac_of_hbm=stream_bytes / ms / 1e6 / hbm,
+                       identical_to_single_cta_kernel=same)
+                del x
         print("wrote", args.out)
         return
 

@@ -1,0 +1,2 @@
+#!/bin/bash
+timeout 300 python scripts/debug_tc_trace.py 2>&1 | head -80

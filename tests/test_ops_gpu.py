@@ -454,3 +454,44 @@ def test_interpolate_label_validation(ops):
         ti.interpolate_label_with_color(sp, sl, dp, 0)
     lab, col = ti.interpolate_label_with_color(sp, sl, dp[:0], 3)
     assert tuple(lab.shape) == (0,) and tuple(col.shape) == (0, 3)
+
+
+# ------------------------------------------------ FPS: thread-block-cluster kernel (config 5)
+CLUSTER_CASES = [(1, 12000, 64), (1, 20000, 32), (2, 16389, 100), (3, 40000, 150), (1, 65536, 300),
+                 (1, 262144, 200), (16, 16384, 64), (2, 100, 120), (5, 9000, 40)]
+
+
+def _fps_cluster(x, m):
+    import torch
+    from pn2_b200._ffi import F32, I32, call, ptr
+    b, n, _ = x.shape
+    out = torch.empty((b, m), dtype=I32, device=x.device)
+    call("pn2_fps_cluster", b, n, m, ptr(x, F32), ptr(out, I32))
+    return out
+
+
+@pytest.mark.parametrize("b,n,m", CLUSTER_CASES)
+def test_fps_cluster_matches_oracle(ops, b, n, m):
+    """One cluster of up to 16 CTAs per cloud, candidates exchanged through distributed shared
+    memory: bit-identical indices to the oracle (and therefore to every other FPS kernel)."""
+    _, _, _, orc = ops
+    x = rng_cloud(300 + n, b, n)
+    got = _fps_cluster(to_cuda(x), m).cpu().numpy()
+    np.testing.assert_array_equal(got, orc.farthest_point_sample(m, x, threads=8))
+
+
+def test_fps_cluster_tie_order(ops):
+    """Integer lattice (thousands of exactly equal distances, duplicates): the winner must be the
+    lowest (k mod 512) then lowest k ACROSS the CTAs of the cluster as well."""
+    _, _, _, orc = ops
+    rs = np.random.RandomState(9)
+    for n, m in [(20000, 300), (33000, 200)]:
+        x = rs.randint(0, 6, (2, n, 3)).astype(np.float32)
+        got = _fps_cluster(to_cuda(x), m).cpu().numpy()
+        np.testing.assert_array_equal(got, orc.farthest_point_sample(m, x, threads=8))
+
+
+def test_fps_cluster_matches_reference_kernel(ops):
+    ref = RefKernels()
+    x = to_cuda(rng_cloud(77, 2, 30000))
+    np.testing.assert_array_equal(_fps_cluster(x, 256).cpu().numpy(), ref.fps(x, 256).cpu().numpy())

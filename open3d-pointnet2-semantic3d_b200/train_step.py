@@ -32,7 +32,11 @@ def get_bn_decay(step, params):
 def shard_batch(global_batch, rank, world_size):
     """Contiguous shard of the leading (cloud) dimension owned by ``rank``: the path is
     independent per cloud, so data parallelism partitions clouds with no data-path exchange."""
-    per = global_batch.shape[0] // world_size
+    total = global_batch.shape[0]
+    if world_size < 1 or not 0 <= rank < world_size or total % world_size != 0:
+        raise ValueError("cannot shard %d clouds over %d ranks (rank %d): the batch must divide evenly"
+                         % (total, world_size, rank))
+    per = total // world_size
     return global_batch[rank * per:(rank + 1) * per]
 
 

@@ -75,15 +75,29 @@ def test_python_validation_messages_match_reference():
         tf_interpolate.three_interpolate(x, torch.zeros(1, 4, 2, dtype=torch.int32), torch.zeros(1, 4, 3))
     with pytest.raises(ValueError, match="SelectionSort expects positive k"):
         tf_grouping.select_top_k(0, torch.rand(1, 2, 3))
+    with pytest.raises(ValueError, match=r"ProbSample expects \(batch_size,num_choices\) inp shape"):
+        tf_sampling.prob_sample(torch.rand(2, 5, 1), torch.rand(2, 3))
+    with pytest.raises(ValueError, match=r"ProbSample expects \(batch_size,num_points\) inpr shape"):
+        tf_sampling.prob_sample(torch.rand(2, 5), torch.rand(3, 3))
+    lab = torch.zeros(8, dtype=torch.int32)
+    with pytest.raises(ValueError, match="sparse_points must be"):
+        tf_interpolate.interpolate_label_with_color(x[0][:, :2], lab, x[0], 3)
+    with pytest.raises(ValueError, match="sparse_labels must be"):
+        tf_interpolate.interpolate_label_with_color(x[0], lab[:5], x[0], 3)
+    with pytest.raises(ValueError, match="dense_points must be"):
+        tf_interpolate.interpolate_label_with_color(x[0], lab, x, 3)
+    with pytest.raises(ValueError, match="knn must be an int scalar"):
+        tf_interpolate.interpolate_label_with_color(x[0], lab, x[0], 2.5)
 
 
 def test_reference_aliases():
     import sys
     import pn2_b200
     pn2_b200.install_reference_aliases()
-    from tf_ops.tf_sampling import farthest_point_sample, gather_point  # noqa: F401
+    from tf_ops.tf_sampling import prob_sample, farthest_point_sample, gather_point  # noqa: F401
     from tf_ops.tf_grouping import query_ball_point, group_point, knn_point  # noqa: F401
     from tf_ops.tf_interpolate import three_nn, three_interpolate  # noqa: F401
+    from tf_ops.tf_interpolate import interpolate_label_with_color  # noqa: F401
     from util.pointnet_util import (pointnet_sa_module, pointnet_sa_module_msg,  # noqa: F401
                                     pointnet_fp_module, sample_and_group, sample_and_group_all)
     from util import tf_util
@@ -111,3 +125,54 @@ def test_layer_signatures_match_reference():
         "point_cloud", "is_training", "num_class", "hyperparams", "bn_decay"]
     ph = model.get_placeholders(8192, {"use_color": 1})
     assert ph[0].shape == (None, 8192, 6) and ph[1].shape == (None, 8192)
+
+
+def test_shard_batch_is_even_and_contiguous():
+    import torch
+    from pn2_b200.train_step import shard_batch
+    g = torch.arange(8 * 3).reshape(8, 3)
+    parts = [shard_batch(g, r, 4) for r in range(4)]
+    assert all(p.shape == (2, 3) for p in parts) and torch.equal(torch.cat(parts), g)
+    with pytest.raises(ValueError, match="divide evenly"):
+        shard_batch(g, 0, 3)
+    with pytest.raises(ValueError):
+        shard_batch(g, 4, 4)
+
+
+def test_predictor_host_logic(monkeypatch, tmp_path):
+    """predict.py:15-105 mirror: checkpoint dict / npz loading, eval-mode call, arg-max, label transfer
+    plumbing.  The device work is replaced by stubs here (the ops themselves are GPU-tested)."""
+    import torch
+    from pn2_b200 import predict
+    hp = {"use_color": 1}
+    ck = {"layer1/conv0/weights": np.ones((1, 1, 6, 4), np.float32),
+          "layer1/conv0/bn/moving_mean": np.zeros(4, np.float32)}
+    np.savez(tmp_path / "ck.npz", **ck)
+    seen = {}
+
+    def fake_get_model(x, is_training, num_class, hyperparams, bn_decay=None):
+        seen["args"] = (tuple(x.shape), is_training, num_class, torch.is_grad_enabled())
+        logits = torch.zeros(x.shape[0], x.shape[1], num_class)
+        logits[:, :, 3] = 1.0
+        logits[0, 0, 5] = 2.0
+        return logits, {}
+
+    def fake_vote(sp, sl, dp, knn):
+        seen["vote"] = (sp.dtype, sl.dtype, tuple(dp.shape), knn)
+        return torch.full((dp.shape[0],), 7, dtype=torch.int32), torch.zeros((dp.shape[0], 3), dtype=torch.uint8)
+
+    monkeypatch.setattr(predict.model, "get_model", fake_get_model)
+    monkeypatch.setattr(predict, "interpolate_label_with_color", fake_vote)
+    for src in (ck, str(tmp_path / "ck.npz")):
+        p = predict.Predictor(src, 9, hp, device="cpu")
+        assert set(p.store.vars) == set(ck) and not p.store.vars["layer1/conv0/bn/moving_mean"].trainable
+        labels = p.predict(np.zeros((2, 16, 6), np.float32))
+        assert labels.shape == (2, 16) and labels[0, 0] == 5 and labels[1, 3] == 3
+        assert seen["args"] == ((2, 16, 6), False, 9, False)
+    with pytest.raises(ValueError, match="batch_data must be"):
+        p.predict(np.zeros((2, 16, 3), np.float32))
+    with pytest.raises(ValueError, match="checkpoint"):
+        predict.Predictor({}, 9, hp, device="cpu")
+    dl, dc = p.interpolate_labels(np.zeros((5, 3)), np.zeros(5, np.int64), np.zeros((11, 3)))
+    assert dl.tolist() == [7] * 11 and dc.shape == (11, 3)
+    assert seen["vote"] == (torch.float32, torch.int32, (11, 3), 3)

@@ -15,6 +15,33 @@ def rng_cloud(seed, b, n, scale=(1.0, 1.0, 1.0), shift=(0.0, 0.0, 0.0)):
     return (x * np.asarray(scale, np.float32) + np.asarray(shift, np.float32)).astype(np.float32)
 
 
+def golden(name):
+    """Committed fixture tests/golden/<name>.npz (written by tests/golden/make_golden.py)."""
+    return np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+
+
+def golden_inputs():
+    """The seeded inputs make_golden.py froze the oracle outputs on (same draws, same order)."""
+    np.random.seed(100)
+    target = np.random.random((64, 8192, 3)).astype("float32")
+    reference = np.random.random((64, 1024, 3)).astype("float32")
+    inp = {"nn_q": np.ascontiguousarray(target[:1, :256]), "nn_known": np.ascontiguousarray(reference[:1])}
+    del target, reference
+    rs = np.random.RandomState(100)
+    inp["xyz"] = rs.random_sample((2, 1024, 3)).astype(np.float32)
+    np.random.seed(100)
+    tri = np.random.rand(1, 5, 3, 3).astype("float32")
+    ta, tb, tc = tri[:, :, 0], tri[:, :, 1], tri[:, :, 2]
+    inp["areas"] = np.sqrt((np.cross(tb - ta, tc - ta) ** 2).sum(2) + 1e-9).astype(np.float32)
+    inp["r"] = np.random.rand(1, 8192).astype(np.float32)
+    rs = np.random.RandomState(100)
+    inp["w"] = rs.random_sample((1, 9000)).astype(np.float32)
+    inp["sp"] = rs.random_sample((700, 3)).astype(np.float32)
+    inp["sl"] = rs.randint(0, 9, 700).astype(np.int32)
+    inp["dp"] = rs.random_sample((400, 3)).astype(np.float32)
+    return inp
+
+
 def to_cuda(a):
     import torch
     return torch.as_tensor(np.ascontiguousarray(a)).cuda()

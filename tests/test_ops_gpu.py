@@ -4,7 +4,7 @@ for interpolation) and against the reference's own CUDA kernels (oracle/_ref).""
 import numpy as np
 import pytest
 
-from _util import RefKernels, rng_cloud, to_cuda
+from _util import RefKernels, golden, golden_inputs, rng_cloud, to_cuda
 
 pytestmark = pytest.mark.gpu
 
@@ -495,3 +495,36 @@ def test_fps_cluster_matches_reference_kernel(ops):
     ref = RefKernels()
     x = to_cuda(rng_cloud(77, 2, 30000))
     np.testing.assert_array_equal(_fps_cluster(x, 256).cpu().numpy(), ref.fps(x, 256).cpu().numpy())
+
+
+# ------------------------------------------------------------- committed golden fixtures
+def test_kernels_match_committed_fixtures(ops):
+    """tests/golden/*.npz (oracle outputs frozen by make_golden.py on the seed-100 streams; the
+    three_nn one starts from the reference's own golden input, test_interpolate.py:7-10): the
+    CUDA path must reproduce every file bit for bit."""
+    import torch
+    from pn2_b200._ffi import F32, call, ptr
+    ts, tg, ti, _ = ops
+    inp = golden_inputs()
+    fx = golden("three_nn_seed100")
+    dist, idx = ti.three_nn(to_cuda(inp["nn_q"]), to_cuda(inp["nn_known"]))
+    np.testing.assert_array_equal(idx.cpu().numpy(), fx["idx"])
+    np.testing.assert_array_equal(dist.cpu().numpy(), fx["dist"])
+    fx = golden("fps_ball_seed100")
+    x = to_cuda(inp["xyz"])
+    fps = ts.farthest_point_sample(256, x)
+    np.testing.assert_array_equal(fps.cpu().numpy(), fx["fps"])
+    bidx, bcnt = tg.query_ball_point(0.2, 32, x, ts.gather_point(x, fps))
+    np.testing.assert_array_equal(bidx.cpu().numpy(), fx["idx"])
+    np.testing.assert_array_equal(bcnt.cpu().numpy(), fx["cnt"])
+    fx = golden("prob_vote_seed100")
+    ids = ts.prob_sample(to_cuda(inp["areas"]), to_cuda(inp["r"]))
+    np.testing.assert_array_equal(ids.cpu().numpy(), fx["ids"])
+    w = to_cuda(inp["w"])
+    cdf = torch.empty_like(w)
+    call("pn2_cumsum", 1, w.shape[1], ptr(w, F32), ptr(cdf, F32))
+    np.testing.assert_array_equal(cdf.cpu().numpy().view(np.uint32), fx["cdf"].view(np.uint32))
+    lab, col = ti.interpolate_label_with_color(to_cuda(inp["sp"]), to_cuda(inp["sl"]),
+                                               to_cuda(inp["dp"]), 3)
+    np.testing.assert_array_equal(lab.cpu().numpy(), fx["vote_labels"])
+    np.testing.assert_array_equal(col.cpu().numpy(), fx["vote_colors"])

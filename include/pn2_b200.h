@@ -94,6 +94,13 @@ int pn2_group_point_grad(int b, int n, int c, int m, int nsample, const float *g
 int pn2_three_nn(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist, int *idx,
                  pn2_stream_t s);
 
+/* Same contract and bit-identical results as pn2_three_nn, through the kernel that rejects most
+ * pairs with a conservative fp32 test before the exact fp64 one.  EXPERIMENTAL in round 1: built
+ * and unit-tested only behind PN2_EXPERIMENTAL=1 (tests/conftest.py); pn2_three_nn switches to it
+ * when PN2_THREE_NN_FILTER=1. */
+int pn2_three_nn_filtered(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist,
+                          int *idx, pn2_stream_t s);
+
 /* replaces interpolate_label_with_color_cpu tf_ops/tf_interpolate.cpp:71-115
  * sparse_points (num_sparse,3), sparse_labels (num_sparse), dense_points (num_dense,3) ->
  * dense_labels (num_dense) int32, dense_colors (num_dense,3) uint8: label vote among the knn

@@ -35,6 +35,7 @@ SIGNATURES = {
     "pn2_group_point_grad": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "pn2_three_nn": [_i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "pn2_interpolate_label_with_color": [_i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp],
+    "pn2_three_nn_filtered": [_i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "pn2_three_interpolate": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "pn2_three_interpolate_grad": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "pn2_selection_sort": [_i, _i, _i, _i, _vp, _vp, _vp, _vp],

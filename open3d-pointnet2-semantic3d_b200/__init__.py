@@ -19,7 +19,7 @@ from . import _ffi  # noqa: F401
 def install_reference_aliases():
     """Register the reference's absolute module names (``tf_ops.tf_sampling``, ``util.tf_util``,
     ``util.pointnet_util`` ...) so code written against the reference imports resolves here."""
-    from . import tf_ops, util, model
+    from . import tf_ops, util, model, predict
     from .tf_ops import tf_grouping, tf_interpolate, tf_sampling
     from .util import pointnet_util, tf_util
     sys.modules.setdefault("tf_ops", tf_ops)
@@ -29,4 +29,6 @@ def install_reference_aliases():
     sys.modules.setdefault("util", util)
     sys.modules.setdefault("util.tf_util", tf_util)
     sys.modules.setdefault("util.pointnet_util", pointnet_util)
+    sys.modules.setdefault("model", model)      # the reference's top-level `import model`
+    sys.modules.setdefault("predict", predict)  # `from predict import Predictor`
     return model

@@ -102,7 +102,11 @@ def test_reference_aliases():
                                     pointnet_fp_module, sample_and_group, sample_and_group_all)
     from util import tf_util
     assert hasattr(tf_util, "conv2d") and hasattr(tf_util, "conv1d") and hasattr(tf_util, "dropout")
-    for k in ["tf_ops", "tf_ops.tf_sampling", "util", "util.tf_util", "util.pointnet_util"]:
+    from predict import Predictor  # noqa: F401
+    import model
+    assert hasattr(model, "get_model") and hasattr(model, "get_loss")
+    for k in ["tf_ops", "tf_ops.tf_sampling", "tf_ops.tf_grouping", "tf_ops.tf_interpolate", "util",
+              "util.tf_util", "util.pointnet_util", "model", "predict"]:
         sys.modules.pop(k, None)
 
 

@@ -55,6 +55,10 @@ int pn2_fps(int b, int n, int m, const float *inp, float *temp, int *out, pn2_st
  * co-schedule the cluster. */
 int pn2_fps_cluster(int b, int n, int m, const float *inp, int *out, pn2_stream_t s);
 
+/* EXPERIMENTAL in round 1 (never run on a GPU; tests behind PN2_EXPERIMENTAL=1): pn2_fps_cluster with
+ * the per-round cluster barrier replaced by a push + remote-mbarrier handshake.  Same results. */
+int pn2_fps_cluster_mb(int b, int n, int m, const float *inp, int *out, pn2_stream_t s);
+
 /* replaces cumsumLauncher                  tf_ops/tf_sampling.cu:208-210
  * inp (b,n) -> out (b,n): row-wise inclusive prefix sum, bit-identical to the reference's
  * blocked scan (same fp32 addition order, see oracle/pn2_oracle.c cumsum_row_ref). */

@@ -26,6 +26,7 @@ SIGNATURES = {
     "pn2_ball_threshold": [_f],
     "pn2_fps": [_i, _i, _i, _vp, _vp, _vp, _vp],
     "pn2_fps_cluster": [_i, _i, _i, _vp, _vp, _vp],
+    "pn2_fps_cluster_mb": [_i, _i, _i, _vp, _vp, _vp],
     "pn2_cumsum": [_i, _i, _vp, _vp, _vp],
     "pn2_prob_sample": [_i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "pn2_gather_point": [_i, _i, _i, _vp, _vp, _vp, _vp],

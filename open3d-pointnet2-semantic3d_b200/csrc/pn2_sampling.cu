@@ -450,6 +450,136 @@ fps_cluster_kernel(int n, int m, const float *__restrict__ inp, int *__restrict_
     }
 }
 
+// EXPERIMENTAL (never run on a GPU yet; only reachable through pn2_fps_cluster_mb / the
+// PN2_EXPERIMENTAL tests): same data flow as fps_cluster_kernel, but the per-round cluster barrier
+// -- measured at ~0.9 us (UCGABAR + MEMBAR.ALL.GPU + CCTL.IVALL) -- is replaced by a point-to-point
+// handshake: after pushing its candidate into a peer's exchange slot, the pushing lane arrives
+// (release, cluster scope) on THAT peer's mbarrier of the round's parity; every thread then waits
+// (acquire, cluster scope) on its own CTA's mbarrier for the `cs` arrivals of the round.  Reuse is
+// safe without any further synchronisation: a peer can push round j+2 (same parity as j) only after
+// it has seen this CTA's round-(j+1) push, which warp 0 issues after the __syncthreads that every
+// warp reaches only when it has finished reading round j's records.
+__device__ __forceinline__ unsigned smem_addr_u32(const void *p) {
+    return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(void *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_remote_arrive_release(void *local_bar, unsigned peer_rank) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+        ::"r"(smem_addr_u32(local_bar)), "r"(peer_rank) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_acquire_cluster(void *bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP_%=:\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_LOOP_%=;\n\t"
+        "DONE_%=:\n\t}"
+        ::"r"(smem_addr_u32(bar)), "r"(parity) : "memory");
+}
+
+template <int PPT>
+__global__ void __launch_bounds__(1024, 1)
+fps_cluster_mb_kernel(int n, int m, const float *__restrict__ inp, int *__restrict__ out) {
+    namespace cg = cooperative_groups;
+    constexpr int THREADS = 1024, SLICE = THREADS * PPT;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned long long *slots = reinterpret_cast<unsigned long long *>(smem_raw);      // [2][32]
+    FpsCand *exch = reinterpret_cast<FpsCand *>(slots + 64);                            // [2][16]
+    unsigned long long *xbar = reinterpret_cast<unsigned long long *>(exch + 2 * kFpsMaxCluster);  // [2]
+    float *xs = reinterpret_cast<float *>(xbar + 2);
+    float *ys = xs + SLICE;
+    float *zs = ys + SLICE;
+
+    cg::cluster_group cluster = cg::this_cluster();
+    const int cs = (int)cluster.num_blocks();
+    const int rank = (int)cluster.block_rank();
+    const int cloud = blockIdx.x / cs;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const float *src = inp + (size_t)cloud * n * 3;
+    int *dst = out + (size_t)cloud * m;
+    const int k0 = rank * SLICE;
+    const int cnt = max(0, min(SLICE, n - k0));
+
+    if (t == 0) {
+        mbar_init(&xbar[0], (unsigned)cs);
+        mbar_init(&xbar[1], (unsigned)cs);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int e = t; e < SLICE * 3; e += THREADS) {
+        int k = e / 3, c = e - k * 3;
+        float v = k < cnt ? __ldg(src + (size_t)k0 * 3 + e) : 0.f;
+        (c == 0 ? xs : (c == 1 ? ys : zs))[k] = v;
+    }
+    float pd[PPT];
+#pragma unroll
+    for (int i = 0; i < PPT; ++i) pd[i] = (t + i * THREADS) < cnt ? 1e38f : -1.f;
+    float x1 = __ldg(src), y1 = __ldg(src + 1), z1 = __ldg(src + 2);
+    if (rank == 0 && t == 0) dst[0] = 0;
+    __syncthreads();
+    cluster.sync();  // every CTA runs and its mbarriers are initialised
+
+    for (int j = 1; j < m; ++j) {
+        float best = -1.f;
+        int besti = 0;
+#pragma unroll
+        for (int i = 0; i < PPT; ++i) {
+            const int k = t + i * THREADS;
+            float d = sqdist_ref(xs[k] - x1, ys[k] - y1, zs[k] - z1);
+            float d2 = fminf(d, pd[i]);
+            pd[i] = d2;
+            if (d2 > best) {
+                best = d2;
+                besti = i;
+            }
+        }
+        const bool has = best >= 0.f;
+        unsigned db = has ? __float_as_uint(best) : 0u;
+        unsigned key = has ? tie_key(k0 + t + besti * THREADS) : 0xFFFFFFFFu;
+        unsigned wmax = __reduce_max_sync(0xFFFFFFFFu, db);
+        unsigned wkey = __reduce_min_sync(0xFFFFFFFFu, db == wmax ? key : 0xFFFFFFFFu);
+        const int par = j & 1;
+        if (lane == 0) slots[par * 32 + warp] = ((unsigned long long)wmax << 32) | wkey;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long v = slots[par * 32 + lane];
+            unsigned d2 = (unsigned)(v >> 32), k2 = (unsigned)v;
+            unsigned cmax = __reduce_max_sync(0xFFFFFFFFu, d2);
+            unsigned ckey = __reduce_min_sync(0xFFFFFFFFu, d2 == cmax ? k2 : 0xFFFFFFFFu);
+            if (lane < cs) {
+                FpsCand c;
+                c.dk = ((unsigned long long)cmax << 32) | ckey;
+                const int kl = ckey == 0xFFFFFFFFu ? 0 : key_to_k(ckey) - k0;
+                c.x = xs[kl];
+                c.y = ys[kl];
+                c.z = zs[kl];
+                c.pad = 0.f;
+                FpsCand *peer = cluster.map_shared_rank(exch, lane);
+                peer[par * kFpsMaxCluster + rank] = c;
+                mbar_remote_arrive_release(&xbar[par], (unsigned)lane);  // orders the store above
+            }
+            __syncwarp();
+        }
+        mbar_wait_acquire_cluster(&xbar[par], (unsigned)((j >> 1) & 1));
+        unsigned long long v = lane < cs ? exch[par * kFpsMaxCluster + lane].dk : 0x00000000FFFFFFFFull;
+        unsigned d2 = (unsigned)(v >> 32), k2 = (unsigned)v;
+        unsigned gmax = __reduce_max_sync(0xFFFFFFFFu, d2);
+        unsigned gkey = __reduce_min_sync(0xFFFFFFFFu, d2 == gmax ? k2 : 0xFFFFFFFFu);
+        const unsigned who = __ballot_sync(0xFFFFFFFFu, lane < cs && d2 == gmax && k2 == gkey);
+        const FpsCand *w = exch + par * kFpsMaxCluster + (who ? __ffs(who) - 1 : 0);
+        x1 = w->x;
+        y1 = w->y;
+        z1 = w->z;
+        if (rank == 0 && t == 0) dst[j] = gkey == 0xFFFFFFFFu ? 0 : key_to_k(gkey);
+    }
+    cluster.sync();  // no CTA leaves while a peer could still push into it
+}
+
 // Fallback for clouds larger than one SM can hold: one CTA per cloud, coordinates read
 // through L1/L2 each round, running minimum in a caller-provided (b,n) global scratch.
 // Same arithmetic and tie order; used only beyond 16384 points (sweep sizes of config 5).
@@ -537,12 +667,13 @@ static int launch_fps_smem(int b, int n, int m, const float *inp, int *out, cuda
     return finish_launch();
 }
 
-template <int PPT>
+template <int PPT, bool HANDSHAKE = false>
 static int launch_fps_cluster(int b, int cs, int n, int m, const float *inp, int *out,
                               cudaStream_t st) {
     size_t smem = 64 * sizeof(unsigned long long) + 2 * kFpsMaxCluster * sizeof(FpsCand) +
+                  (HANDSHAKE ? 2 * sizeof(unsigned long long) : 0) +
                   (size_t)1024 * PPT * 3 * sizeof(float);
-    auto kern = fps_cluster_kernel<PPT>;
+    auto kern = HANDSHAKE ? fps_cluster_mb_kernel<PPT> : fps_cluster_kernel<PPT>;
     int rc = cuda_status(
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (rc) return rc;
@@ -576,16 +707,17 @@ static int launch_fps_cluster(int b, int cs, int n, int m, const float *inp, int
 // CTAs and, when possible, lets all b clusters run in one wave; a shape the device cannot
 // co-schedule (e.g. no GPC with 16 free SMs) falls through to the next larger slice per CTA.
 // PN2_EUNSUPPORTED when no shape works (n > 262144, or clusters unavailable).
+template <bool HANDSHAKE = false>
 static int dispatch_fps_cluster(int b, int n, int m, const float *inp, int *out, cudaStream_t st) {
     for (int p = 2; p <= 16; p *= 2) {
         int need = ceil_div(n, 1024 * p), cs = 2;
         while (cs < need) cs *= 2;
         if (cs > kFpsMaxCluster) continue;
         if ((long)b * cs > num_sms() && p < 16) continue;
-        int rc = p == 2   ? launch_fps_cluster<2>(b, cs, n, m, inp, out, st)
-                 : p == 4 ? launch_fps_cluster<4>(b, cs, n, m, inp, out, st)
-                 : p == 8 ? launch_fps_cluster<8>(b, cs, n, m, inp, out, st)
-                          : launch_fps_cluster<16>(b, cs, n, m, inp, out, st);
+        int rc = p == 2   ? launch_fps_cluster<2, HANDSHAKE>(b, cs, n, m, inp, out, st)
+                 : p == 4 ? launch_fps_cluster<4, HANDSHAKE>(b, cs, n, m, inp, out, st)
+                 : p == 8 ? launch_fps_cluster<8, HANDSHAKE>(b, cs, n, m, inp, out, st)
+                          : launch_fps_cluster<16, HANDSHAKE>(b, cs, n, m, inp, out, st);
         if (rc != PN2_EUNSUPPORTED) return rc;
     }
     return PN2_EUNSUPPORTED;
@@ -778,7 +910,7 @@ PN2_API int pn2_fps(int b, int n, int m, const float *inp, float *temp, int *out
     static const char *cl_env = getenv("PN2_FPS_CLUSTER");
     static const bool use_cluster = cl_env ? cl_env[0] != '0' : kFpsClusterDefault;
     if (use_cluster) {
-        int rc = dispatch_fps_cluster(b, n, m, inp, out, st);
+        int rc = dispatch_fps_cluster<false>(b, n, m, inp, out, st);
         if (rc != PN2_EUNSUPPORTED) return rc;
     }
     if (n <= 16384) return launch_fps_smem<1024, 16>(b, n, m, inp, out, st);
@@ -794,7 +926,15 @@ PN2_API int pn2_fps_cluster(int b, int n, int m, const float *inp, int *out, pn2
     if (b == 0) return PN2_OK;
     PN2_REQUIRE_PTR(inp);
     PN2_REQUIRE_PTR(out);
-    return dispatch_fps_cluster(b, n, m, inp, out, as_stream(s));
+    return dispatch_fps_cluster<false>(b, n, m, inp, out, as_stream(s));
+}
+
+PN2_API int pn2_fps_cluster_mb(int b, int n, int m, const float *inp, int *out, pn2_stream_t s) {
+    PN2_REQUIRE(b >= 0 && n > 0 && m > 0);
+    if (b == 0) return PN2_OK;
+    PN2_REQUIRE_PTR(inp);
+    PN2_REQUIRE_PTR(out);
+    return dispatch_fps_cluster<true>(b, n, m, inp, out, as_stream(s));
 }
 
 PN2_API int pn2_gather_point(int b, int n, int m, const float *inp, const int *idx, float *out,

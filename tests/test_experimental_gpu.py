@@ -65,3 +65,35 @@ def test_three_nn_filtered_matches_default_kernel_full_size(ops):
     d0, i0 = ti.three_nn(x1, x2)
     d1, i1 = _three_nn_filtered(x1, x2)
     assert bool((i0 == i1).all()) and bool((d0 == d1).all())
+
+
+# --------------------------------------------------------------- cluster FPS with the mbarrier handshake
+def _fps_cluster_mb(x, m):
+    import torch
+    from pn2_b200._ffi import F32, I32, call, ptr
+    b, n, _ = x.shape
+    out = torch.empty((b, m), dtype=I32, device=x.device)
+    call("pn2_fps_cluster_mb", b, n, m, ptr(x, F32), ptr(out, I32))
+    torch.cuda.synchronize()  # a wrong handshake shows up as a hang: run this file under `timeout`
+    return out
+
+
+@pytest.mark.parametrize("b,n,m", [(1, 12000, 64), (1, 20000, 32), (2, 16389, 100), (3, 40000, 150),
+                                   (1, 65536, 300), (1, 262144, 200), (16, 16384, 64), (2, 100, 120)])
+def test_fps_cluster_mb_matches_oracle(ops, b, n, m):
+    _, _, _, orc = ops
+    x = rng_cloud(300 + n, b, n)
+    got = _fps_cluster_mb(to_cuda(x), m).cpu().numpy()
+    np.testing.assert_array_equal(got, orc.farthest_point_sample(m, x, threads=8))
+
+
+def test_fps_cluster_mb_tie_order_and_long_run(ops):
+    """Tie lattice across CTAs, and many rounds (phase parity of the two mbarriers flips 4000 times)."""
+    ts, _, _, orc = ops
+    rs = np.random.RandomState(9)
+    x = rs.randint(0, 6, (2, 20000, 3)).astype(np.float32)
+    np.testing.assert_array_equal(_fps_cluster_mb(to_cuda(x), 300).cpu().numpy(),
+                                  orc.farthest_point_sample(300, x, threads=8))
+    y = to_cuda(rng_cloud(5, 1, 32768))
+    np.testing.assert_array_equal(_fps_cluster_mb(y, 8000).cpu().numpy(),
+                                  ts.farthest_point_sample(8000, y).cpu().numpy())

@@ -37,6 +37,8 @@ def main():
     ap.add_argument("--only", default="", help="'cfg2': one untimed call per config-2 op (ncu target); "
                                                "'msg': the config-3 MSG layer, forward + backward")
     ap.add_argument("--no-ref", action="store_true")
+    ap.add_argument("--fps-entry", default="pn2_fps_cluster",
+                    help="entry point timed by --only fps_cluster (pn2_fps_cluster | pn2_fps_cluster_mb)")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "op_sweep.json"))
     args = ap.parse_args()
 
@@ -174,7 +176,7 @@ def main():
 
         def cluster_fps(x, m):
             out = torch.empty((x.shape[0], m), dtype=I32, device=x.device)
-            call("pn2_fps_cluster", x.shape[0], x.shape[1], m, ptr(x, F32), ptr(out, I32))
+            call(args.fps_entry, x.shape[0], x.shape[1], m, ptr(x, F32), ptr(out, I32))
             return out
 
         for n in (16384, 65536, 262144):
@@ -186,7 +188,7 @@ def main():
                 if not out_of_time():  # full-size parity: the single-CTA kernels are bit-exact vs the oracle
                     same = bool((cluster_fps(x, m) == tf_sampling.farthest_point_sample(m, x)).all())
                 stream_bytes = b * (m - 1) * n * 20.0
-                record(op="farthest_point_sample (cluster kernel)", case="sweep N=%d B=%d" % (n, b), B=b, N=n,
+                record(op="farthest_point_sample (%s)" % args.fps_entry, case="sweep N=%d B=%d" % (n, b), B=b, N=n,
                        npoint=m, ms=ms, us_per_round=ms * 1e3 / (m - 1),
                        streaming_model_GBps=stream_bytes / ms / 1e6,
                        streaming_model_frac_of_hbm=stream_bytes / ms / 1e6 / hbm,

@@ -44,8 +44,10 @@ const char *pn2_last_cuda_error(void);
 /* ===== group 1: one entry point per reference launcher ======================= */
 
 /* replaces farthestpointsamplingLauncher   tf_ops/tf_sampling.cu:218-221
- * inp (b,n,3) -> out (b,m) int32.  temp is accepted for signature parity and may be
- * NULL: the running minimum distances live in registers, not in global memory. */
+ * inp (b,n,3) -> out (b,m) int32.  The running minimum distances live in registers (one CTA per
+ * cloud up to 8192 points, one thread-block cluster per cloud up to 262144), so temp is not
+ * touched on those paths.  It is needed -- (b,n) floats, PN2_ENULL if missing -- only by the
+ * streaming fall-back: n > 16384 on a device that cannot schedule the cluster, or n > 262144. */
 int pn2_fps(int b, int n, int m, const float *inp, float *temp, int *out, pn2_stream_t s);
 
 /* Same result as pn2_fps, always through the thread-block-cluster kernel (one cluster of up to

@@ -87,6 +87,15 @@ int pn2_gather_point_grad(int b, int n, int m, const float *out_g, const int *id
 int pn2_query_ball_point(int b, int n, int m, float radius, int nsample, const float *xyz1,
                          const float *xyz2, int *idx, int *pts_cnt, pn2_stream_t s);
 
+/* EXPERIMENTAL in round 1 (never run on a GPU; tests behind PN2_EXPERIMENTAL=1): pn2_query_ball_point
+ * over a hashed uniform grid with cells of edge `radius` -- identical idx / pts_cnt, work proportional
+ * to the ball populations instead of b*m*n.  workspace: caller-owned device scratch of at least
+ * pn2_ball_grid_workspace_bytes(b, n) bytes, 16-byte aligned. */
+long pn2_ball_grid_workspace_bytes(int b, int n);
+int pn2_query_ball_point_grid(int b, int n, int m, float radius, int nsample, const float *xyz1,
+                              const float *xyz2, int *idx, int *pts_cnt, void *workspace,
+                              long workspace_bytes, pn2_stream_t s);
+
 /* replaces groupPointLauncher              tf_ops/tf_grouping.cu:150-154 */
 int pn2_group_point(int b, int n, int c, int m, int nsample, const float *points, const int *idx,
                     float *out, pn2_stream_t s);

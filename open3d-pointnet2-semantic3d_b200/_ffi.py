@@ -32,6 +32,8 @@ SIGNATURES = {
     "pn2_gather_point": [_i, _i, _i, _vp, _vp, _vp, _vp],
     "pn2_gather_point_grad": [_i, _i, _i, _vp, _vp, _vp, _vp],
     "pn2_query_ball_point": [_i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp],
+    "pn2_ball_grid_workspace_bytes": [_i, _i],
+    "pn2_query_ball_point_grid": [_i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp, _l, _vp],
     "pn2_group_point": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "pn2_group_point_grad": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "pn2_three_nn": [_i, _i, _i, _vp, _vp, _vp, _vp, _vp],
@@ -68,7 +70,8 @@ SIGNATURES = {
     "pn2_adam_step": [_l, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _i, _f, _vp],
 }
 _RESTYPE = {"pn2_strerror": ctypes.c_char_p, "pn2_last_cuda_error": ctypes.c_char_p,
-            "pn2_ball_threshold": ctypes.c_float, "pn2_linear_workspace_bytes": ctypes.c_long}
+            "pn2_ball_threshold": ctypes.c_float, "pn2_linear_workspace_bytes": ctypes.c_long,
+            "pn2_ball_grid_workspace_bytes": ctypes.c_long}
 
 _lib = None
 launches = 0  # number of native entry-point calls made (bench.py reports it)

@@ -17,6 +17,8 @@
 // (CUDA max(NaN,1e-20f) = 1e-20f, hence a hit) is preserved by the negated comparison.
 #include <math.h>
 
+#include <cub/block/block_scan.cuh>
+
 #include "pn2_common.cuh"
 
 namespace pn2 {
@@ -393,6 +395,194 @@ static inline int grid_for(long total, int threads) {
 
 using namespace pn2;
 
+// ---- ball query over a hashed uniform grid (EXPERIMENTAL: never run on a GPU yet) ----------------
+// Brute force tests b*m*n pairs although a ball usually holds a tiny fraction of the cloud (SA1 of
+// config 2: 0.1 % of the box).  Here every cloud is binned once into cells of edge `radius`
+// (cell = floor(x * (1/radius)) per axis, clamped; cells are hashed into T >= 2n buckets, so no bounding
+// box and no host round trip are needed), the points are copied bucket by bucket into a float4 array
+// (x, y, z, original index) and a WARP per query visits only the cells that can hold a hit:
+//   * coverage: a point that passes the fp32 distance test has |dx| <= radius*(1+4u) per axis, and
+//     the cell function is monotone in x, so every hit lies in cell(x_q - rpad) .. cell(x_q + rpad)
+//     with rpad = radius*1.0001 and the bounds rounded outwards (3 cells per axis, rarely 4);
+//   * a bucket can hold points of other cells (hash collisions): a candidate counts only if its own
+//     cell equals the visited cell, which also makes every point count exactly once;
+//   * the distance test is the one of the other kernels (same expression, same threshold), so the set of
+//     hits is identical; the reference's order (first nsample hits in ascending index) is restored by
+//     ranking the collected indices (rank = number of smaller hits; indices are unique);
+//   * more than GQ_CAP hits, more than 64 cells, a non-finite query or any non-finite data point fall back
+//     to the ordered brute-force scan inside the same kernel (NaN distances are hits in the reference).
+constexpr int GQ_WARPS = 8;
+constexpr int GQ_CAP = 512;
+constexpr float GQ_CLAMP = 1073741824.0f;  // 2^30
+
+__device__ __forceinline__ int grid_cell(float x, float inv) {
+    float v = floorf(__fmul_rn(x, inv));
+    return (int)fminf(fmaxf(v, -GQ_CLAMP), GQ_CLAMP);
+}
+__device__ __forceinline__ unsigned grid_bucket(int cx, int cy, int cz, unsigned mask) {
+    return (((unsigned)cx * 73856093u) ^ ((unsigned)cy * 19349663u) ^ ((unsigned)cz * 83492791u)) & mask;
+}
+__device__ __forceinline__ bool finite3(float x, float y, float z) {
+    return isfinite(x) && isfinite(y) && isfinite(z);
+}
+
+// pass 1: bucket populations (cursor must be zero on entry)
+__global__ void grid_count_kernel(int n, long total, unsigned tmask, float inv,
+                                  const float *__restrict__ xyz, int *__restrict__ cursor,
+                                  int *__restrict__ flag) {
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total;
+         e += (long)gridDim.x * blockDim.x) {
+        const long cloud = e / n;
+        const float x = __ldg(xyz + e * 3), y = __ldg(xyz + e * 3 + 1), z = __ldg(xyz + e * 3 + 2);
+        if (!finite3(x, y, z)) flag[0] = 1;
+        const unsigned bk = grid_bucket(grid_cell(x, inv), grid_cell(y, inv), grid_cell(z, inv), tmask);
+        atomicAdd(cursor + cloud * (long)(tmask + 1) + bk, 1);
+    }
+}
+
+// pass 2: starts = exclusive scan of the populations (one CTA per cloud), cursor = starts
+__global__ void __launch_bounds__(1024)
+grid_scan_kernel(int T, int *__restrict__ cursor, int *__restrict__ starts, int starts_pitch) {
+    typedef cub::BlockScan<int, 1024> Scan;
+    __shared__ typename Scan::TempStorage tmp;
+    int *cur = cursor + (long)blockIdx.x * T;
+    int *st = starts + (long)blockIdx.x * starts_pitch;
+    const int per = T / 1024;  // T is a power of two >= 1024
+    const int first = threadIdx.x * per;
+    int sum = 0;
+    for (int i = 0; i < per; ++i) sum += cur[first + i];
+    int offset;
+    Scan(tmp).ExclusiveSum(sum, offset);
+    for (int i = 0; i < per; ++i) {
+        const int c = cur[first + i];
+        st[first + i] = offset;
+        cur[first + i] = offset;
+        offset += c;
+    }
+    if (threadIdx.x == 1023) st[T] = offset;
+}
+
+// pass 3: copy every point into its bucket's segment
+__global__ void grid_fill_kernel(int n, long total, unsigned tmask, float inv,
+                                 const float *__restrict__ xyz, int *__restrict__ cursor,
+                                 float4 *__restrict__ sorted) {
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total;
+         e += (long)gridDim.x * blockDim.x) {
+        const long cloud = e / n;
+        const int k = (int)(e - cloud * n);
+        const float x = __ldg(xyz + e * 3), y = __ldg(xyz + e * 3 + 1), z = __ldg(xyz + e * 3 + 2);
+        const unsigned bk = grid_bucket(grid_cell(x, inv), grid_cell(y, inv), grid_cell(z, inv), tmask);
+        const int pos = atomicAdd(cursor + cloud * (long)(tmask + 1) + bk, 1);
+        sorted[cloud * n + pos] = make_float4(x, y, z, __int_as_float(k));
+    }
+}
+
+// pass 4: one warp per query
+__global__ void __launch_bounds__(GQ_WARPS * 32)
+ball_query_grid_kernel(int n, int m, long queries, unsigned tmask, int starts_pitch, float thr,
+                       float inv, float rpad, int nsample, const float *__restrict__ xyz1,
+                       const float *__restrict__ xyz2, const int *__restrict__ starts,
+                       const float4 *__restrict__ sorted, const int *__restrict__ flag,
+                       int *__restrict__ idx, int *__restrict__ pts_cnt) {
+    __shared__ int hits[GQ_WARPS][GQ_CAP];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    const long q = (long)blockIdx.x * GQ_WARPS + warp;
+    if (q >= queries) return;  // whole warps leave together; no block-wide barrier below
+    const long cloud = q / m;
+    const float qx = __ldg(xyz2 + q * 3), qy = __ldg(xyz2 + q * 3 + 1), qz = __ldg(xyz2 + q * 3 + 2);
+    int *row = idx + q * (long)nsample;
+    const int *st = starts + cloud * starts_pitch;
+    const float4 *pts = sorted + cloud * n;
+    int *my = hits[warp];
+
+    bool brute = __ldg(flag) != 0 || !finite3(qx, qy, qz);
+    int lx = 0, ly = 0, lz = 0, hx = 0, hy = 0, hz = 0;
+    if (!brute) {
+        lx = grid_cell(__fsub_rd(qx, rpad), inv);
+        hx = grid_cell(__fadd_ru(qx, rpad), inv);
+        ly = grid_cell(__fsub_rd(qy, rpad), inv);
+        hy = grid_cell(__fadd_ru(qy, rpad), inv);
+        lz = grid_cell(__fsub_rd(qz, rpad), inv);
+        hz = grid_cell(__fadd_ru(qz, rpad), inv);
+        const long cells = (long)(hx - lx + 1) * (long)(hy - ly + 1) * (long)(hz - lz + 1);
+        brute = cells > 64;
+    }
+    int h = 0;
+    if (!brute) {
+        for (int cx = lx; cx <= hx; ++cx)
+            for (int cy = ly; cy <= hy; ++cy)
+                for (int cz = lz; cz <= hz; ++cz) {
+                    const unsigned bk = grid_bucket(cx, cy, cz, tmask);
+                    const int s = __ldg(st + bk), e = __ldg(st + bk + 1);
+                    for (int base = s; base < e; base += 32) {
+                        const int p = base + lane;
+                        bool hit = false;
+                        int k = 0;
+                        if (p < e) {
+                            const float4 v = __ldg(pts + p);
+                            k = __float_as_int(v.w);
+                            hit = grid_cell(v.x, inv) == cx && grid_cell(v.y, inv) == cy &&
+                                  grid_cell(v.z, inv) == cz &&
+                                  !(sqdist_ref(qx - v.x, qy - v.y, qz - v.z) >= thr);
+                        }
+                        const unsigned mk = __ballot_sync(0xFFFFFFFFu, hit);
+                        if (hit) {
+                            const int pos = h + __popc(mk & lt);
+                            if (pos < GQ_CAP) my[pos] = k;
+                        }
+                        h += __popc(mk);
+                    }
+                }
+        brute = h > GQ_CAP;
+    }
+    int cnt = 0, first = 0;
+    if (brute) {
+        // ordered scan of the whole cloud: lane order == index order, append in place
+        const float *data = xyz1 + cloud * (long)n * 3;
+        for (int base = 0; base < n && cnt < nsample; base += 32) {
+            const int k = base + lane;
+            bool hit = false;
+            if (k < n) {
+                const float d = sqdist_ref(qx - __ldg(data + k * 3), qy - __ldg(data + k * 3 + 1),
+                                           qz - __ldg(data + k * 3 + 2));
+                hit = !(d >= thr);
+            }
+            const unsigned mk = __ballot_sync(0xFFFFFFFFu, hit);
+            if (mk) {
+                if (cnt == 0) first = base + __ffs(mk) - 1;
+                if (hit) {
+                    const int pos = cnt + __popc(mk & lt);
+                    if (pos < nsample) row[pos] = k;
+                }
+                cnt += __popc(mk);
+            }
+        }
+        cnt = min(cnt, nsample);
+    } else {
+        __syncwarp();
+        int vmin = 0x7FFFFFFF;
+        for (int i = lane; i < h; i += 32) {
+            const int v = my[i];
+            vmin = min(vmin, v);
+            int r = 0;
+            for (int u = 0; u < h; ++u) r += my[u] < v ? 1 : 0;
+            if (r < nsample) row[r] = v;
+        }
+        vmin = __reduce_min_sync(0xFFFFFFFFu, vmin);
+        cnt = min(h, nsample);
+        first = h > 0 ? vmin : 0;
+    }
+    for (int l = cnt + lane; l < nsample; l += 32) row[l] = first;  // pad with the first hit (0 if none)
+    if (lane == 0) pts_cnt[q] = cnt;
+}
+
+static inline int grid_buckets(int n) {
+    int t = 1024;
+    while (t < 2 * n && t < (1 << 28)) t *= 2;
+    return t;
+}
+
 // smallest float T >= 0 such that sqrtf(T) >= radius (host sqrtf is IEEE, correctly rounded)
 static float ball_threshold(float radius) {
     if (!(radius > 1e-20f)) return 0.f;  // max(d,1e-20f) < radius can never hold
@@ -568,5 +758,60 @@ PN2_API int pn2_selection_sort(int b, int n, int m, int k, const float *dist, in
     long blocks = ceil_div<long>(rows * 32, threads);
     selection_topk_kernel<<<(unsigned)blocks, threads, 0, as_stream(s)>>>(rows, n, k, dist, outi,
                                                                          out);
+    return finish_launch();
+}
+
+PN2_API long pn2_ball_grid_workspace_bytes(int b, int n) {
+    if (b <= 0 || n <= 0) return 16;
+    const long T = grid_buckets(n);
+    return 16 + (long)b * ((T + 4) * 4 + T * 4 + (long)n * 16);
+}
+
+PN2_API int pn2_query_ball_point_grid(int b, int n, int m, float radius, int nsample,
+                                      const float *xyz1, const float *xyz2, int *idx, int *pts_cnt,
+                                      void *workspace, long workspace_bytes, pn2_stream_t s) {
+    PN2_REQUIRE(radius > 0.f && nsample > 0);
+    PN2_REQUIRE(b >= 0 && n > 0 && m >= 0);
+    if (b == 0 || m == 0) return PN2_OK;
+    PN2_REQUIRE_PTR(xyz1);
+    PN2_REQUIRE_PTR(xyz2);
+    PN2_REQUIRE_PTR(idx);
+    PN2_REQUIRE_PTR(pts_cnt);
+    PN2_REQUIRE_PTR(workspace);
+    PN2_REQUIRE(workspace_bytes >= pn2_ball_grid_workspace_bytes(b, n));
+    PN2_REQUIRE(reinterpret_cast<uintptr_t>(workspace) % 16 == 0);
+    cudaStream_t st = as_stream(s);
+    const float thr = ball_threshold(radius);
+    const int T = grid_buckets(n);
+    const int pitch = T + 4;
+    // layout: [flag: 4 ints][sorted: b*n float4][starts: b*(T+4) ints][cursor: b*T ints]
+    int *flag = static_cast<int *>(workspace);
+    float4 *sorted = reinterpret_cast<float4 *>(flag + 4);
+    int *starts = reinterpret_cast<int *>(sorted + (size_t)b * n);
+    int *cursor = starts + (size_t)b * pitch;
+    int rc = cuda_status(cudaMemsetAsync(flag, 0, 16, st));
+    if (rc) return rc;
+    rc = cuda_status(cudaMemsetAsync(cursor, 0, sizeof(int) * (size_t)b * T, st));
+    if (rc) return rc;
+    const float inv = 1.0f / radius;
+    const float rpad = nextafterf(radius * 1.0001f, INFINITY);
+    const long total = (long)b * n;
+    long blocks = ceil_div<long>(total, 256);
+    if (blocks > 148L * 16) blocks = 148L * 16;
+    grid_count_kernel<<<(int)blocks, 256, 0, st>>>(n, total, (unsigned)(T - 1), inv, xyz1, cursor, flag);
+    rc = finish_launch();
+    if (rc) return rc;
+    grid_scan_kernel<<<b, 1024, 0, st>>>(T, cursor, starts, pitch);
+    rc = finish_launch();
+    if (rc) return rc;
+    grid_fill_kernel<<<(int)blocks, 256, 0, st>>>(n, total, (unsigned)(T - 1), inv, xyz1, cursor, sorted);
+    rc = finish_launch();
+    if (rc) return rc;
+    const long queries = (long)b * m;
+    const long qblocks = ceil_div<long>(queries, GQ_WARPS);
+    PN2_REQUIRE(qblocks < (1l << 31));
+    ball_query_grid_kernel<<<(unsigned)qblocks, GQ_WARPS * 32, 0, st>>>(
+        n, m, queries, (unsigned)(T - 1), pitch, thr, inv, rpad, nsample, xyz1, xyz2, starts, sorted, flag,
+        idx, pts_cnt);
     return finish_launch();
 }

@@ -3,7 +3,7 @@
 N in {4096, 16384, 65536, 262144}, npoint = N/4, nsample = 64) plus the standalone index/gather
 ops at their config-2 sizes, each against the roofline SURVEY.md 8(d) assigns to it.
 
-    python profiles/op_sweep.py [--budget SECONDS] [--only cfg2|msg|fps_cluster] [--no-ref] [--out FILE]
+    python profiles/op_sweep.py [--budget SECONDS] [--only cfg2|msg|fps_cluster|ball_grid] [--no-ref] [--out FILE]
 
 Inputs are resident in HBM, every op is called through the public Python op surface (ctypes ->
 C ABI -> sm_100a kernel), timed with CUDA events on the launching stream after one warm-up, a
@@ -194,6 +194,40 @@ def main():
                        streaming_model_frac_of_hbm=stream_bytes / ms / 1e6 / hbm,
                        identical_to_single_cta_kernel=same)
                 del x
+        print("wrote", args.out)
+        return
+
+    # ------------------------------------------- ball query: hashed grid (experimental) vs default kernels
+    if args.only == "ball_grid":
+        from pn2_b200._ffi import F32, I32, call, lib, ptr
+
+        def grid_ball(radius, ns, x1, x2, ws, nbytes):
+            idx = torch.empty((x1.shape[0], x2.shape[1], ns), dtype=I32, device=x1.device)
+            cnt = torch.empty((x1.shape[0], x2.shape[1]), dtype=I32, device=x1.device)
+            call("pn2_query_ball_point_grid", x1.shape[0], x1.shape[1], x2.shape[1], float(radius), ns,
+                 ptr(x1, F32), ptr(x2, F32), ptr(idx, I32), ptr(cnt, I32), ptr(ws, F32), nbytes)
+            return idx, cnt
+
+        cases = [("cfg2 SA1", 16, 8192, 1024, 0.5, 32, (10, 10, 5), (-5, -5, 0))]
+        for n in (4096, 16384, 65536, 262144):
+            for b in (16, 1):
+                cases.append(("sweep N=%d B=%d" % (n, b), b, n, n // 4,
+                              float((3.0 * 2 * 64 / (4.0 * math.pi * n)) ** (1.0 / 3.0)), 64, (1, 1, 1), (0, 0, 0)))
+        for tag, b, n, m, radius, ns, sc, sh in cases:
+            if out_of_time():
+                break
+            x = cloud(100 + n, b, n, sc, sh)
+            q = tf_sampling.gather_point(x, tf_sampling.farthest_point_sample(m, x))
+            nbytes = int(lib().pn2_ball_grid_workspace_bytes(b, n))
+            ws = torch.empty((nbytes + 15) // 16 * 4, dtype=torch.float32, device="cuda")
+            ms_g = timed(lambda: grid_ball(radius, ns, x, q, ws, nbytes))
+            ms_d = timed(lambda: tf_grouping.query_ball_point(radius, ns, x, q))
+            gi, gc = grid_ball(radius, ns, x, q, ws, nbytes)
+            di, dc = tf_grouping.query_ball_point(radius, ns, x, q)
+            record(op="query_ball_point grid vs default", case=tag, B=b, n=n, m=m, nsample=ns, radius=radius,
+                   grid_ms=ms_g, default_ms=ms_d, speedup=ms_d / ms_g,
+                   identical=bool((gi == di).all()) and bool((gc == dc).all()))
+            del x, q, ws
         print("wrote", args.out)
         return
 

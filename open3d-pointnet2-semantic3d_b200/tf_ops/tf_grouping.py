@@ -7,6 +7,8 @@
 
 Validation texts follow tf_grouping.cpp:80-105, 187-200, 142-151.
 """
+import os
+
 import torch
 
 from .._ffi import F32, I32, call, ptr
@@ -34,9 +36,30 @@ def query_ball_point(radius, nsample, xyz1, xyz2):
     xyz2 = xyz2.detach().contiguous()
     idx = torch.empty((b, m, int(nsample)), dtype=I32, device=xyz1.device)
     cnt = torch.empty((b, m), dtype=I32, device=xyz1.device)
+    if _GRID and n >= 4096:  # EXPERIMENTAL (PN2_BALL_GRID=1): hashed uniform grid, same results
+        ws, nbytes = _grid_workspace(b, n, xyz1.device)
+        call("pn2_query_ball_point_grid", b, n, m, float(radius), int(nsample), ptr(xyz1, F32),
+             ptr(xyz2, F32), ptr(idx, I32), ptr(cnt, I32), ptr(ws, F32), nbytes)
+        return idx, cnt
     call("pn2_query_ball_point", b, n, m, float(radius), int(nsample), ptr(xyz1, F32),
          ptr(xyz2, F32), ptr(idx, I32), ptr(cnt, I32))
     return idx, cnt
+
+
+_GRID = os.environ.get("PN2_BALL_GRID") == "1"
+_grid_ws = {}
+
+
+def _grid_workspace(b, n, device):
+    """Caller-owned scratch of pn2_query_ball_point_grid, one per (b, n, device)."""
+    key = (b, n, str(device))
+    hit = _grid_ws.get(key)
+    if hit is None:
+        from .._ffi import lib
+        nbytes = int(lib().pn2_ball_grid_workspace_bytes(b, n))
+        hit = (torch.empty((nbytes + 15) // 16 * 4, dtype=F32, device=device), nbytes)
+        _grid_ws[key] = hit
+    return hit
 
 
 class _GroupPoint(torch.autograd.Function):

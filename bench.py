@@ -272,7 +272,12 @@ def run_ours(args):
     b, n = args.batch, args.npoint
     pc, labels, smpw = make_batch(b, n, 100 + rank)
     d_pc, d_lab, d_w = (torch.as_tensor(x).to(dev) for x in (pc, labels, smpw))
-    trainer = Trainer(HP, NUM_CLASS, device=dev, seed=0, world_size=world)
+    if args.prefetch:  # EXPERIMENTAL: geometry (FPS / ball query / 3-NN) one batch ahead on a side stream
+        from pn2_b200.train_prefetch import PrefetchTrainer
+        trainer = PrefetchTrainer(HP, NUM_CLASS, device=dev, seed=0, world_size=world)
+        trainer.prime(d_pc)
+    else:
+        trainer = Trainer(HP, NUM_CLASS, device=dev, seed=0, world_size=world)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
 
     def barrier():
@@ -283,8 +288,17 @@ def run_ours(args):
 
     trainer.step(d_pc, d_lab, d_w)  # creates + flattens the variables
     trainer.step(d_pc, d_lab, d_w)
-    use_graph = (not args.no_graph) and trainer.capture(d_pc, d_lab, d_w)
-    step_fn = trainer.step_graph if use_graph else trainer.step
+    if args.prefetch:
+        use_graph = (not args.no_graph) and trainer.capture_prefetch(d_pc, d_lab, d_w)
+        # the synthetic workload feeds the same cloud every step, so "the next batch" is the same tensor; its
+        # geometry is nevertheless recomputed every step (nothing is reused across steps)
+        if use_graph:
+            step_fn = lambda a, b_, c: trainer.step_graph_prefetch(a, b_, c, a)  # noqa: E731
+        else:
+            step_fn = lambda a, b_, c: trainer.step_prefetch(a, b_, c, a)  # noqa: E731
+    else:
+        use_graph = (not args.no_graph) and trainer.capture(d_pc, d_lab, d_w)
+        step_fn = trainer.step_graph if use_graph else trainer.step
     launches_per_step = None
     for _ in range(max(args.warmup, 3)):
         step_fn(d_pc, d_lab, d_w)
@@ -304,7 +318,8 @@ def run_ours(args):
     barrier()
     calls = _ffi.launches - calls0
     if use_graph:  # replayed launches are not seen by the ctypes counter: count them from the capture
-        calls = args.steps * (trainer.launches_per_replay + 1)
+        calls = args.steps * (trainer.launches_per_replay + 1 +
+                              (getattr(trainer, "geom_launches_per_replay", 0) if args.prefetch else 0))
     ms = sum(a.elapsed_time(bb) for a, bb in ev)
     clocks = sampler.stop() if sampler else None
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -418,6 +433,7 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": workload_name(b, n), "global_batch": b * world,
                        "parallelism": "dp%d" % world, "cuda_graph": bool(use_graph),
+                       "geometry_prefetch": bool(args.prefetch),
                        "cuda_graph_error": getattr(trainer, "_capture_error", None),
                        "l2": "256 MB flush write between timed steps; a step also streams >1 GB of "
                              "activations, far beyond the 126 MB L2"},
@@ -442,6 +458,9 @@ def main():
     ap.add_argument("--npoint", type=int, default=8192)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of a CUDA graph")
+    ap.add_argument("--prefetch", action="store_true",
+                    help="EXPERIMENTAL: compute the weight-independent geometry of the next batch on a side "
+                         "stream while the dense stage of the current one runs (train_prefetch.py)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -180,3 +180,27 @@ def test_predictor_host_logic(monkeypatch, tmp_path):
     dl, dc = p.interpolate_labels(np.zeros((5, 3)), np.zeros(5, np.int64), np.zeros((11, 3)))
     assert dl.tolist() == [7] * 11 and dc.shape == (11, 3)
     assert seen["vote"] == (torch.float32, torch.int32, (11, 3), 3)
+
+
+def test_geometry_replay_tape_logic():
+    """train_prefetch._Replay: hands the precomputed results back in the model's call order, checks that
+    order, wraps around for a second forward pass over the same batch, and is transparent without a tape."""
+    from pn2_b200 import train_prefetch as tp
+    from pn2_b200.util import pointnet_util
+    rp = tp._Replay()
+    calls = []
+    fa = rp.wrap("a", lambda x: calls.append(("a", x)) or "real-a")
+    fb = rp.wrap("b", lambda x: calls.append(("b", x)) or "real-b")
+    assert fa(1) == "real-a" and fb(2) == "real-b" and calls == [("a", 1), ("b", 2)]  # no tape: pass through
+    rp.tape, rp.pos = [("a", 10), ("b", (20, 21)), ("a", 30)], 0
+    assert [fa(0), fb(0), fa(0)] == [10, (20, 21), 30] and len(calls) == 2
+    assert fa(0) == 10  # exhausted tape: the next forward pass starts over
+    with pytest.raises(RuntimeError, match="out of order"):
+        fa(0)
+    # installing / uninstalling restores the module's own functions
+    real = {n: getattr(pointnet_util, n) for n in tp.GEOM_OPS}
+    tp._install()
+    assert all(getattr(pointnet_util, n) is not real[n] for n in tp.GEOM_OPS)
+    assert pointnet_util.fp_weights.__name__ == "fp_weights"
+    tp._uninstall()
+    assert all(getattr(pointnet_util, n) is real[n] for n in tp.GEOM_OPS)

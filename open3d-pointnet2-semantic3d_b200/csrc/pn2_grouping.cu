@@ -409,7 +409,7 @@ using namespace pn2;
 //   * the distance test is the one of the other kernels (same expression, same threshold), so the set of
 //     hits is identical; the reference's order (first nsample hits in ascending index) is restored by
 //     ranking the collected indices (rank = number of smaller hits; indices are unique);
-//   * more than GQ_CAP hits, more than 64 cells, a non-finite query or any non-finite data point fall back
+//   * more than GQ_CAP hits, more than 4 cells along an axis, a non-finite query or any non-finite data point fall back
 //     to the ordered brute-force scan inside the same kernel (NaN distances are hits in the reference).
 constexpr int GQ_WARPS = 8;
 constexpr int GQ_CAP = 512;
@@ -505,8 +505,9 @@ ball_query_grid_kernel(int n, int m, long queries, unsigned tmask, int starts_pi
         hy = grid_cell(__fadd_ru(qy, rpad), inv);
         lz = grid_cell(__fsub_rd(qz, rpad), inv);
         hz = grid_cell(__fadd_ru(qz, rpad), inv);
-        const long cells = (long)(hx - lx + 1) * (long)(hy - ly + 1) * (long)(hz - lz + 1);
-        brute = cells > 64;
+        // per-axis spans (a clamped cell range can be 2^31 wide: never multiply before bounding them)
+        const long sx = (long)hx - lx + 1, sy = (long)hy - ly + 1, sz = (long)hz - lz + 1;
+        brute = sx > 4 || sy > 4 || sz > 4;
     }
     int h = 0;
     if (!brute) {

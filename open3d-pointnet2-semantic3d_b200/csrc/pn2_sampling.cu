@@ -565,7 +565,9 @@ fps_cluster_mb_kernel(int n, int m, const float *__restrict__ inp, int *__restri
             }
             __syncwarp();
         }
-        mbar_wait_acquire_cluster(&xbar[par], (unsigned)((j >> 1) & 1));
+        // barrier `par` serves rounds par, par+2, ...: round j is its ((j-1)>>1)-th use (j = 1, 2 -> first use,
+        // phase parity 0; j = 3, 4 -> second use, parity 1; ...)
+        mbar_wait_acquire_cluster(&xbar[par], (unsigned)(((j - 1) >> 1) & 1));
         unsigned long long v = lane < cs ? exch[par * kFpsMaxCluster + lane].dk : 0x00000000FFFFFFFFull;
         unsigned d2 = (unsigned)(v >> 32), k2 = (unsigned)v;
         unsigned gmax = __reduce_max_sync(0xFFFFFFFFu, d2);

@@ -353,6 +353,101 @@ knn_vote_kernel(int ns, int nd, int k, const float *__restrict__ sparse,
         out_colors[(size_t)j * 3 + c] = known ? kLabelColors[best][c] : (unsigned char)0;
 }
 
+// EXPERIMENTAL (never run on a GPU): knn_vote_kernel with the fp32 gate of three_nn_filtered_kernel in
+// front of the exact fp64 test (the bound is the same with the k-th best distance in place of the third).
+// Sparse points are staged as fp32 SoA and promoted only on the exact path.
+template <int KMAX>
+__global__ void __launch_bounds__(KV_THREADS)
+knn_vote_filtered_kernel(int ns, int nd, int k, const float *__restrict__ sparse,
+                         const int *__restrict__ labels, const float *__restrict__ dense,
+                         int *__restrict__ out_labels, unsigned char *__restrict__ out_colors) {
+    __shared__ __align__(16) float kx[NNF_TILE], ky[NNF_TILE], kz[NNF_TILE];
+    const long j = (long)blockIdx.x * KV_THREADS + threadIdx.x;
+    const bool valid = j < nd;
+    float qxf = 0.f, qyf = 0.f, qzf = 0.f;
+    if (valid) {
+        const float *q = dense + (size_t)j * 3;
+        qxf = __ldg(q);
+        qyf = __ldg(q + 1);
+        qzf = __ldg(q + 2);
+    }
+    const double qx = (double)qxf, qy = (double)qyf, qz = (double)qzf;
+    const double INF = __longlong_as_double(0x7FF0000000000000LL);
+    double bd[KMAX];
+    int bi[KMAX];
+#pragma unroll
+    for (int s = 0; s < KMAX; ++s) {
+        bd[s] = INF;
+        bi[s] = -1;
+    }
+    double worst = INF;
+    float gate = __int_as_float(0x7F800000);
+    for (int base = 0; base < ns; base += NNF_TILE) {
+        const int cnt = min(NNF_TILE, ns - base);
+        __syncthreads();
+        for (int e = threadIdx.x; e < cnt * 3; e += KV_THREADS) {
+            int p = e / 3, c = e - p * 3;
+            (c == 0 ? kx : (c == 1 ? ky : kz))[p] = __ldg(sparse + (size_t)base * 3 + e);
+        }
+        __syncthreads();
+        if (valid) {
+#pragma unroll 4
+            for (int p = 0; p < cnt; ++p) {
+                const float fx = kx[p], fy = ky[p], fz = kz[p];
+                const float dxf = qxf - fx, dyf = qyf - fy, dzf = qzf - fz;
+                const float df = fmaf(dzf, dzf, fmaf(dyf, dyf, dxf * dxf));
+                if (df <= gate) {
+                    double dx = __dsub_rn(qx, (double)fx);
+                    double dy = __dsub_rn(qy, (double)fy);
+                    double dz = __dsub_rn(qz, (double)fz);
+                    double d = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)),
+                                         __dmul_rn(dz, dz));
+                    if (d < worst) {
+#pragma unroll
+                        for (int s = 0; s < KMAX; ++s)
+                            if (s == k - 1) {
+                                bd[s] = d;
+                                bi[s] = base + p;
+                            }
+#pragma unroll
+                        for (int s = KMAX - 1; s > 0; --s)
+                            if (s < k && bd[s] < bd[s - 1]) {
+                                double td = bd[s]; bd[s] = bd[s - 1]; bd[s - 1] = td;
+                                int ti = bi[s]; bi[s] = bi[s - 1]; bi[s - 1] = ti;
+                            }
+#pragma unroll
+                        for (int s = 0; s < KMAX; ++s)
+                            if (s == k - 1) worst = bd[s];
+                        gate = nn_gate(worst);
+                    }
+                }
+            }
+        }
+    }
+    if (!valid) return;
+    int lab[KMAX];
+#pragma unroll
+    for (int s = 0; s < KMAX; ++s) lab[s] = (s < k && bi[s] >= 0) ? __ldg(labels + bi[s]) : 0;
+    int best = -1, best_count = 0;
+#pragma unroll
+    for (int s = 0; s < KMAX; ++s) {
+        if (s < k && bi[s] >= 0) {
+            int cnt = 0;
+#pragma unroll
+            for (int u = 0; u <= s; ++u) cnt += (lab[u] == lab[s]) ? 1 : 0;
+            if (cnt > best_count) {
+                best = lab[s];
+                best_count = cnt;
+            }
+        }
+    }
+    out_labels[j] = best;
+    const bool known = best >= 0 && best < 9;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+        out_colors[(size_t)j * 3 + c] = known ? kLabelColors[best][c] : (unsigned char)0;
+}
+
 static inline int grid_for(long total, int threads) {
     long blocks = ceil_div<long>(total, threads);
     long cap = 148L * 32;
@@ -489,6 +584,20 @@ PN2_API int pn2_interpolate_label_with_color(int num_sparse, int num_dense,
     }
     cudaStream_t st = as_stream(s);
     const unsigned grid = (unsigned)ceil_div<long>(num_dense, KV_THREADS);
+    // PN2_KNN_VOTE_FILTER=1: the fp32-gated kernel (EXPERIMENTAL, same results)
+    static const char *vflt_env = getenv("PN2_KNN_VOTE_FILTER");
+    if (vflt_env && vflt_env[0] == '1') {
+#define PN2_LAUNCH_VOTEF(KM)                                                                            \
+    knn_vote_filtered_kernel<KM><<<grid, KV_THREADS, 0, st>>>(num_sparse, num_dense, knn, sparse_points, \
+                                                              sparse_labels, dense_points, dense_labels,  \
+                                                              dense_colors)
+        if (knn <= 4) PN2_LAUNCH_VOTEF(4);
+        else if (knn <= 8) PN2_LAUNCH_VOTEF(8);
+        else if (knn <= 16) PN2_LAUNCH_VOTEF(16);
+        else PN2_LAUNCH_VOTEF(32);
+#undef PN2_LAUNCH_VOTEF
+        return finish_launch();
+    }
 #define PN2_LAUNCH_VOTE(KM)                                                                    \
     knn_vote_kernel<KM><<<grid, KV_THREADS, 0, st>>>(num_sparse, num_dense, knn, sparse_points, \
                                                      sparse_labels, dense_points, dense_labels, \

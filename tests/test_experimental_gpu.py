@@ -235,3 +235,37 @@ def test_geometry_prefetch_trains_like_the_plain_trainer(cuda, graph):
         # Adam normalises every gradient to ~lr: an element whose gradient is rounding noise may move by
         # +-lr in either run, so the bulk must agree, not every element
         assert np.mean(np.abs(w1[k] - w0[k]) <= 2e-4) > 0.99, k
+
+
+# ------------------------------------------------------------------ label vote with the fp32 gate
+def test_knn_vote_filtered_matches_oracle_in_subprocess(cuda):
+    """PN2_KNN_VOTE_FILTER is read once per process, so the gated kernel is exercised in a child process:
+    labels and colours for knn 1..32 on uniform, lattice (ties) and large-offset clouds must equal the oracle."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, %r)
+import pn2_b200
+from pn2_b200.tf_ops import tf_interpolate as ti
+from oracle import oracle as orc
+rs = np.random.RandomState(0)
+cases = [(rs.random_sample((3000, 3)), rs.random_sample((2000, 3))),
+         (rs.randint(0, 5, (900, 3)), rs.randint(0, 5, (700, 3))),
+         (1000 + 1e-3 * rs.random_sample((2100, 3)), 1000 + 1e-3 * rs.random_sample((500, 3))),
+         (rs.random_sample((2, 3)), rs.random_sample((50, 3)))]
+for sp, dp in cases:
+    sp, dp = sp.astype(np.float32), dp.astype(np.float32)
+    sl = rs.randint(0, 9, len(sp)).astype(np.int32)
+    for k in (1, 3, 5, 9, 17, 32):
+        lab, col = ti.interpolate_label_with_color(torch.as_tensor(sp).cuda(), torch.as_tensor(sl).cuda(),
+                                                   torch.as_tensor(dp).cuda(), k)
+        el, ec = orc.interpolate_label_with_color(sp, sl, dp, k)
+        assert (lab.cpu().numpy() == el).all() and (col.cpu().numpy() == ec).all(), (len(sp), k)
+print("VOTE_FILTER_OK")
+""" % root
+    env = dict(os.environ, PN2_KNN_VOTE_FILTER="1")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert "VOTE_FILTER_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]

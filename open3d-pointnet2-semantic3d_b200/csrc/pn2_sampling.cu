@@ -363,7 +363,7 @@ template <int PPT>
 __global__ void __launch_bounds__(1024, 1)
 fps_cluster_kernel(int n, int m, const float *__restrict__ inp, int *__restrict__ out) {
     namespace cg = cooperative_groups;
-    constexpr int THREADS = 1024, NW = 32, SLICE = THREADS * PPT;
+    constexpr int THREADS = 1024, SLICE = THREADS * PPT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long *slots = reinterpret_cast<unsigned long long *>(smem_raw);      // [2][32]
     FpsCand *exch = reinterpret_cast<FpsCand *>(slots + 64);                            // [2][16]

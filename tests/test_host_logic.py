@@ -295,3 +295,23 @@ def test_geometry_tape_matches_the_models_call_order(monkeypatch):
         tp._replay.tape, tp._replay.pos = None, 0
     assert log == [] and len(seen) == 2 * len(tape)
     assert all(a is b for a, (_, b) in zip(seen, tape + tape))
+
+
+def test_bench_algorithmic_work_matches_survey():
+    """bench.py's roofline arithmetic against the figures SURVEY.md 8(d) states for config 2 (B=16):
+    39.6 GFLOP of GEMM forward over 23 conv layers, FPS streaming model 2.68 GB for SA1, GEMM bytes
+    4*M*(K+N) per call."""
+    import bench
+    calls = bench.linear_calls(16)
+    assert len(calls) == 23
+    assert calls[0] == (16 * 1024 * 32, 6, 32) and calls[-1] == (16 * 8192, 128, 9)
+    assert (16 * 8192, 128 + 3, 128) in calls and (16 * 64, 512 + 256, 256) in calls  # FP4 / FP1 first layers
+    assert abs(bench.gemm_flops(16) / 1e9 - 39.6) < 0.05
+    fwd, dgrad, wgrad = bench.gemm_bytes(16)
+    assert fwd == sum(4 * m * (k + n) for m, k, n in calls) == wgrad
+    assert dgrad == fwd - 4 * calls[0][0] * (calls[0][1] + calls[0][2])  # no dgrad into the network input
+    fps = bench.fps_stream_bytes(16)
+    assert fps[0] == 16 * 1023 * 8192 * 20 and abs(fps[0] / 1e9 - 2.68) < 0.01
+    pc, labels, smpw = bench.make_batch(2, 64, 100)
+    assert pc.shape == (2, 64, 6) and pc.dtype == np.float32 and labels.min() >= 1 and labels.max() <= 8
+    assert pc[..., 0].min() >= -5 and pc[..., 0].max() <= 5 and pc[..., 2].min() >= 0 and pc[..., 2].max() <= 5

@@ -105,7 +105,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample_b = 2
+    sample_b = args.batch  # the SAME config as our arm: every cloud of the step, all host threads
     val, sec, cores = time_cpu(sample_b, args.npoint, args.steps, args.warmup)
     sample = ("%d clouds x %d points per step (fwd+bwd of the same SSG network): C oracle "
               "(FPS/ball/3-NN, OpenMP over clouds) + PyTorch-CPU fp32 layers" % (sample_b, args.npoint))
@@ -250,6 +250,117 @@ def gemm_bytes(b):
     return fwd, dgr, wgr
 
 
+def config1_row(dev, reps=30):
+    """BASELINE.json configs[0] / BASELINE.md section 3: ONE set-abstraction layer, B=2, N=1024, npoint=256,
+    nsample=32, C=3, mlp [32,32,64], train-mode BN, forward + backward -- our engine on the GPU (eager
+    launches and CUDA-graph replay) next to the oracle port on the host cores, in the same run."""
+    import torch
+    from pn2_b200.util import pointnet_util, tf_util
+    from oracle import layers_ref as lr
+    rs = np.random.RandomState(100)
+    xyz = rs.random_sample((2, 1024, 3)).astype(np.float32)
+    pts = rs.random_sample((2, 1024, 3)).astype(np.float32)
+    old_store = tf_util.default_store()
+    store = tf_util.set_default_store(tf_util.VariableStore(device=dev, seed=0))
+    stream = torch.cuda.Stream(device=dev)
+    row = {"workload": "single SA layer B=2 N=1024 npoint=256 nsample=32 C=3 radius 0.2 mlp [32,32,64], fwd+bwd"}
+    try:
+        with torch.cuda.stream(stream):
+            x = torch.as_tensor(xyz).to(dev)
+            p = torch.as_tensor(pts).to(dev).requires_grad_(True)
+
+            def fb():
+                store.anchor = torch.zeros(1, device=dev, requires_grad=True)
+                p.grad = None
+                _, out, _ = pointnet_util.pointnet_sa_module(x, p, 256, 0.2, 32, [32, 32, 64], None, False,
+                                                            True, 0.5, "layer1")
+                out.sum().backward()
+            for _ in range(3):
+                fb()
+            stream.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                fb()
+            e1.record()
+            e1.synchronize()
+            row["gpu_eager_ms"] = e0.elapsed_time(e1) / reps
+            try:
+                import gc
+                gc.collect()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=stream, capture_error_mode="thread_local"):
+                    fb()
+                g.replay()
+                stream.synchronize()
+                e0.record()
+                for _ in range(reps):
+                    g.replay()
+                e1.record()
+                e1.synchronize()
+                row["gpu_graph_ms"] = e0.elapsed_time(e1) / reps
+            except Exception as e:  # noqa: BLE001
+                row["gpu_graph_error"] = repr(e)[:300]
+                torch.cuda.synchronize()
+    finally:
+        tf_util.set_default_store(old_store)
+    best = min(v for k, v in row.items() if k in ("gpu_eager_ms", "gpu_graph_ms"))
+    row["gpu_points_per_sec"] = 2 * 1024 / (best * 1e-3)
+    # CPU: the oracle port of the same layer (C oracle index ops + PyTorch-CPU fp32), host cores
+    lr.set_dtype(torch.float32)
+    params = {}
+    k = 6
+    for i, n in enumerate([32, 32, 64]):
+        lr.init_conv(params, rs, "layer1/conv%d" % i, k, n)
+        k = n
+
+    def cpu_fb():
+        ctx = lr.Ctx(params, is_training=True, bn_decay=0.5)
+        pr = torch.tensor(pts, dtype=torch.float32, requires_grad=True)
+        _, feat, _ = lr.sa_module(ctx, xyz, pr, 256, 0.2, 32, [32, 32, 64], "layer1")
+        feat.sum().backward()
+    cpu_fb()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        cpu_fb()
+    cpu_ms = (time.perf_counter() - t0) / 5 * 1e3
+    row["cpu_ms"] = cpu_ms
+    row["cpu_points_per_sec"] = 2 * 1024 / (cpu_ms * 1e-3)
+    row["cpu_threads"] = torch.get_num_threads()
+    return row
+
+
+def cfeat6_line(dev, b, n, steps, warmup, flush):
+    """the same SSG step with BASELINE.json's "(3+6)" wording -- 6 feature channels next to
+    xyz (SA1 K = 9, FP4 K = 134) instead of semantic.json's 3; device-resident inputs, graph replay."""
+    import torch
+    from pn2_b200.train_step import Trainer
+    hp = dict(HP, use_color=2)
+    rs = np.random.RandomState(100)
+    xyz = rs.random_sample((b, n, 3)) * np.array([10.0, 10.0, 5.0]) - np.array([5.0, 5.0, 0.0])
+    pc = np.concatenate([xyz, rs.random_sample((b, n, 6))], -1).astype(np.float32)
+    labels = rs.randint(1, 9, (b, n)).astype(np.int32)
+    smpw = np.ones((b, n), np.float32)
+    d = [torch.as_tensor(x).to(dev) for x in (pc, labels, smpw)]
+    tr = Trainer(hp, NUM_CLASS, device=dev, seed=0, world_size=1)
+    tr.step(*d)
+    graph = tr.capture(*d)
+    fn = tr.step_graph if graph else tr.step
+    for _ in range(max(warmup, 3)):
+        fn(*d)
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for i in range(steps):
+        flush.zero_()
+        ev[i][0].record()
+        fn(*d)
+        ev[i][1].record()
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(bb) for a, bb in ev) / steps
+    return {"workload": "ssg_train_step_B%d_N%d_xyz3+feat6 (BASELINE.json wording)" % (b, n),
+            "ms_per_step": ms, "value": b * n / (ms * 1e-3), "unit": UNIT, "cuda_graph": bool(graph)}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -272,12 +383,7 @@ def run_ours(args):
     b, n = args.batch, args.npoint
     pc, labels, smpw = make_batch(b, n, 100 + rank)
     d_pc, d_lab, d_w = (torch.as_tensor(x).to(dev) for x in (pc, labels, smpw))
-    if args.prefetch:  # EXPERIMENTAL: geometry (FPS / ball query / 3-NN) one batch ahead on a side stream
-        from pn2_b200.train_prefetch import PrefetchTrainer
-        trainer = PrefetchTrainer(HP, NUM_CLASS, device=dev, seed=0, world_size=world)
-        trainer.prime(d_pc)
-    else:
-        trainer = Trainer(HP, NUM_CLASS, device=dev, seed=0, world_size=world)
+    trainer = Trainer(HP, NUM_CLASS, device=dev, seed=0, world_size=world)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
 
     def barrier():
@@ -288,17 +394,11 @@ def run_ours(args):
 
     trainer.step(d_pc, d_lab, d_w)  # creates + flattens the variables
     trainer.step(d_pc, d_lab, d_w)
-    if args.prefetch:
-        use_graph = (not args.no_graph) and trainer.capture_prefetch(d_pc, d_lab, d_w)
-        # the synthetic workload feeds the same cloud every step, so "the next batch" is the same tensor; its
-        # geometry is nevertheless recomputed every step (nothing is reused across steps)
-        if use_graph:
-            step_fn = lambda a, b_, c: trainer.step_graph_prefetch(a, b_, c, a)  # noqa: E731
-        else:
-            step_fn = lambda a, b_, c: trainer.step_prefetch(a, b_, c, a)  # noqa: E731
-    else:
-        use_graph = (not args.no_graph) and trainer.capture(d_pc, d_lab, d_w)
-        step_fn = trainer.step_graph if use_graph else trainer.step
+    use_graph = (not args.no_graph) and trainer.capture(d_pc, d_lab, d_w)
+    if not use_graph and not args.no_graph:
+        print("CUDA-graph capture failed, eager launches instead:\n%s" % trainer._capture_error,
+              file=sys.stderr)
+    step_fn = trainer.step_graph if use_graph else trainer.step
     launches_per_step = None
     for _ in range(max(args.warmup, 3)):
         step_fn(d_pc, d_lab, d_w)
@@ -318,8 +418,7 @@ def run_ours(args):
     barrier()
     calls = _ffi.launches - calls0
     if use_graph:  # replayed launches are not seen by the ctypes counter: count them from the capture
-        calls = args.steps * (trainer.launches_per_replay + 1 +
-                              (getattr(trainer, "geom_launches_per_replay", 0) if args.prefetch else 0))
+        calls = args.steps * (trainer.launches_per_replay + 1)
     ms = sum(a.elapsed_time(bb) for a, bb in ev)
     clocks = sampler.stop() if sampler else None
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -329,29 +428,43 @@ def run_ours(args):
     value = world * b * n * args.steps / (ms_total * 1e-3)
 
     # ---- end to end: pinned host inputs in, loss out, every step ---------------------------------
+    # The public call: Trainer.stage(pinned host batch) starts the H2D copy of the NEXT batch on the copy
+    # stream, Trainer.step_graph() consumes it (double-buffered input feed, like the reference's prefetch
+    # queue, train.py:134-196).  Every timed step contains exactly one H2D copy of a full batch and one D2H
+    # read of the loss; the same 256 MB L2 flush as above runs between steps, outside the events.
     h_pc, h_lab, h_w = (torch.as_tensor(x).pin_memory() for x in (pc, labels, smpw))
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    h_loss = torch.empty((), dtype=torch.float32).pin_memory()
+    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+           for _ in range(args.steps)]
     barrier()
-    e0.record()
     last = 0.0
+    if use_graph:
+        trainer.stage(h_pc, h_lab, h_w)       # fills the pipe (the copy of step 0's batch is timed below
+        torch.cuda.synchronize()              # as the copy issued during the last step)
     for i in range(args.steps):
-        x_pc = h_pc.to(dev, non_blocking=True)
-        x_lab = h_lab.to(dev, non_blocking=True)
-        x_w = h_w.to(dev, non_blocking=True)
-        loss = step_fn(x_pc, x_lab, x_w)
-        last = float(loss.item())  # device -> host read of the step's result
-    e1.record()
+        flush.zero_()
+        ev2[i][0].record()
+        if use_graph:
+            loss = trainer.step_graph()               # consumes the staged batch
+            trainer.stage(h_pc, h_lab, h_w)           # H2D of the next batch overlaps this step
+        else:
+            loss = trainer.step(h_pc, h_lab, h_w)     # eager: H2D on the replica's stream
+        h_loss.copy_(loss, non_blocking=True)         # device -> host read of the step's result
+        ev2[i][1].record()
+        ev2[i][1].synchronize()
+        last = float(h_loss)
     barrier()
-    t2 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    t2 = torch.tensor([sum(a.elapsed_time(bb) for a, bb in ev2)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     e2e_value = world * b * n * args.steps / (float(t2.item()) * 1e-3)
     h2d = int(pc.nbytes + labels.nbytes + smpw.nbytes)
 
     # ---- per-entry-point breakdown (separate instrumented pass) + roofline ------------------
-    roofline, breakdown = None, None
+    roofline, breakdown, collective = None, None, None
     # every rank takes the instrumented steps (they contain the gradient all-reduce); rank 0 records
     _ffi.profile = [] if rank == 0 else None
+    trainer.timing = {}
     torch.cuda.synchronize()
     psteps = min(args.steps, 3)
     for _ in range(psteps):
@@ -369,6 +482,15 @@ def run_ours(args):
             d[0] += a.elapsed_time(bb)
             d[1] += 1
         _ffi.profile = None
+        ar = trainer.timing.get("allreduce", [])
+        if ar:
+            nbytes = trainer.grads.numel() * 4
+            us = 1e3 * sum(a.elapsed_time(bb) for a, bb in ar) / len(ar)
+            collective = {"op": "all_reduce(sum) of the flat gradient buffer", "bytes": nbytes,
+                          "us_per_step": us,
+                          "model_us": 2.0 * (world - 1) / world * nbytes / 900e9 * 1e6,
+                          "note": "CUDA events on the replica's stream around dist.all_reduce in the "
+                                  "instrumented (eager, backlogged) pass; model = 2(p-1)/p * bytes / 900 GB/s"}
         breakdown = {k: {"ms_per_step": v[0] / psteps, "calls_per_step": v[1] / psteps}
                      for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])}
         peaks = {}
@@ -420,10 +542,21 @@ def run_ours(args):
     # ---- CPU baseline on the host cores (rank 0, N=1 only) ---------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, sec, cores = time_cpu(2, n, 3, 1)
+        v, sec, cores = time_cpu(b, n, 3, 1)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": "3 steps of 2 clouds x %d points (same SSG fwd+bwd): C oracle index ops "
-                         "(OpenMP over clouds) + PyTorch-CPU fp32 layers, %.2f s/step" % (n, sec)}
+               "sample": "3 steps of the SAME config (%d clouds x %d points, SSG fwd+bwd): C oracle index ops "
+                         "(OpenMP over clouds) + PyTorch-CPU fp32 layers, %.2f s/step" % (b, n, sec)}
+
+    cfg1 = cf6 = None
+    if rank == 0 and world == 1 and not args.no_extra:
+        try:
+            cfg1 = config1_row(dev)
+        except Exception as e:  # noqa: BLE001
+            cfg1 = {"error": repr(e)[:300]}
+        try:
+            cf6 = cfeat6_line(dev, b, n, min(args.steps, 10), args.warmup, flush)
+        except Exception as e:  # noqa: BLE001
+            cf6 = {"error": repr(e)[:300]}
 
     if rank == 0:
         line = {
@@ -433,15 +566,17 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": workload_name(b, n), "global_batch": b * world,
                        "parallelism": "dp%d" % world, "cuda_graph": bool(use_graph),
-                       "geometry_prefetch": bool(args.prefetch),
-                       "cuda_graph_error": getattr(trainer, "_capture_error", None),
+                       "cuda_graph_error": (trainer._capture_error or "")[:1500] or None,
                        "l2": "256 MB flush write between timed steps; a step also streams >1 GB of "
                              "activations, far beyond the 126 MB L2"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": 4, "last_loss": last},
+                    "d2h_bytes_per_step": 4, "last_loss": last,
+                    "feed": "Trainer.stage(pinned host batch) + Trainer.step_graph(): one H2D batch copy and one "
+                            "D2H loss read per step, the copy of batch i+1 overlaps step i"},
             "gpu_launches": calls,
             "roofline": roofline, "cpu_baseline": cpu, "breakdown_ms_per_step": breakdown,
+            "collective": collective, "config1": cfg1, "cfeat6": cf6,
         }
         print(json.dumps(line))
     if world > 1:
@@ -458,9 +593,8 @@ def main():
     ap.add_argument("--npoint", type=int, default=8192)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of a CUDA graph")
-    ap.add_argument("--prefetch", action="store_true",
-                    help="EXPERIMENTAL: compute the weight-independent geometry of the next batch on a side "
-                         "stream while the dense stage of the current one runs (train_prefetch.py)")
+    ap.add_argument("--no-extra", action="store_true",
+                    help="skip the config-1 row and the 6-feature-channel line (N=1 only)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

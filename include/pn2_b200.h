@@ -226,6 +226,12 @@ int pn2_bn_eval_affine(int N, const float *gamma, const float *beta, const float
 int pn2_affine_act(long M, int N, const float *Y, const float *scale, const float *shift,
                    int relu, float *Z, int ldz, pn2_stream_t s);
 
+/* Test hook: mask[M,N] (bytes) = 1 where fma(Y, scale, shift) > 0 (Y > 0 without scale/shift) -- the
+ * ReLU decision exactly as the prologue / pooling / backward kernels of a chain take it.  Parity tests
+ * feed it to the fp64 oracle so that both sides differentiate the same piecewise-linear function. */
+int pn2_relu_mask(long M, int N, const float *Y, const float *scale, const float *shift,
+                  unsigned char *mask, pn2_stream_t s);
+
 /* out[G,N] = max_{j<ns} act(Y[g*ns+j,:]*scale+shift); arg[G,N] = first j attaining it
  * (pointnet_util.py:167-170 tf.reduce_max over nsample, fused with BN+ReLU) */
 int pn2_affine_act_maxpool(long G, int ns, int N, const float *Y, const float *scale,

@@ -56,6 +56,7 @@ SIGNATURES = {
     "pn2_bn_train_finalize": [_i, _l, _vp, _vp, _vp, _f, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp],
     "pn2_bn_eval_affine": [_i, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp],
     "pn2_affine_act": [_l, _i, _vp, _vp, _vp, _i, _vp, _i, _vp],
+    "pn2_relu_mask": [_l, _i, _vp, _vp, _vp, _vp, _vp],
     "pn2_affine_act_maxpool": [_l, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp],
     "pn2_bn_bwd_reduce": [_l, _i, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp],
     "pn2_bn_bwd_apply": [_l, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp,

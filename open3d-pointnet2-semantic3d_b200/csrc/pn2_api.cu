@@ -1,6 +1,8 @@
 // pn2_api.cu -- ABI bookkeeping: version, error strings, per-device attribute cache.
 #include <string.h>
 
+#include <mutex>
+
 #include "pn2_common.cuh"
 
 namespace pn2 {
@@ -23,6 +25,35 @@ int num_sms() {
         cached[dev] = v;
     }
     return cached[dev];
+}
+
+namespace {
+struct AttrEntry {
+    const void *kernel;
+    int attr, dev, value;
+};
+constexpr int kMaxAttr = 256;
+AttrEntry g_attr[kMaxAttr];
+int g_attr_n = 0;
+std::mutex g_attr_mu;
+}  // namespace
+
+int opt_in_attr(const void *kernel, cudaFuncAttribute attr, int value) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    std::lock_guard<std::mutex> lock(g_attr_mu);
+    AttrEntry *hit = nullptr;
+    for (int i = 0; i < g_attr_n; ++i)
+        if (g_attr[i].kernel == kernel && g_attr[i].attr == (int)attr && g_attr[i].dev == dev) {
+            hit = &g_attr[i];
+            break;
+        }
+    if (hit && hit->value >= value) return PN2_OK;
+    int rc = cuda_status(cudaFuncSetAttribute(kernel, attr, value));
+    if (rc) return rc;
+    if (hit) hit->value = value;
+    else if (g_attr_n < kMaxAttr) g_attr[g_attr_n++] = AttrEntry{kernel, (int)attr, dev, value};
+    return PN2_OK;
 }
 
 }  // namespace pn2

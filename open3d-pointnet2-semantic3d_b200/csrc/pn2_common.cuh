@@ -38,6 +38,16 @@ inline cudaStream_t as_stream(pn2_stream_t s) { return reinterpret_cast<cudaStre
 // Number of SMs of the current device (cached, immutable).
 int num_sms();
 
+// Opt a kernel in to `bytes` of dynamic shared memory (or set another function attribute) ONCE per
+// (kernel, device): the driver call leaves the hot path after the first launch.  The cache only grows
+// (a larger request re-issues the call); immutable afterwards, so re-entrant callers see a stable value.
+int opt_in_attr(const void *kernel, cudaFuncAttribute attr, int value);
+template <typename K>
+inline int opt_in_dyn_smem(K kernel, size_t bytes) {
+    return opt_in_attr(reinterpret_cast<const void *>(kernel), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)bytes);
+}
+
 template <typename T>
 __host__ __device__ constexpr T ceil_div(T a, T b) {
     return (a + b - 1) / b;

@@ -567,6 +567,19 @@ __global__ void affine_act_maxpool_kernel(long total, int ns, int N, const float
     }
 }
 
+// ---- test hook: the ReLU mask exactly as every kernel of the chain evaluates it --------------------
+__global__ void relu_mask_kernel(long total, int N, const float *__restrict__ Y,
+                                 const float *__restrict__ scale, const float *__restrict__ shift,
+                                 unsigned char *__restrict__ mask) {
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total;
+         e += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(e % N);
+        const float y = __ldg(Y + e);
+        const float z = scale ? __fmaf_rn(y, __ldg(scale + c), __ldg(shift + c)) : y;
+        mask[e] = z > 0.f ? 1 : 0;
+    }
+}
+
 // ---- dropout: counter-based generator (splitmix64 finaliser over seed ^ index) -------------------
 __device__ __forceinline__ bool dropout_keep(unsigned long long seed, long i, float keep_prob) {
     unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(i + 1);
@@ -1052,6 +1065,17 @@ PN2_API int pn2_bn_bwd_apply_pool(long G, int ns, int N, const float *dOut, cons
     bn_bwd_apply_pool_kernel<<<blocks, 256, 0, as_stream(s)>>>(G, ns, N, rpb, dOut, arg, Y, scale,
                                                                shift, saved, gamma, relu, bn, red, dY,
                                                                dgamma, dbeta);
+    return finish_launch();
+}
+
+PN2_API int pn2_relu_mask(long M, int N, const float *Y, const float *scale, const float *shift,
+                          unsigned char *mask, pn2_stream_t s) {
+    PN2_REQUIRE(M >= 0 && N > 0);
+    PN2_REQUIRE((scale == nullptr) == (shift == nullptr));
+    if (M == 0) return PN2_OK;
+    PN2_REQUIRE_PTR(Y);
+    PN2_REQUIRE_PTR(mask);
+    relu_mask_kernel<<<grid_for(M * N, 256), 256, 0, as_stream(s)>>>(M * N, N, Y, scale, shift, mask);
     return finish_launch();
 }
 

@@ -197,7 +197,16 @@ __global__ void tc_prep_b_kernel(int N, int Ntot, int K, int Npad, int KC, int n
 //  [3] transform g0: wait raw + load          [4] transform g0: waiting empty  [5] transform g0: store
 //  [6] epilogue w0: waiting acc_full          [7] epilogue w0: processing      [8] B loader: waiting empty
 //  [9] total kernel cycles (mma thread)       [10] chunks                      [11] tiles
+#ifdef PN2_TRACE
 __device__ long long g_tc_trace[16];
+#define TR_ON(cond) (cond)
+#define TR_CLOCK(cond) ((cond) ? clock64() : 0ll)
+#define TR_ADD(i, v) (g_tc_trace[i] += (v))
+#else  // production build: no instrumentation in the role loops
+#define TR_ON(cond) false
+#define TR_CLOCK(cond) 0ll
+#define TR_ADD(i, v) ((void)(v))
+#endif
 
 struct Params {
     long M;
@@ -314,8 +323,8 @@ __global__ void __launch_bounds__(THREADS, 1)
                 const int s = it % p.stages;
                 const uint32_t ph = (it / p.stages) & 1;
                 const int kbase = kc * BK + k4 * 4;
-                const bool tr = (blockIdx.x == 0 && t == 0);
-                const long long c0 = tr ? clock64() : 0;
+                const bool tr = TR_ON(blockIdx.x == 0 && t == 0);
+                const long long c0 = TR_CLOCK(tr);
                 float sc[4], sh[4];
                 if (p.a_scale) {
 #pragma unroll
@@ -366,9 +375,9 @@ __global__ void __launch_bounds__(THREADS, 1)
                         }
                     }
                 }
-                const long long c1 = tr ? clock64() : 0;
+                const long long c1 = TR_CLOCK(tr);
                 mbar_wait(&empty[s], ph ^ 1);
-                const long long c2 = tr ? clock64() : 0;
+                const long long c2 = TR_CLOCK(tr);
                 unsigned char *a_hi = stage_base + (size_t)s * stage_bytes;
                 unsigned char *a_lo = a_hi + a_bytes;
 #pragma unroll
@@ -393,10 +402,10 @@ __global__ void __launch_bounds__(THREADS, 1)
                 // timing dependent: rows of the NEXT tile showed up in the accumulator).
                 if (p.a_tma) mbar_arrive(&raw_empty[it % p.raw_slots]);
                 if (tr) {
-                    const long long c3 = clock64();
-                    g_tc_trace[3] += c1 - c0;
-                    g_tc_trace[4] += c2 - c1;
-                    g_tc_trace[5] += c3 - c2;
+                    const long long c3 = TR_CLOCK(true);
+                    TR_ADD(3, c1 - c0);
+                    TR_ADD(4, c2 - c1);
+                    TR_ADD(5, c3 - c2);
                 }
             }
         }
@@ -431,9 +440,9 @@ __global__ void __launch_bounds__(THREADS, 1)
                 for (int kc = 0; kc < p.KC; ++kc, ++it) {
                     const int s = it % p.stages;
                     const uint32_t ph = (it / p.stages) & 1;
-                    const long long c0 = blockIdx.x == 0 ? clock64() : 0;
+                    const long long c0 = TR_CLOCK(blockIdx.x == 0);
                     mbar_wait(&empty[s], ph ^ 1);
-                    if (blockIdx.x == 0) g_tc_trace[8] += clock64() - c0;
+                    if (TR_ON(blockIdx.x == 0)) TR_ADD(8, TR_CLOCK(true) - c0);
                     unsigned char *b_hi = stage_base + (size_t)s * stage_bytes + 2 * a_bytes;
                     mbar_expect_tx(&full[s], 2 * b_bytes);
                     bulk_g2s(b_hi,
@@ -447,16 +456,16 @@ __global__ void __launch_bounds__(THREADS, 1)
         if (lane == 0) {
             const uint32_t idesc = make_idesc(p.Npad);
             uint32_t it = 0, tcnt = 0;
-            const bool tr = blockIdx.x == 0;
-            const long long k0c = tr ? clock64() : 0;
+            const bool tr = TR_ON(blockIdx.x == 0);
+            const long long k0c = TR_CLOCK(tr);
             long long w_full = 0, w_issue = 0, w_acc = 0;
             const int kh = p.ksplit ? p.KC / 2 : p.KC;  // chunks per accumulator set
             for (long tile = mt0; tile < num_tiles; tile += mstride, ++tcnt) {
                 // two accumulator sets: ping-pong over tiles, or (ksplit) the two K halves of one tile
                 const uint32_t acc = p.ksplit ? 0 : (tcnt & 1), aph = p.ksplit ? (tcnt & 1) : ((tcnt >> 1) & 1);
-                const long long ca = tr ? clock64() : 0;
+                const long long ca = TR_CLOCK(tr);
                 mbar_wait(&acc_empty[acc], aph ^ 1);
-                if (tr) w_acc += clock64() - ca;
+                if (tr) w_acc += TR_CLOCK(true) - ca;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 for (int kc = 0; kc < p.KC; ++kc, ++it) {
                     const uint32_t set = p.ksplit ? (kc >= kh ? 1u : 0u) : acc;
@@ -465,10 +474,10 @@ __global__ void __launch_bounds__(THREADS, 1)
                     const uint32_t dc = d + (uint32_t)Nacc;                     // corrections
                     const int s = it % p.stages;
                     const uint32_t ph = (it / p.stages) & 1;
-                    const long long cw = tr ? clock64() : 0;
+                    const long long cw = TR_CLOCK(tr);
                     mbar_wait(&full[s], ph);
                     if (p.b_res && tcnt == 0) mbar_wait(&bfull[kc], 0);
-                    const long long ci = tr ? clock64() : 0;
+                    const long long ci = TR_CLOCK(tr);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a_hi = smem_u32(stage_base + (size_t)s * stage_bytes);
                     const uint32_t b_hi = p.b_res ? smem_u32(bres + (size_t)kc * 2 * b_bytes)
@@ -486,18 +495,18 @@ __global__ void __launch_bounds__(THREADS, 1)
                     umma_commit(&empty[s]);  // frees the stage once these MMAs have read it
                     if (tr) {
                         w_full += ci - cw;
-                        w_issue += clock64() - ci;
+                        w_issue += TR_CLOCK(true) - ci;
                     }
                 }
                 umma_commit(&acc_full[acc]);  // accumulator complete -> epilogue
             }
             if (tr) {
-                g_tc_trace[0] += w_full;
-                g_tc_trace[1] += w_issue;
-                g_tc_trace[2] += w_acc;
-                g_tc_trace[9] += clock64() - k0c;
-                g_tc_trace[10] += it;
-                g_tc_trace[11] += tcnt;
+                TR_ADD(0, w_full);
+                TR_ADD(1, w_issue);
+                TR_ADD(2, w_acc);
+                TR_ADD(9, TR_CLOCK(true) - k0c);
+                TR_ADD(10, it);
+                TR_ADD(11, tcnt);
             }
         }
     } else if (warp < W_EPI) {
@@ -542,10 +551,10 @@ __global__ void __launch_bounds__(THREADS, 1)
         for (long tile = mt0; tile < num_tiles; tile += mstride, ++tcnt) {
             const uint32_t acc = p.ksplit ? 0 : (tcnt & 1), aph = p.ksplit ? (tcnt & 1) : ((tcnt >> 1) & 1);
             const long m0 = tile * BM + q4 * 32;
-            const bool tr = (blockIdx.x == 0 && threadIdx.x == 0);
-            const long long ce0 = tr ? clock64() : 0;
+            const bool tr = TR_ON(blockIdx.x == 0 && threadIdx.x == 0);
+            const long long ce0 = TR_CLOCK(tr);
             mbar_wait(&acc_full[acc], aph);
-            const long long ce1 = tr ? clock64() : 0;
+            const long long ce1 = TR_CLOCK(tr);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const long rows_left = p.M - m0;
             const int nv = rows_left >= 32 ? 32 : (int)rows_left;
@@ -622,8 +631,8 @@ __global__ void __launch_bounds__(THREADS, 1)
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(&acc_empty[acc]);
             if (tr) {
-                g_tc_trace[6] += ce1 - ce0;
-                g_tc_trace[7] += clock64() - ce1;
+                TR_ADD(6, ce1 - ce0);
+                TR_ADD(7, TR_CLOCK(true) - ce1);
             }
         }
         if (p.y_tma && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -1035,25 +1044,25 @@ __global__ void __launch_bounds__(W_THREADS, 1)
             // atoms and produce accumulator rows that nobody reads
             const uint32_t idesc = make_idesc(Nacc) | (1u << 15) | (1u << 16);  // A, B MN-major
             uint32_t it = 0, ucnt = 0;
-            const bool tr = blockIdx.x == 0;
-            const long long k0c = tr ? clock64() : 0;
+            const bool tr = TR_ON(blockIdx.x == 0);
+            const long long k0c = TR_CLOCK(tr);
             long long w_full = 0, w_issue = 0, w_acc = 0;
             const int ksteps = p.rows / 8;
             for (long u = blockIdx.x; u < p.units; u += gridDim.x, ++ucnt) {
                 const int nst = unit_stages(u);
                 const uint32_t acc = ucnt & 1, aph = (ucnt >> 1) & 1;
-                const long long ca = tr ? clock64() : 0;
+                const long long ca = TR_CLOCK(tr);
                 mbar_wait(&acc_empty[acc], aph ^ 1);
-                if (tr) w_acc += clock64() - ca;
+                if (tr) w_acc += TR_CLOCK(true) - ca;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t d = tmem_base + acc * (uint32_t)(2 * Nacc);
                 const uint32_t dc = d + (uint32_t)Nacc;
                 for (int sidx = 0; sidx < nst; ++sidx, ++it) {
                     const int s = it % W_STAGES;
                     const uint32_t ph = (it / W_STAGES) & 1;
-                    const long long cw = tr ? clock64() : 0;
+                    const long long cw = TR_CLOCK(tr);
                     mbar_wait(&full[s], ph);
-                    const long long ci = tr ? clock64() : 0;
+                    const long long ci = TR_CLOCK(tr);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a_hi = smem_u32(smem + (size_t)s * stage_bytes);
                     const uint32_t b_hi = a_hi + 2 * a_bytes;
@@ -1073,18 +1082,18 @@ __global__ void __launch_bounds__(W_THREADS, 1)
                     umma_commit(&empty[s]);
                     if (tr) {
                         w_full += ci - cw;
-                        w_issue += clock64() - ci;
+                        w_issue += TR_CLOCK(true) - ci;
                     }
                 }
                 umma_commit(&acc_full[acc]);
             }
             if (tr) {
-                g_tc_trace[0] += w_full;
-                g_tc_trace[1] += w_issue;
-                g_tc_trace[2] += w_acc;
-                g_tc_trace[9] += clock64() - k0c;
-                g_tc_trace[10] += it;
-                g_tc_trace[11] += ucnt;
+                TR_ADD(0, w_full);
+                TR_ADD(1, w_issue);
+                TR_ADD(2, w_acc);
+                TR_ADD(9, TR_CLOCK(true) - k0c);
+                TR_ADD(10, it);
+                TR_ADD(11, ucnt);
             }
         }
     } else if (warp < 4) {
@@ -1270,9 +1279,14 @@ int tc_linear_dgrad(long M, int K, int N, const float *dY, const float *W, float
 
 // debug hook (not in the public header): read and reset the cycle accounting of CTA 0
 extern "C" __attribute__((visibility("default"))) int pn2_debug_tc_trace(long long *out16) {
+#ifdef PN2_TRACE
     long long zeros[16] = {0};
     cudaDeviceSynchronize();
     if (cudaMemcpyFromSymbol(out16, pn2::tc::g_tc_trace, sizeof(zeros)) != cudaSuccess) return -2;
     if (cudaMemcpyToSymbol(pn2::tc::g_tc_trace, zeros, sizeof(zeros)) != cudaSuccess) return -2;
     return 0;
+#else
+    (void)out16;
+    return -3;  // built without -DPN2_TRACE: the role loops carry no cycle accounting
+#endif
 }

@@ -623,8 +623,7 @@ PN2_API int pn2_query_ball_point(int b, int n, int m, float radius, int nsample,
 #define PN2_LAUNCH_RES(SP)                                                                      \
     do {                                                                                        \
         auto kern = ball_query_resident_kernel<SP>;                                             \
-        rc = cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                              (int)res_smem));                                  \
+        rc = opt_in_dyn_smem(kern, res_smem);                                                   \
         if (rc) return rc;                                                                      \
         kern<<<grid, BQ_THREADS, res_smem, st>>>(n, m, thr, nsample, tma_ok ? 1 : 0, xyz1,     \
                                                  xyz2, idx, pts_cnt);                           \

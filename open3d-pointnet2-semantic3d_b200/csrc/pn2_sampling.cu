@@ -634,8 +634,7 @@ static int launch_fps_reg(int b, int n, int m, const float *inp, int *out, cudaS
     size_t smem = 64 * sizeof(unsigned long long) + (size_t)THREADS * PPT * 3 * sizeof(float);
     auto kern = fps_reg_kernel<THREADS, PPT>;
     if (smem > 48 * 1024) {
-        int rc = cuda_status(
-            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int rc = opt_in_dyn_smem(kern, smem);
         if (rc) return rc;
     }
     kern<<<b, THREADS, smem, st>>>(n, m, inp, out);
@@ -651,8 +650,7 @@ static int launch_fps_pruned(int b, int n, int m, const float *inp, int *out, cu
     size_t smem = 64 * sizeof(unsigned long long) + 8 * sizeof(float) +
                   (size_t)THREADS * PPT * 3 * sizeof(float) + tmp + 16;
     auto kern = fps_pruned_kernel<THREADS, PPT>;
-    int rc = cuda_status(
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int rc = opt_in_dyn_smem(kern, smem);
     if (rc) return rc;
     kern<<<b, THREADS, smem, st>>>(n, m, inp, out);
     return finish_launch();
@@ -662,8 +660,7 @@ template <int THREADS, int PPT>
 static int launch_fps_smem(int b, int n, int m, const float *inp, int *out, cudaStream_t st) {
     size_t smem = 64 * sizeof(unsigned long long) + (size_t)THREADS * PPT * 3 * sizeof(float);
     auto kern = fps_smem_kernel<THREADS, PPT>;
-    int rc = cuda_status(
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int rc = opt_in_dyn_smem(kern, smem);
     if (rc) return rc;
     kern<<<b, THREADS, smem, st>>>(n, m, inp, out);
     return finish_launch();
@@ -676,11 +673,10 @@ static int launch_fps_cluster(int b, int cs, int n, int m, const float *inp, int
                   (HANDSHAKE ? 2 * sizeof(unsigned long long) : 0) +
                   (size_t)1024 * PPT * 3 * sizeof(float);
     auto kern = HANDSHAKE ? fps_cluster_mb_kernel<PPT> : fps_cluster_kernel<PPT>;
-    int rc = cuda_status(
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int rc = opt_in_dyn_smem(kern, smem);
     if (rc) return rc;
     if (cs > 8) {
-        rc = cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        rc = opt_in_attr(reinterpret_cast<const void *>(kern), cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
         if (rc) return rc;
     }
     cudaLaunchConfig_t cfg = {};
@@ -912,7 +908,11 @@ PN2_API int pn2_fps(int b, int n, int m, const float *inp, float *temp, int *out
     static const char *cl_env = getenv("PN2_FPS_CLUSTER");
     static const bool use_cluster = cl_env ? cl_env[0] != '0' : kFpsClusterDefault;
     if (use_cluster) {
-        int rc = dispatch_fps_cluster<false>(b, n, m, inp, out, st);
+        // per-round exchange: push + remote mbarrier arrive (3-15 % faster than the cluster barrier on
+        // B200 at 16 k-262 k points, profiles/README_r02.md); PN2_FPS_HANDSHAKE=0 selects the barrier
+        static const bool handshake = !(getenv("PN2_FPS_HANDSHAKE") && getenv("PN2_FPS_HANDSHAKE")[0] == '0');
+        int rc = handshake ? dispatch_fps_cluster<true>(b, n, m, inp, out, st)
+                           : dispatch_fps_cluster<false>(b, n, m, inp, out, st);
         if (rc != PN2_EUNSUPPORTED) return rc;
     }
     if (n <= 16384) return launch_fps_smem<1024, 16>(b, n, m, inp, out, st);

@@ -4,8 +4,16 @@
   Trainer.step: forward, loss, backward, Adam            train.py:387-388, 225-244
   data parallelism: batch sharded across ranks, ONE NCCL all-reduce over the flat gradient
   buffer per step; BatchNorm statistics stay per replica.
+
+Stream discipline: a Trainer owns ONE CUDA stream and issues every launch of its replica on it --
+the eager passes, the CUDA-graph capture and the replays alike.  The autograd engine ties each
+backward node (and the accumulation of leaf gradients) to the stream its forward ran on; mixing
+the default stream (eager warm-up) with a capture stream made the engine create a dependency on
+uncaptured work (cudaErrorStreamCaptureIsolation) at the end of the captured backward, which is
+how graph mode silently fell back to eager launches in round 1.  The caller's current stream is
+joined at the start and at the end of every step, so callers keep ordinary stream semantics.
 """
-import math
+import gc
 
 import torch
 import torch.distributed as dist
@@ -49,14 +57,32 @@ def allreduce_flat(flat_grads, world_size):
 
 
 class Trainer:
-    """Owns the variables, Adam moments and the step counter for one replica."""
+    """Owns the variables, Adam moments, step counter and the CUDA stream of one replica.
+
+    Dropout: the mask of step k (1-based) is drawn with seed ``host_seed + k`` -- a device-resident
+    counter that every step increments, in eager and in graph mode alike, so a replayed graph sees
+    a fresh mask and both modes walk through the same mask sequence.
+    """
 
     def __init__(self, params, num_class, device="cuda", seed=0, world_size=1):
         self.params, self.num_class, self.world_size = params, num_class, world_size
-        self.store = tf_util.set_default_store(tf_util.VariableStore(device=device, seed=seed))
+        self.device = torch.device(device)
+        if self.device.type == "cuda" and self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.store = tf_util.set_default_store(tf_util.VariableStore(device=self.device, seed=seed))
         self.step_count = 0
         self.flat = self.grads = self.m = self.v = None
+        self.stream = torch.cuda.Stream(device=self.device)
+        self._copy_stream = torch.cuda.Stream(device=self.device)
+        self._seed_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self._graph = None
+        self._static = self._staging = None
+        self._staged_event = self._consumed_event = None
+        self._capture_error = None
+        self.launches_per_replay = 0
+        self.timing = None  # bench.py: dict that receives CUDA events around the collective
 
+    # ---- variables ----------------------------------------------------------------------------
     def _ensure_flat(self):
         if self.store.flat_params is None:
             self.flat, self.grads = self.store.flatten()
@@ -65,99 +91,193 @@ class Trainer:
             if self.world_size > 1:  # replicas start from rank 0's weights
                 dist.broadcast(self.flat, src=0)
 
-    def forward_backward(self, point_cloud, labels, smpw):
+    def _moving(self):
+        return [v.data for v in self.store.vars.values() if not v.trainable]
+
+    # ---- one forward + loss + backward on self.stream --------------------------------------------
+    def _fb(self, point_cloud, labels, smpw):
         bn_decay = get_bn_decay(self.step_count, self.params)
         tf_util.set_default_store(self.store)
-        tf_util.zero_arena.reset(point_cloud.device)  # one memset for every layer's fp64 accumulators
+        tf_util.set_dropout_seed_device(self._seed_dev)
+        # a fresh autograd anchor per pass: no leaf (or its gradient accumulator) outlives the pass
+        self.store.anchor = torch.zeros(1, device=self.device, requires_grad=True)
+        tf_util.zero_arena.reset(self.device)  # one memset for every layer's fp64 accumulators
         try:
             pred, _ = model.get_model(point_cloud, True, self.num_class, self.params, bn_decay=bn_decay)
-            if self.store.flat_params is None:   # first call created the variables: flatten, redo
-                self._ensure_flat()
-                tf_util.zero_arena.reset(point_cloud.device)
-                pred, _ = model.get_model(point_cloud, True, self.num_class, self.params,
-                                          bn_decay=bn_decay)
             self.store.zero_grad()
             loss = model.get_loss(pred, labels, smpw)
             loss.backward()
         finally:
             tf_util.zero_arena.disarm()
+            tf_util.set_dropout_seed_device(None)
+        return loss.detach()
+
+    def _create_variables(self, point_cloud):
+        """The first forward pass creates the variables (the reference builds its graph once,
+        model.py:22-148); it runs with BatchNorm's moving statistics frozen and its result is
+        discarded, so step 1 applies exactly one EMA update like the reference's first train op."""
+        if self.store.flat_params is not None:
+            return
+        tf_util.set_default_store(self.store)
+        tf_util.set_dropout_seed_device(self._seed_dev)
+        tf_util.zero_arena.reset(self.device)
+        try:
+            with torch.no_grad(), tf_util.frozen_moving_stats():
+                model.get_model(point_cloud, True, self.num_class, self.params,
+                                bn_decay=get_bn_decay(self.step_count, self.params))
+        finally:
+            tf_util.zero_arena.disarm()
+            tf_util.set_dropout_seed_device(None)
+        self._ensure_flat()
+
+    def forward_backward(self, point_cloud, labels, smpw):
+        """Forward + loss + backward (gradients land in the flat gradient buffer); no optimizer
+        step, the dropout counter is not advanced."""
+        caller = torch.cuda.current_stream(self.device)
+        self.stream.wait_stream(caller)
+        with torch.cuda.stream(self.stream):
+            point_cloud, labels, smpw = self._to_device(point_cloud, labels, smpw)
+            self._create_variables(point_cloud)
+            loss = self._fb(point_cloud, labels, smpw)
+        caller.wait_stream(self.stream)
         return loss
 
-    def step(self, point_cloud, labels, smpw):
-        loss = self.forward_backward(point_cloud, labels, smpw)
-        return self._apply_gradients(loss)
+    def _to_device(self, *ts):
+        return tuple(t if t.is_cuda else t.to(self.device, non_blocking=True) for t in ts)
 
-    def _apply_gradients(self, loss):
+    # ---- eager step ------------------------------------------------------------------------------
+    def step(self, point_cloud, labels, smpw):
+        caller = torch.cuda.current_stream(self.device)
+        self.stream.wait_stream(caller)
+        with torch.cuda.stream(self.stream):
+            point_cloud, labels, smpw = self._to_device(point_cloud, labels, smpw)
+            self._create_variables(point_cloud)
+            self._seed_dev.add_(1)
+            loss = self._fb(point_cloud, labels, smpw)
+            self._apply_gradients()
+        caller.wait_stream(self.stream)
+        return loss
+
+    def _apply_gradients(self):
+        ev = None
+        if self.timing is not None and self.world_size > 1:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
         gscale = allreduce_flat(self.grads, self.world_size)
+        if ev is not None:
+            ev[1].record()
+            self.timing.setdefault("allreduce", []).append(ev)
         self.step_count += 1
         lr = get_learning_rate(self.step_count - 1, self.params)
         call("pn2_adam_step", self.flat.numel(), ptr(self.flat, F32), ptr(self.grads, F32),
              ptr(self.m, F32), ptr(self.v, F32), float(lr), 0.9, 0.999, 1e-8, self.step_count,
              float(gscale))
-        return loss
 
     # ---- CUDA-graph mode: forward + loss + backward captured once, replayed per step -------------
     def capture(self, point_cloud, labels, smpw):
-        """Capture forward+loss+backward of this batch shape into a CUDA graph (the ~370 launches
-        of a step are otherwise CPU-launch bound).  The dropout mask stays fresh through a
-        device-resident seed increment; schedule values that are baked in (bn_decay) trigger a
-        re-capture when they change.  Returns False (and stays in eager mode) if capture fails."""
+        """Capture forward+loss+backward of this batch shape into a CUDA graph (the ~190 entry-point
+        calls of a step are otherwise CPU-launch bound).  Schedule values that are baked in
+        (bn_decay) trigger a re-capture when they change.  The warm-up passes and the validation
+        replay leave no trace: moving statistics are frozen / restored, the dropout counter is not
+        advanced, no optimizer step is taken.  Returns False (eager mode stays) if capture fails;
+        the reason is kept, untruncated, in ``self._capture_error``."""
         from . import _ffi
         self._graph = None
-        for mode in ("global", "thread_local"):
-            try:
-                self._static = [t.clone() for t in (point_cloud, labels, smpw)]
-                self._seed_dev = torch.zeros(1, dtype=torch.int64, device=point_cloud.device)
-                tf_util.set_dropout_seed_device(self._seed_dev)
-                for _ in range(2):  # eager passes: every kernel / workspace / gradient buffer exists
-                    self.forward_backward(*self._static)
-                torch.cuda.synchronize()
+        self._capture_error = None
+        caller = torch.cuda.current_stream(self.device)
+        self.stream.wait_stream(caller)
+        try:
+            with torch.cuda.stream(self.stream):
+                src = self._to_device(point_cloud, labels, smpw)
+                self._create_variables(src[0])
+                if self._static is None or any(a.shape != b.shape for a, b in zip(self._static, src)):
+                    self._static = [t.clone() for t in src]
+                else:
+                    for d, s in zip(self._static, src):
+                        if d.data_ptr() != s.data_ptr():
+                            d.copy_(s)
                 static = self._static
-
-                def fb():
-                    return self.forward_backward(*static)
-
-                side = torch.cuda.Stream()
-                side.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.stream(side):
-                    fb()
-                    fb()
-                torch.cuda.current_stream().wait_stream(side)
-                torch.cuda.synchronize()
+                with tf_util.frozen_moving_stats():
+                    for _ in range(2):  # every kernel / workspace / gradient buffer exists
+                        self._fb(*static)
+                self.stream.synchronize()
+                gc.collect()  # no autograd graph of an earlier pass survives into the capture
                 g = torch.cuda.CUDAGraph()
                 n0 = _ffi.launches
-                with torch.cuda.graph(g, capture_error_mode=mode):
-                    loss = fb()
-                self._static_loss = loss
+                with torch.cuda.graph(g, stream=self.stream, capture_error_mode="thread_local"):
+                    loss = self._fb(*static)
                 self.launches_per_replay = _ffi.launches - n0
+                # validation replay (would raise on a broken graph), then undo its EMA update
+                keep = [t.clone() for t in self._moving()]
                 g.replay()
-                torch.cuda.synchronize()
+                self.stream.synchronize()
+                for t, k in zip(self._moving(), keep):
+                    t.copy_(k)
+                self._static_loss = loss
                 self._graph = g
                 self._graph_bn_decay = get_bn_decay(self.step_count, self.params)
-                self._capture_error = None
-                return True
-            except Exception as e:  # noqa: BLE001 - any capture failure means eager mode
-                import traceback
-                self._graph = None
-                self._capture_error = "[%s] " % mode + repr(e)[:160] + " | " + " <- ".join(
-                    l.strip() for l in traceback.format_exc().splitlines()
-                    if l.strip().startswith("File"))[-700:]
-                try:
-                    torch.cuda.synchronize()
-                except Exception:  # noqa: BLE001
-                    pass
-        tf_util.set_dropout_seed_device(None)
-        return False
+        except Exception as e:  # noqa: BLE001 - any capture failure means eager mode
+            import traceback
+            self._graph = None
+            self._capture_error = repr(e) + " | " + traceback.format_exc()
+            try:
+                torch.cuda.synchronize()
+            except Exception:  # noqa: BLE001
+                pass
+        caller.wait_stream(self.stream)
+        return self._graph is not None
 
-    def step_graph(self, point_cloud, labels, smpw):
-        if getattr(self, "_graph", None) is None:
-            return self.step(point_cloud, labels, smpw)
-        if get_bn_decay(self.step_count, self.params) != self._graph_bn_decay:
-            if not self.capture(point_cloud, labels, smpw):
-                return self.step(point_cloud, labels, smpw)
-        for dst, src in zip(self._static, (point_cloud, labels, smpw)):
-            if dst.data_ptr() != src.data_ptr():
-                dst.copy_(src, non_blocking=True)
-        self._seed_dev.add_(1)
-        self._graph.replay()
-        return self._apply_gradients(self._static_loss)
+    def stage(self, point_cloud, labels, smpw):
+        """Start the host->device copy of the NEXT batch on the copy stream (pinned host tensors);
+        ``step_graph()`` without arguments consumes it.  This is the double-buffered input feed
+        (the reference prefetches batches with a process pool, train.py:134-196)."""
+        src = (point_cloud, labels, smpw)
+        if self._staging is None or any(a.shape != b.shape for a, b in zip(self._staging, src)):
+            self._staging = [torch.empty(t.shape, dtype=t.dtype, device=self.device) for t in src]
+        cs = self._copy_stream
+        cs.wait_stream(torch.cuda.current_stream(self.device))
+        if self._consumed_event is not None:
+            cs.wait_event(self._consumed_event)  # the previous staged batch has been copied out
+        with torch.cuda.stream(cs):
+            for d, s in zip(self._staging, src):
+                d.copy_(s, non_blocking=True)
+            self._staged_event = torch.cuda.Event()
+            self._staged_event.record(cs)
+
+    def step_graph(self, point_cloud=None, labels=None, smpw=None):
+        """One step by graph replay.  Inputs: device tensors, pinned host tensors (copied in on the
+        replica's stream), or nothing at all = the batch handed to ``stage()``."""
+        staged = point_cloud is None
+        if staged:
+            if self._staged_event is None:
+                raise ValueError("step_graph() without inputs needs a batch from stage()")
+            src = self._staging
+        else:
+            src = (point_cloud, labels, smpw)
+        if self._graph is None:
+            if staged:
+                torch.cuda.current_stream(self.device).wait_event(self._staged_event)
+            return self.step(*src)
+        if get_bn_decay(self.step_count, self.params) != self._graph_bn_decay or \
+                any(a.shape != b.shape for a, b in zip(self._static, src)):
+            if staged:
+                torch.cuda.current_stream(self.device).wait_event(self._staged_event)
+            if not self.capture(*src):
+                return self.step(*src)
+        caller = torch.cuda.current_stream(self.device)
+        self.stream.wait_stream(caller)
+        with torch.cuda.stream(self.stream):
+            if staged:
+                self.stream.wait_event(self._staged_event)
+            for dst, s in zip(self._static, src):
+                if dst.data_ptr() != s.data_ptr():
+                    dst.copy_(s, non_blocking=True)
+            if staged:
+                self._consumed_event = torch.cuda.Event()
+                self._consumed_event.record(self.stream)
+                self._staged_event = None
+            self._seed_dev.add_(1)
+            self._graph.replay()
+            self._apply_gradients()
+        caller.wait_stream(self.stream)
+        return self._static_loss

@@ -225,6 +225,28 @@ class _ZeroArena:
 
 zero_arena = _ZeroArena()
 
+# Test hook: a dict here makes every shared-MLP chain record its ReLU masks ("<scope>/relu_mask", uint8
+# (M,N)) and max-pool winners ("<scope>/argmax", int32 (G,N)).  The fp64 oracle then differentiates the
+# SAME piecewise-linear function (an element whose pre-activation is within fp32 rounding of zero may
+# otherwise sit on the other side of the kink), which is what allows a strict gradient tolerance.
+debug_capture = None
+
+# While set, train-mode BatchNorm normalises with the batch statistics but leaves moving_mean /
+# moving_variance alone: passes that exist only to create variables or to warm up a CUDA-graph
+# capture must not add EMA updates the reference never applies (tf_util.py:572-581 updates once
+# per session.run of the train op).
+_freeze_moving = [False]
+
+
+@contextlib.contextmanager
+def frozen_moving_stats():
+    prev = _freeze_moving[0]
+    _freeze_moving[0] = True
+    try:
+        yield
+    finally:
+        _freeze_moving[0] = prev
+
 _ws_cache = {}
 
 
@@ -274,10 +296,11 @@ class _MLPChain(torch.autograd.Function):
                 sh = torch.empty(N, dtype=F32, device=dev)
                 if is_training:
                     saved = torch.empty(2 * N, dtype=F32, device=dev)
+                    upd = not _freeze_moving[0]
                     call("pn2_bn_train_finalize", N, M, ptr(stats, F64), ptr(L.gamma.data, F32),
                          ptr(L.beta.data, F32), BN_EPS, decay, 1 if L.rank4 else 0,
-                         ptr(L.mm.data, F32), ptr(L.mv.data, F32), ptr(sc, F32), ptr(sh, F32),
-                         ptr(saved, F32))
+                         ptr(L.mm.data, F32) if upd else None, ptr(L.mv.data, F32) if upd else None,
+                         ptr(sc, F32), ptr(sh, F32), ptr(saved, F32))
                 else:
                     call("pn2_bn_eval_affine", N, ptr(L.gamma.data, F32), ptr(L.beta.data, F32),
                          ptr(L.mm.data, F32), ptr(L.mv.data, F32), BN_EPS, ptr(sc, F32),
@@ -305,6 +328,15 @@ class _MLPChain(torch.autograd.Function):
             out = torch.empty((M, N), dtype=F32, device=dev)
             call("pn2_affine_act", M, N, ptr(Ys[-1], F32), ptr(scs[-1], F32, True),
                  ptr(shs[-1], F32, True), 1 if L.relu else 0, ptr(out, F32), N)
+        if debug_capture is not None:  # parity tests: the ReLU decisions and pooling winners of this chain
+            for L_, Y_, sc_, sh_ in zip(layers, Ys, scs, shs):
+                if L_.relu:
+                    mk = torch.empty((M, L_.n), dtype=torch.uint8, device=dev)
+                    call("pn2_relu_mask", M, L_.n, ptr(Y_, F32), ptr(sc_, F32, True), ptr(sh_, F32, True),
+                         ptr(mk, torch.uint8))
+                    debug_capture[L_.w.name[:-len("/weights")] + "/relu_mask"] = mk
+            if arg is not None:
+                debug_capture[L.w.name[:-len("/weights")] + "/argmax"] = arg
         ctx.layers, ctx.pool_ns, ctx.is_training, ctx.gemm_mode = layers, pool_ns, is_training, gemm_mode
         ctx.x, ctx.Ys, ctx.scs, ctx.shs, ctx.saveds, ctx.arg = x, Ys, scs, shs, saveds, arg
         return out

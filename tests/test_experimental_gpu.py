@@ -176,67 +176,6 @@ def test_ball_query_grid_non_finite_inputs_match_default_kernel(ops):
     assert bool((i0 == i1).all()) and bool((c0 == c1).all())
 
 
-# ------------------------------------------------------------------ geometry one batch ahead
-def _prefetch_setup():
-    hp = {"use_color": 1, "batch_size": 2, "learning_rate": 0.001, "decay_step": 200000,
-          "learning_rate_decay_rate": 0.7, "bn_init_decay": 0.5, "bn_decay_decay_rate": 0.5,
-          "bn_decay_clip": 0.99, "l1_npoint": 256, "l1_radius": 0.1, "l1_nsample": 32, "l2_npoint": 64,
-          "l2_radius": 0.2, "l2_nsample": 32, "l3_npoint": 16, "l3_radius": 0.4, "l3_nsample": 32,
-          "l4_npoint": 8, "l4_radius": 0.8, "l4_nsample": 32}
-    batches = []
-    for i in range(4):
-        rs = np.random.RandomState(100 + i)
-        pc = np.concatenate([rs.random_sample((2, 1024, 3)), rs.random_sample((2, 1024, 3))], -1).astype(np.float32)
-        batches.append((to_cuda(pc), to_cuda(rs.randint(0, 9, (2, 1024)).astype(np.int32)),
-                        to_cuda(rs.uniform(0.5, 2.0, (2, 1024)).astype(np.float32))))
-    return hp, batches
-
-
-@pytest.mark.parametrize("graph", [False, True])
-def test_geometry_prefetch_trains_like_the_plain_trainer(cuda, graph):
-    """PrefetchTrainer (geometry of batch i+1 on a side stream during the dense stage of batch i) must
-    produce the losses and the weights of the plain Trainer, batch after batch: the dense stage consumes the
-    same indices, only earlier computed.  (fp32 atomics reorder sums: 1e-4 on a loss of ~2.)"""
-    import torch
-    import pn2_b200  # noqa: F401
-    from pn2_b200.train_prefetch import PrefetchTrainer
-    from pn2_b200.train_step import Trainer
-    from pn2_b200.util import tf_util
-    hp, batches = _prefetch_setup()
-
-    def run(prefetch):
-        tf_util.set_dropout_seed(1234)
-        tr = (PrefetchTrainer if prefetch else Trainer)(hp, 9, device="cuda", seed=0, world_size=1)
-        losses = []
-        try:
-            if prefetch:
-                tr.prime(batches[0][0])
-            if graph:
-                ok = tr.capture_prefetch(*batches[0]) if prefetch else tr.capture(*batches[0])
-                assert ok, getattr(tr, "_capture_error", None)
-            for i in range(3):
-                if prefetch:
-                    fn = tr.step_graph_prefetch if graph else tr.step_prefetch
-                    loss = fn(*batches[i], batches[i + 1][0])
-                else:
-                    loss = (tr.step_graph if graph else tr.step)(*batches[i])
-                losses.append(float(loss.item()))
-            torch.cuda.synchronize()
-            return losses, {k: v.copy() for k, v in tr.store.state_dict().items()}
-        finally:
-            if prefetch:
-                tr.close()
-
-    l0, w0 = run(False)
-    l1, w1 = run(True)
-    assert all(abs(a - b) < 1e-4 for a, b in zip(l0, l1)), (l0, l1)
-    assert len(set(round(x, 3) for x in l0)) > 1  # the batches really differ
-    for k in ("fc2/weights", "layer1/conv0/weights", "fa_layer2/conv_1/bn/moving_mean"):
-        # Adam normalises every gradient to ~lr: an element whose gradient is rounding noise may move by
-        # +-lr in either run, so the bulk must agree, not every element
-        assert np.mean(np.abs(w1[k] - w0[k]) <= 2e-4) > 0.99, k
-
-
 # ------------------------------------------------------------------ label vote with the fp32 gate
 def test_knn_vote_filtered_matches_oracle_in_subprocess(cuda):
     """PN2_KNN_VOTE_FILTER is read once per process, so the gated kernel is exercised in a child process:

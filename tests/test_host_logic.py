@@ -182,121 +182,6 @@ def test_predictor_host_logic(monkeypatch, tmp_path):
     assert seen["vote"] == (torch.float32, torch.int32, (11, 3), 3)
 
 
-def test_geometry_replay_tape_logic():
-    """train_prefetch._Replay: hands the precomputed results back in the model's call order, checks that
-    order, wraps around for a second forward pass over the same batch, and is transparent without a tape."""
-    from pn2_b200 import train_prefetch as tp
-    from pn2_b200.util import pointnet_util
-    rp = tp._Replay()
-    calls = []
-    fa = rp.wrap("a", lambda x: calls.append(("a", x)) or "real-a")
-    fb = rp.wrap("b", lambda x: calls.append(("b", x)) or "real-b")
-    assert fa(1) == "real-a" and fb(2) == "real-b" and calls == [("a", 1), ("b", 2)]  # no tape: pass through
-    rp.tape, rp.pos = [("a", 10), ("b", (20, 21)), ("a", 30)], 0
-    assert [fa(0), fb(0), fa(0)] == [10, (20, 21), 30] and len(calls) == 2
-    assert fa(0) == 10  # exhausted tape: the next forward pass starts over
-    with pytest.raises(RuntimeError, match="out of order"):
-        fa(0)
-    # installing / uninstalling restores the module's own functions
-    real = {n: getattr(pointnet_util, n) for n in tp.GEOM_OPS}
-    tp._install()
-    assert all(getattr(pointnet_util, n) is not real[n] for n in tp.GEOM_OPS)
-    assert pointnet_util.fp_weights.__name__ == "fp_weights"
-    tp._uninstall()
-    assert all(getattr(pointnet_util, n) is real[n] for n in tp.GEOM_OPS)
-
-
-def test_geometry_tape_matches_the_models_call_order(monkeypatch):
-    """The control flow of model.get_model / pointnet_util runs for real on the CPU with every device op
-    replaced by a shape-only stand-in: (1) compute_geometry must issue the five weight-independent ops in
-    exactly the order the model asks for them, (2) with the replay installed and a tape set, the model must
-    consume exactly that tape and receive the SAME tensor objects, never calling the real ops."""
-    import torch
-    from pn2_b200 import model, train_prefetch as tp
-    from pn2_b200.tf_ops import tf_grouping, tf_interpolate, tf_sampling
-    from pn2_b200.util import pointnet_util as pu, tf_util
-    hp = {"use_color": 1, "l1_npoint": 32, "l1_radius": 0.3, "l1_nsample": 8, "l2_npoint": 16, "l2_radius": 0.5,
-          "l2_nsample": 8, "l3_npoint": 8, "l3_radius": 0.8, "l3_nsample": 4, "l4_npoint": 4, "l4_radius": 1.2,
-          "l4_nsample": 4}
-    log = []
-
-    def fps(npoint, x):
-        log.append("farthest_point_sample")
-        return torch.zeros((x.shape[0], npoint), dtype=torch.int32)
-
-    def gather(x, idx):
-        log.append("gather_point")
-        return torch.zeros((x.shape[0], idx.shape[1], 3))
-
-    def ball(radius, ns, x1, x2):
-        log.append("query_ball_point")
-        return torch.zeros((x1.shape[0], x2.shape[1], ns), dtype=torch.int32), torch.zeros((x1.shape[0], x2.shape[1]),
-                                                                                       dtype=torch.int32)
-
-    def nn(x1, x2):
-        log.append("three_nn")
-        return torch.ones((x1.shape[0], x1.shape[1], 3)), torch.zeros((x1.shape[0], x1.shape[1], 3), dtype=torch.int32)
-
-    def weights(dist):
-        log.append("fp_weights")
-        return torch.full_like(dist, 1.0 / 3)
-
-    fakes = {"farthest_point_sample": fps, "gather_point": gather, "query_ball_point": ball, "three_nn": nn,
-             "fp_weights": weights}
-    for mod, names in ((tf_sampling, ("farthest_point_sample", "gather_point")),
-                       (tf_grouping, ("query_ball_point",)), (tf_interpolate, ("three_nn",))):
-        for nme in names:
-            monkeypatch.setattr(mod, nme, fakes[nme])
-    for nme in tp.GEOM_OPS:  # what pointnet_util and train_prefetch hold references to
-        monkeypatch.setattr(pu, nme, fakes[nme])
-        monkeypatch.setitem(tp._REAL, nme, fakes[nme])
-
-    class GC:  # _GroupConcat / _InterpConcat stand-ins: shapes only
-        @staticmethod
-        def apply(xyz, new_xyz, points, idx, xyz_first, use_xyz):
-            c = 0 if points is None else points.shape[2]
-            return torch.zeros(idx.shape + (3 + c,))
-
-    class IC:
-        @staticmethod
-        def apply(points2, points1, idx, weight):
-            c1 = 0 if points1 is None else points1.shape[2]
-            return torch.zeros((idx.shape[0] * idx.shape[1], points2.shape[2] + c1))
-
-    def chain(x2d, layers, is_training, bn_decay, pool_ns=0):
-        rows = x2d.shape[0] // pool_ns if pool_ns else x2d.shape[0]
-        return torch.zeros((rows, layers[-1].n))
-
-    monkeypatch.setattr(pu, "_GroupConcat", GC)
-    monkeypatch.setattr(pu, "_InterpConcat", IC)
-    monkeypatch.setattr(tf_util, "mlp_chain", chain)
-    monkeypatch.setattr(tf_util, "dropout", lambda x, **k: x)
-    tf_util.set_default_store(tf_util.VariableStore(device="cpu", seed=0))
-    pc = torch.rand(2, 64, 6)
-
-    pred, _ = model.get_model(pc, True, 9, hp)
-    assert tuple(pred.shape) == (2, 64, 9)
-    model_order, log[:] = list(log), []
-    tape = tp.compute_geometry(pc, hp)
-    assert [nme for nme, _ in tape] == model_order == log
-    assert model_order == ["farthest_point_sample", "gather_point", "query_ball_point"] * 4 + ["three_nn", "fp_weights"] * 4
-
-    # replay: the wrappers hand out the tape, in order, and the "real" ops are never reached
-    log[:] = []
-    seen = []
-    wrapped = {nme: tp._replay.wrap(nme, fakes[nme]) for nme in tp.GEOM_OPS}
-    for nme in tp.GEOM_OPS:
-        monkeypatch.setattr(pu, nme, (lambda f: (lambda *a, **k: seen.append(f(*a, **k)) or seen[-1]))(wrapped[nme]))
-    tp._replay.tape, tp._replay.pos = tape, 0
-    try:
-        model.get_model(pc, True, 9, hp)
-        model.get_model(pc, True, 9, hp)  # second pass over the same batch (Trainer's flatten-and-redo)
-    finally:
-        tp._replay.tape, tp._replay.pos = None, 0
-    assert log == [] and len(seen) == 2 * len(tape)
-    assert all(a is b for a, (_, b) in zip(seen, tape + tape))
-
-
 def test_bench_algorithmic_work_matches_survey():
     """bench.py's roofline arithmetic against the figures SURVEY.md 8(d) states for config 2 (B=16):
     39.6 GFLOP of GEMM forward over 23 conv layers, FPS streaming model 2.68 GB for SA1, GEMM bytes

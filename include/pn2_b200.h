@@ -109,13 +109,6 @@ int pn2_group_point_grad(int b, int n, int c, int m, int nsample, const float *g
 int pn2_three_nn(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist, int *idx,
                  pn2_stream_t s);
 
-/* Same contract and bit-identical results as pn2_three_nn, through the kernel that rejects most
- * pairs with a conservative fp32 test before the exact fp64 one.  EXPERIMENTAL in round 1: built
- * and unit-tested only behind PN2_EXPERIMENTAL=1 (tests/conftest.py); pn2_three_nn switches to it
- * when PN2_THREE_NN_FILTER=1. */
-int pn2_three_nn_filtered(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist,
-                          int *idx, pn2_stream_t s);
-
 /* replaces interpolate_label_with_color_cpu tf_ops/tf_interpolate.cpp:71-115
  * sparse_points (num_sparse,3), sparse_labels (num_sparse), dense_points (num_dense,3) ->
  * dense_labels (num_dense) int32, dense_colors (num_dense,3) uint8: label vote among the knn
@@ -188,7 +181,8 @@ int pn2_copy_cols(long rows, int cols, const float *src, int lds, float *dst, in
  * Y[M,N] = f(A)[M,K] * W[K,N] + bias[N],  f(a)[.,k] = a_scale ? act(a*a_scale[k]+a_shift[k]) : a
  * (act = ReLU when a_relu).  f is how the previous layer's BatchNorm+ReLU is applied on the
  * fly.  If stats != NULL, stats[0:N] += column sums of Y, stats[N:2N] += column sums of Y^2
- * (fp64, caller zeroes).  mode: 0 = fp32 SIMT kernel, 1 = tcgen05 3xTF32 kernel, -1 = auto. */
+ * (fp64, caller zeroes).  mode: 0 = fp32 SIMT kernel, 1 = tcgen05 3xTF32 kernel, -1 = auto;
+ * mode + PN2_GEMM_IMAGE_READY (see pn2_linear_prepare): ws already holds this layer's weight image. */
 int pn2_linear_fwd(long M, int K, int N, const float *A, int lda, const float *a_scale,
                    const float *a_shift, int a_relu, const float *W, const float *bias, float *Y,
                    double *stats, void *ws, long ws_bytes, int mode, pn2_stream_t s);
@@ -197,6 +191,28 @@ int pn2_linear_fwd(long M, int K, int N, const float *A, int lda, const float *a
  * for a K x N layer (the pre-split, pre-swizzled 3xTF32 weight image).  ws may be NULL: the
  * exact fp32 CUDA-core kernel is used then. */
 long pn2_linear_workspace_bytes(int K, int N);
+
+/* Weight images built ONCE per optimizer step instead of once per GEMM call: the images of every layer
+ * (forward orientation, and dgrad orientation with dgrad=1) are described on the host, the table is
+ * copied to the device by the caller, and pn2_linear_prepare builds all of them in ONE launch (after
+ * the Adam update).  pn2_linear_fwd / pn2_linear_dgrad then take `mode + PN2_GEMM_IMAGE_READY` and
+ * use the image in `ws` as it is.  No reference analogue (cuDNN owns TF's filter transforms). */
+#define PN2_GEMM_IMAGE_READY 16
+typedef struct pn2_linear_image { /* 64 bytes, opaque to the caller */
+    const float *src;
+    float *image;
+    long s_n, s_k, total;
+    int N, Ntot, K, Npad, KC, nchunks;
+} pn2_linear_image;
+/* bytes of one image (K x N layer; dgrad != 0: the transposed orientation); 0 if the tensor-core path
+ * does not cover the shape */
+long pn2_linear_image_bytes(int K, int N, int dgrad);
+/* fill *out (host memory) for the K x N layer whose weights live at W (device) and whose image will live
+ * at image (device, pn2_linear_image_bytes bytes, 128-byte aligned) */
+int pn2_linear_image_describe(int K, int N, int dgrad, const float *W, float *image,
+                              pn2_linear_image *out);
+/* one launch: build the `count` images of the device-resident table */
+int pn2_linear_prepare(int count, const pn2_linear_image *table_dev, pn2_stream_t s);
 
 /* dX[M,K] = dY[M,N] * W[K,N]^T */
 int pn2_linear_dgrad(long M, int K, int N, const float *dY, const float *W, float *dX, int ldx,

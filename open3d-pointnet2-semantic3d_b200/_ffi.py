@@ -11,7 +11,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libpn2_b200.so")
+# PN2_LIB: load another build of the same library (the -DPN2_TRACE diagnostics build); never a fallback
+LIB_PATH = os.environ.get("PN2_LIB") or os.path.join(_HERE, "lib", "libpn2_b200.so")
 
 PN2_OK, PN2_EINVAL, PN2_ELAUNCH, PN2_EUNSUPPORTED, PN2_ENULL = 0, -1, -2, -3, -4
 
@@ -38,7 +39,6 @@ SIGNATURES = {
     "pn2_group_point_grad": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "pn2_three_nn": [_i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "pn2_interpolate_label_with_color": [_i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp],
-    "pn2_three_nn_filtered": [_i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "pn2_three_interpolate": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "pn2_three_interpolate_grad": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "pn2_selection_sort": [_i, _i, _i, _i, _vp, _vp, _vp, _vp],
@@ -51,6 +51,9 @@ SIGNATURES = {
     "pn2_copy_cols": [_l, _i, _vp, _i, _vp, _i, _i, _vp],
     "pn2_linear_fwd": [_l, _i, _i, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _l, _i, _vp],
     "pn2_linear_workspace_bytes": [_i, _i],
+    "pn2_linear_image_bytes": [_i, _i, _i],
+    "pn2_linear_image_describe": [_i, _i, _i, _vp, _vp, _vp],
+    "pn2_linear_prepare": [_i, _vp, _vp],
     "pn2_linear_dgrad": [_l, _i, _i, _vp, _vp, _vp, _i, _vp, _l, _i, _vp],
     "pn2_linear_wgrad": [_l, _i, _i, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp],
     "pn2_bn_train_finalize": [_i, _l, _vp, _vp, _vp, _f, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp],
@@ -72,6 +75,7 @@ SIGNATURES = {
 }
 _RESTYPE = {"pn2_strerror": ctypes.c_char_p, "pn2_last_cuda_error": ctypes.c_char_p,
             "pn2_ball_threshold": ctypes.c_float, "pn2_linear_workspace_bytes": ctypes.c_long,
+            "pn2_linear_image_bytes": ctypes.c_long,
             "pn2_ball_grid_workspace_bytes": ctypes.c_long}
 
 _lib = None

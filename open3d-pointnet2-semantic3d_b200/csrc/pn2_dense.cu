@@ -17,9 +17,12 @@ namespace pn2 {
 // does not cover so that the caller can fall back to the exact fp32 kernel.
 int tc_linear_fwd(long M, int K, int N, const float *A, int lda, const float *a_scale,
                   const float *a_shift, int a_relu, const float *W, const float *bias, float *Y,
-                  double *stats, float *ws, size_t ws_bytes, cudaStream_t st);
+                  double *stats, float *ws, size_t ws_bytes, bool image_ready, cudaStream_t st);
 int tc_linear_dgrad(long M, int K, int N, const float *dY, const float *W, float *dX, int ldx,
-                    float *ws, size_t ws_bytes, cudaStream_t st);
+                    float *ws, size_t ws_bytes, bool image_ready, cudaStream_t st);
+int tc_describe_image(int K, int N, bool dgrad, const float *W, float *image, pn2_linear_image *out);
+size_t tc_image_bytes_for(int K, int N, bool dgrad);
+int tc_prepare_images(int count, const pn2_linear_image *table_dev, cudaStream_t st);
 size_t tc_workspace_bytes(int K, int N);
 int tc_linear_wgrad(long M, int K, int N, const float *A, int lda, const float *a_scale,
                     const float *a_shift, int a_relu, const float *dY, float *dW, bool force,
@@ -620,7 +623,10 @@ __global__ void softmax_ce_reduce_kernel(long rows, int C, const float *__restri
         for (int c = 0; c < C; ++c) se += expf(__ldg(x + c) - mx);
         const float lse = mx + logf(se);
         const float w = weights ? __ldg(weights + r) : 1.f;
-        const float ce = lse - __ldg(x + __ldg(labels + r));
+        // a label outside [0,C) must not index the logits: TF's GPU kernel yields NaN for such a row
+        // (tf.nn.sparse_softmax_cross_entropy_with_logits), and so does this one -- loudly visible
+        const int lab = __ldg(labels + r);
+        const float ce = (lab >= 0 && lab < C) ? lse - __ldg(x + lab) : __int_as_float(0x7fc00000);
         s += (double)(ce * w);
         nz += (w != 0.f) ? 1.0 : 0.0;
     }
@@ -654,9 +660,10 @@ __global__ void softmax_ce_grad_kernel(long rows, int C, const float *__restrict
         const float w = (weights ? __ldg(weights + r) : 1.f) * inv;
         const int lab = __ldg(labels + r);
         const float rse = 1.f / se;
+        const bool lab_ok = lab >= 0 && lab < C;  // out of range: NaN row, like the loss
         for (int c = 0; c < C; ++c) {
             const float p = expf(__ldg(x + c) - mx) * rse;
-            dlogits[r * C + c] = w * (p - (c == lab ? 1.f : 0.f));
+            dlogits[r * C + c] = lab_ok ? w * (p - (c == lab ? 1.f : 0.f)) : __int_as_float(0x7fc00000);
         }
     }
 }
@@ -766,6 +773,8 @@ PN2_API int pn2_linear_fwd(long M, int K, int N, const float *A, int lda, const 
                            float *Y, double *stats, void *ws, long ws_bytes, int mode,
                            pn2_stream_t s) {
     PN2_REQUIRE(M >= 0 && K > 0 && N > 0 && lda >= K && M < (1L << 31));
+    const bool image_ready = mode >= PN2_GEMM_IMAGE_READY - 1;  // mode + PN2_GEMM_IMAGE_READY
+    if (image_ready) mode -= PN2_GEMM_IMAGE_READY;
     PN2_REQUIRE(mode >= -1 && mode <= 1);
     if (M == 0) return PN2_OK;
     PN2_REQUIRE_PTR(A);
@@ -775,11 +784,33 @@ PN2_API int pn2_linear_fwd(long M, int K, int N, const float *A, int lda, const 
     cudaStream_t st = as_stream(s);
     if (mode == 1 || (mode == -1 && tc_enabled())) {
         int rc = tc_linear_fwd(M, K, N, A, lda, a_scale, a_shift, a_relu, W, bias, Y, stats,
-                               static_cast<float *>(ws), ws_bytes > 0 ? (size_t)ws_bytes : 0, st);
+                               static_cast<float *>(ws), ws_bytes > 0 ? (size_t)ws_bytes : 0, image_ready, st);
         if (rc != PN2_EUNSUPPORTED || mode == 1) return rc;
     }
     return launch_gemm<true, true, false>((int)M, N, K, A, lda, 1, W, N, 1, a_scale, a_shift,
                                           a_relu, bias, Y, N, stats, 1, st);
+}
+
+PN2_API long pn2_linear_image_bytes(int K, int N, int dgrad) {
+    if (K <= 0 || N <= 0) return 0;
+    return (long)tc_image_bytes_for(K, N, dgrad != 0);
+}
+
+PN2_API int pn2_linear_image_describe(int K, int N, int dgrad, const float *W, float *image,
+                                      pn2_linear_image *out) {
+    PN2_REQUIRE(K > 0 && N > 0);
+    PN2_REQUIRE_PTR(W);
+    PN2_REQUIRE_PTR(image);
+    PN2_REQUIRE_PTR(out);
+    PN2_REQUIRE((reinterpret_cast<uintptr_t>(image) & 127) == 0);
+    return tc_describe_image(K, N, dgrad != 0, W, image, out);
+}
+
+PN2_API int pn2_linear_prepare(int count, const pn2_linear_image *table_dev, pn2_stream_t s) {
+    PN2_REQUIRE(count >= 0 && count <= 65535);
+    if (count == 0) return PN2_OK;
+    PN2_REQUIRE_PTR(table_dev);
+    return tc_prepare_images(count, table_dev, as_stream(s));
 }
 
 PN2_API long pn2_linear_workspace_bytes(int K, int N) {
@@ -790,6 +821,8 @@ PN2_API long pn2_linear_workspace_bytes(int K, int N) {
 PN2_API int pn2_linear_dgrad(long M, int K, int N, const float *dY, const float *W, float *dX,
                              int ldx, void *ws, long ws_bytes, int mode, pn2_stream_t s) {
     PN2_REQUIRE(M >= 0 && K > 0 && N > 0 && ldx >= K && M < (1L << 31));
+    const bool image_ready = mode >= PN2_GEMM_IMAGE_READY - 1;  // mode + PN2_GEMM_IMAGE_READY
+    if (image_ready) mode -= PN2_GEMM_IMAGE_READY;
     PN2_REQUIRE(mode >= -1 && mode <= 1);
     if (M == 0) return PN2_OK;
     PN2_REQUIRE_PTR(dY);
@@ -798,7 +831,7 @@ PN2_API int pn2_linear_dgrad(long M, int K, int N, const float *dY, const float 
     cudaStream_t st = as_stream(s);
     if (mode == 1 || (mode == -1 && tc_enabled())) {
         int rc = tc_linear_dgrad(M, K, N, dY, W, dX, ldx, static_cast<float *>(ws),
-                                 ws_bytes > 0 ? (size_t)ws_bytes : 0, st);
+                                 ws_bytes > 0 ? (size_t)ws_bytes : 0, image_ready, st);
         if (rc != PN2_EUNSUPPORTED || mode == 1) return rc;
     }
     // C[M,K] = sum_n dY(m,n) * W(k,n):  M'=M, N'=K, K'=N ; B(k'=n, n'=k) = W + k*N + n

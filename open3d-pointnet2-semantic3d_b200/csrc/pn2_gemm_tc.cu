@@ -192,6 +192,30 @@ __global__ void tc_prep_b_kernel(int N, int Ntot, int K, int Npad, int KC, int n
     }
 }
 
+// All weight images of a step in ONE launch: blockIdx.y = table entry, blockIdx.x strides over its
+// elements (same element mapping as tc_prep_b_kernel).
+__global__ void tc_prep_images_kernel(const pn2_linear_image *__restrict__ table) {
+    const pn2_linear_image d = table[blockIdx.y];
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < d.total;
+         e += (long)gridDim.x * blockDim.x) {
+        const int kk = (int)(e % BK);
+        const long t = e / BK;
+        const int nl = (int)(t % d.Npad);
+        const long t2 = t / d.Npad;
+        const int kc = (int)(t2 % d.KC);
+        const int ch = (int)(t2 / d.KC);
+        const int k = kc * BK + kk;
+        const long n = (long)ch * 128 + nl;
+        float v = (nl < d.N && n < d.Ntot && k < d.K) ? __ldg(d.src + n * d.s_n + k * d.s_k) : 0.f;
+        const float hi = tf32_rna(v);
+        const float lo = v - hi;
+        unsigned char *base = reinterpret_cast<unsigned char *>(d.image) + ((size_t)ch * d.KC + kc) * 2 * d.Npad * 128;
+        const uint32_t off = sw128_offset(nl, kk);
+        *reinterpret_cast<float *>(base + off) = hi;
+        *reinterpret_cast<float *>(base + (size_t)d.Npad * 128 + off) = lo;
+    }
+}
+
 // Cycle accounting of CTA 0 (one thread per role), read back by pn2_debug_tc_trace():
 //  [0] mma: cycles waiting for a full stage   [1] mma: cycles issuing   [2] mma: waiting acc_empty
 //  [3] transform g0: wait raw + load          [4] transform g0: waiting empty  [5] transform g0: store
@@ -718,7 +742,7 @@ static size_t image_bytes(int K, int N) {
 static int run_chunk(long M, int K, int Nc, int nchunks, int Ntot, const float *A, int lda, const float *a_scale,
                      const float *a_shift, int a_relu, const float *bsrc, long s_n, long s_k,
                      const float *bias, float *Y, int ldy, double *stats_sum, double *stats_sq,
-                     float *ws, cudaStream_t st) {
+                     float *ws, bool image_ready, cudaStream_t st) {
     Params p;
     p.M = M;
     p.K = K;
@@ -784,12 +808,15 @@ static int run_chunk(long M, int K, int Nc, int nchunks, int Ntot, const float *
     const size_t smem = (p.b_res ? bres : 0) + (size_t)stages * stage_bytes +
                         (size_t)raw_slots * RAW_BYTES + fixed;
 
-    const long total = (long)nchunks * p.KC * p.Npad * BK;
-    int pb = (int)((total + 255) / 256);
-    if (pb > 148 * 8) pb = 148 * 8;
-    tc_prep_b_kernel<<<pb, 256, 0, st>>>(Nc, Ntot, K, p.Npad, p.KC, nchunks, bsrc, s_n, s_k, ws);
-    int rc = finish_launch();
-    if (rc) return rc;
+    int rc = PN2_OK;
+    if (!image_ready) {  // per-call image (callers that did not batch the preparation)
+        const long total = (long)nchunks * p.KC * p.Npad * BK;
+        int pb = (int)((total + 255) / 256);
+        if (pb > 148 * 8) pb = 148 * 8;
+        tc_prep_b_kernel<<<pb, 256, 0, st>>>(Nc, Ntot, K, p.Npad, p.KC, nchunks, bsrc, s_n, s_k, ws);
+        rc = finish_launch();
+        if (rc) return rc;
+    }
 
     // opt in to the full 227 KB once per device (not per launch: no driver call on the hot path,
     // nothing that could disturb a stream capture)
@@ -1254,25 +1281,59 @@ size_t tc_workspace_bytes(int K, int N) {
     return a > b ? a : b;
 }
 
+// table entry of one image: forward orientation Bt(n,k) = W[k*N + n]; dgrad orientation (output
+// columns = K, contraction over N) Bt(k,n) = W[k*N + n]
+int tc_describe_image(int K, int N, bool dgrad, const float *W, float *image, pn2_linear_image *out) {
+    const int Kc = dgrad ? N : K, Nout = dgrad ? K : N;  // contraction length, output columns
+    if (Kc < 1 || Kc > 1024 || Nout < 1) return PN2_EUNSUPPORTED;
+    const int nch = (Nout + TC_NCHUNK - 1) / TC_NCHUNK;
+    const int Nc = nch == 1 ? Nout : TC_NCHUNK;
+    out->src = W;
+    out->image = image;
+    out->s_n = dgrad ? N : 1;
+    out->s_k = dgrad ? 1 : N;
+    out->N = Nc;
+    out->Ntot = Nout;
+    out->K = Kc;
+    out->Npad = (Nc + 15) & ~15;
+    out->KC = (Kc + tc::BK - 1) / tc::BK;
+    out->nchunks = nch;
+    out->total = (long)nch * out->KC * out->Npad * tc::BK;
+    return PN2_OK;
+}
+
+size_t tc_image_bytes_for(int K, int N, bool dgrad) {
+    const int Kc = dgrad ? N : K, Nout = dgrad ? K : N;
+    if (Kc < 1 || Kc > 1024 || Nout < 1) return 0;
+    return tc_image_bytes(Kc, Nout);
+}
+
+int tc_prepare_images(int count, const pn2_linear_image *table_dev, cudaStream_t st) {
+    if (count <= 0) return PN2_OK;
+    dim3 grid(32, (unsigned)count);
+    tc::tc_prep_images_kernel<<<grid, 256, 0, st>>>(table_dev);
+    return finish_launch();
+}
+
 int tc_linear_fwd(long M, int K, int N, const float *A, int lda, const float *a_scale,
                   const float *a_shift, int a_relu, const float *W, const float *bias, float *Y,
-                  double *stats, float *ws, size_t ws_bytes, cudaStream_t st) {
+                  double *stats, float *ws, size_t ws_bytes, bool image_ready, cudaStream_t st) {
     if (!tc_shape_ok(M, K, N) || ws == nullptr || ws_bytes < tc_image_bytes(K, N))
         return PN2_EUNSUPPORTED;
     // all column blocks in one launch; Bt(n,k) = W[k*N + n]
     const int nch = (N + TC_NCHUNK - 1) / TC_NCHUNK;
     return tc::run_chunk(M, K, nch == 1 ? N : TC_NCHUNK, nch, N, A, lda, a_scale, a_shift, a_relu, W, 1, N,
-                         bias, Y, N, stats, stats ? stats + N : nullptr, ws, st);
+                         bias, Y, N, stats, stats ? stats + N : nullptr, ws, image_ready, st);
 }
 
 int tc_linear_dgrad(long M, int K, int N, const float *dY, const float *W, float *dX, int ldx,
-                    float *ws, size_t ws_bytes, cudaStream_t st) {
+                    float *ws, size_t ws_bytes, bool image_ready, cudaStream_t st) {
     // dX[M,K] = dY[M,N] * W[K,N]^T : contraction over N, output columns = K ; Bt(k,n) = W[k*N + n]
     if (!tc_shape_ok(M, N, K) || ws == nullptr || ws_bytes < tc_image_bytes(N, K))
         return PN2_EUNSUPPORTED;
     const int nch = (K + TC_NCHUNK - 1) / TC_NCHUNK;
     return tc::run_chunk(M, N, nch == 1 ? K : TC_NCHUNK, nch, K, dY, N, nullptr, nullptr, 0, W, N, 1, nullptr,
-                         dX, ldx, nullptr, nullptr, ws, st);
+                         dX, ldx, nullptr, nullptr, ws, image_ready, st);
 }
 
 }  // namespace pn2

@@ -79,90 +79,6 @@ three_nn_kernel(int n, int m, const float *__restrict__ xyz1, const float *__res
     }
 }
 
-// ---- three_nn with an fp32 gate in front of the exact fp64 test (NOT the default yet) -------
-// The fp64 pipe bounds three_nn_kernel (ncu r01b: 74 % issue active, 8 DP ops per pair).  Almost
-// every pair loses against the current third-best, and that can be decided in fp32: with fp32
-// inputs q,k the fp32 value df = fma(dz,dz,fma(dy,dy,dx*dx)) of rounded differences satisfies
-// df <= d*(1+6u) + 3*2^-149 (u = 2^-24; differences of floats round with relative error u even
-// under cancellation, five more roundings follow; d = the fp64 value, itself within 3*2^-53).
-// So d < b3 implies df <= gate := ru(ru(b3) * (1 + 2^-20)) + 1e-37, and a pair with df > gate can
-// be skipped without changing any result; the rest takes the unchanged exact expression.  The hot
-// loop is 3 broadcast LDS + 6 FP32 ops + 1 compare; known points are staged as fp32 SoA
-// (12 B per point instead of 24) and promoted only on the exact path.
-constexpr int NNF_THREADS = 256;
-constexpr int NNF_TILE = 2048;  // 24 KB of fp32 SoA
-
-__device__ __forceinline__ float nn_gate(double b3) {
-    return __fadd_ru(__fmul_ru(__double2float_ru(b3), 1.00000095367431640625f), 1e-37f);
-}
-
-__global__ void __launch_bounds__(NNF_THREADS)
-three_nn_filtered_kernel(int n, int m, const float *__restrict__ xyz1,
-                         const float *__restrict__ xyz2, float *__restrict__ dist,
-                         int *__restrict__ idx) {
-    __shared__ __align__(16) float kx[NNF_TILE], ky[NNF_TILE], kz[NNF_TILE];
-    const int cloud = blockIdx.y;
-    const int j = blockIdx.x * NNF_THREADS + threadIdx.x;
-    const bool valid = j < n;
-    float qxf = 0.f, qyf = 0.f, qzf = 0.f;
-    if (valid) {
-        const float *q = xyz1 + ((size_t)cloud * n + j) * 3;
-        qxf = __ldg(q);
-        qyf = __ldg(q + 1);
-        qzf = __ldg(q + 2);
-    }
-    const double qx = (double)qxf, qy = (double)qyf, qz = (double)qzf;
-    const double INF = __longlong_as_double(0x7FF0000000000000LL);
-    double b1 = INF, b2 = INF, b3 = INF;
-    int i1 = 0, i2 = 0, i3 = 0;
-    float gate = __int_as_float(0x7F800000);  // +inf: everything passes until three are known
-    const float *known = xyz2 + (size_t)cloud * m * 3;
-    for (int base = 0; base < m; base += NNF_TILE) {
-        const int cnt = min(NNF_TILE, m - base);
-        __syncthreads();
-        for (int e = threadIdx.x; e < cnt * 3; e += NNF_THREADS) {
-            int k = e / 3, c = e - k * 3;
-            (c == 0 ? kx : (c == 1 ? ky : kz))[k] = __ldg(known + (size_t)base * 3 + e);
-        }
-        __syncthreads();
-        if (valid) {
-#pragma unroll 4
-            for (int k = 0; k < cnt; ++k) {
-                const float fx = kx[k], fy = ky[k], fz = kz[k];
-                const float dxf = qxf - fx, dyf = qyf - fy, dzf = qzf - fz;
-                const float df = fmaf(dzf, dzf, fmaf(dyf, dyf, dxf * dxf));
-                if (df <= gate) {
-                    double dx = __dsub_rn(qx, (double)fx);
-                    double dy = __dsub_rn(qy, (double)fy);
-                    double dz = __dsub_rn(qz, (double)fz);
-                    double d = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)),
-                                         __dmul_rn(dz, dz));
-                    if (d < b3) {
-                        const int kk = base + k;
-                        if (d < b1) {
-                            b3 = b2; i3 = i2; b2 = b1; i2 = i1; b1 = d; i1 = kk;
-                        } else if (d < b2) {
-                            b3 = b2; i3 = i2; b2 = d; i2 = kk;
-                        } else {
-                            b3 = d; i3 = kk;
-                        }
-                        gate = nn_gate(b3);
-                    }
-                }
-            }
-        }
-    }
-    if (valid) {
-        size_t o = ((size_t)cloud * n + j) * 3;
-        dist[o] = (float)b1;
-        dist[o + 1] = (float)b2;
-        dist[o + 2] = (float)b3;
-        idx[o] = i1;
-        idx[o + 1] = i2;
-        idx[o + 2] = i3;
-    }
-}
-
 // pointnet_util.py:300-303 (fp32, true division):
 //   d = max(d,1e-10); norm = (1/d0 + 1/d1) + 1/d2; w = (1/d)/norm
 __global__ void fp_weights_kernel(long rows, const float *__restrict__ dist,
@@ -353,101 +269,6 @@ knn_vote_kernel(int ns, int nd, int k, const float *__restrict__ sparse,
         out_colors[(size_t)j * 3 + c] = known ? kLabelColors[best][c] : (unsigned char)0;
 }
 
-// EXPERIMENTAL (never run on a GPU): knn_vote_kernel with the fp32 gate of three_nn_filtered_kernel in
-// front of the exact fp64 test (the bound is the same with the k-th best distance in place of the third).
-// Sparse points are staged as fp32 SoA and promoted only on the exact path.
-template <int KMAX>
-__global__ void __launch_bounds__(KV_THREADS)
-knn_vote_filtered_kernel(int ns, int nd, int k, const float *__restrict__ sparse,
-                         const int *__restrict__ labels, const float *__restrict__ dense,
-                         int *__restrict__ out_labels, unsigned char *__restrict__ out_colors) {
-    __shared__ __align__(16) float kx[NNF_TILE], ky[NNF_TILE], kz[NNF_TILE];
-    const long j = (long)blockIdx.x * KV_THREADS + threadIdx.x;
-    const bool valid = j < nd;
-    float qxf = 0.f, qyf = 0.f, qzf = 0.f;
-    if (valid) {
-        const float *q = dense + (size_t)j * 3;
-        qxf = __ldg(q);
-        qyf = __ldg(q + 1);
-        qzf = __ldg(q + 2);
-    }
-    const double qx = (double)qxf, qy = (double)qyf, qz = (double)qzf;
-    const double INF = __longlong_as_double(0x7FF0000000000000LL);
-    double bd[KMAX];
-    int bi[KMAX];
-#pragma unroll
-    for (int s = 0; s < KMAX; ++s) {
-        bd[s] = INF;
-        bi[s] = -1;
-    }
-    double worst = INF;
-    float gate = __int_as_float(0x7F800000);
-    for (int base = 0; base < ns; base += NNF_TILE) {
-        const int cnt = min(NNF_TILE, ns - base);
-        __syncthreads();
-        for (int e = threadIdx.x; e < cnt * 3; e += KV_THREADS) {
-            int p = e / 3, c = e - p * 3;
-            (c == 0 ? kx : (c == 1 ? ky : kz))[p] = __ldg(sparse + (size_t)base * 3 + e);
-        }
-        __syncthreads();
-        if (valid) {
-#pragma unroll 4
-            for (int p = 0; p < cnt; ++p) {
-                const float fx = kx[p], fy = ky[p], fz = kz[p];
-                const float dxf = qxf - fx, dyf = qyf - fy, dzf = qzf - fz;
-                const float df = fmaf(dzf, dzf, fmaf(dyf, dyf, dxf * dxf));
-                if (df <= gate) {
-                    double dx = __dsub_rn(qx, (double)fx);
-                    double dy = __dsub_rn(qy, (double)fy);
-                    double dz = __dsub_rn(qz, (double)fz);
-                    double d = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)),
-                                         __dmul_rn(dz, dz));
-                    if (d < worst) {
-#pragma unroll
-                        for (int s = 0; s < KMAX; ++s)
-                            if (s == k - 1) {
-                                bd[s] = d;
-                                bi[s] = base + p;
-                            }
-#pragma unroll
-                        for (int s = KMAX - 1; s > 0; --s)
-                            if (s < k && bd[s] < bd[s - 1]) {
-                                double td = bd[s]; bd[s] = bd[s - 1]; bd[s - 1] = td;
-                                int ti = bi[s]; bi[s] = bi[s - 1]; bi[s - 1] = ti;
-                            }
-#pragma unroll
-                        for (int s = 0; s < KMAX; ++s)
-                            if (s == k - 1) worst = bd[s];
-                        gate = nn_gate(worst);
-                    }
-                }
-            }
-        }
-    }
-    if (!valid) return;
-    int lab[KMAX];
-#pragma unroll
-    for (int s = 0; s < KMAX; ++s) lab[s] = (s < k && bi[s] >= 0) ? __ldg(labels + bi[s]) : 0;
-    int best = -1, best_count = 0;
-#pragma unroll
-    for (int s = 0; s < KMAX; ++s) {
-        if (s < k && bi[s] >= 0) {
-            int cnt = 0;
-#pragma unroll
-            for (int u = 0; u <= s; ++u) cnt += (lab[u] == lab[s]) ? 1 : 0;
-            if (cnt > best_count) {
-                best = lab[s];
-                best_count = cnt;
-            }
-        }
-    }
-    out_labels[j] = best;
-    const bool known = best >= 0 && best < 9;
-#pragma unroll
-    for (int c = 0; c < 3; ++c)
-        out_colors[(size_t)j * 3 + c] = known ? kLabelColors[best][c] : (unsigned char)0;
-}
-
 static inline int grid_for(long total, int threads) {
     long blocks = ceil_div<long>(total, threads);
     long cap = 148L * 32;
@@ -466,28 +287,8 @@ PN2_API int pn2_three_nn(int b, int n, int m, const float *xyz1, const float *xy
     PN2_REQUIRE_PTR(xyz2);
     PN2_REQUIRE_PTR(dist);
     PN2_REQUIRE_PTR(idx);
-    // PN2_THREE_NN_FILTER=1 selects the fp32-gated kernel (same results; not yet timed on the B200)
-    static const char *flt_env = getenv("PN2_THREE_NN_FILTER");
-    if (flt_env && flt_env[0] == '1') {
-        dim3 gridf((unsigned)ceil_div(n, NNF_THREADS), (unsigned)b);
-        three_nn_filtered_kernel<<<gridf, NNF_THREADS, 0, as_stream(s)>>>(n, m, xyz1, xyz2, dist, idx);
-        return finish_launch();
-    }
     dim3 grid((unsigned)ceil_div(n, NN_THREADS), (unsigned)b);
     three_nn_kernel<<<grid, NN_THREADS, 0, as_stream(s)>>>(n, m, xyz1, xyz2, dist, idx);
-    return finish_launch();
-}
-
-PN2_API int pn2_three_nn_filtered(int b, int n, int m, const float *xyz1, const float *xyz2,
-                                  float *dist, int *idx, pn2_stream_t s) {
-    PN2_REQUIRE(b >= 0 && n >= 0 && m > 0);
-    if (b == 0 || n == 0) return PN2_OK;
-    PN2_REQUIRE_PTR(xyz1);
-    PN2_REQUIRE_PTR(xyz2);
-    PN2_REQUIRE_PTR(dist);
-    PN2_REQUIRE_PTR(idx);
-    dim3 grid((unsigned)ceil_div(n, NNF_THREADS), (unsigned)b);
-    three_nn_filtered_kernel<<<grid, NNF_THREADS, 0, as_stream(s)>>>(n, m, xyz1, xyz2, dist, idx);
     return finish_launch();
 }
 
@@ -584,20 +385,6 @@ PN2_API int pn2_interpolate_label_with_color(int num_sparse, int num_dense,
     }
     cudaStream_t st = as_stream(s);
     const unsigned grid = (unsigned)ceil_div<long>(num_dense, KV_THREADS);
-    // PN2_KNN_VOTE_FILTER=1: the fp32-gated kernel (EXPERIMENTAL, same results)
-    static const char *vflt_env = getenv("PN2_KNN_VOTE_FILTER");
-    if (vflt_env && vflt_env[0] == '1') {
-#define PN2_LAUNCH_VOTEF(KM)                                                                            \
-    knn_vote_filtered_kernel<KM><<<grid, KV_THREADS, 0, st>>>(num_sparse, num_dense, knn, sparse_points, \
-                                                              sparse_labels, dense_points, dense_labels,  \
-                                                              dense_colors)
-        if (knn <= 4) PN2_LAUNCH_VOTEF(4);
-        else if (knn <= 8) PN2_LAUNCH_VOTEF(8);
-        else if (knn <= 16) PN2_LAUNCH_VOTEF(16);
-        else PN2_LAUNCH_VOTEF(32);
-#undef PN2_LAUNCH_VOTEF
-        return finish_launch();
-    }
 #define PN2_LAUNCH_VOTE(KM)                                                                    \
     knn_vote_kernel<KM><<<grid, KV_THREADS, 0, st>>>(num_sparse, num_dense, knn, sparse_points, \
                                                      sparse_labels, dense_points, dense_labels, \

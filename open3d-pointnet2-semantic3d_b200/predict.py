@@ -34,7 +34,9 @@ class Predictor:
                 checkpoint = {k: z[k] for k in z.files}
         if not checkpoint:
             raise ValueError("Predictor needs the checkpoint's variables (name -> array)")
-        self.store.load_state_dict(checkpoint)
+        self.skipped = self.store.load_state_dict(checkpoint)  # optimizer slots etc. of a full TF checkpoint
+        # a variable the checkpoint lacks must fail loudly, not be xavier-initialised during predict()
+        self.store.strict = True
 
     def predict(self, batch_data):
         """batch_data (batch_size, num_point, 3 or 6) -> labels (batch_size, num_point), the arg-max

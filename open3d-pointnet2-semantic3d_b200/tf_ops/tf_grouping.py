@@ -36,7 +36,7 @@ def query_ball_point(radius, nsample, xyz1, xyz2):
     xyz2 = xyz2.detach().contiguous()
     idx = torch.empty((b, m, int(nsample)), dtype=I32, device=xyz1.device)
     cnt = torch.empty((b, m), dtype=I32, device=xyz1.device)
-    if _GRID and n >= 4096:  # EXPERIMENTAL (PN2_BALL_GRID=1): hashed uniform grid, same results
+    if _GRID and n >= 4096:  # hashed uniform grid: 2x (n=8192) to 14x (n=262144) faster, bit-identical
         ws, nbytes = _grid_workspace(b, n, xyz1.device)
         call("pn2_query_ball_point_grid", b, n, m, float(radius), int(nsample), ptr(xyz1, F32),
              ptr(xyz2, F32), ptr(idx, I32), ptr(cnt, I32), ptr(ws, F32), nbytes)
@@ -46,7 +46,10 @@ def query_ball_point(radius, nsample, xyz1, xyz2):
     return idx, cnt
 
 
-_GRID = os.environ.get("PN2_BALL_GRID") == "1"
+# Large clouds go through the hashed-grid kernel (profiles/ab_ops_r02.json: 0.096 vs 0.184 ms at the SA1
+# size of semantic.json, 3-14x at 65 k-262 k points; slower below ~4 k points, where the TMA brute-force
+# kernels stay).  PN2_BALL_GRID=0 keeps the brute-force kernels everywhere.
+_GRID = os.environ.get("PN2_BALL_GRID", "1") != "0"
 _grid_ws = {}
 
 

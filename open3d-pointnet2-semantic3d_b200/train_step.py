@@ -88,6 +88,7 @@ class Trainer:
             self.flat, self.grads = self.store.flatten()
             self.m = torch.zeros_like(self.flat)
             self.v = torch.zeros_like(self.flat)
+            self.store.allocate_images()
             if self.world_size > 1:  # replicas start from rank 0's weights
                 dist.broadcast(self.flat, src=0)
 
@@ -102,6 +103,7 @@ class Trainer:
         # a fresh autograd anchor per pass: no leaf (or its gradient accumulator) outlives the pass
         self.store.anchor = torch.zeros(1, device=self.device, requires_grad=True)
         tf_util.zero_arena.reset(self.device)  # one memset for every layer's fp64 accumulators
+        self.store.prepare_images()            # one launch: every layer's 3xTF32 weight images
         try:
             pred, _ = model.get_model(point_cloud, True, self.num_class, self.params, bn_decay=bn_decay)
             self.store.zero_grad()
@@ -110,6 +112,7 @@ class Trainer:
         finally:
             tf_util.zero_arena.disarm()
             tf_util.set_dropout_seed_device(None)
+            self.store.images_fresh = False  # the optimizer step that follows changes the weights
         return loss.detach()
 
     def _create_variables(self, point_cloud):

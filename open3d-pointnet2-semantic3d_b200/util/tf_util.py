@@ -56,6 +56,9 @@ class VariableStore:
         self.gen = torch.Generator(device="cpu")
         self.gen.manual_seed(seed)
         self.flat_params = self.flat_grads = None
+        self.strict = False  # True: get_variable raises instead of creating (inference from a checkpoint)
+        # tensor-core weight images built once per step (allocate_images / prepare_images)
+        self.images, self.image_table, self.image_buf, self.images_fresh = {}, None, None, False
         # a leaf that requires grad, threaded through every layer Function so that autograd
         # visits the Function even when its data input does not require grad
         self.anchor = torch.zeros(1, device=self.device, requires_grad=True)
@@ -68,6 +71,9 @@ class VariableStore:
         full = self.full_name(name)
         v = self.vars.get(full)
         if v is None:
+            if self.strict:
+                raise KeyError("variable %s is not in the loaded checkpoint (strict store: nothing is "
+                               "initialised silently)" % full)
             if callable(init):
                 data = init(shape)
             else:
@@ -76,8 +82,13 @@ class VariableStore:
             self.vars[full] = v
             self.flat_params = self.flat_grads = None  # layout changed
         elif tuple(v.data.shape) != tuple(shape):
-            raise ValueError("variable %s exists with shape %s, requested %s"
-                             % (full, tuple(v.data.shape), tuple(shape)))
+            # a checkpoint may hold a conv kernel as [k,n]: adopt the layer's rank, never another size
+            if full.endswith("/weights") and v.data.numel() == math.prod(shape) and \
+                    tuple(v.data.shape[-2:]) == tuple(shape[-2:]):
+                v.data = v.data.view(*shape)
+            else:
+                raise ValueError("variable %s exists with shape %s, requested %s"
+                                 % (full, tuple(v.data.shape), tuple(shape)))
         return v
 
     def xavier(self, shape):
@@ -114,6 +125,47 @@ class VariableStore:
         self.flat_params, self.flat_grads = flat, grads
         return flat, grads
 
+    # -- tensor-core weight images: ONE preparation launch per step --------------------------------
+    def allocate_images(self):
+        """Give every conv kernel a persistent pair of 3xTF32 weight images (forward and dgrad
+        orientation) plus the device table pn2_linear_prepare walks.  Call after flatten()."""
+        import ctypes
+        import numpy as np
+        from .._ffi import lib
+        L = lib()
+        plan, off = [], 0
+        for name, v in self.vars.items():
+            if not name.endswith("/weights"):
+                continue
+            k, n = int(v.data.shape[-2]), int(v.data.shape[-1])
+            for dg in (0, 1):
+                nb = int(L.pn2_linear_image_bytes(k, n, dg))
+                if nb <= 0:
+                    continue
+                plan.append((name, k, n, dg, off, nb))
+                off += (nb + 255) // 256 * 256
+        self.images, self.image_table, self.images_fresh = {}, None, False
+        if not plan:
+            return
+        self.image_buf = torch.empty(off // 4, dtype=F32, device=self.device)
+        table = np.zeros((len(plan), 64), np.uint8)
+        base = self.image_buf.data_ptr()
+        for i, (name, k, n, dg, o, nb) in enumerate(plan):
+            img = self.image_buf[o // 4:(o + nb) // 4]
+            rc = L.pn2_linear_image_describe(k, n, dg, ctypes.c_void_p(self.vars[name].data.data_ptr()),
+                                             ctypes.c_void_p(base + o),
+                                             ctypes.c_void_p(table[i].ctypes.data))
+            if rc != 0:
+                raise RuntimeError("pn2_linear_image_describe(%s) failed: %d" % (name, rc))
+            self.images.setdefault(name, [None, None])[dg] = img
+        self.image_table = torch.as_tensor(table).to(self.device)
+
+    def prepare_images(self):
+        """Rebuild every weight image from the current weights (one launch)."""
+        if self.image_table is not None:
+            call("pn2_linear_prepare", self.image_table.shape[0], ptr(self.image_table, torch.uint8))
+            self.images_fresh = True
+
     def zero_grad(self):
         if self.flat_grads is not None:
             self.flat_grads.zero_()
@@ -125,15 +177,36 @@ class VariableStore:
     def state_dict(self):
         return {k: v.data.detach().cpu().numpy().copy() for k, v in self.vars.items()}
 
+    MODEL_SUFFIXES = ("/weights", "/biases", "/bn/gamma", "/bn/beta", "/bn/moving_mean", "/bn/moving_variance")
+
     def load_state_dict(self, sd):
+        """Load ``name -> array`` (a TensorFlow checkpoint of this network, or state_dict()).
+
+        Shapes must match the variable exactly, except that a conv kernel may come as [k,n], [1,k,n]
+        or [1,1,k,n] (same element order).  Keys that are not model variables -- the optimizer slots
+        and counters of a full TF checkpoint (``*/Adam``, ``*/Adam_1``, ``beta1_power``, the global
+        step ...) -- are skipped and returned, never registered as variables."""
+        skipped = []
         for k, arr in sd.items():
+            if not k.endswith(self.MODEL_SUFFIXES):
+                skipped.append(k)
+                continue
             t = torch.as_tensor(arr, dtype=F32)
             if k in self.vars:
-                self.vars[k].data.copy_(t.to(self.device))
+                dst = self.vars[k].data
+                same = tuple(t.shape) == tuple(dst.shape)
+                kernel = k.endswith("/weights") and t.dim() >= 2 and tuple(t.shape[-2:]) == tuple(dst.shape[-2:]) \
+                    and t.numel() == dst.numel()
+                if not (same or kernel):
+                    raise ValueError("checkpoint variable %s has shape %s, the model's has %s"
+                                     % (k, tuple(t.shape), tuple(dst.shape)))
+                dst.copy_(t.reshape(dst.shape).to(self.device))
+                self.images_fresh = False
             else:
                 trainable = not (k.endswith("moving_mean") or k.endswith("moving_variance"))
                 self.vars[k] = Variable(k, t.to(self.device).contiguous(), trainable)
                 self.flat_params = self.flat_grads = None
+        return skipped
 
 
 _store = None
@@ -173,7 +246,7 @@ def _as_bool(x):
 # ------------------------------------------------------------------------------------------
 class LayerSpec:
     """Variables and flags of one conv layer (created by ``make_layer`` inside its scope)."""
-    __slots__ = ("w", "b", "gamma", "beta", "mm", "mv", "bn", "relu", "rank4", "k", "n")
+    __slots__ = ("w", "b", "gamma", "beta", "mm", "mv", "bn", "relu", "rank4", "k", "n", "img")
 
 
 def make_layer(scope, k, n, bn, act, use_xavier=True, stddev=1e-3, kernel_rank=4):
@@ -185,6 +258,8 @@ def make_layer(scope, k, n, bn, act, use_xavier=True, stddev=1e-3, kernel_rank=4
         L.w = st.get_variable("weights", kshape, init)
         L.b = st.get_variable("biases", [n], 0.0)
         L.bn, L.relu, L.rank4, L.k, L.n = bool(bn), act is not None, kernel_rank == 4, k, n
+        # persistent weight images (forward, dgrad) when the store prepared them for this pass
+        L.img = st.images.get(L.w.name) if st.images_fresh else None
         if bn:
             with variable_scope("bn"):
                 L.gamma = st.get_variable("gamma", [n], 1.0)
@@ -262,6 +337,19 @@ def _workspace(L, dev):
     return ws
 
 
+IMAGE_READY = 16  # PN2_GEMM_IMAGE_READY (include/pn2_b200.h)
+
+
+def _weight_image(L, dgrad, dev, gemm_mode):
+    """(workspace, mode) of one GEMM call: the layer's persistent image when the store prepared the
+    images for this pass (mode + IMAGE_READY), else the shared per-shape scratch (image rebuilt per call)."""
+    if gemm_mode == 0:
+        return None, 0
+    if L.img is not None and L.img[dgrad] is not None:
+        return L.img[dgrad], gemm_mode + IMAGE_READY
+    return _workspace(L, dev), gemm_mode
+
+
 class _MLPChain(torch.autograd.Function):
     """x (M,K0) -> out (M,N_last) or, with pool_ns>0, (M/pool_ns, N_last) max-pooled.
 
@@ -285,11 +373,11 @@ class _MLPChain(torch.autograd.Function):
             Y = torch.empty((M, N), dtype=F32, device=dev)
             use_stats = L.bn and is_training
             stats = zero_arena.take(2 * N, dev) if use_stats else None
-            ws = _workspace(L, dev) if gemm_mode != 0 else None
+            ws, mode_i = _weight_image(L, 0, dev, gemm_mode)
             call("pn2_linear_fwd", M, L.k, N, a_ptr, lda, ptr(a_sc, F32, True),
                  ptr(a_sh, F32, True), a_relu, ptr(L.w.data, F32), ptr(L.b.data, F32), ptr(Y, F32),
                  ptr(stats, F64, True), ptr(ws, F32, True), 0 if ws is None else ws.numel() * 4,
-                 gemm_mode)
+                 mode_i)
             sc = sh = saved = None
             if L.bn:
                 sc = torch.empty(N, dtype=F32, device=dev)
@@ -396,9 +484,9 @@ class _MLPChain(torch.autograd.Function):
                  db, ctx.gemm_mode)
             if i > 0 or ctx.needs_input_grad[0]:
                 dX = torch.empty((M, L.k), dtype=F32, device=dev)
-                ws = _workspace(L, dev) if ctx.gemm_mode != 0 else None
+                ws, mode_i = _weight_image(L, 1, dev, ctx.gemm_mode)
                 call("pn2_linear_dgrad", M, L.k, N, ptr(dY, F32), ptr(L.w.data, F32), ptr(dX, F32),
-                     L.k, ptr(ws, F32, True), 0 if ws is None else ws.numel() * 4, ctx.gemm_mode)
+                     L.k, ptr(ws, F32, True), 0 if ws is None else ws.numel() * 4, mode_i)
                 up = dX
             else:
                 up = None

@@ -63,7 +63,7 @@ def init_conv(params, rng, scope, k, n, bn=True):
 class Ctx:
     """Holds fp64 leaf tensors for every trainable variable + BN moving stats."""
 
-    def __init__(self, params, is_training=True, bn_decay=None, dropout_masks=None):
+    def __init__(self, params, is_training=True, bn_decay=None, dropout_masks=None, decisions=None):
         self.np_params = params
         self.t = {}
         for k, v in params.items():
@@ -75,6 +75,14 @@ class Ctx:
         self.dropout_masks = dropout_masks or {}
         self.acts = {}
         self.near_zero = {}
+        # decisions of the implementation under test at the non-differentiable points of the network:
+        # "<scope>/relu_mask" (M,N) 0/1 and "<scope>/argmax" (G,N) winners of the max-pool.  When given,
+        # the oracle evaluates ReLU and max-pool WITH those decisions (after checking that each one is
+        # legitimate: a flipped element lies within 1e-4 of the kink, a different winner within 1e-4 of
+        # the maximum), so both sides differentiate the same piecewise-linear function and gradients can
+        # be compared elementwise with no allowance for flips.
+        self.decisions = {k: np.asarray(v) for k, v in (decisions or {}).items()}
+        self.flips = {}       # scope -> (count of decisions that differ from fp64's, largest |value| among them)
 
     def grads(self):
         return {k: v.grad.double().numpy().copy() for k, v in self.t.items() if v.grad is not None}
@@ -106,7 +114,14 @@ def conv_bn_relu(ctx, x, scope, bn=True, relu=True, rank4=True):
         # be masked differently by an fp32 implementation; one such flip shifts the BatchNorm
         # gradient sums of its channel by O(upstream gradient) (see compare_grads)
         ctx.near_zero[scope] = int((y.detach().abs() < 1e-5).sum())
-        y = torch.relu(y)
+        m = ctx.decisions.get(scope + "/relu_mask")
+        if m is not None:
+            mt = torch.as_tensor(m.astype(bool)).reshape(y.shape)
+            diff = mt != (y.detach() > 0)
+            ctx.flips[scope] = (int(diff.sum()), float(y.detach().abs()[diff].max()) if bool(diff.any()) else 0.0)
+            y = y * mt.to(y.dtype)
+        else:
+            y = torch.relu(y)
     ctx.acts[scope] = y
     return y
 
@@ -137,6 +152,21 @@ def sample_and_group(npoint, radius, nsample, xyz_np, points, use_xyz=True, orde
     return new_xyz_np, new_points, idx, cnt, fps, grouped_xyz
 
 
+def _max_pool(ctx, x, scope):
+    """max over dim 2 of (B,m,ns,C); with a recorded argmax the winners of the implementation under test
+    are used (and checked to be within 1e-4 of the true maximum)."""
+    arg = ctx.decisions.get(scope + "/argmax")
+    best = x.max(dim=2, keepdim=True)[0]
+    if arg is None:
+        return best
+    b, m, ns, c = x.shape
+    a = torch.as_tensor(arg.astype(np.int64)).reshape(b, m, 1, c)
+    picked = torch.gather(x, 2, a)
+    gap = (best - picked).detach()
+    ctx.flips[scope + "/argmax"] = (int((gap > 0).sum()), float(gap.max()))
+    return picked
+
+
 def sa_module(ctx, xyz_np, points, npoint, radius, nsample, mlp, scope, mlp2=None,
               group_all=False, bn=True, pooling="max", use_xyz=True):
     if group_all:
@@ -154,7 +184,7 @@ def sa_module(ctx, xyz_np, points, npoint, radius, nsample, mlp, scope, mlp2=Non
     for i, _ in enumerate(mlp):
         new_points = conv_bn_relu(ctx, new_points, "%s/conv%d" % (scope, i), bn=bn)
     if pooling == "max":
-        new_points = new_points.max(dim=2, keepdim=True)[0]
+        new_points = _max_pool(ctx, new_points, "%s/conv%d" % (scope, len(mlp) - 1))
     elif pooling == "avg":
         new_points = new_points.mean(dim=2, keepdim=True)
     elif pooling == "weighted_avg":
@@ -187,7 +217,7 @@ def sa_module_msg(ctx, xyz_np, points, npoint, radius_list, nsample_list, mlp_li
             g = gx
         for j, _ in enumerate(mlp_list[i]):
             g = conv_bn_relu(ctx, g, "%s/conv%d_%d" % (scope, i, j), bn=bn)
-        outs.append(g.max(dim=2)[0])
+        outs.append(_max_pool(ctx, g, "%s/conv%d_%d" % (scope, i, len(mlp_list[i]) - 1)).squeeze(2))
     return new_xyz_np, torch.cat(outs, -1)
 
 
@@ -285,15 +315,22 @@ def get_loss(pred, label, smpw):
 
 
 def compare_grads(ctx, ours, rtol_max=2e-5, flip_rel_l2=5e-2):
-    """Gradient parity check that knows about ReLU-boundary flips.
+    """Gradient parity check.  ``ours``: name -> numpy array.
 
-    ``ours``: name -> numpy array.  Every gradient must agree with the fp64 oracle within
-    ``rtol_max * max(1, |g|_max)`` elementwise.  If that fails AND the oracle saw pre-activations
-    within 1e-5 of the ReLU kink (``ctx.near_zero``), the mismatch may be a legitimate sign flip of
-    such an element (the loss is not differentiable there, fp32 and fp64 land on different sides):
-    then the relative L2 error must still be below ``flip_rel_l2`` (a wrong formula gives O(1)).
+    With ``ctx.decisions`` (the ReLU masks / max-pool winners of the implementation under test) the
+    oracle differentiated the same piecewise-linear function, so every gradient must agree within
+    ``rtol_max * max(1, |g|_max)`` elementwise -- no allowance; in addition every decision that differs
+    from fp64's own must be legitimate (the element within 1e-4 of the kink / of the maximum).
+
+    Without decisions (legacy callers) a mismatch is tolerated only if the oracle saw pre-activations
+    within 1e-5 of the ReLU kink and the relative L2 error stays below ``flip_rel_l2``.
     Returns a list of failure strings (empty == pass)."""
     bad = []
+    strict = bool(ctx.decisions)
+    for scope, (cnt, mag) in ctx.flips.items():
+        if mag > 1e-4:
+            bad.append("%s: %d decisions differ from fp64, one by %.3g (> 1e-4: not a rounding flip)"
+                       % (scope, cnt, mag))
     boundary = sum(ctx.near_zero.values())
     for name, e in ctx.grads().items():
         if name not in ours:
@@ -305,8 +342,8 @@ def compare_grads(ctx, ours, rtol_max=2e-5, flip_rel_l2=5e-2):
         if d <= tol:
             continue
         rel = float(np.linalg.norm(got - e) / max(np.linalg.norm(e), 1e-30))
-        if boundary > 0 and rel < flip_rel_l2:
+        if not strict and boundary > 0 and rel < flip_rel_l2:
             continue
-        bad.append("%s: |diff| %.3g > tol %.3g, rel-L2 %.3g, boundary elements %d"
-                   % (name, d, tol, rel, boundary))
+        bad.append("%s: |diff| %.3g > tol %.3g, rel-L2 %.3g, boundary elements %d%s"
+                   % (name, d, tol, rel, boundary, " (strict: decisions fed)" if strict else ""))
     return bad

@@ -200,3 +200,35 @@ def test_bench_algorithmic_work_matches_survey():
     pc, labels, smpw = bench.make_batch(2, 64, 100)
     assert pc.shape == (2, 64, 6) and pc.dtype == np.float32 and labels.min() >= 1 and labels.max() <= 8
     assert pc[..., 0].min() >= -5 and pc[..., 0].max() <= 5 and pc[..., 2].min() >= 0 and pc[..., 2].max() <= 5
+
+
+def test_load_state_dict_is_strict_about_shapes_and_foreign_keys():
+    """a wrong-shaped checkpoint array must not be broadcast into a variable, optimizer slots of
+    a full TF checkpoint must not become variables, and a strict store never initialises a missing one."""
+    import torch
+    from pn2_b200.util import tf_util
+    st = tf_util.VariableStore(device="cpu", seed=0)
+    tf_util.set_default_store(st)
+    L = tf_util.make_layer("layer1/conv0", 6, 32, True, tf_util.relu)
+    w = np.arange(6 * 32, dtype=np.float32).reshape(6, 32)
+    skipped = st.load_state_dict({"layer1/conv0/weights": w,                    # [k,n] into [1,1,k,n]: allowed
+                                  "layer1/conv0/weights/Adam": np.zeros((1, 1, 6, 32), np.float32),
+                                  "beta1_power": np.float32(0.9),
+                                  "layer9/conv0/bn/moving_mean": np.zeros(4, np.float32)})
+    assert sorted(skipped) == ["beta1_power", "layer1/conv0/weights/Adam"]
+    assert torch.equal(L.w.data.reshape(6, 32), torch.as_tensor(w))
+    assert "layer9/conv0/bn/moving_mean" in st.vars and not st.vars["layer9/conv0/bn/moving_mean"].trainable
+    assert "beta1_power" not in st.vars and "layer1/conv0/weights/Adam" not in st.vars
+    with pytest.raises(ValueError, match="shape"):
+        st.load_state_dict({"layer1/conv0/bn/gamma": np.ones((1, 1, 6, 32), np.float32)})  # would broadcast
+    with pytest.raises(ValueError, match="shape"):
+        st.load_state_dict({"layer1/conv0/weights": np.zeros((32, 6), np.float32)})        # transposed
+    st.strict = True
+    tf_util.make_layer("layer1/conv0", 6, 32, True, tf_util.relu)  # exists: fine
+    with pytest.raises(KeyError, match="not in the loaded checkpoint"):
+        tf_util.make_layer("layer1/conv1", 32, 32, True, tf_util.relu)
+    # a [k,n] kernel loaded BEFORE the layer exists adopts the layer's rank on first use
+    st2 = tf_util.set_default_store(tf_util.VariableStore(device="cpu", seed=0))
+    st2.load_state_dict({"fc1/weights": np.zeros((128, 128), np.float32)})
+    L2 = tf_util.make_layer("fc1", 128, 128, False, None, kernel_rank=3)
+    assert tuple(L2.w.data.shape) == (1, 128, 128)

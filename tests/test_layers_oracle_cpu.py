@@ -212,3 +212,48 @@ def test_full_model_shapes_variables_and_finite_difference_gradients():
         lm = loss_of(pp)[1].item()
         fd = (lp - lm) / (2 * eps)
         assert abs(fd - grads[name][pos]) < 3e-6 + 1e-5 * abs(fd), (name, fd, grads[name][pos])
+
+
+def test_decisions_make_the_oracle_differentiate_the_given_piecewise_function():
+    """lr.Ctx(decisions=...): with its own ReLU masks / pooling winners the oracle's outputs and gradients
+    are unchanged; a flipped near-zero element changes the gradient path but is accepted as a rounding flip;
+    a flip far from the kink is reported by compare_grads."""
+    import torch
+    from oracle import layers_ref as lr
+    rs = np.random.RandomState(5)
+    xyz = rs.random_sample((2, 128, 3)).astype(np.float32)
+    pts = rs.random_sample((2, 128, 3)).astype(np.float32)
+    params = {}
+    k = 6
+    for i, n in enumerate([8, 16]):
+        lr.init_conv(params, rs, "sa/conv%d" % i, k, n)
+        k = n
+
+    def run(decisions=None):
+        ctx = lr.Ctx(params, is_training=True, bn_decay=0.5, decisions=decisions)
+        p = torch.tensor(pts, dtype=torch.float64, requires_grad=True)
+        _, out, _ = lr.sa_module(ctx, xyz, p, 16, 0.4, 8, [8, 16], "sa")
+        out.sum().backward()
+        return ctx, out.detach().numpy(), ctx.grads()
+
+    ctx0, out0, g0 = run()
+    own = {}
+    for scope in ("sa/conv0", "sa/conv1"):
+        own[scope + "/relu_mask"] = (ctx0.acts[scope].detach().numpy() > 0).reshape(-1, ctx0.acts[scope].shape[-1]).astype(np.uint8)
+    act = ctx0.acts["sa/conv1"].detach()
+    own["sa/conv1/argmax"] = act.argmax(dim=2).numpy().reshape(-1, act.shape[-1]).astype(np.int32)
+    ctx1, out1, g1 = run(own)
+    np.testing.assert_allclose(out1, out0, atol=1e-12)
+    for k2 in g0:
+        np.testing.assert_allclose(g1[k2], g0[k2], atol=1e-12)
+    assert not lr.compare_grads(ctx1, g0) and all(c == 0 for c, _ in ctx1.flips.values())
+    # a decision far from the kink is not a rounding flip
+    bad = dict(own)
+    m = own["sa/conv0/relu_mask"].copy()
+    pre = ctx0.acts["sa/conv0"].detach().numpy().reshape(m.shape)
+    r, c = np.unravel_index(np.argmax(pre), pre.shape)
+    m[r, c] = 0
+    bad["sa/conv0/relu_mask"] = m
+    ctx2, _, _ = run(bad)
+    msgs = lr.compare_grads(ctx2, g0)
+    assert any("not a rounding flip" in s for s in msgs), msgs

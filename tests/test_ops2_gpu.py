@@ -1,13 +1,13 @@
-"""GPU tests of kernels that exist but are NOT on any default path yet: they were written after the
-round's GPU budget was spent, so nothing here has run on a B200.  Skipped unless PN2_EXPERIMENTAL=1
-(tests/conftest.py); the first GPU call of the next round runs them, and a kernel is switched on by
-default only after its test is green and its timing is recorded under profiles/."""
+"""GPU parity of the two kernels promoted to default paths in round 2 after their tests ran green on a
+B200 and an A/B timing was recorded (profiles/README_r02.md): the cluster FPS with the push + remote
+mbarrier handshake (default of pn2_fps above 8192 points) and the hashed-grid ball query (default of
+tf_grouping.query_ball_point at n >= 4096).  Both are also called through their explicit entry points."""
 import numpy as np
 import pytest
 
 from _util import rng_cloud, to_cuda
 
-pytestmark = [pytest.mark.gpu, pytest.mark.experimental]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture(scope="module")
@@ -16,55 +16,6 @@ def ops(cuda):
     from pn2_b200.tf_ops import tf_grouping, tf_interpolate, tf_sampling
     from oracle import oracle as orc
     return tf_sampling, tf_grouping, tf_interpolate, orc
-
-
-def _three_nn_filtered(x1, x2):
-    import torch
-    from pn2_b200._ffi import F32, I32, call, ptr
-    b, n, _ = x1.shape
-    m = x2.shape[1]
-    dist = torch.empty((b, n, 3), dtype=F32, device=x1.device)
-    idx = torch.empty((b, n, 3), dtype=I32, device=x1.device)
-    call("pn2_three_nn_filtered", b, n, m, ptr(x1, F32), ptr(x2, F32), ptr(dist, F32), ptr(idx, I32))
-    return dist, idx
-
-
-def _nn_cases():
-    rs = np.random.RandomState(0)
-    u = lambda *s: rs.random_sample(s)  # noqa: E731
-    return {
-        "uniform": (u(2, 3000, 3), u(2, 2500, 3)),
-        "cfg2_fp4": (u(16, 8192, 3) * [10, 10, 5], u(16, 1024, 3) * [10, 10, 5]),
-        "offset_1e3": (1000 + 1e-3 * u(1, 700, 3), 1000 + 1e-3 * u(1, 4100, 3)),
-        "offset_1e5": (1e5 + u(1, 700, 3), 1e5 + u(1, 2049, 3)),
-        "lattice": (rs.randint(0, 3, (2, 500, 3)), rs.randint(0, 3, (2, 900, 3))),
-        "tiny": (1e-22 * u(1, 300, 3), 1e-22 * u(1, 700, 3)),
-        "duplicates": (np.repeat(u(1, 100, 3), 4, 1), np.repeat(u(1, 300, 3), 5, 1)),
-        "huge": (1e18 * u(1, 300, 3), 1e18 * u(1, 800, 3)),
-        "anisotropic": (u(1, 500, 3) * [1e-3, 1, 1e3], u(1, 3000, 3) * [1e-3, 1, 1e3]),
-        "three_known": (u(2, 100, 3), u(2, 3, 3)),
-    }
-
-
-@pytest.mark.parametrize("name", sorted(_nn_cases()))
-def test_three_nn_filtered_is_bit_identical(ops, name):
-    """The fp32 gate may only skip pairs that cannot enter the top 3: indices and distances must equal
-    the oracle's bit for bit, also under cancellation (large offsets), underflow (1e-22), overflow of
-    the fp32 distance (1e18) and on tie lattices."""
-    _, _, _, orc = ops
-    x1, x2 = (np.ascontiguousarray(a, dtype=np.float32) for a in _nn_cases()[name])
-    dist, idx = _three_nn_filtered(to_cuda(x1), to_cuda(x2))
-    ed, ei = orc.three_nn(x1, x2, threads=8)
-    np.testing.assert_array_equal(idx.cpu().numpy(), ei)
-    np.testing.assert_array_equal(dist.cpu().numpy().view(np.uint32), ed.view(np.uint32))
-
-
-def test_three_nn_filtered_matches_default_kernel_full_size(ops):
-    _, _, ti, _ = ops
-    x1, x2 = to_cuda(rng_cloud(1, 16, 8192)), to_cuda(rng_cloud(2, 16, 1024))
-    d0, i0 = ti.three_nn(x1, x2)
-    d1, i1 = _three_nn_filtered(x1, x2)
-    assert bool((i0 == i1).all()) and bool((d0 == d1).all())
 
 
 # --------------------------------------------------------------- cluster FPS with the mbarrier handshake
@@ -174,37 +125,3 @@ def test_ball_query_grid_non_finite_inputs_match_default_kernel(ops):
     i0, c0 = tg.query_ball_point(0.2, 16, a, b)
     i1, c1 = _ball_grid(0.2, 16, a, b)
     assert bool((i0 == i1).all()) and bool((c0 == c1).all())
-
-
-# ------------------------------------------------------------------ label vote with the fp32 gate
-def test_knn_vote_filtered_matches_oracle_in_subprocess(cuda):
-    """PN2_KNN_VOTE_FILTER is read once per process, so the gated kernel is exercised in a child process:
-    labels and colours for knn 1..32 on uniform, lattice (ties) and large-offset clouds must equal the oracle."""
-    import os
-    import subprocess
-    import sys
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    code = r"""
-import sys, numpy as np, torch
-sys.path.insert(0, %r)
-import pn2_b200
-from pn2_b200.tf_ops import tf_interpolate as ti
-from oracle import oracle as orc
-rs = np.random.RandomState(0)
-cases = [(rs.random_sample((3000, 3)), rs.random_sample((2000, 3))),
-         (rs.randint(0, 5, (900, 3)), rs.randint(0, 5, (700, 3))),
-         (1000 + 1e-3 * rs.random_sample((2100, 3)), 1000 + 1e-3 * rs.random_sample((500, 3))),
-         (rs.random_sample((2, 3)), rs.random_sample((50, 3)))]
-for sp, dp in cases:
-    sp, dp = sp.astype(np.float32), dp.astype(np.float32)
-    sl = rs.randint(0, 9, len(sp)).astype(np.int32)
-    for k in (1, 3, 5, 9, 17, 32):
-        lab, col = ti.interpolate_label_with_color(torch.as_tensor(sp).cuda(), torch.as_tensor(sl).cuda(),
-                                                   torch.as_tensor(dp).cuda(), k)
-        el, ec = orc.interpolate_label_with_color(sp, sl, dp, k)
-        assert (lab.cpu().numpy() == el).all() and (col.cpu().numpy() == ec).all(), (len(sp), k)
-print("VOTE_FILTER_OK")
-""" % root
-    env = dict(os.environ, PN2_KNN_VOTE_FILTER="1")
-    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
-    assert "VOTE_FILTER_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]

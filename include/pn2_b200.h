@@ -129,10 +129,19 @@ int pn2_three_interpolate_grad(int b, int n, int c, int m, const float *grad_out
                                const float *weight, float *grad_points, pn2_stream_t s);
 
 /* replaces selectionSortLauncher           tf_ops/tf_grouping.cu:145-149 ("next" scope)
- * dist (b,m,n) -> outi (b,m,n), out (b,m,n); only the first k of each row are meaningful
- * and, unlike the reference, ONLY the first k entries are written. */
+ * dist (b,m,n) -> outi (b,m,n), out (b,m,n): the reference's swap-based partial selection sort, bit for
+ * bit -- the first k of each row ascending (ties in the reference's permuted-position order), the rest of
+ * the row in the order the swaps leave it.  k > 128 with n > 128: PN2_EUNSUPPORTED. */
 int pn2_selection_sort(int b, int n, int m, int k, const float *dist, int *outi, float *out,
                        pn2_stream_t s);
+
+/* Fused k nearest neighbours: knn_point of tf_ops/tf_grouping.py:64-89 (squared-distance matrix (b,m,n)
+ * in TF + selectionSortLauncher, tf_grouping.cu:95-136) WITHOUT the matrix: distances are evaluated on the
+ * fly in fp32 ((dx*dx + dy*dy) + dz*dz, left to right over the c coordinates), the selection is the
+ * reference's (ties included).  xyz1 (b,n,c) data, xyz2 (b,m,c) queries -> val (b,m,k) squared distances,
+ * idx (b,m,k).  1 <= k <= min(n, 128). */
+int pn2_knn_point(int b, int n, int c, int m, int k, const float *xyz1, const float *xyz2, float *val,
+                  int *idx, pn2_stream_t s);
 
 /* ===== group 2: fused layer pieces (no reference launcher; they replace the TF
  * graph ops util/pointnet_util.py and util/tf_util.py string between the custom

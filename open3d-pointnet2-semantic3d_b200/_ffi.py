@@ -42,6 +42,7 @@ SIGNATURES = {
     "pn2_three_interpolate": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "pn2_three_interpolate_grad": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "pn2_selection_sort": [_i, _i, _i, _i, _vp, _vp, _vp, _vp],
+    "pn2_knn_point": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "pn2_group_concat": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp],
     "pn2_group_concat_ld": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _i, _vp],
     "pn2_group_concat_grad": [_i, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp],

@@ -340,48 +340,222 @@ __global__ void group_concat_grad_kernel(int n, int m, int ns, int c, int w, int
     }
 }
 
-// ---- selection sort ("next" scope, tf_grouping.cu:95-136): k passes of arg-min ------------
-// one warp per (b,m) row; out/outi get the k smallest in ascending order, ties -> earliest.
-__global__ void selection_topk_kernel(long rows, int n, int k, const float *__restrict__ dist,
-                                      int *__restrict__ outi, float *__restrict__ out) {
-    long row = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
-    int lane = threadIdx.x & 31;
-    if (row >= rows) return;
-    const float *d = dist + row * n;
-    float *o = out + row * n;
-    int *oi = outi + row * n;
-    // The reference's swap-based selection sort equals: repeatedly take the minimum of the
-    // not-yet-selected entries, earliest position (in the CURRENT, swapped order) on ties.
-    // For distinct values that is the k smallest ascending; exact tie order of the swapped
-    // array is reproduced by tests only on tie-free data.
-    float prev_v = -INFINITY;
-    int prev_i = -1;
-    for (int s = 0; s < k && s < n; ++s) {
-        float bv = INFINITY;
-        int bi = 0x7FFFFFFF;
-        for (int t = lane; t < n; t += 32) {
-            float v = __ldg(d + t);
-            bool after = (v > prev_v) || (v == prev_v && t > prev_i);
-            if (after && (v < bv || (v == bv && t < bi))) {
-                bv = v;
+// ---- selection sort / k nearest neighbours (tf_grouping.cu:95-136, tf_grouping.py:64-89) ----------
+// The reference runs k passes of a swap-based selection sort over a row of n distances: pass s finds
+// the first minimum (strict '<') of positions s..n-1 of the CURRENT array and swaps it with position
+// s.  The swaps permute the array, so among equal distances "first" means first in the permuted
+// order, not lowest index.  A warp reproduces that exactly WITHOUT the array: positions whose content
+// differs from the original row are at most k (each pass displaces one element), so they are kept in
+// a small per-warp table (position, value, original index) plus one bit per position; a pass scans the
+// untouched positions straight from the row source (a distance matrix, or distances evaluated on the
+// fly from the coordinates -- the fused kNN never materialises the (b,m,n) matrix) and then the table.
+// NaN follows the reference's comparisons: `p[t] < p[min]` is false for NaN on either side.
+constexpr int SEL_WARPS = 8;
+constexpr int SEL_KMAX = 128;  // table entries per warp (one per pass)
+
+struct RowFromMatrix {
+    const float *d;
+    __device__ __forceinline__ float operator()(int t) const { return __ldg(d + t); }
+};
+template <int C>
+struct RowFromXyz {  // tf_grouping.py:79-82: reduce_sum((xyz1 - xyz2)**2, -1), fp32, left to right
+    const float *x1;
+    const float *q;
+    int c;
+    __device__ __forceinline__ float operator()(int t) const {
+        const float *p = x1 + (size_t)t * (C > 0 ? C : c);
+        float acc = 0.f;
+        if (C > 0) {
+#pragma unroll
+            for (int i = 0; i < (C > 0 ? C : 1); ++i) {
+                const float df = __fsub_rn(__ldg(p + i), q[i]);
+                acc = i == 0 ? __fmul_rn(df, df) : __fadd_rn(acc, __fmul_rn(df, df));
+            }
+        } else {
+            for (int i = 0; i < c; ++i) {
+                const float df = __fsub_rn(__ldg(p + i), __ldg(q + i));
+                acc = i == 0 ? __fmul_rn(df, df) : __fadd_rn(acc, __fmul_rn(df, df));
+            }
+        }
+        return acc;
+    }
+};
+
+// (value, position) of the warp's best candidate under the reference's scan order: smaller value,
+// then lower position; NaN never wins.  pos == INT_MAX: no candidate.
+__device__ __forceinline__ void sel_reduce(float &v, int &pos, int &aux) {
+#pragma unroll
+    for (int off = 16; off; off >>= 1) {
+        const float ov = __shfl_xor_sync(0xFFFFFFFFu, v, off);
+        const int op = __shfl_xor_sync(0xFFFFFFFFu, pos, off);
+        const int oa = __shfl_xor_sync(0xFFFFFFFFu, aux, off);
+        if (op != 0x7FFFFFFF && (pos == 0x7FFFFFFF || ov < v || (ov == v && op < pos))) {
+            v = ov;
+            pos = op;
+            aux = oa;
+        }
+    }
+}
+
+// One row: writes the first min(k,n) selected (value, original index) pairs through `emit(s, v, i)`;
+// `bits` (n bits, zeroed by the caller's warp), tpos/tval/tidx: the warp's table in shared memory.
+template <typename Row, typename Emit>
+__device__ __forceinline__ int selection_passes(const Row &row, int n, int k, unsigned *bits, int *tpos,
+                                                float *tval, int *tidx, Emit emit) {
+    const int lane = threadIdx.x & 31;
+    int nt = 0;
+    const int passes = k < n ? k : n;
+    for (int s = 0; s < passes; ++s) {
+        // content of position s: displaced element or the original
+        float cs_v;
+        int cs_i;
+        {
+            float v = 0.f;
+            int pos = 0x7FFFFFFF, aux = 0;
+            for (int e = lane; e < nt; e += 32)
+                if (tpos[e] == s) {
+                    v = tval[e];
+                    pos = s;
+                    aux = tidx[e];
+                }
+            // at most one live entry per position: a plain "any lane has it" reduction
+            const unsigned has = __ballot_sync(0xFFFFFFFFu, pos == s);
+            if (has) {
+                const int src = __ffs(has) - 1;
+                cs_v = __shfl_sync(0xFFFFFFFFu, v, src);
+                cs_i = __shfl_sync(0xFFFFFFFFu, aux, src);
+            } else {
+                cs_v = row(s);
+                cs_i = s;
+            }
+        }
+        // untouched positions t > s (original content), then displaced ones
+        float bv = 0.f;
+        int bp = 0x7FFFFFFF, bi = 0;
+        for (int t = s + 1 + lane; t < n; t += 32) {
+            if (bits[t >> 5] >> (t & 31) & 1u) continue;
+            const float d = row(t);
+            if (d == d && (bp == 0x7FFFFFFF || d < bv)) {  // ascending t per lane: strict '<' keeps the first
+                bv = d;
+                bp = t;
                 bi = t;
             }
         }
-#pragma unroll
-        for (int off = 16; off; off >>= 1) {
-            float ov = __shfl_xor_sync(0xFFFFFFFFu, bv, off);
-            int oi2 = __shfl_xor_sync(0xFFFFFFFFu, bi, off);
-            if (ov < bv || (ov == bv && oi2 < bi)) {
-                bv = ov;
-                bi = oi2;
+        for (int e = lane; e < nt; e += 32) {
+            const int tp = tpos[e];
+            const float d = tval[e];
+            if (tp > s && d == d && (bp == 0x7FFFFFFF || d < bv || (d == bv && tp < bp))) {
+                bv = d;
+                bp = tp;
+                bi = tidx[e];
             }
         }
-        if (lane == 0) {
-            o[s] = bv;
-            oi[s] = bi;
+        sel_reduce(bv, bp, bi);
+        // the reference keeps min = s unless something is strictly smaller than the content of s
+        const bool move = bp != 0x7FFFFFFF && bv < cs_v;
+        const float out_v = move ? bv : cs_v;
+        const int out_i = move ? bi : cs_i;
+        emit(s, out_v, out_i);
+        if (move) {  // content of s goes to position bp
+            bool updated = false;
+            for (int e = lane; e < nt; e += 32)
+                if (tpos[e] == bp) {
+                    tval[e] = cs_v;
+                    tidx[e] = cs_i;
+                    updated = true;
+                }
+            const bool any = __any_sync(0xFFFFFFFFu, updated);
+            if (!any && lane == 0) {
+                tpos[nt] = bp;
+                tval[nt] = cs_v;
+                tidx[nt] = cs_i;
+                bits[bp >> 5] |= 1u << (bp & 31);
+            }
+            if (!any) ++nt;
         }
-        prev_v = bv;
-        prev_i = bi;
+        __syncwarp();
+    }
+    return nt;
+}
+
+__global__ void __launch_bounds__(32 * SEL_WARPS)
+selection_sort_kernel(long rows, int n, int k, const float *__restrict__ dist, int *__restrict__ outi,
+                      float *__restrict__ out) {
+    extern __shared__ unsigned sel_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int words = (n + 31) >> 5;
+    unsigned *bits = sel_smem + (size_t)warp * words;
+    int *tpos = reinterpret_cast<int *>(sel_smem + (size_t)SEL_WARPS * words) + warp * SEL_KMAX;
+    float *tval = reinterpret_cast<float *>(sel_smem + (size_t)SEL_WARPS * words + SEL_WARPS * SEL_KMAX) +
+                  warp * SEL_KMAX;
+    int *tidx = reinterpret_cast<int *>(sel_smem + (size_t)SEL_WARPS * words + 2 * SEL_WARPS * SEL_KMAX) +
+                warp * SEL_KMAX;
+    for (long row = blockIdx.x * (long)SEL_WARPS + warp; row < rows; row += (long)gridDim.x * SEL_WARPS) {
+        for (int w = lane; w < words; w += 32) bits[w] = 0u;
+        __syncwarp();
+        const float *d = dist + row * n;
+        float *o = out + row * n;
+        int *oi = outi + row * n;
+        RowFromMatrix src{d};
+        const int nt = selection_passes(src, n, k, bits, tpos, tval, tidx, [&](int s, float v, int i) {
+            if (lane == 0) {
+                o[s] = v;
+                oi[s] = i;
+            }
+        });
+        // the tail of the permuted array (the reference returns it, tf_grouping.cu:108-113): original
+        // content except at displaced positions
+        const int passes = k < n ? k : n;
+        for (int t = passes + lane; t < n; t += 32) {
+            if (!(bits[t >> 5] >> (t & 31) & 1u)) {
+                o[t] = __ldg(d + t);
+                oi[t] = t;
+            }
+        }
+        for (int e = lane; e < nt; e += 32)
+            if (tpos[e] >= passes) {
+                o[tpos[e]] = tval[e];
+                oi[tpos[e]] = tidx[e];
+            }
+        __syncwarp();
+    }
+}
+
+template <int C>
+__global__ void __launch_bounds__(32 * SEL_WARPS)
+knn_point_kernel(int n, int c, int m, int k, const float *__restrict__ xyz1, const float *__restrict__ xyz2,
+                 float *__restrict__ val, int *__restrict__ idx) {
+    extern __shared__ unsigned sel_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int words = (n + 31) >> 5;
+    unsigned *bits = sel_smem + (size_t)warp * words;
+    int *tpos = reinterpret_cast<int *>(sel_smem + (size_t)SEL_WARPS * words) + warp * SEL_KMAX;
+    float *tval = reinterpret_cast<float *>(sel_smem + (size_t)SEL_WARPS * words + SEL_WARPS * SEL_KMAX) +
+                  warp * SEL_KMAX;
+    int *tidx = reinterpret_cast<int *>(sel_smem + (size_t)SEL_WARPS * words + 2 * SEL_WARPS * SEL_KMAX) +
+                warp * SEL_KMAX;
+    const int cloud = blockIdx.y;
+    const int cc = C > 0 ? C : c;
+    const float *x1 = xyz1 + (size_t)cloud * n * cc;
+    for (int j = blockIdx.x * SEL_WARPS + warp; j < m; j += gridDim.x * SEL_WARPS) {
+        for (int w = lane; w < words; w += 32) bits[w] = 0u;
+        __syncwarp();
+        const float *q = xyz2 + ((size_t)cloud * m + j) * cc;
+        float qreg[C > 0 ? C : 1];
+        if (C > 0) {
+#pragma unroll
+            for (int i = 0; i < (C > 0 ? C : 1); ++i) qreg[i] = __ldg(q + i);
+        }
+        RowFromXyz<C> src{x1, C > 0 ? qreg : q, cc};
+        float *ov = val + ((size_t)cloud * m + j) * k;
+        int *oi = idx + ((size_t)cloud * m + j) * k;
+        selection_passes(src, n, k, bits, tpos, tval, tidx, [&](int s, float v, int i) {
+            if (lane == 0) {
+                ov[s] = v;
+                oi[s] = i;
+            }
+        });
+        __syncwarp();
     }
 }
 
@@ -745,6 +919,10 @@ PN2_API int pn2_group_concat_grad(int b, int n, int m, int nsample, int c, const
     return finish_launch();
 }
 
+static size_t selection_smem(int n) {
+    return ((size_t)SEL_WARPS * ((n + 31) / 32) + 3 * (size_t)SEL_WARPS * SEL_KMAX) * 4;
+}
+
 PN2_API int pn2_selection_sort(int b, int n, int m, int k, const float *dist, int *outi,
                                float *out, pn2_stream_t s) {
     PN2_REQUIRE(k > 0);  // tf_grouping.cpp:142-144 "SelectionSort expects positive k"
@@ -754,10 +932,45 @@ PN2_API int pn2_selection_sort(int b, int n, int m, int k, const float *dist, in
     PN2_REQUIRE_PTR(dist);
     PN2_REQUIRE_PTR(outi);
     PN2_REQUIRE_PTR(out);
-    int threads = 128;
-    long blocks = ceil_div<long>(rows * 32, threads);
-    selection_topk_kernel<<<(unsigned)blocks, threads, 0, as_stream(s)>>>(rows, n, k, dist, outi,
-                                                                         out);
+    if (k > SEL_KMAX && n > SEL_KMAX) return PN2_EUNSUPPORTED;  // table of displaced elements
+    const size_t smem = selection_smem(n);
+    if (smem > 200 * 1024) return PN2_EUNSUPPORTED;
+    int rc = opt_in_dyn_smem(selection_sort_kernel, smem);
+    if (rc) return rc;
+    long blocks = ceil_div<long>(rows, SEL_WARPS);
+    if (blocks > 148L * 8) blocks = 148L * 8;
+    selection_sort_kernel<<<(unsigned)blocks, 32 * SEL_WARPS, smem, as_stream(s)>>>(rows, n, k, dist, outi, out);
+    return finish_launch();
+}
+
+/* Fused kNN (tf_grouping.py:64-89 without its (b,m,n) distance tensor): val (b,m,k) squared distances,
+ * idx (b,m,k), the first k entries of the reference's selection sort, bit for bit (ties included). */
+PN2_API int pn2_knn_point(int b, int n, int c, int m, int k, const float *xyz1, const float *xyz2,
+                          float *val, int *idx, pn2_stream_t s) {
+    PN2_REQUIRE(k > 0 && c > 0);
+    PN2_REQUIRE(b >= 0 && n > 0 && m >= 0);
+    PN2_REQUIRE(k <= n);  // tf.slice(outi, [0,0,0], [-1,-1,k]) needs k <= n
+    if (b == 0 || m == 0) return PN2_OK;
+    PN2_REQUIRE_PTR(xyz1);
+    PN2_REQUIRE_PTR(xyz2);
+    PN2_REQUIRE_PTR(val);
+    PN2_REQUIRE_PTR(idx);
+    if (k > SEL_KMAX) return PN2_EUNSUPPORTED;
+    const size_t smem = selection_smem(n);
+    if (smem > 200 * 1024) return PN2_EUNSUPPORTED;
+    unsigned gx = (unsigned)ceil_div(m, SEL_WARPS);
+    if ((long)gx * b > 148L * 16) gx = (unsigned)max(1L, 148L * 16 / b);
+    dim3 grid(gx, (unsigned)b);
+    int rc;
+    if (c == 3) {
+        rc = opt_in_dyn_smem(knn_point_kernel<3>, smem);
+        if (rc) return rc;
+        knn_point_kernel<3><<<grid, 32 * SEL_WARPS, smem, as_stream(s)>>>(n, c, m, k, xyz1, xyz2, val, idx);
+    } else {
+        rc = opt_in_dyn_smem(knn_point_kernel<0>, smem);
+        if (rc) return rc;
+        knn_point_kernel<0><<<grid, 32 * SEL_WARPS, smem, as_stream(s)>>>(n, c, m, k, xyz1, xyz2, val, idx);
+    }
     return finish_launch();
 }
 

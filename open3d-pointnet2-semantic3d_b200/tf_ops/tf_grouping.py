@@ -108,21 +108,32 @@ def group_point_grad(points, idx, grad_out):
 
 
 def select_top_k(k, dist):
-    """dist (B,m,n) -> (idx (B,m,n) int32, dist_out (B,m,n)); only [..., :k] is meaningful
-    (the k smallest, ascending).  Entries beyond k are NOT the reference's permutation."""
+    """dist (B,m,n) -> (idx (B,m,n) int32, dist_out (B,m,n)): the reference's partial selection sort
+    (tf_grouping.cu:95-136) bit for bit -- the k smallest ascending in [..., :k] (ties in the reference's
+    order), the remainder of each row in the order its swaps leave it."""
     _need(int(k) > 0, "SelectionSort expects positive k")
     _need(dist.dim() == 3, "SelectionSort expects (b,m,n) dist shape.")
     b, m, n = dist.shape
     dist = dist.detach().contiguous()
-    outi = torch.zeros((b, m, n), dtype=I32, device=dist.device)
-    out = torch.zeros((b, m, n), dtype=F32, device=dist.device)
+    outi = torch.empty((b, m, n), dtype=I32, device=dist.device)
+    out = torch.empty((b, m, n), dtype=F32, device=dist.device)
     call("pn2_selection_sort", b, n, m, int(k), ptr(dist, F32), ptr(outi, I32), ptr(out, F32))
     return outi, out
 
 
 def knn_point(k, xyz1, xyz2):
-    """k nearest data points of every query (tf_grouping.py:64-89): squared-distance matrix
-    (b,m,n) followed by select_top_k.  Returns (val (B,m,k), idx (B,m,k))."""
-    d = ((xyz2.detach()[:, :, None, :] - xyz1.detach()[:, None, :, :]) ** 2).sum(-1)
-    outi, out = select_top_k(k, d)
-    return out[:, :, :k].contiguous(), outi[:, :, :k].contiguous()
+    """k nearest data points of every query (tf_grouping.py:64-89).  xyz1 (B,n,c) data, xyz2 (B,m,c)
+    queries -> (val (B,m,k) squared distances, idx (B,m,k) int32).  One fused kernel: distances on the
+    fly + the reference's selection, no (b,m,n) tensor (csrc/pn2_grouping.cu knn_point_kernel)."""
+    k = int(k)
+    _need(k > 0, "SelectionSort expects positive k")
+    _need(xyz1.dim() == 3 and xyz2.dim() == 3 and xyz1.shape[0] == xyz2.shape[0]
+          and xyz1.shape[2] == xyz2.shape[2], "knn_point expects (b,n,c) xyz1 and (b,m,c) xyz2")
+    b, n, c = xyz1.shape
+    m = xyz2.shape[1]
+    _need(k <= n, "knn_point: k must not exceed the number of data points")
+    x1, x2 = xyz1.detach().contiguous(), xyz2.detach().contiguous()
+    val = torch.empty((b, m, k), dtype=F32, device=x1.device)
+    idx = torch.empty((b, m, k), dtype=I32, device=x1.device)
+    call("pn2_knn_point", b, n, c, m, k, ptr(x1, F32), ptr(x2, F32), ptr(val, F32), ptr(idx, I32))
+    return val, idx

@@ -134,10 +134,14 @@ def group_rows(x, idx):
     return out.reshape(b, m, ns, x.shape[2])
 
 
-def sample_and_group(npoint, radius, nsample, xyz_np, points, use_xyz=True, order="xyz_first"):
+def sample_and_group(npoint, radius, nsample, xyz_np, points, use_xyz=True, order="xyz_first", knn=False):
     fps = orc.farthest_point_sample(npoint, xyz_np)
     new_xyz_np = orc.gather_point(xyz_np, fps)
-    idx, cnt = orc.query_ball_point(radius, nsample, xyz_np, new_xyz_np)
+    if knn:  # pointnet_util.py:39-40
+        _, idx = orc.knn_point(nsample, xyz_np, new_xyz_np)
+        cnt = None
+    else:
+        idx, cnt = orc.query_ball_point(radius, nsample, xyz_np, new_xyz_np)
     xyz = _t(xyz_np)
     grouped_xyz = group_rows(xyz, idx) - _t(new_xyz_np)[:, :, None, :]
     if points is not None:

@@ -167,6 +167,18 @@ def select_top_k(k, dist):
     return outi, out
 
 
+def knn_point(k, xyz1, xyz2):
+    """tf_grouping.py:64-89: (val (b,m,k) squared distances, idx (b,m,k)) -- the first k entries of the
+    reference's selection sort over the fp32 distance rows."""
+    xyz1, xyz2 = _f32(xyz1), _f32(xyz2)
+    b, n, c = xyz1.shape
+    m = xyz2.shape[1]
+    val = np.empty((b, m, k), np.float32)
+    idx = np.empty((b, m, k), np.int32)
+    lib().orc_knn_point(_ci(b), _ci(n), _ci(c), _ci(m), _ci(k), _p(xyz1), _p(xyz2), _p(val), _p(idx))
+    return val, idx
+
+
 def cumsum(inp):
     """Row-wise inclusive prefix sum in the reference's rounding order (tf_sampling.cu:7-92)."""
     inp = _f32(inp)

@@ -20,6 +20,7 @@
  *   orc_three_interpolate      tf_ops/tf_interpolate.cpp:307-330
  *   orc_three_interpolate_grad tf_ops/tf_interpolate.cpp:397-421 (+memset :477)
  *   orc_selection_sort         tf_ops/tf_grouping.cu:95-136
+ *   orc_knn_point              tf_ops/tf_grouping.py:64-89 (+ tf_grouping.cu:95-136)
  *   orc_interpolate_label_with_color  tf_ops/tf_interpolate.cpp:71-115 (kNN label vote)
  *   orc_cumsum                 tf_ops/tf_sampling.cu:7-92 (prefix sum, reference rounding order)
  *   orc_prob_sample            tf_ops/tf_sampling.cu:7-110 (cumsum + binary search)
@@ -301,6 +302,44 @@ ORC_API void orc_selection_sort(int b, int n, int m, int k, const float *dist,
             }
         }
     }
+}
+
+/* tf_grouping.py:64-89 knn_point: dist = reduce_sum((xyz1 - xyz2)**2, -1) in fp32 (left to right over
+ * the c coordinates, separate multiply and add), select_top_k(k, dist) = the selection sort above, then the
+ * first k columns.  The (b,m,n) matrix is built one row at a time.  PARITY UNPINNED for the summation
+ * order of the three squares (TensorFlow absent; test_tf_ops.py:9-36 asserts nothing). */
+ORC_API void orc_knn_point(int b, int n, int c, int m, int k, const float *xyz1, const float *xyz2,
+                           float *val, int *idx) {
+    float *p = (float *)malloc(sizeof(float) * (size_t)n);
+    int *pi = (int *)malloc(sizeof(int) * (size_t)n);
+    for (int i = 0; i < b; ++i)
+        for (int j = 0; j < m; ++j) {
+            const float *q = xyz2 + ((size_t)i * m + j) * c;
+            for (int t = 0; t < n; ++t) {
+                const float *x = xyz1 + ((size_t)i * n + t) * c;
+                float acc = 0.f;
+                for (int a = 0; a < c; ++a) {
+                    const float df = x[a] - q[a];
+                    const float sq = df * df;
+                    acc = a == 0 ? sq : acc + sq;
+                }
+                p[t] = acc;
+                pi[t] = t;
+            }
+            for (int s = 0; s < k && s < n; ++s) {
+                int mn = s;
+                for (int t = s + 1; t < n; ++t)
+                    if (p[t] < p[mn]) mn = t;
+                if (mn != s) {
+                    float tf = p[mn]; p[mn] = p[s]; p[s] = tf;
+                    int ti = pi[mn]; pi[mn] = pi[s]; pi[s] = ti;
+                }
+                val[((size_t)i * m + j) * k + s] = p[s];
+                idx[((size_t)i * m + j) * k + s] = pi[s];
+            }
+        }
+    free(p);
+    free(pi);
 }
 
 /* ------------------------------------------------------------------------- */

@@ -5,7 +5,7 @@
  * tf_ops/tf_sampling.cu and tf_ops/tf_grouping.cu where they lie under
  * /root/reference (never copied into this repo) and links them with this shim
  * into oracle/_ref/libref_tfops.so.  The shim only forwards to the launchers the
- * reference defines (tf_sampling.cu:208-229, tf_grouping.cu:138-162) and adds the
+ * reference defines (tf_sampling.cu:208-229, tf_grouping.cu:138-162, incl. selectionSortLauncher :145-149) and adds the
  * memsets the reference's TF glue performs (tf_sampling.cpp:236,
  * tf_grouping.cpp:271) plus a device synchronise + error code, because the
  * reference launchers use the legacy default stream and never check errors.
@@ -21,6 +21,7 @@ void gatherpointLauncher(int b, int n, int m, const float* inp, const int* idx, 
 void scatteraddpointLauncher(int b, int n, int m, const float* out_g, const int* idx, float* inp_g);
 void queryBallPointLauncher(int b, int n, int m, float radius, int nsample, const float* xyz1,
                             const float* xyz2, int* idx, int* pts_cnt);
+void selectionSortLauncher(int b, int n, int m, int k, const float* dist, int* outi, float* out);
 void groupPointLauncher(int b, int n, int c, int m, int nsample, const float* points,
                         const int* idx, float* out);
 void groupPointGradLauncher(int b, int n, int c, int m, int nsample, const float* grad_out,
@@ -64,6 +65,11 @@ int ref_query_ball_point(int b, int n, int m, float radius, int nsample, const f
                          const float* xyz2, int* idx, int* pts_cnt, int sync) {
     cudaMemset(idx, 0, sizeof(int) * (size_t)b * m * nsample);
     queryBallPointLauncher(b, n, m, radius, nsample, xyz1, xyz2, idx, pts_cnt);
+    return finish(sync);
+}
+/* tf_grouping.cu:145-149: partial selection sort of every (b,m) row of the distance matrix */
+int ref_selection_sort(int b, int n, int m, int k, const float* dist, int* outi, float* out, int sync) {
+    selectionSortLauncher(b, n, m, k, dist, outi, out);
     return finish(sync);
 }
 int ref_group_point(int b, int n, int c, int m, int nsample, const float* points, const int* idx,

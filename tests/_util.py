@@ -115,3 +115,34 @@ class RefKernels:
         rc = self.lib.ref_gather_point(b, n, m, self._p(inp), self._p(idx), self._p(out), 1)
         assert rc == 0, rc
         return out
+
+    def selection_sort(self, k, dist):
+        """-> (outi, out): the reference's own selection_sort_gpu (tf_grouping.cu:95-136)."""
+        import torch
+        b, m, n = dist.shape
+        outi = torch.empty((b, m, n), dtype=torch.int32, device=dist.device)
+        out = torch.empty((b, m, n), dtype=torch.float32, device=dist.device)
+        torch.cuda.synchronize()
+        rc = self.lib.ref_selection_sort(b, n, m, int(k), self._p(dist), self._p(outi), self._p(out), 1)
+        assert rc == 0, rc
+        return outi, out
+
+    def gather_point_grad(self, inp, idx, out_g):
+        import torch
+        b, n, _ = inp.shape
+        m = idx.shape[1]
+        g = torch.empty((b, n, 3), dtype=torch.float32, device=inp.device)
+        torch.cuda.synchronize()
+        rc = self.lib.ref_gather_point_grad(b, n, m, self._p(out_g), self._p(idx), self._p(g), 1)
+        assert rc == 0, rc
+        return g
+
+    def group_point_grad(self, points, idx, grad_out):
+        import torch
+        b, n, c = points.shape
+        _, m, ns = idx.shape
+        g = torch.empty((b, n, c), dtype=torch.float32, device=points.device)
+        torch.cuda.synchronize()
+        rc = self.lib.ref_group_point_grad(b, n, c, m, ns, self._p(grad_out), self._p(idx), self._p(g), 1)
+        assert rc == 0, rc
+        return g

@@ -10,7 +10,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("script", ["sim_scan.py", "sim_grid.py"])
+@pytest.mark.parametrize("script", ["sim_scan.py", "sim_grid.py", "sim_select.py"])
 def test_emulation_agrees_with_oracle(script):
     if script == "sim_grid.py":  # needs pn2_ball_threshold from the built library
         import __graft_entry__ as g

@@ -148,6 +148,27 @@ def test_sample_and_group_intermediates(env):
     np.testing.assert_array_equal(np3.cpu().numpy(), exp[..., 3:].astype(np.float32))
 
 
+def test_sample_and_group_knn_branch(env):
+    """knn=True (pointnet_util.py:39-40): the fused kNN kernel feeds the grouping; indices and grouped
+    tensors against the oracle, at the reference's own smoke-test shape (test_tf_ops.py:9-24 runs
+    knn_point(64, ...) + group_point on (32,512,64) / (32,128,3) without asserting anything)."""
+    pu, _, _, lr, _ = env
+    import torch
+    rs = np.random.RandomState(100)
+    xyz = rs.random_sample((4, 512, 3)).astype(np.float32)
+    pts = rs.random_sample((4, 512, 64)).astype(np.float32)
+    e_xyz, e_np, e_idx, _, _, e_gx = lr.sample_and_group(128, 0.1, 64, xyz, torch.tensor(pts, dtype=torch.float64),
+                                                        knn=True)
+    new_xyz, new_points, idx, grouped_xyz = pu.sample_and_group(128, 0.1, 64, to_cuda(xyz), to_cuda(pts), knn=True)
+    np.testing.assert_array_equal(idx.cpu().numpy(), e_idx)
+    np.testing.assert_array_equal(new_xyz.cpu().numpy(), e_xyz)
+    np.testing.assert_allclose(new_points.cpu().numpy(), e_np.numpy(), atol=1e-7)
+    np.testing.assert_allclose(grouped_xyz.cpu().numpy(), e_gx.numpy(), atol=1e-7)
+    # every query is a data point: its nearest neighbour is itself
+    fps = env[0].farthest_point_sample(128, to_cuda(xyz)).cpu().numpy()
+    np.testing.assert_array_equal(idx.cpu().numpy()[:, :, 0], fps)
+
+
 @pytest.mark.parametrize("pooling,mlp2,group_all", [("avg", None, False), ("max_and_avg", None, False),
                                                     ("weighted_avg", None, False),
                                                     ("max", [48, 24], False), ("max", None, True)])

@@ -287,14 +287,115 @@ def test_three_interpolate_grad_check_like_reference(ops):
         assert abs(fd - an) / max(1.0, abs(an)) < 1e-4
 
 
-def test_select_top_k_and_knn(ops):
-    _, tg, _, orc = ops
+def _ref_kernels():
+    from _util import RefKernels
+    try:
+        return RefKernels()
+    except FileNotFoundError:
+        pytest.skip("oracle/_ref not built")
+
+
+def _selection_cases():
     rs = np.random.RandomState(9)
-    d = rs.random_sample((2, 20, 300)).astype(np.float32)
-    outi, out = tg.select_top_k(16, to_cuda(d))
-    ei, eo = orc.select_top_k(16, d)
-    np.testing.assert_array_equal(outi.cpu().numpy()[:, :, :16], ei[:, :, :16])
-    np.testing.assert_array_equal(out.cpu().numpy()[:, :, :16], eo[:, :, :16])
+    nan = rs.randint(0, 4, (1, 12, 150)).astype(np.float32)
+    nan[0, :, ::7] = np.nan
+    nan[0, 3, 0] = np.nan
+    inf = rs.randint(0, 3, (1, 9, 100)).astype(np.float32)
+    inf[inf == 2] = np.inf
+    return {"random": rs.random_sample((2, 20, 300)), "ties4": rs.randint(0, 4, (2, 33, 257)),
+            "ties2": rs.randint(0, 2, (1, 17, 64)), "zeros": np.zeros((1, 5, 90)), "nan": nan, "inf": inf,
+            "wide": rs.random_sample((1, 3, 5000)), "narrow": rs.randint(0, 3, (2, 7, 9))}
+
+
+@pytest.mark.parametrize("name", sorted(_selection_cases()))
+@pytest.mark.parametrize("k", [1, 16, 128])
+def test_select_top_k_matches_oracle_and_reference_kernel(ops, name, k):
+    """The WHOLE output rows (first k and the permuted tail) against the C oracle and against the
+    reference's own selection_sort_gpu running on the same GPU -- ties, NaN and inf included."""
+    _, tg, _, orc = ops
+    d = np.ascontiguousarray(_selection_cases()[name], np.float32)
+    if k > d.shape[2] and d.shape[2] > 128:
+        pytest.skip("k > 128 with n > 128 is not supported")
+    dd = to_cuda(d)
+    outi, out = tg.select_top_k(k, dd)
+    ei, eo = orc.select_top_k(k, d)
+    np.testing.assert_array_equal(outi.cpu().numpy(), ei)
+    np.testing.assert_array_equal(out.cpu().numpy().view(np.uint32), eo.view(np.uint32))
+    ri, ro = _ref_kernels().selection_sort(k, dd)
+    assert bool((ri == outi).all()) and bool((ro.view(torch_i32()) == out.view(torch_i32())).all())
+
+
+def torch_i32():
+    import torch
+    return torch.int32
+
+
+def _sqdist_matrix(x1, x2):
+    """(b,m,n) fp32 matrix exactly as tf_grouping.py:79-82 evaluates it (left to right, no fma)."""
+    d = (x1[:, None, :, :] - x2[:, :, None, :]).astype(np.float32)
+    sq = (d * d).astype(np.float32)
+    acc = sq[..., 0]
+    for a in range(1, sq.shape[-1]):
+        acc = (acc + sq[..., a]).astype(np.float32)
+    return acc
+
+
+@pytest.mark.parametrize("b,n,m,k,c,kind", [(2, 1024, 256, 32, 3, "uniform"), (32, 512, 128, 32, 3, "uniform"),
+                                           (1, 8192, 100, 64, 3, "uniform"), (2, 300, 50, 16, 3, "lattice"),
+                                           (1, 200, 30, 128, 3, "duplicates"), (2, 400, 60, 8, 5, "uniform"),
+                                           (1, 64, 10, 64, 2, "lattice")])
+def test_knn_point_fused_matches_oracle_and_reference_selection(ops, b, n, m, k, c, kind):
+    """knn_point (one fused kernel, no (b,m,n) tensor) == the oracle restatement of tf_grouping.py:64-89 ==
+    the reference's own selection kernel applied to the fp32 distance matrix; (32,512)/(32,128), k=32 is the
+    reference's smoke-test shape (test_tf_ops.py:9-24)."""
+    _, tg, _, orc = ops
+    rs = np.random.RandomState(n + k)
+    if kind == "uniform":
+        x1, x2 = rs.random_sample((b, n, c)), rs.random_sample((b, m, c))
+    elif kind == "lattice":
+        x1, x2 = rs.randint(0, 4, (b, n, c)), rs.randint(0, 4, (b, m, c))
+    else:
+        x1 = np.repeat(rs.random_sample((b, n // 4, c)), 4, 1)
+        x2 = x1[:, :m] + 0.0
+    x1, x2 = np.ascontiguousarray(x1, np.float32), np.ascontiguousarray(x2, np.float32)
+    val, idx = tg.knn_point(k, to_cuda(x1), to_cuda(x2))
+    ev, ei = orc.knn_point(k, x1, x2)
+    np.testing.assert_array_equal(idx.cpu().numpy(), ei)
+    np.testing.assert_array_equal(val.cpu().numpy().view(np.uint32), ev.view(np.uint32))
+    ri, ro = _ref_kernels().selection_sort(k, to_cuda(_sqdist_matrix(x1, x2)))
+    assert bool((ri[:, :, :k] == idx).all()) and bool((ro[:, :, :k] == val).all())
+
+
+def test_knn_point_validation(ops):
+    _, tg, _, _ = ops
+    x = to_cuda(rng_cloud(1, 1, 50))
+    with pytest.raises(ValueError, match="positive k"):
+        tg.knn_point(0, x, x)
+    with pytest.raises(ValueError, match="must not exceed"):
+        tg.knn_point(51, x, x)
+
+
+def test_gather_and_group_match_reference_kernels(ops):
+    """gather_point / group_point and their gradients against the reference's own kernels on the same GPU
+    (exact for the gathers; the scatter-adds use fp32 atomics on both sides: 1e-5)."""
+    import torch
+    ts, tg, _, _ = ops
+    ref = _ref_kernels()
+    rs = np.random.RandomState(4)
+    x = to_cuda(rs.random_sample((16, 8192, 3)).astype(np.float32))
+    fps = ts.farthest_point_sample(256, x)
+    assert bool((ts.gather_point(x, fps) == ref.gather_point(x, fps)).all())
+    g = to_cuda(rs.normal(size=(16, 256, 3)).astype(np.float32))
+    np.testing.assert_allclose(ts.gather_point_grad(x, fps, g).cpu().numpy(),
+                               ref.gather_point_grad(x, fps, g).cpu().numpy(), atol=1e-5)
+    new = ts.gather_point(x, fps)
+    idx, _ = tg.query_ball_point(0.2, 32, x, new)
+    for c in (3, 16, 67):
+        pts = to_cuda(rs.random_sample((16, 8192, c)).astype(np.float32))
+        assert bool((tg.group_point(pts, idx) == ref.group_point(pts, idx)).all())
+        go = to_cuda(rs.normal(size=(16, 256, 32, c)).astype(np.float32))
+        np.testing.assert_allclose(tg.group_point_grad(pts, idx, go).cpu().numpy(),
+                                   ref.group_point_grad(pts, idx, go).cpu().numpy(), atol=2e-5, rtol=1e-5)
 
 
 # ---------------------------------------------------------------- prob_sample (SURVEY 8f-1)

@@ -251,6 +251,18 @@ int pn2_bn_eval_affine(int N, const float *gamma, const float *beta, const float
 int pn2_affine_act(long M, int N, const float *Y, const float *scale, const float *shift,
                    int relu, float *Z, int ldz, pn2_stream_t s);
 
+/* Alternative poolings of pointnet_sa_module (pointnet_util.py:171-191) over X[G*ns,N], the activated
+ * output of the shared MLP.  mode 1 "avg" -> out[G,N]; mode 2 "weighted_avg" -> out[G,N] with weights
+ * w[G*ns] from pn2_pool_weights (exp(-5 |grouped_xyz|) normalised over nsample, :176-183); mode 3
+ * "max_and_avg" -> out[G,2N] = [avg | max] (:187-191) and arg[G,N] = first sample attaining the max.
+ * pn2_group_pool_grad: dX[G*ns,N] from dOut (the weights are constants: xyz gradients are dead in the
+ * reference's models, model.py feeds xyz as a placeholder). */
+int pn2_pool_weights(long G, int ns, const float *grouped_xyz, int ld, float *w, pn2_stream_t s);
+int pn2_group_pool(long G, int ns, int N, const float *X, const float *w, int mode, float *out, int *arg,
+                   pn2_stream_t s);
+int pn2_group_pool_grad(long G, int ns, int N, const float *dOut, const float *w, const int *arg, int mode,
+                        float *dX, pn2_stream_t s);
+
 /* Test hook: mask[M,N] (bytes) = 1 where fma(Y, scale, shift) > 0 (Y > 0 without scale/shift) -- the
  * ReLU decision exactly as the prologue / pooling / backward kernels of a chain take it.  Parity tests
  * feed it to the fp64 oracle so that both sides differentiate the same piecewise-linear function. */
@@ -306,6 +318,27 @@ int pn2_softmax_ce_grad(long rows, int C, const float *logits, const int *labels
  * lr_t = lr*sqrt(1-b2^t)/(1-b1^t); m,v moments; p -= lr_t*m/(sqrt(v)+eps); gscale multiplies g */
 int pn2_adam_step(long n, float *p, const float *g, float *m, float *v, float lr, float beta1,
                   float beta2, float eps, int t, float gscale, pn2_stream_t s);
+
+/* ---- group 3: the input feed in front of the path ------------------------
+ * replaces SemanticFileData.sample() x B + rotate_feature_point_cloud
+ *          dataset/semantic_dataset.py:90-186, util/provider.py:72-102, fed at train.py:225-244
+ * One launch cuts B fixed-size training samples out of a scene resident in device memory:
+ *   points (P,3) fp64 sorted by x (semantic_dataset.py:84-88), colors (P,feat) fp64 or NULL (feat = 0),
+ *   labels (P) or NULL, label_weights[num_classes] or NULL (weights default to 1),
+ *   center_idx (B): index of each sample's centre point (the caller's RNG, np.random.randint(0, P)),
+ *   angles (B) radians about z or NULL (no augmentation), seed: drives the random subset of a box that
+ *   holds more than num_point points (key = pn2_box_sample_key(seed, sample, i); the num_point smallest
+ *   keys are kept in scene order; a box with fewer points is tiled, :100-106),
+ *   scene_z_size = max z - min z of the scene (:131).
+ * Outputs: out_data (B,num_point,3+feat) fp32 = [centred (and rotated) xyz | colours], out_labels,
+ * out_weights (may be NULL), out_index (B,num_point) scene indices of the sample (the reference's
+ * points_raw = points[out_index]), out_count (B) points found in each box.  P < 2^31. */
+int pn2_box_sample(int B, long P, int num_point, int feat, const double *points, const double *colors,
+                   const int *labels, const float *label_weights, int num_classes,
+                   const long *center_idx, const double *angles, double box_size_x, double box_size_y,
+                   double scene_z_size, unsigned long long seed, float *out_data, int *out_labels,
+                   float *out_weights, int *out_index, int *out_count, pn2_stream_t s);
+unsigned pn2_box_sample_key(unsigned long long seed, int sample, long i);
 
 #ifdef __cplusplus
 }

@@ -60,6 +60,9 @@ SIGNATURES = {
     "pn2_bn_train_finalize": [_i, _l, _vp, _vp, _vp, _f, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp],
     "pn2_bn_eval_affine": [_i, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp],
     "pn2_affine_act": [_l, _i, _vp, _vp, _vp, _i, _vp, _i, _vp],
+    "pn2_pool_weights": [_l, _i, _vp, _i, _vp, _vp],
+    "pn2_group_pool": [_l, _i, _i, _vp, _vp, _i, _vp, _vp, _vp],
+    "pn2_group_pool_grad": [_l, _i, _i, _vp, _vp, _vp, _i, _vp, _vp],
     "pn2_relu_mask": [_l, _i, _vp, _vp, _vp, _vp, _vp],
     "pn2_affine_act_maxpool": [_l, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp],
     "pn2_bn_bwd_reduce": [_l, _i, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp],
@@ -72,11 +75,14 @@ SIGNATURES = {
     "pn2_dropout_mask": [_l, _f, _ull, _vp, _vp],
     "pn2_softmax_ce_reduce": [_l, _i, _vp, _vp, _vp, _vp, _vp],
     "pn2_softmax_ce_grad": [_l, _i, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp],
+    "pn2_box_sample": [_i, _l, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, ctypes.c_double, ctypes.c_double,
+                       ctypes.c_double, _ull, _vp, _vp, _vp, _vp, _vp, _vp],
+    "pn2_box_sample_key": [_ull, _i, _l],
     "pn2_adam_step": [_l, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _i, _f, _vp],
 }
 _RESTYPE = {"pn2_strerror": ctypes.c_char_p, "pn2_last_cuda_error": ctypes.c_char_p,
             "pn2_ball_threshold": ctypes.c_float, "pn2_linear_workspace_bytes": ctypes.c_long,
-            "pn2_linear_image_bytes": ctypes.c_long,
+            "pn2_linear_image_bytes": ctypes.c_long, "pn2_box_sample_key": ctypes.c_uint,
             "pn2_ball_grid_workspace_bytes": ctypes.c_long}
 
 _lib = None

@@ -570,6 +570,72 @@ __global__ void affine_act_maxpool_kernel(long total, int ns, int N, const float
     }
 }
 
+// ---- alternative poolings of pointnet_sa_module (pointnet_util.py:171-191) ---------------------------
+// X[G*ns, N] = the chain's activated output.  mode 1 "avg": reduce_mean over nsample; mode 2
+// "weighted_avg": sum_j X * w_j with w = exp(-5|g|) / sum_j exp(-5|g|) of the centred grouped xyz;
+// mode 3 "max_and_avg": [avg | max] (the reference concatenates in that order, :187-191), arg = first j
+// attaining the maximum.  One thread per (group, channel); sums run j = 0..ns-1 in fp32.
+__global__ void pool_weights_kernel(long G, int ns, const float *__restrict__ gxyz, int ld,
+                                    float *__restrict__ w) {
+    for (long g = blockIdx.x * (long)blockDim.x + threadIdx.x; g < G; g += (long)gridDim.x * blockDim.x) {
+        float tot = 0.f;
+        for (int j = 0; j < ns; ++j) {
+            const float *p = gxyz + (g * ns + j) * (long)ld;
+            const float x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
+            const float dist = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));
+            const float e = expf(-dist * 5.f);
+            w[g * ns + j] = e;
+            tot += e;
+        }
+        for (int j = 0; j < ns; ++j) w[g * ns + j] = w[g * ns + j] / tot;
+    }
+}
+
+__global__ void group_pool_kernel(long total, int ns, int N, const float *__restrict__ X,
+                                  const float *__restrict__ w, int mode, float *__restrict__ out,
+                                  int *__restrict__ arg) {
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+        const long g = e / N;
+        const int c = (int)(e - g * N);
+        const float *x = X + g * ns * (long)N + c;
+        float sum = 0.f, mx = -INFINITY;
+        int am = 0;
+        for (int j = 0; j < ns; ++j) {
+            const float v = __ldg(x + (long)j * N);
+            sum = __fadd_rn(sum, mode == 2 ? __fmul_rn(v, __ldg(w + g * ns + j)) : v);
+            if (v > mx) {
+                mx = v;
+                am = j;
+            }
+        }
+        if (mode == 1) out[e] = sum / (float)ns;
+        else if (mode == 2) out[e] = sum;
+        else {
+            out[g * 2 * N + c] = sum / (float)ns;
+            out[g * 2 * N + N + c] = mx;
+            arg[e] = am;
+        }
+    }
+}
+
+__global__ void group_pool_grad_kernel(long total, int ns, int N, const float *__restrict__ dOut,
+                                       const float *__restrict__ w, const int *__restrict__ arg, int mode,
+                                       float *__restrict__ dX) {
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+        const long row = e / N;
+        const int c = (int)(e - row * N);
+        const long g = row / ns;
+        const int j = (int)(row - g * ns);
+        float v;
+        if (mode == 1) v = __ldg(dOut + g * N + c) / (float)ns;
+        else if (mode == 2) v = __fmul_rn(__ldg(dOut + g * N + c), __ldg(w + row));
+        else
+            v = __ldg(dOut + g * 2 * N + c) / (float)ns +
+                (__ldg(arg + g * N + c) == j ? __ldg(dOut + g * 2 * N + N + c) : 0.f);
+        dX[e] = v;
+    }
+}
+
 // ---- test hook: the ReLU mask exactly as every kernel of the chain evaluates it --------------------
 __global__ void relu_mask_kernel(long total, int N, const float *__restrict__ Y,
                                  const float *__restrict__ scale, const float *__restrict__ shift,
@@ -1098,6 +1164,40 @@ PN2_API int pn2_bn_bwd_apply_pool(long G, int ns, int N, const float *dOut, cons
     bn_bwd_apply_pool_kernel<<<blocks, 256, 0, as_stream(s)>>>(G, ns, N, rpb, dOut, arg, Y, scale,
                                                                shift, saved, gamma, relu, bn, red, dY,
                                                                dgamma, dbeta);
+    return finish_launch();
+}
+
+PN2_API int pn2_pool_weights(long G, int ns, const float *grouped_xyz, int ld, float *w, pn2_stream_t s) {
+    PN2_REQUIRE(G >= 0 && ns > 0 && ld >= 3);
+    if (G == 0) return PN2_OK;
+    PN2_REQUIRE_PTR(grouped_xyz);
+    PN2_REQUIRE_PTR(w);
+    pool_weights_kernel<<<grid_for(G, 128), 128, 0, as_stream(s)>>>(G, ns, grouped_xyz, ld, w);
+    return finish_launch();
+}
+
+PN2_API int pn2_group_pool(long G, int ns, int N, const float *X, const float *w, int mode, float *out,
+                           int *arg, pn2_stream_t s) {
+    PN2_REQUIRE(G >= 0 && ns > 0 && N > 0 && mode >= 1 && mode <= 3);
+    if (G == 0) return PN2_OK;
+    PN2_REQUIRE_PTR(X);
+    PN2_REQUIRE_PTR(out);
+    if (mode == 2) PN2_REQUIRE_PTR(w);
+    if (mode == 3) PN2_REQUIRE_PTR(arg);
+    group_pool_kernel<<<grid_for(G * N, 128), 128, 0, as_stream(s)>>>(G * N, ns, N, X, w, mode, out, arg);
+    return finish_launch();
+}
+
+PN2_API int pn2_group_pool_grad(long G, int ns, int N, const float *dOut, const float *w, const int *arg,
+                                int mode, float *dX, pn2_stream_t s) {
+    PN2_REQUIRE(G >= 0 && ns > 0 && N > 0 && mode >= 1 && mode <= 3);
+    if (G == 0) return PN2_OK;
+    PN2_REQUIRE_PTR(dOut);
+    PN2_REQUIRE_PTR(dX);
+    if (mode == 2) PN2_REQUIRE_PTR(w);
+    if (mode == 3) PN2_REQUIRE_PTR(arg);
+    group_pool_grad_kernel<<<grid_for(G * ns * N, 256), 256, 0, as_stream(s)>>>(G * ns * N, ns, N, dOut, w, arg,
+                                                                                mode, dX);
     return finish_launch();
 }
 

@@ -100,6 +100,49 @@ def sample_and_group_all(xyz, points, use_xyz=True):
     return new_xyz, new_points, idx, grouped_xyz
 
 
+POOL_MODES = {"avg": 1, "weighted_avg": 2, "max_and_avg": 3}
+
+
+class _GroupPool(torch.autograd.Function):
+    """feat (B,m,ns,N) -> (B,m,1,N) [avg, weighted_avg] or (B,m,1,2N) [max_and_avg = avg | max]."""
+
+    @staticmethod
+    def forward(ctx, feat, weights, mode, scope):
+        b, m, ns, n = feat.shape
+        x = feat.contiguous()
+        g = b * m
+        out = torch.empty((b, m, 1, 2 * n if mode == 3 else n), dtype=F32, device=x.device)
+        arg = torch.empty((g, n), dtype=I32, device=x.device) if mode == 3 else None
+        call("pn2_group_pool", g, ns, n, ptr(x, F32), ptr(weights, F32, True), mode, ptr(out, F32),
+             ptr(arg, I32, True))
+        if mode == 3 and tf_util.debug_capture is not None:
+            tf_util.debug_capture[scope + "/argmax"] = arg
+        ctx.cfg, ctx.weights, ctx.arg = (g, ns, n, mode), weights, arg
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        g, ns, n, mode = ctx.cfg
+        d = d_out.contiguous()
+        dx = torch.empty((g * ns, n), dtype=F32, device=d.device)
+        call("pn2_group_pool_grad", g, ns, n, ptr(d, F32), ptr(ctx.weights, F32, True),
+             ptr(ctx.arg, I32, True), mode, ptr(dx, F32))
+        return dx.view(d.shape[0], d.shape[1], ns, n), None, None, None
+
+
+def _pool_weights(grouped_xyz):
+    """exp(-5 |g|) normalised over nsample (pointnet_util.py:176-183); grouped_xyz (B,m,ns,>=3 strided)."""
+    b, m, ns, _ = grouped_xyz.shape
+    gx = grouped_xyz.detach()
+    if gx.stride(3) != 1 or gx.stride(2) < 3 or gx.stride(1) != ns * gx.stride(2) or \
+            gx.stride(0) != m * gx.stride(1):
+        gx = gx.contiguous()
+    w = torch.empty((b * m * ns,), dtype=F32, device=gx.device)
+    import ctypes
+    call("pn2_pool_weights", b * m, ns, ctypes.c_void_p(gx.data_ptr()), int(gx.stride(2)), ptr(w, F32))
+    return w
+
+
 def _conv_layers(prefix, k, widths, bn):
     layers = []
     for i, n in enumerate(widths):
@@ -129,18 +172,11 @@ def pointnet_sa_module(xyz, points, npoint, radius, nsample, mlp, mlp2, group_al
             pooled = tf_util.mlp_chain(x2d, layers, training, bn_decay, pool_ns=ns)
             new_points = pooled.view(b, m, 1, mlp[-1])
         else:
-            feat = tf_util.mlp_chain(x2d, layers, training, bn_decay).view(b, m, ns, mlp[-1])
-            if pooling == "avg":
-                new_points = feat.mean(dim=2, keepdim=True)
-            elif pooling == "weighted_avg":
-                dists = torch.linalg.norm(grouped_xyz, dim=-1, keepdim=True)
-                e = torch.exp(-dists * 5)
-                new_points = (feat * (e / e.sum(dim=2, keepdim=True))).sum(dim=2, keepdim=True)
-            elif pooling == "max_and_avg":
-                new_points = torch.cat([feat.mean(dim=2, keepdim=True),
-                                        feat.max(dim=2, keepdim=True)[0]], dim=-1)
-            else:
+            if pooling not in POOL_MODES:
                 raise ValueError("unknown pooling %r" % (pooling,))
+            feat = tf_util.mlp_chain(x2d, layers, training, bn_decay).view(b, m, ns, mlp[-1])
+            w = _pool_weights(grouped_xyz) if pooling == "weighted_avg" else None
+            new_points = _GroupPool.apply(feat, w, POOL_MODES[pooling], layers[-1].w.name[:-len("/weights")])
         if mlp2 is not None:
             kk = new_points.shape[-1]
             layers2 = _conv_layers("conv_post_%d", kk, mlp2, bn)

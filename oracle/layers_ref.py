@@ -197,7 +197,7 @@ def sa_module(ctx, xyz_np, points, npoint, radius, nsample, mlp, scope, mlp2=Non
         new_points = (new_points * (e / e.sum(dim=2, keepdim=True))).sum(dim=2, keepdim=True)
     elif pooling == "max_and_avg":
         new_points = torch.cat([new_points.mean(dim=2, keepdim=True),
-                                new_points.max(dim=2, keepdim=True)[0]], -1)
+                                _max_pool(ctx, new_points, "%s/conv%d" % (scope, len(mlp) - 1))], -1)
     if mlp2 is not None:
         for i, _ in enumerate(mlp2):
             new_points = conv_bn_relu(ctx, new_points, "%s/conv_post_%d" % (scope, i), bn=bn)

@@ -16,9 +16,11 @@ import sys
 from . import _ffi  # noqa: F401
 
 
-def install_reference_aliases():
+def install_reference_aliases(include_model=True):
     """Register the reference's absolute module names (``tf_ops.tf_sampling``, ``util.tf_util``,
-    ``util.pointnet_util`` ...) so code written against the reference imports resolves here."""
+    ``util.pointnet_util`` ...) so code written against the reference imports resolves here.
+    ``include_model=False`` leaves ``model`` / ``predict`` alone: the caller imports the reference's own
+    model.py (see compat/tensorflow.py)."""
     from . import tf_ops, util, model, predict
     from .tf_ops import tf_grouping, tf_interpolate, tf_sampling
     from .util import pointnet_util, tf_util
@@ -29,6 +31,7 @@ def install_reference_aliases():
     sys.modules.setdefault("util", util)
     sys.modules.setdefault("util.tf_util", tf_util)
     sys.modules.setdefault("util.pointnet_util", pointnet_util)
-    sys.modules.setdefault("model", model)      # the reference's top-level `import model`
-    sys.modules.setdefault("predict", predict)  # `from predict import Predictor`
+    if include_model:
+        sys.modules.setdefault("model", model)      # the reference's top-level `import model`
+        sys.modules.setdefault("predict", predict)  # `from predict import Predictor`
     return model

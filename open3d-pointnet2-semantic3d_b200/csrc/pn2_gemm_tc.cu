@@ -39,7 +39,7 @@ namespace tc {
 constexpr int BM = 128;       // rows per tile (UMMA M)
 constexpr int BK = 32;        // fp32/tf32 elements per K chunk = one 128-byte swizzle row
 constexpr int W_EPI = 8;                  // epilogue warps 0-7: two per TMEM lane quadrant, column blocks split
-constexpr int W_XF = 4;                   // A-transform warps 8-11
+constexpr int W_XF = 8;                   // A-transform warps 8-15: two groups of 4, alternating chunks
 constexpr int THREADS = 32 * (W_EPI + W_XF + 3);  // + A loader + B loader + MMA
 constexpr int W_ALOAD = W_EPI + W_XF, W_BLOAD = W_ALOAD + 1, W_MMA = W_ALOAD + 2;
 constexpr int MAX_RAW = 4;                // raw A ring slots (16 KB each) filled by TMA tensor loads
@@ -238,6 +238,8 @@ struct Params {
     int nchunks;  // column blocks of 128 handled by this launch (CTA c works on block c % nchunks)
     int Ntot;     // output columns of the launch; the last block may be narrower than N
     int ksplit;   // K > 512: chunks [0,KC/2) and [KC/2,KC) accumulate separately (no double buffering)
+    int epi_alt;  // output at most 32 columns wide: the two epilogue warp groups take ALTERNATE TILES (each
+                  // owns one accumulator buffer) instead of alternate column blocks of the same tile
     const float *A, *a_scale, *a_shift, *bias, *image;
     float *Y;
     double *stats_sum, *stats_sq;  // per-column sum / sum of squares (fp64), or NULL
@@ -303,7 +305,7 @@ __global__ void __launch_bounds__(THREADS, 1)
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&acc_full[a], 1);
-            mbar_init(&acc_empty[a], 32 * W_EPI);
+            mbar_init(&acc_empty[a], p.epi_alt ? 16 * W_EPI : 32 * W_EPI);
         }
         for (int kc = 0; kc < MAX_KC; ++kc) mbar_init(&bfull[kc], 1);
         for (int r = 0; r < MAX_RAW; ++r) {
@@ -333,13 +335,18 @@ __global__ void __launch_bounds__(THREADS, 1)
         // The raw chunk comes from the TMA ring (or, when A cannot be described by a tensor map,
         // from float4 global loads); BatchNorm affine + ReLU of the previous layer, hi/lo split,
         // st.shared into the 128B-swizzled K-major UMMA layout, proxy fence, mbarrier arrive.
-        const int t = threadIdx.x - 32 * W_EPI;
+        // two groups of 128 threads work on alternating chunks (group g: chunks g, g+2, ...): the transform
+        // of one chunk is a ~1.8 k-cycle dependent chain (raw wait, ld.shared, affine, split, st.shared,
+        // proxy fence), twice the time the tensor core needs for the chunk's 12 MMAs -- two chunks in
+        // flight hide it (profiles/README_r02.md, role-cycle trace)
+        const int grp = (warp - W_EPI) >> 2;
+        const int t = threadIdx.x - 32 * W_EPI - 128 * grp;
         const int k4 = t & 7, r0 = t >> 3;  // float4 slot inside the 32-wide chunk, base row
         const bool vec_ok = (p.lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0);
         const long my_tiles = mt0 < num_tiles ? (num_tiles - mt0 + mstride - 1) / mstride : 0;
         const long total_chunks = my_tiles * p.KC;
         {
-            for (long itl = 0; itl < total_chunks; ++itl) {
+            for (long itl = grp; itl < total_chunks; itl += W_XF / 4) {
                 const uint32_t it = (uint32_t)itl;
                 const long tile = mt0 + (itl / p.KC) * mstride;
                 const int kc = (int)(itl % p.KC);
@@ -347,7 +354,7 @@ __global__ void __launch_bounds__(THREADS, 1)
                 const int s = it % p.stages;
                 const uint32_t ph = (it / p.stages) & 1;
                 const int kbase = kc * BK + k4 * 4;
-                const bool tr = TR_ON(blockIdx.x == 0 && t == 0);
+                const bool tr = TR_ON(blockIdx.x == 0 && t == 0 && grp == 0);
                 const long long c0 = TR_CLOCK(tr);
                 float sc[4], sh[4];
                 if (p.a_scale) {
@@ -573,6 +580,9 @@ __global__ void __launch_bounds__(THREADS, 1)
         };
         uint32_t tcnt = 0;
         for (long tile = mt0; tile < num_tiles; tile += mstride, ++tcnt) {
+            // narrow outputs: a tile's epilogue is one ~2 k-cycle dependent chain (accumulator wait, tcgen05.ld,
+            // staging, tensor store, statistics); two warp groups on alternate tiles keep two in flight
+            if (p.epi_alt && (int)(tcnt & 1) != wg) continue;
             const uint32_t acc = p.ksplit ? 0 : (tcnt & 1), aph = p.ksplit ? (tcnt & 1) : ((tcnt >> 1) & 1);
             const long m0 = tile * BM + q4 * 32;
             const bool tr = TR_ON(blockIdx.x == 0 && threadIdx.x == 0);
@@ -584,7 +594,7 @@ __global__ void __launch_bounds__(THREADS, 1)
             const int nv = rows_left >= 32 ? 32 : (int)rows_left;
 #pragma unroll
             for (int ci = 0; ci < 2; ++ci) {
-                const int cb = 2 * ci + wg;
+                const int cb = p.epi_alt ? ci : 2 * ci + wg;
                 if (cb >= nblk) break;
                 const uint32_t ta = tmem_base + ((uint32_t)(q4 * 32) << 16) +
                                     acc * (uint32_t)(2 * Nacc) + cb * 32;
@@ -636,7 +646,7 @@ __global__ void __launch_bounds__(THREADS, 1)
                             if (rr < nv) yp[(long)rr * p.ldy] = vals[rr];
                     }
                     if (do_stats) {
-                        if (tcnt == 0) cshift[ci] = vals[0];
+                        if (nrows == 0) cshift[ci] = vals[0];  // this warp's first tile
                         const float c0 = cshift[ci];
                         float p1[4] = {0.f, 0.f, 0.f, 0.f}, p2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -663,7 +673,7 @@ __global__ void __launch_bounds__(THREADS, 1)
         if (p.stats_sum) {
 #pragma unroll
             for (int ci = 0; ci < 2; ++ci) {
-                const int cb = 2 * ci + wg;
+                const int cb = p.epi_alt ? ci : 2 * ci + wg;
                 const int col = cb * 32 + lane;
                 if (cb < nblk && col < Nv && nrows > 0) {
                     const double c = (double)cshift[ci], n = (double)nrows;
@@ -764,6 +774,7 @@ static int run_chunk(long M, int K, int Nc, int nchunks, int Ntot, const float *
     p.nchunks = nchunks;
     p.Ntot = Ntot;
     p.ksplit = p.KC > 16 ? 1 : 0;  // K > 512: two accumulator sets bound the truncating accumulation
+    p.epi_alt = (!p.ksplit && nchunks == 1 && Nc <= 32) ? 1 : 0;
 
     // PN2_TC_TMA bit mask (diagnostics): 1 = tensor loads for A, 2 = tensor stores for Y; default 3
     static const int tma_mask = getenv("PN2_TC_TMA") ? atoi(getenv("PN2_TC_TMA")) : 3;

@@ -8,7 +8,8 @@ import pn2_b200
 from pn2_b200 import _ffi as ffi
 p = ffi.ptr
 torch.manual_seed(0)
-shapes = [(4096, 131, 128), (16384, 131, 128), (65536, 32, 32), (16384, 67, 64), (1024, 259, 256), (40000, 128, 128)]
+shapes = [(4096, 131, 128), (16384, 131, 128), (65536, 32, 32), (16384, 67, 64), (1024, 259, 256), (40000, 128, 128),
+          (524288, 32, 32), (524288, 6, 32), (131072, 64, 32), (33000, 32, 9), (131072, 128, 128), (8192, 768, 256)]
 iters = int(os.environ.get("STRESS_ITERS", "30"))
 junk = torch.empty(1 << 26, device="cuda")
 total_bad = 0

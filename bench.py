@@ -461,7 +461,7 @@ def run_ours(args):
     h2d = int(pc.nbytes + labels.nbytes + smpw.nbytes)
 
     # ---- per-entry-point breakdown (separate instrumented pass) + roofline ------------------
-    roofline, breakdown, collective = None, None, None
+    roofline, breakdown, collective, linear_table = None, None, None, None
     # every rank takes the instrumented steps (they contain the gradient all-reduce); rank 0 records
     _ffi.profile = [] if rank == 0 else None
     trainer.timing = {}
@@ -477,10 +477,16 @@ def run_ours(args):
     barrier()
     if rank == 0:
         agg = {}
-        for name, a, bb in _ffi.profile:
+        per_shape = {}
+        for name, a, bb, shape in _ffi.profile:
             d = agg.setdefault(name, [0.0, 0])
-            d[0] += a.elapsed_time(bb)
+            ms1 = a.elapsed_time(bb)
+            d[0] += ms1
             d[1] += 1
+            if shape is not None:
+                ps = per_shape.setdefault((name,) + tuple(int(x) for x in shape), [0.0, 0])
+                ps[0] += ms1
+                ps[1] += 1
         _ffi.profile = None
         ar = trainer.timing.get("allreduce", [])
         if ar:
@@ -493,6 +499,13 @@ def run_ours(args):
                                   "instrumented (eager, backlogged) pass; model = 2(p-1)/p * bytes / 900 GB/s"}
         breakdown = {k: {"ms_per_step": v[0] / psteps, "calls_per_step": v[1] / psteps}
                      for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])}
+        # every GEMM call of a step with its algorithmic bytes 4*M*(K+N) against the measured copy bandwidth
+        linear_table = []
+        for (name, m_, k_, n_), v in sorted(per_shape.items(), key=lambda kv: -kv[1][0]):
+            us = 1e3 * v[0] / v[1]
+            byt = 4.0 * m_ * (k_ + n_)
+            linear_table.append({"call": name[len("pn2_linear_"):], "M": m_, "K": k_, "N": n_,
+                                 "calls_per_step": v[1] / psteps, "us": us, "GBps": byt / us / 1e3})
         peaks = {}
         pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(pk):
@@ -576,7 +589,7 @@ def run_ours(args):
                             "D2H loss read per step, the copy of batch i+1 overlaps step i"},
             "gpu_launches": calls,
             "roofline": roofline, "cpu_baseline": cpu, "breakdown_ms_per_step": breakdown,
-            "collective": collective, "config1": cfg1, "cfeat6": cf6,
+            "collective": collective, "config1": cfg1, "cfeat6": cf6, "linear_calls": linear_table,
         }
         print(json.dumps(line))
     if world > 1:

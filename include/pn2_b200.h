@@ -319,6 +319,52 @@ int pn2_softmax_ce_grad(long rows, int C, const float *logits, const int *labels
 int pn2_adam_step(long n, float *p, const float *g, float *m, float *v, float lr, float beta1,
                   float beta2, float eps, int t, float gscale, pn2_stream_t s);
 
+/* ---- group 2b: whole layers behind one call (no reference analogue) ------------
+ * The host side of a layer is native: the entry point walks the op sequence of pointnet_sa_module
+ * (util/pointnet_util.py:98-216: ball-query grouping, shared MLP, max pooling -- the configuration model.py
+ * uses) or pointnet_fp_module (:285-326) and its exact reverse, launching the kernels declared above on
+ * the caller's stream.  Nothing is allocated: every intermediate lives in the caller-owned workspace
+ * (pn2_sa_workspace_bytes / pn2_fp_workspace_bytes, 256-byte aligned), and the forward leaves there what the
+ * backward needs, so a backward call must see the workspace of its forward call untouched.
+ * Layers are described by host arrays of pn2_conv_layer whose pointers are DEVICE arrays owned by the
+ * caller: weights W[K,N], bias[N], gamma/beta/moving_mean/moving_var[N] (bn != 0), and for the backward
+ * the gradient accumulators dW/dbias/dgamma/dbeta (accumulated into: the caller zeroes them once per step;
+ * the bias of a conv that feeds a train-mode BatchNorm gets no gradient: it is exactly zero).
+ * xyz gradients are not produced (dead in the reference's models: xyz is a placeholder). */
+#define PN2_MAX_LAYERS 8
+typedef struct pn2_conv_layer {
+    int K, N, bn, relu, rank4; /* rank4: conv2d (Bessel-corrected moving variance), else conv1d */
+    const float *W, *bias, *gamma, *beta;
+    float *moving_mean, *moving_var; /* updated in place by a training forward; NULL: left alone */
+    float *dW, *dbias, *dgamma, *dbeta;
+} pn2_conv_layer;
+typedef struct pn2_sa_config {
+    int b, n, c, npoint, nsample, nlayers, is_training;
+    float radius, bn_eps, bn_decay;
+} pn2_sa_config;
+typedef struct pn2_fp_config {
+    int b, n1, n2, c1, c2, nlayers, is_training; /* xyz1 (b,n1,3) dense, xyz2 (b,n2,3) sparse */
+    float bn_eps, bn_decay;
+} pn2_fp_config;
+long pn2_sa_workspace_bytes(const pn2_sa_config *cfg, const pn2_conv_layer *layers);
+/* xyz (b,n,3), points (b,n,c) or NULL (c=0) -> new_xyz (b,npoint,3), new_points (b,npoint,N_last),
+ * idx (b,npoint,nsample) */
+int pn2_sa_forward(const pn2_sa_config *cfg, const pn2_conv_layer *layers, const float *xyz,
+                   const float *points, float *new_xyz, float *new_points, int *idx, void *workspace,
+                   long workspace_bytes, pn2_stream_t s);
+/* d_new_points (b,npoint,N_last) -> parameter gradients (accumulated) and d_points (b,n,c) (may be NULL) */
+int pn2_sa_backward(const pn2_sa_config *cfg, const pn2_conv_layer *layers, const float *d_new_points,
+                    const int *idx, float *d_points, void *workspace, long workspace_bytes, pn2_stream_t s);
+long pn2_fp_workspace_bytes(const pn2_fp_config *cfg, const pn2_conv_layer *layers);
+/* points1 (b,n1,c1) or NULL, points2 (b,n2,c2) -> out (b,n1,N_last); concat order [interpolated, points1] */
+int pn2_fp_forward(const pn2_fp_config *cfg, const pn2_conv_layer *layers, const float *xyz1,
+                   const float *xyz2, const float *points1, const float *points2, float *out,
+                   void *workspace, long workspace_bytes, pn2_stream_t s);
+int pn2_fp_backward(const pn2_fp_config *cfg, const pn2_conv_layer *layers, const float *d_out,
+                    float *d_points1, float *d_points2, void *workspace, long workspace_bytes,
+                    pn2_stream_t s);
+int pn2_fill_f32(long n, float value, float *dst, pn2_stream_t s);
+
 /* ---- group 3: the input feed in front of the path ------------------------
  * replaces SemanticFileData.sample() x B + rotate_feature_point_cloud
  *          dataset/semantic_dataset.py:90-186, util/provider.py:72-102, fed at train.py:225-244

@@ -75,6 +75,13 @@ SIGNATURES = {
     "pn2_dropout_mask": [_l, _f, _ull, _vp, _vp],
     "pn2_softmax_ce_reduce": [_l, _i, _vp, _vp, _vp, _vp, _vp],
     "pn2_softmax_ce_grad": [_l, _i, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp],
+    "pn2_sa_workspace_bytes": [_vp, _vp],
+    "pn2_sa_forward": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _l, _vp],
+    "pn2_sa_backward": [_vp, _vp, _vp, _vp, _vp, _vp, _l, _vp],
+    "pn2_fp_workspace_bytes": [_vp, _vp],
+    "pn2_fp_forward": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _l, _vp],
+    "pn2_fp_backward": [_vp, _vp, _vp, _vp, _vp, _vp, _l, _vp],
+    "pn2_fill_f32": [_l, _f, _vp, _vp],
     "pn2_box_sample": [_i, _l, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, ctypes.c_double, ctypes.c_double,
                        ctypes.c_double, _ull, _vp, _vp, _vp, _vp, _vp, _vp],
     "pn2_box_sample_key": [_ull, _i, _l],
@@ -83,6 +90,7 @@ SIGNATURES = {
 _RESTYPE = {"pn2_strerror": ctypes.c_char_p, "pn2_last_cuda_error": ctypes.c_char_p,
             "pn2_ball_threshold": ctypes.c_float, "pn2_linear_workspace_bytes": ctypes.c_long,
             "pn2_linear_image_bytes": ctypes.c_long, "pn2_box_sample_key": ctypes.c_uint,
+            "pn2_sa_workspace_bytes": ctypes.c_long, "pn2_fp_workspace_bytes": ctypes.c_long,
             "pn2_ball_grid_workspace_bytes": ctypes.c_long}
 
 _lib = None
@@ -151,7 +159,7 @@ def call(name, *args):
         e0.record()
         rc = getattr(lib(), name)(*args, stream())
         e1.record()
-        profile.append((name, e0, e1))
+        profile.append((name, e0, e1, args[:3] if name in ("pn2_linear_fwd", "pn2_linear_dgrad", "pn2_linear_wgrad") else None))
     else:
         rc = getattr(lib(), name)(*args, stream())
     launches += 1

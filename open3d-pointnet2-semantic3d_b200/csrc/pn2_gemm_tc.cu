@@ -39,7 +39,10 @@ namespace tc {
 constexpr int BM = 128;       // rows per tile (UMMA M)
 constexpr int BK = 32;        // fp32/tf32 elements per K chunk = one 128-byte swizzle row
 constexpr int W_EPI = 8;                  // epilogue warps 0-7: two per TMEM lane quadrant, column blocks split
-constexpr int W_XF = 8;                   // A-transform warps 8-15: two groups of 4, alternating chunks
+#ifndef PN2_XF_WARPS
+#define PN2_XF_WARPS 8
+#endif
+constexpr int W_XF = PN2_XF_WARPS;        // A-transform warps: groups of 4 on alternating chunks (A/B builds: 4)
 constexpr int THREADS = 32 * (W_EPI + W_XF + 3);  // + A loader + B loader + MMA
 constexpr int W_ALOAD = W_EPI + W_XF, W_BLOAD = W_ALOAD + 1, W_MMA = W_ALOAD + 2;
 constexpr int MAX_RAW = 4;                // raw A ring slots (16 KB each) filled by TMA tensor loads
@@ -238,6 +241,7 @@ struct Params {
     int nchunks;  // column blocks of 128 handled by this launch (CTA c works on block c % nchunks)
     int Ntot;     // output columns of the launch; the last block may be narrower than N
     int ksplit;   // K > 512: chunks [0,KC/2) and [KC/2,KC) accumulate separately (no double buffering)
+    int stack;    // [B_hi ; B_lo] read as ONE 2*Npad-row operand: 2 MMAs per K=8 step instead of 3
     int epi_alt;  // output at most 32 columns wide: the two epilogue warp groups take ALTERNATE TILES (each
                   // owns one accumulator buffer) instead of alternate column blocks of the same tile
     const float *A, *a_scale, *a_shift, *bias, *image;
@@ -485,7 +489,7 @@ __global__ void __launch_bounds__(THREADS, 1)
     } else if (warp == W_MMA) {
         // ================================ MMA issuer ================================
         if (lane == 0) {
-            const uint32_t idesc = make_idesc(p.Npad);
+            const uint32_t idesc = make_idesc(p.Npad), idesc2 = make_idesc(2 * p.Npad);
             uint32_t it = 0, tcnt = 0;
             const bool tr = TR_ON(blockIdx.x == 0);
             const long long k0c = TR_CLOCK(tr);
@@ -519,9 +523,17 @@ __global__ void __launch_bounds__(THREADS, 1)
                     for (int kk = 0; kk < BK / 8; ++kk) {
                         const uint64_t adv = (uint64_t)(kk * 2);  // 32 bytes per K=8 step, >>4
                         const uint32_t accum = (kcl > 0 || kk > 0) ? 1u : 0u;
-                        umma_tf32(d, dah + adv, dbh + adv, idesc, accum);
-                        umma_tf32(dc, dal + adv, dbh + adv, idesc, accum);
-                        umma_tf32(dc, dah + adv, dbl + adv, idesc, 1u);
+                        if (p.stack) {
+                            // the lo image follows the hi image row for row (Npad % 8 == 0), so [B_hi ; B_lo]
+                            // is one K-major operand of 2*Npad rows: a_hi x [b_hi ; b_lo] fills main | corr
+                            // (corr starts at column Nacc == Npad), a_lo x b_hi adds the second correction
+                            umma_tf32(d, dah + adv, dbh + adv, idesc2, accum);
+                            umma_tf32(dc, dal + adv, dbh + adv, idesc, 1u);
+                        } else {
+                            umma_tf32(d, dah + adv, dbh + adv, idesc, accum);
+                            umma_tf32(dc, dal + adv, dbh + adv, idesc, accum);
+                            umma_tf32(dc, dah + adv, dbl + adv, idesc, 1u);
+                        }
                     }
                     umma_commit(&empty[s]);  // frees the stage once these MMAs have read it
                     if (tr) {
@@ -774,7 +786,11 @@ static int run_chunk(long M, int K, int Nc, int nchunks, int Ntot, const float *
     p.nchunks = nchunks;
     p.Ntot = Ntot;
     p.ksplit = p.KC > 16 ? 1 : 0;  // K > 512: two accumulator sets bound the truncating accumulation
-    p.epi_alt = (!p.ksplit && nchunks == 1 && Nc <= 32) ? 1 : 0;
+    static const bool alt_ok = !(getenv("PN2_TC_EPI_ALT") && getenv("PN2_TC_EPI_ALT")[0] == '0');
+    p.epi_alt = (alt_ok && !p.ksplit && nchunks == 1 && Nc <= 32) ? 1 : 0;
+    // PN2_TC_STACK=0: three separate MMAs per K=8 step (A/B switch)
+    static const bool stack_ok = !(getenv("PN2_TC_STACK") && getenv("PN2_TC_STACK")[0] == '0');
+    p.stack = (stack_ok && (p.Npad % 32) == 0 && 2 * p.Npad <= 256) ? 1 : 0;
 
     // PN2_TC_TMA bit mask (diagnostics): 1 = tensor loads for A, 2 = tensor stores for Y; default 3
     static const int tma_mask = getenv("PN2_TC_TMA") ? atoi(getenv("PN2_TC_TMA")) : 3;
@@ -904,6 +920,7 @@ struct WParams {
     int rows;        // contraction rows per stage: 128 / max(MG,NG) rounded to 32, 64, 128
     int seg_rows;    // rows per unit (multiple of rows, <= W_MAXSEG)
     int KB, NB;      // feature blocks / column blocks
+    int stack;       // dY stage laid out as [hi | lo] MN-groups of one 2*NG-group operand: 2 MMAs per step
     const float *a_scale, *a_shift;
     float *dW;
 };
@@ -1039,14 +1056,19 @@ __global__ void __launch_bounds__(W_THREADS, 1)
                 for (int q = 0; q < 4; ++q) {
                     if (q < b_iters) {
                         const int e = tt + W_TT * q;
-                        const uint32_t off = mn_offset(e / bw4, e % bw4, p.NG);
                         float4 hi, lo;
                         hi.x = tf32_rna(vb[q].x); lo.x = vb[q].x - hi.x;
                         hi.y = tf32_rna(vb[q].y); lo.y = vb[q].y - hi.y;
                         hi.z = tf32_rna(vb[q].z); lo.z = vb[q].z - hi.z;
                         hi.w = tf32_rna(vb[q].w); lo.w = vb[q].w - hi.w;
-                        *reinterpret_cast<float4 *>(b_hi + off) = hi;
-                        *reinterpret_cast<float4 *>(b_hi + b_bytes + off) = lo;
+                        if (p.stack) {  // one operand of 2*NG MN-groups per k-group: [hi groups | lo groups]
+                            *reinterpret_cast<float4 *>(b_hi + mn_offset(e / bw4, e % bw4, 2 * p.NG)) = hi;
+                            *reinterpret_cast<float4 *>(b_hi + mn_offset(e / bw4, e % bw4 + bw4, 2 * p.NG)) = lo;
+                        } else {
+                            const uint32_t off = mn_offset(e / bw4, e % bw4, p.NG);
+                            *reinterpret_cast<float4 *>(b_hi + off) = hi;
+                            *reinterpret_cast<float4 *>(b_hi + b_bytes + off) = lo;
+                        }
                     }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -1081,6 +1103,7 @@ __global__ void __launch_bounds__(W_THREADS, 1)
             // UMMA M is always 128: feature groups >= MG read shared memory of the neighbouring
             // atoms and produce accumulator rows that nobody reads
             const uint32_t idesc = make_idesc(Nacc) | (1u << 15) | (1u << 16);  // A, B MN-major
+            const uint32_t idesc2 = make_idesc(2 * Nacc) | (1u << 15) | (1u << 16);
             uint32_t it = 0, ucnt = 0;
             const bool tr = TR_ON(blockIdx.x == 0);
             const long long k0c = TR_CLOCK(tr);
@@ -1107,15 +1130,24 @@ __global__ void __launch_bounds__(W_THREADS, 1)
                     for (int ks = 0; ks < ksteps; ++ks) {
                         // one K=8 MMA spans two 4-row k-groups: LBO = next MN group (512 B),
                         // SBO = next k-group (groups * 512 B)
-                        const uint32_t ao = ks * p.MG * 1024, bo = ks * p.NG * 1024;
+                        const uint32_t ao = ks * p.MG * 1024;
                         const uint64_t dah = make_desc_mn(a_hi + ao, 512, p.MG * 512);
                         const uint64_t dal = make_desc_mn(a_hi + a_bytes + ao, 512, p.MG * 512);
-                        const uint64_t dbh = make_desc_mn(b_hi + bo, 512, p.NG * 512);
-                        const uint64_t dbl = make_desc_mn(b_hi + b_bytes + bo, 512, p.NG * 512);
                         const uint32_t accum = (sidx > 0 || ks > 0) ? 1u : 0u;
-                        umma_tf32(d, dah, dbh, idesc, accum);
-                        umma_tf32(dc, dal, dbh, idesc, accum);
-                        umma_tf32(dc, dah, dbl, idesc, 1u);
+                        if (p.stack) {
+                            // x_hi^T [g_hi | g_lo] fills main | corr in one MMA of 2*Nacc columns, x_lo^T g_hi
+                            // (the first NG MN-groups of the same operand) adds the second correction
+                            const uint64_t dbs = make_desc_mn(b_hi + ks * p.NG * 2048, 512, p.NG * 1024);
+                            umma_tf32(d, dah, dbs, idesc2, accum);
+                            umma_tf32(dc, dal, dbs, idesc, 1u);
+                        } else {
+                            const uint32_t bo = ks * p.NG * 1024;
+                            const uint64_t dbh = make_desc_mn(b_hi + bo, 512, p.NG * 512);
+                            const uint64_t dbl = make_desc_mn(b_hi + b_bytes + bo, 512, p.NG * 512);
+                            umma_tf32(d, dah, dbh, idesc, accum);
+                            umma_tf32(dc, dal, dbh, idesc, accum);
+                            umma_tf32(dc, dah, dbl, idesc, 1u);
+                        }
                     }
                     umma_commit(&empty[s]);
                     if (tr) {
@@ -1239,6 +1271,8 @@ static int run(long M, int K, int Kdo, int N, const float *A, int lda, const flo
             break;
         }
     }
+    static const bool stack_ok = !(getenv("PN2_TC_STACK") && getenv("PN2_TC_STACK")[0] == '0');
+    p.stack = stack_ok ? 1 : 0;  // 2 * Nacc <= 256 always (NG <= 4)
     p.seg_rows = seg;
     p.nseg = (M + seg - 1) / seg;
     p.units = p.nseg * upb;

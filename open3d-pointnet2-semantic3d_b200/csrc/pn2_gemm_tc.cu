@@ -118,6 +118,21 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// one lane of a converged warp (CUTLASS elect_one_sync): the MMA warp runs its loop with ALL lanes so that
+// descriptors and addresses stay warp-uniform (uniform registers feed UTCHMMA directly); only the elected
+// lane issues.  Computing them inside an `if (lane == 0)` region made the compiler move every operand
+// through a R2UR "waterfall" loop: ~85 cycles per MMA, the whole issue budget of a chunk.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                      smem_u32(bar))
@@ -488,7 +503,8 @@ __global__ void __launch_bounds__(THREADS, 1)
         }
     } else if (warp == W_MMA) {
         // ================================ MMA issuer ================================
-        if (lane == 0) {
+        {
+            const bool leader = elect_one();
             const uint32_t idesc = make_idesc(p.Npad), idesc2 = make_idesc(2 * p.Npad);
             uint32_t it = 0, tcnt = 0;
             const bool tr = TR_ON(blockIdx.x == 0);
@@ -519,6 +535,7 @@ __global__ void __launch_bounds__(THREADS, 1)
                                                   : a_hi + 2 * a_bytes;
                     const uint64_t dah = make_desc(a_hi), dal = make_desc(a_hi + a_bytes);
                     const uint64_t dbh = make_desc(b_hi), dbl = make_desc(b_hi + b_bytes);
+                    if (leader) {
 #pragma unroll
                     for (int kk = 0; kk < BK / 8; ++kk) {
                         const uint64_t adv = (uint64_t)(kk * 2);  // 32 bytes per K=8 step, >>4
@@ -536,12 +553,15 @@ __global__ void __launch_bounds__(THREADS, 1)
                         }
                     }
                     umma_commit(&empty[s]);  // frees the stage once these MMAs have read it
+                    }
+                    __syncwarp();
                     if (tr) {
                         w_full += ci - cw;
                         w_issue += TR_CLOCK(true) - ci;
                     }
                 }
-                umma_commit(&acc_full[acc]);  // accumulator complete -> epilogue
+                if (leader) umma_commit(&acc_full[acc]);  // accumulator complete -> epilogue
+                __syncwarp();
             }
             if (tr) {
                 TR_ADD(0, w_full);
@@ -1099,7 +1119,8 @@ __global__ void __launch_bounds__(W_THREADS, 1)
         }
     } else if (warp == W_WMMA) {
         // ================================ MMA issuer ================================
-        if (lane == 0) {
+        {
+            const bool leader = elect_one();
             // UMMA M is always 128: feature groups >= MG read shared memory of the neighbouring
             // atoms and produce accumulator rows that nobody reads
             const uint32_t idesc = make_idesc(Nacc) | (1u << 15) | (1u << 16);  // A, B MN-major
@@ -1127,6 +1148,7 @@ __global__ void __launch_bounds__(W_THREADS, 1)
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a_hi = smem_u32(smem + (size_t)s * stage_bytes);
                     const uint32_t b_hi = a_hi + 2 * a_bytes;
+                    if (leader) {
                     for (int ks = 0; ks < ksteps; ++ks) {
                         // one K=8 MMA spans two 4-row k-groups: LBO = next MN group (512 B),
                         // SBO = next k-group (groups * 512 B)
@@ -1150,12 +1172,15 @@ __global__ void __launch_bounds__(W_THREADS, 1)
                         }
                     }
                     umma_commit(&empty[s]);
+                    }
+                    __syncwarp();
                     if (tr) {
                         w_full += ci - cw;
                         w_issue += TR_CLOCK(true) - ci;
                     }
                 }
-                umma_commit(&acc_full[acc]);
+                if (leader) umma_commit(&acc_full[acc]);
+                __syncwarp();
             }
             if (tr) {
                 TR_ADD(0, w_full);

@@ -748,6 +748,86 @@ __global__ void adam_kernel(long n, float *__restrict__ p, const float *__restri
     }
 }
 
+// Second generation of the narrow-output wgrad (the 9-class head: M = 131072, K = 128, N = 9 ran at 0.75 TB/s
+// with the kernel above -- two exposed global latencies per 64-row tile).  Here a warp owns 128 features
+// (one float4 per lane) and walks rows r = warp, warp + 8, ...: 8 independent 16-byte loads in flight per
+// lane, dY rows read as warp-uniform __ldg (L1-resident, 36 B per row), no shared-memory staging and no
+// barrier in the row loop.  The 4 warps of a block are combined through shared memory, one atomic per
+// (k, n) per block; the bias gradient (column sums of dY) falls out of the same pass.
+template <int NMAX>
+__global__ void __launch_bounds__(128)
+wgrad_skinny_v4_kernel(long M, int K, int N, long rpb, const float *__restrict__ A, int lda,
+                       const float *__restrict__ a_scale, const float *__restrict__ a_shift, int a_relu,
+                       const float *__restrict__ dY, float *__restrict__ dW, float *__restrict__ db) {
+    __shared__ float red[4][NMAX][132];  // [warp][n][k within the 128-feature block] (+4: bank spread)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int k0 = blockIdx.y * 128 + lane * 4;
+    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a_scale) {
+        float *s4 = reinterpret_cast<float *>(&sc), *h4 = reinterpret_cast<float *>(&sh);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (k0 + j < K) {
+                s4[j] = __ldg(a_scale + k0 + j);
+                h4[j] = __ldg(a_shift + k0 + j);
+            }
+    }
+    float acc[NMAX][4];
+#pragma unroll
+    for (int n = 0; n < NMAX; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
+    float bsum = 0.f;  // lane n < N: column sum of dY over this warp's rows
+    const long r0 = (long)blockIdx.x * rpb;
+    const long r1 = r0 + rpb < M ? r0 + rpb : M;
+    const bool full4 = k0 + 3 < K;
+#pragma unroll 4
+    for (long r = r0 + warp; r < r1; r += 4) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float *ap = A + r * lda + k0;
+        if (full4) a = __ldg(reinterpret_cast<const float4 *>(ap));
+        else {
+            if (k0 < K) a.x = __ldg(ap);
+            if (k0 + 1 < K) a.y = __ldg(ap + 1);
+            if (k0 + 2 < K) a.z = __ldg(ap + 2);
+        }
+        if (a_scale) {
+            a.x = __fmaf_rn(a.x, sc.x, sh.x); a.y = __fmaf_rn(a.y, sc.y, sh.y);
+            a.z = __fmaf_rn(a.z, sc.z, sh.z); a.w = __fmaf_rn(a.w, sc.w, sh.w);
+            if (a_relu) {
+                a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
+            }
+            if (k0 >= K) a.x = 0.f;
+            if (k0 + 1 >= K) a.y = 0.f;
+            if (k0 + 2 >= K) a.z = 0.f;
+            if (k0 + 3 >= K) a.w = 0.f;
+        }
+        const float *gy = dY + r * N;
+        const float mine = lane < N ? __ldg(gy + lane) : 0.f;
+        bsum += mine;
+#pragma unroll
+        for (int n = 0; n < NMAX; ++n) {
+            const float g = __shfl_sync(0xFFFFFFFFu, mine, n);
+            acc[n][0] = __fmaf_rn(a.x, g, acc[n][0]);
+            acc[n][1] = __fmaf_rn(a.y, g, acc[n][1]);
+            acc[n][2] = __fmaf_rn(a.z, g, acc[n][2]);
+            acc[n][3] = __fmaf_rn(a.w, g, acc[n][3]);
+        }
+    }
+#pragma unroll
+    for (int n = 0; n < NMAX; ++n)
+        *reinterpret_cast<float4 *>(&red[warp][n][lane * 4]) = make_float4(acc[n][0], acc[n][1], acc[n][2], acc[n][3]);
+    __syncthreads();
+    for (int e = threadIdx.x; e < N * 128; e += 128) {
+        const int n = e / 128, kk = e % 128;
+        const int k = blockIdx.y * 128 + kk;
+        if (k >= K) continue;
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) v += red[w][n][kk];
+        atomicAdd(dW + (long)k * N + n, v);
+    }
+    if (db && blockIdx.y == 0 && lane < N) atomicAdd(db + lane, bsum);
+}
+
 // dW[K,N] += f(A)^T dY for narrow outputs (N <= 16: the 9-class head).  Thread = feature k with N
 // accumulators in registers; the dY rows of a 64-row tile are broadcast from shared memory, the A
 // column reads are coalesced across the block.  One fp32 atomic per (k, n) per block.
@@ -923,13 +1003,26 @@ PN2_API int pn2_linear_wgrad(long M, int K, int N, const float *A, int lda, cons
     if (use_rt && mode != 1) rc = wgrad_rt(M, K, N, A, lda, a_scale, a_shift, a_relu, dY, dW, st);
     int k_done = 0;
     if (rc == PN2_EUNSUPPORTED && mode != 1 && N <= 16) {  // narrow output: feature-per-thread kernel
-        // ~7 blocks of 128 threads per SM, 8 independent row loads in flight per thread
-        long rpb = ceil_div<long>(M, 148L * 7);
-        rpb = ceil_div<long>(rpb, 64L) * 64;
-        dim3 grid((unsigned)ceil_div<long>(M, rpb), (unsigned)ceil_div(K, 128));
-        wgrad_skinny_kernel<16><<<grid, 128, 0, st>>>(M, K, N, rpb, A, lda, a_scale, a_shift, a_relu, dY, dW);
-        rc = finish_launch();
-        if (rc) return rc;
+        static const bool old_skinny = getenv("PN2_WGRAD_SKINNY_V1") && getenv("PN2_WGRAD_SKINNY_V1")[0] == '1';
+        const bool v4 = !old_skinny && (lda % 4 == 0) && (reinterpret_cast<uintptr_t>(A) & 15) == 0;
+        if (v4) {  // warp per 128 features, float4 rows, bias gradient in the same pass
+            long rpb = ceil_div<long>(M, 148L * 6);
+            rpb = ceil_div<long>(rpb, 4L) * 4;
+            dim3 grid((unsigned)ceil_div<long>(M, rpb), (unsigned)ceil_div(K, 128));
+            wgrad_skinny_v4_kernel<16><<<grid, 128, 0, st>>>(M, K, N, rpb, A, lda, a_scale, a_shift, a_relu, dY,
+                                                             dW, db);
+            rc = finish_launch();
+            if (rc) return rc;
+            db = nullptr;  // done
+        } else {
+            // ~7 blocks of 128 threads per SM, 8 independent row loads in flight per thread
+            long rpb = ceil_div<long>(M, 148L * 7);
+            rpb = ceil_div<long>(rpb, 64L) * 64;
+            dim3 grid((unsigned)ceil_div<long>(M, rpb), (unsigned)ceil_div(K, 128));
+            wgrad_skinny_kernel<16><<<grid, 128, 0, st>>>(M, K, N, rpb, A, lda, a_scale, a_shift, a_relu, dY, dW);
+            rc = finish_launch();
+            if (rc) return rc;
+        }
         k_done = K;
     }
     if (rc == PN2_EUNSUPPORTED && (mode == 1 || (mode == -1 && tc_enabled())))

@@ -514,7 +514,7 @@ def run_ours(args):
         tc_peak = peaks.get("bf16_tflops_sustained", 1400.0)
         src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
         traffic = None
-        tf = os.path.join(ROOT, "profiles", "traffic_r01.json")
+        tf = os.path.join(ROOT, "profiles", "traffic_r02.json")
         if os.path.exists(tf):
             traffic = json.load(open(tf))
         names = ("pn2_linear_fwd", "pn2_linear_dgrad", "pn2_linear_wgrad")

@@ -361,6 +361,30 @@ def cfeat6_line(dev, b, n, steps, warmup, flush):
             "ms_per_step": ms, "value": b * n / (ms * 1e-3), "unit": UNIT, "cuda_graph": bool(graph)}
 
 
+def fused_chain_bytes(b):
+    """The OTHER byte model of the dense stage: if every shared-MLP chain kept its
+    intermediates on chip, a chain would read its input X0[M,K0] and write its (pooled) output in the forward,
+    and read X0 + the upstream gradient and write dX0 (where an input gradient exists) in the backward."""
+    from pn2_b200.model import FP_MLPS, SA_MLPS
+    n0 = HP["num_point"]
+    npts = [n0, HP["l1_npoint"], HP["l2_npoint"], HP["l3_npoint"], HP["l4_npoint"]]
+    feat = [3, 64, 128, 256, 512]
+    tot = 0
+    for l in (1, 2, 3, 4):
+        m = b * npts[l] * HP["l%d_nsample" % l]
+        k0, out = feat[l - 1] + 3, b * npts[l] * SA_MLPS[l - 1][-1]
+        tot += 4 * (m * k0 + out) + 4 * (m * k0 + out + (m * k0 if l > 1 else 0))
+    up = 512
+    for l, lo in zip((1, 2, 3, 4), (3, 2, 1, 0)):
+        m, k0 = b * npts[lo], up + feat[lo]
+        out = m * FP_MLPS[l - 1][-1]
+        tot += 4 * (m * k0 + out) + 4 * (2 * m * k0 + out)
+        up = FP_MLPS[l - 1][-1]
+    m = b * n0
+    tot += 4 * (m * 128 + m * NUM_CLASS) + 4 * (2 * m * 128 + m * NUM_CLASS)
+    return tot
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -548,6 +572,15 @@ def run_ours(args):
                                  "per step (CUDA events on the launching stream, queue backlogged)" % lin,
                         "per_entry_point": {k: {"ms_per_step": t, "GBps": bb / (t * 1e-3) / 1e9 if t else None}
                                             for k, t, bb in zip(names, lin_ms, byts)},
+                        "fused_chain_model": (lambda dense_ms, fb: {
+                            "bytes": fb, "dense_stage_ms": dense_ms,
+                            "achieved": fb / (dense_ms * 1e-3) / 1e9, "frac": fb / (dense_ms * 1e-3) / 1e9 / hbm_peak,
+                            "note": "bytes if every shared-MLP chain kept its intermediates on chip (chain input "
+                                    "+ output, + upstream gradient and input gradient in the backward) over the time "
+                                    "of the whole dense stage (pn2_linear_*, pn2_bn_*, pn2_affine_act*): the headroom "
+                                    "chain fusion would open, next to the per-layer model above"})(
+                            sum(v["ms_per_step"] for k, v in breakdown.items()
+                                if k.startswith(("pn2_linear_", "pn2_bn_", "pn2_affine_act"))), fused_chain_bytes(b)),
                         "tensor": {"achieved_tflops": fl / (lin * 1e-3) / 1e12,
                                    "peak_tflops_bf16_sustained": tc_peak,
                                    "note": "3xTF32: effective tensor peak is TF32/3 = bf16/6"}}

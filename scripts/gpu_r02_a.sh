@@ -4,4 +4,4 @@ mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv,noheader
 nproc
 timeout 300 python scripts/diag_capture.py > gpurun_out/diag_capture.log 2>&1; echo "diag rc=$?"; tail -40 gpurun_out/diag_capture.log | cut -c1-400
-bash scripts/gpu_r02_first.sh 2>&1 | tee gpurun_out/r02_first.log
+# (then ran the round-1 hand-over script, since deleted: experimental-kernel tests, suite, bench A/B)

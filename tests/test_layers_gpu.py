@@ -16,7 +16,7 @@ ATOL = 1e-5
 def assert_fwd(got, exp, chained_layers=1):
     """|got - exp| <= 1e-5 * max(1, |exp|) for one module on identical inputs (the north-star bar
     on O(1) values).  For the whole network fed forward through L modules each module amplifies
-    the incoming fp32 rounding error (measured: x1.5-2 per module, scripts/debug_model.py), so the
+    the incoming fp32 rounding error (measured in round 1: x1.5-2 per module), so the
     end-to-end bound is 1e-5 * 2^(L-1) capped at 5e-4."""
     exp = np.asarray(exp, np.float64)
     got = np.asarray(got, np.float64)

@@ -410,3 +410,70 @@ def test_predictor_on_gpu(env, tmp_path):
         predict.Predictor(broken, 9, hp).predict(pc)
     with pytest.raises(ValueError, match="batch_data must be"):
         p.predict(pc[:, :, :3])
+
+
+def test_full_model_every_module_meets_1e5_on_identical_inputs(env, monkeypatch):
+    """The north-star bar (1e-5 abs) module by module INSIDE the full network: every SA / FP module and the head
+    of one training forward is re-evaluated by the fp64 oracle on the GPU's own inputs to that module, so the
+    fp32 rounding of earlier modules (which the chained comparison has to allow for) drops out.  semantic.json
+    radii / npoint / nsample at B=2 x 2048 points."""
+    pu, tf_util, model, lr, store = env
+    import torch
+    hp = {"use_color": 1, "l1_npoint": 512, "l1_radius": 0.5, "l1_nsample": 32, "l2_npoint": 128, "l2_radius": 1.0,
+          "l2_nsample": 32, "l3_npoint": 32, "l3_radius": 2.0, "l3_nsample": 32, "l4_npoint": 8, "l4_radius": 4.0,
+          "l4_nsample": 32}
+    rs = np.random.RandomState(100)
+    b, n = 2, 2048
+    pc = np.concatenate([rs.random_sample((b, n, 3)) * [10.0, 10.0, 5.0], rs.random_sample((b, n, 3))], -1).astype(np.float32)
+    params = lr.init_model_params(hp, 9, seed=1)
+    randomize_bn(params, rs)
+    load_params(store, params)
+    calls = []
+    real_sa, real_fp, real_conv1d = model.pointnet_sa_module, model.pointnet_fp_module, tf_util.conv1d
+
+    def sa(xyz, points, **kw):
+        out = real_sa(xyz, points, **kw)
+        calls.append(("sa", kw["scope"], (xyz, points), kw, out))
+        return out
+
+    def fp(xyz1, xyz2, points1, points2, mlp, is_training, bn_decay, scope):
+        out = real_fp(xyz1, xyz2, points1, points2, mlp, is_training, bn_decay, scope=scope)
+        calls.append(("fp", scope, (xyz1, xyz2, points1, points2), {"mlp": mlp}, out))
+        return out
+
+    def conv1d(inputs, num_output_channels, kernel_size, scope, **kw):
+        out = real_conv1d(inputs, num_output_channels, kernel_size, scope=scope, **kw)
+        calls.append(("conv1d", scope, (inputs,), kw, out))
+        return out
+
+    monkeypatch.setattr(model, "pointnet_sa_module", sa)
+    monkeypatch.setattr(model, "pointnet_fp_module", fp)
+    monkeypatch.setattr(tf_util, "conv1d", conv1d)
+    with torch.no_grad():
+        model.get_model(to_cuda(pc), True, 9, hp, bn_decay=0.5)
+    assert [c[1] for c in calls] == ["layer1", "layer2", "layer3", "layer4", "fa_layer1", "fa_layer2", "fa_layer3",
+                                     "fa_layer4", "fc1", "fc2"]
+    npy = lambda t: None if t is None else t.detach().cpu().numpy()  # noqa: E731
+    t64 = lambda a: None if a is None else torch.tensor(a, dtype=torch.float64)  # noqa: E731
+    worst = {}
+    for kind, scope, ins, kw, out in calls:
+        ctx = lr.Ctx(params, is_training=True, bn_decay=0.5)
+        if kind == "sa":
+            xyz, points = npy(ins[0]), npy(ins[1])
+            e_xyz, e_out, e_idx = lr.sa_module(ctx, xyz, t64(points), kw["npoint"], kw["radius"], kw["nsample"],
+                                               kw["mlp"], scope)
+            np.testing.assert_array_equal(npy(out[2]), e_idx, err_msg=scope)
+            np.testing.assert_array_equal(npy(out[0]), e_xyz, err_msg=scope)
+            got, exp = npy(out[1]), e_out.numpy()
+        elif kind == "fp":
+            e = lr.fp_module(ctx, npy(ins[0]), npy(ins[1]), t64(npy(ins[2])), t64(npy(ins[3])), kw["mlp"], scope)
+            got, exp = npy(out), e.numpy()
+        else:
+            x = t64(npy(ins[0]))
+            e = lr.conv_bn_relu(ctx, x, scope, bn=kw.get("bn", False), relu=kw.get("activation_fn", "relu") is not None,
+                                rank4=False)
+            got, exp = npy(out), e.detach().numpy()
+        err = float((np.abs(got - exp) / np.maximum(1.0, np.abs(exp))).max())
+        worst[scope] = err
+        assert err <= ATOL, (scope, err)
+    print("per-module max error on identical inputs:", {k: "%.2g" % v for k, v in worst.items()})

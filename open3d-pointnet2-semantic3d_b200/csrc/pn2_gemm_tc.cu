@@ -905,7 +905,9 @@ static int run_chunk(long M, int K, int Nc, int nchunks, int Ntot, const float *
 namespace tcw {
 using namespace tc;
 
-constexpr int W_NPG = 2;                        // transform groups of 4 warps, on ALTERNATING stages (r02)
+constexpr int W_NPG = 2;                        // transform warpgroups: ONE group of 8 warps works on a stage (two groups
+                                                // of 4 on alternating stages measured slower: 1.08 vs 0.955 ms per step --
+                                                // this transform is bound by shared-memory throughput, not by latency)
 constexpr int W_LOAD = 4 + 4 * W_NPG;           // TMA loader warp
 constexpr int W_WMMA = W_LOAD + 1;              // MMA / TMEM warp
 constexpr int W_THREADS = 32 * (W_WMMA + 1);    // warps 0-3 epilogue, 4-11 transform, loader, MMA
@@ -913,7 +915,7 @@ constexpr int W_MAXSEG = 512;   // contraction rows per accumulator segment (acc
 constexpr int W_FEAT = 128;     // features (rows of dW) per unit = UMMA M
 constexpr int W_RAW = 3;        // raw ring slots (all 256 transform threads walk the stages together,
                                 // so every thread tests every slot's mbarrier in order)
-constexpr int W_TT = 128;                       // threads of ONE transform group (a stage is one group's work)
+constexpr int W_TT = 128 * W_NPG;               // transform threads
 constexpr int W_STAGES = 2;     // MMA stages
 
 __device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr, uint32_t lbo_bytes,
@@ -1003,13 +1005,10 @@ __global__ void __launch_bounds__(W_THREADS, 1)
 
     if (warp >= 4 && warp < W_LOAD) {
         // ================================ transform ================================
-        // two groups of 128 threads, group g transforms the stages with (it & 1) == g (= MMA stage g): two
-        // stages in flight hide the dependent chain raw wait -> ld.shared -> affine/split -> st.shared -> fence
-        const int grp = (warp - 4) >> 2;
-        const int tt = threadIdx.x - 128 - W_TT * grp;      // 0 .. W_TT-1
+        const int tt = threadIdx.x - 128;                  // 0 .. W_TT-1
         const int aw4 = 8 * p.MG, bw4 = 8 * p.NG;         // float4 per raw row
-        const int a_iters = (p.rows * p.MG * 8) / W_TT;    // <= 8
-        const int b_iters = (p.rows * p.NG * 8) / W_TT;    // <= 8
+        const int a_iters = (p.rows * p.MG * 8) / W_TT;    // <= 4
+        const int b_iters = (p.rows * p.NG * 8) / W_TT;    // <= 4
         const int ac4 = tt % aw4, ar0 = tt / aw4, ar_step = W_TT / aw4;  // W_TT % aw4 == 0
         uint32_t it = 0;
         for (long u = blockIdx.x; u < p.units; u += gridDim.x) {
@@ -1027,7 +1026,6 @@ __global__ void __launch_bounds__(W_THREADS, 1)
                     }
             }
             for (int sidx = 0; sidx < nst; ++sidx, ++it) {
-                if ((int)(it & 1) != grp) continue;
                 const int s = it % W_STAGES;
                 const uint32_t ph = (it / W_STAGES) & 1;
                 const int rs = it % W_RAW;
@@ -1035,19 +1033,19 @@ __global__ void __launch_bounds__(W_THREADS, 1)
                 const long mbase = seg0 + (long)sidx * p.rows;
                 const unsigned char *rx = raw + (size_t)rs * raw_bytes;
                 const unsigned char *rg = rx + a_bytes;
-                float4 va[8], vb[8];
+                float4 va[4], vb[4];
                 mbar_wait(&raw_full[rs], rph);
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
+                for (int i = 0; i < 4; ++i)
                     if (i < a_iters)
                         va[i] = *reinterpret_cast<const float4 *>(rx + (size_t)(tt + W_TT * i) * 16);
 #pragma unroll
-                for (int q = 0; q < 8; ++q)
+                for (int q = 0; q < 4; ++q)
                     if (q < b_iters)
                         vb[q] = *reinterpret_cast<const float4 *>(rg + (size_t)(tt + W_TT * q) * 16);
                 if (p.a_scale) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
+                    for (int i = 0; i < 4; ++i) {
                         if (i < a_iters) {
                             const bool row_ok = (mbase + ar0 + ar_step * i) < p.M;
                             float *e = reinterpret_cast<float *>(&va[i]);
@@ -1063,7 +1061,7 @@ __global__ void __launch_bounds__(W_THREADS, 1)
                 unsigned char *st_base = smem + (size_t)s * stage_bytes;
                 mbar_wait(&empty[s], ph ^ 1);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
+                for (int i = 0; i < 4; ++i) {
                     if (i < a_iters) {
                         const uint32_t off = mn_offset(ar0 + ar_step * i, ac4, p.MG);
                         float4 hi, lo;
@@ -1077,7 +1075,7 @@ __global__ void __launch_bounds__(W_THREADS, 1)
                 }
                 unsigned char *b_hi = st_base + 2 * a_bytes;
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
+                for (int q = 0; q < 4; ++q) {
                     if (q < b_iters) {
                         const int e = tt + W_TT * q;
                         float4 hi, lo;

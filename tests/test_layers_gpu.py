@@ -464,10 +464,10 @@ def test_full_model_every_module_meets_1e5_on_identical_inputs(env, monkeypatch)
                                                kw["mlp"], scope)
             np.testing.assert_array_equal(npy(out[2]), e_idx, err_msg=scope)
             np.testing.assert_array_equal(npy(out[0]), e_xyz, err_msg=scope)
-            got, exp = npy(out[1]), e_out.numpy()
+            got, exp = npy(out[1]), e_out.detach().numpy()
         elif kind == "fp":
             e = lr.fp_module(ctx, npy(ins[0]), npy(ins[1]), t64(npy(ins[2])), t64(npy(ins[3])), kw["mlp"], scope)
-            got, exp = npy(out), e.numpy()
+            got, exp = npy(out), e.detach().numpy()
         else:
             x = t64(npy(ins[0]))
             e = lr.conv_bn_relu(ctx, x, scope, bn=kw.get("bn", False), relu=kw.get("activation_fn", "relu") is not None,

@@ -191,7 +191,9 @@ def test_graph_replay_matches_eager_steps(cuda):
             np.testing.assert_allclose(mv_x[k], mv_a[k], rtol=1e-6, atol=1e-7, err_msg="%s %s" % (name, k))
         assert max(abs(a - b) for a, b in zip(l_x, l_a)) <= 2e-3, (name, l_x, l_a, noise_l)
         dw = max(float(np.abs(w_x[k] - w_a[k]).max()) for k in w_a)
-        assert dw <= 6.5e-3, (name, dw, noise_w)  # three Adam steps move a weight by at most 3 lr each way
+        # Adam's m/sqrt(v) can exceed 1 after the first step: a sign-flipped near-zero gradient moves a weight by a few
+        # lr per step in either run (measured 2.6e-3 .. 7.1e-3 between identical eager runs); real defects are O(0.1)
+        assert dw <= 2e-2, (name, dw, noise_w)
     # a defect of the kind this test exists for: the same batch replayed (inputs not refreshed) is far outside
     l_stale = [l_a[0]] * 3
     assert max(abs(a - b) for a, b in zip(l_stale, l_a)) > 1e-2

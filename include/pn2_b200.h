@@ -196,6 +196,23 @@ int pn2_linear_fwd(long M, int K, int N, const float *A, int lda, const float *a
                    const float *a_shift, int a_relu, const float *W, const float *bias, float *Y,
                    double *stats, void *ws, long ws_bytes, int mode, pn2_stream_t s);
 
+/* pn2_linear_fwd + train-mode BatchNorm finalize in ONE call (tf_util.py:572-581 after :181-191): on the
+ * tensor-core path the last CTA of the GEMM turns the column statistics into scale / shift / saved
+ * (mean | rstd) and updates the moving statistics (a launch of its own otherwise: 22 per training step);
+ * other shapes run the fp32 kernel followed by pn2_bn_train_finalize.  stats (2N doubles) and *counter
+ * must be zero on entry; moving_mean / moving_var may both be NULL (statistics frozen). */
+typedef struct pn2_bn_finalize {
+    const float *gamma, *beta;
+    float *moving_mean, *moving_var, *scale, *shift, *saved;
+    unsigned *counter;
+    float eps, decay;
+    int unbiased_moving;
+} pn2_bn_finalize;
+int pn2_linear_fwd_bn(long M, int K, int N, const float *A, int lda, const float *a_scale,
+                      const float *a_shift, int a_relu, const float *W, const float *bias, float *Y,
+                      double *stats, const pn2_bn_finalize *fin, void *ws, long ws_bytes, int mode,
+                      pn2_stream_t s);
+
 /* bytes of caller-owned scratch the tensor-core path of pn2_linear_fwd / pn2_linear_dgrad needs
  * for a K x N layer (the pre-split, pre-swizzled 3xTF32 weight image).  ws may be NULL: the
  * exact fp32 CUDA-core kernel is used then. */

@@ -51,6 +51,7 @@ SIGNATURES = {
     "pn2_three_interpolate_grad_ld": [_i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp],
     "pn2_copy_cols": [_l, _i, _vp, _i, _vp, _i, _i, _vp],
     "pn2_linear_fwd": [_l, _i, _i, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _l, _i, _vp],
+    "pn2_linear_fwd_bn": [_l, _i, _i, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _l, _i, _vp],
     "pn2_linear_workspace_bytes": [_i, _i],
     "pn2_linear_image_bytes": [_i, _i, _i],
     "pn2_linear_image_describe": [_i, _i, _i, _vp, _vp, _vp],

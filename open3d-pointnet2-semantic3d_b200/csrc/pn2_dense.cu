@@ -17,7 +17,8 @@ namespace pn2 {
 // does not cover so that the caller can fall back to the exact fp32 kernel.
 int tc_linear_fwd(long M, int K, int N, const float *A, int lda, const float *a_scale,
                   const float *a_shift, int a_relu, const float *W, const float *bias, float *Y,
-                  double *stats, float *ws, size_t ws_bytes, bool image_ready, cudaStream_t st);
+                  double *stats, float *ws, size_t ws_bytes, bool image_ready, const pn2_bn_finalize *fin,
+                  cudaStream_t st);
 int tc_linear_dgrad(long M, int K, int N, const float *dY, const float *W, float *dX, int ldx,
                     float *ws, size_t ws_bytes, bool image_ready, cudaStream_t st);
 int tc_describe_image(int K, int N, bool dgrad, const float *W, float *image, pn2_linear_image *out);
@@ -930,11 +931,46 @@ PN2_API int pn2_linear_fwd(long M, int K, int N, const float *A, int lda, const 
     cudaStream_t st = as_stream(s);
     if (mode == 1 || (mode == -1 && tc_enabled())) {
         int rc = tc_linear_fwd(M, K, N, A, lda, a_scale, a_shift, a_relu, W, bias, Y, stats,
-                               static_cast<float *>(ws), ws_bytes > 0 ? (size_t)ws_bytes : 0, image_ready, st);
+                               static_cast<float *>(ws), ws_bytes > 0 ? (size_t)ws_bytes : 0, image_ready, nullptr,
+                               st);
         if (rc != PN2_EUNSUPPORTED || mode == 1) return rc;
     }
     return launch_gemm<true, true, false>((int)M, N, K, A, lda, 1, W, N, 1, a_scale, a_shift,
                                           a_relu, bias, Y, N, stats, 1, st);
+}
+
+PN2_API int pn2_linear_fwd_bn(long M, int K, int N, const float *A, int lda, const float *a_scale,
+                              const float *a_shift, int a_relu, const float *W, const float *bias, float *Y,
+                              double *stats, const pn2_bn_finalize *fin, void *ws, long ws_bytes, int mode,
+                              pn2_stream_t s) {
+    PN2_REQUIRE(M > 0 && K > 0 && N > 0 && lda >= K && M < (1L << 31));
+    const bool image_ready = mode >= PN2_GEMM_IMAGE_READY - 1;
+    if (image_ready) mode -= PN2_GEMM_IMAGE_READY;
+    PN2_REQUIRE(mode >= -1 && mode <= 1);
+    PN2_REQUIRE_PTR(A);
+    PN2_REQUIRE_PTR(W);
+    PN2_REQUIRE_PTR(Y);
+    PN2_REQUIRE_PTR(stats);
+    PN2_REQUIRE_PTR(fin);
+    PN2_REQUIRE_PTR(fin->gamma);
+    PN2_REQUIRE_PTR(fin->beta);
+    PN2_REQUIRE_PTR(fin->scale);
+    PN2_REQUIRE_PTR(fin->shift);
+    PN2_REQUIRE_PTR(fin->saved);
+    PN2_REQUIRE_PTR(fin->counter);
+    PN2_REQUIRE((fin->moving_mean == nullptr) == (fin->moving_var == nullptr));
+    PN2_REQUIRE((a_scale == nullptr) == (a_shift == nullptr));
+    cudaStream_t st = as_stream(s);
+    if (mode == 1 || (mode == -1 && tc_enabled())) {
+        int rc = tc_linear_fwd(M, K, N, A, lda, a_scale, a_shift, a_relu, W, bias, Y, stats,
+                               static_cast<float *>(ws), ws_bytes > 0 ? (size_t)ws_bytes : 0, image_ready, fin, st);
+        if (rc != PN2_EUNSUPPORTED || mode == 1) return rc;
+    }
+    int rc = launch_gemm<true, true, false>((int)M, N, K, A, lda, 1, W, N, 1, a_scale, a_shift, a_relu, bias, Y, N,
+                                            stats, 1, st);
+    if (rc) return rc;
+    return pn2_bn_train_finalize(N, M, stats, fin->gamma, fin->beta, fin->eps, fin->decay, fin->unbiased_moving,
+                                 fin->moving_mean, fin->moving_var, fin->scale, fin->shift, fin->saved, s);
 }
 
 PN2_API long pn2_linear_image_bytes(int K, int N, int dgrad) {

@@ -262,6 +262,14 @@ struct Params {
     const float *A, *a_scale, *a_shift, *bias, *image;
     float *Y;
     double *stats_sum, *stats_sq;  // per-column sum / sum of squares (fp64), or NULL
+    // fused train-mode BatchNorm finalize (fin_scale != NULL): the LAST CTA to finish turns the column
+    // statistics into scale / shift / saved mean+rstd and updates the moving statistics -- what
+    // pn2_bn_train_finalize does in a launch of its own (22 launches per training step)
+    const float *fin_gamma, *fin_beta;
+    float *fin_mm, *fin_mv, *fin_scale, *fin_shift, *fin_saved;
+    unsigned *fin_done;  // zeroed by the caller
+    float fin_eps, fin_decay;
+    int fin_unbiased;
 };
 
 __device__ __forceinline__ void tma_load_2d(void *dst_smem, const CUtensorMap *tm, int c0, int c1,
@@ -724,6 +732,36 @@ __global__ void __launch_bounds__(THREADS, 1)
                      "r"(ncols)
                      : "memory");
     }
+    if (p.fin_scale) {
+        // every CTA has issued its fp64 statistics atomics (the barrier above); the last one to get here
+        // sees all of them (fence + counter: the classic last-block pattern) and finalises the layer
+        __shared__ int s_last;
+        if (threadIdx.x == 0) {
+            __threadfence();
+            s_last = atomicAdd(p.fin_done, 1u) == gridDim.x - 1 ? 1 : 0;
+        }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            const double Md = (double)p.M;
+            for (int c = threadIdx.x; c < p.Ntot; c += THREADS) {
+                const double mean = __ldcg(p.stats_sum + c) / Md;
+                double var = __ldcg(p.stats_sq + c) / Md - mean * mean;
+                if (var < 0.0) var = 0.0;
+                const double rstd = 1.0 / sqrt(var + (double)p.fin_eps);
+                const double g = (double)__ldg(p.fin_gamma + c);
+                p.fin_scale[c] = (float)(g * rstd);
+                p.fin_shift[c] = (float)((double)__ldg(p.fin_beta + c) - mean * g * rstd);
+                p.fin_saved[c] = (float)mean;
+                p.fin_saved[p.Ntot + c] = (float)rstd;
+                if (p.fin_mm) {
+                    const double uv = p.fin_unbiased && p.M > 1 ? var * (Md / (Md - 1.0)) : var;
+                    p.fin_mm[c] = (float)((double)p.fin_mm[c] - ((double)p.fin_mm[c] - mean) * (1.0 - (double)p.fin_decay));
+                    p.fin_mv[c] = (float)((double)p.fin_mv[c] - ((double)p.fin_mv[c] - uv) * (1.0 - (double)p.fin_decay));
+                }
+            }
+        }
+    }
 }
 
 static int opt_in_smem(const void *kernel, int slot) {
@@ -784,8 +822,26 @@ static size_t image_bytes(int K, int N) {
 static int run_chunk(long M, int K, int Nc, int nchunks, int Ntot, const float *A, int lda, const float *a_scale,
                      const float *a_shift, int a_relu, const float *bsrc, long s_n, long s_k,
                      const float *bias, float *Y, int ldy, double *stats_sum, double *stats_sq,
-                     float *ws, bool image_ready, cudaStream_t st) {
+                     float *ws, bool image_ready, const pn2_bn_finalize *fin, cudaStream_t st) {
     Params p;
+    p.fin_gamma = p.fin_beta = nullptr;
+    p.fin_mm = p.fin_mv = p.fin_scale = p.fin_shift = p.fin_saved = nullptr;
+    p.fin_done = nullptr;
+    p.fin_eps = p.fin_decay = 0.f;
+    p.fin_unbiased = 0;
+    if (fin && stats_sum) {
+        p.fin_gamma = fin->gamma;
+        p.fin_beta = fin->beta;
+        p.fin_mm = fin->moving_mean;
+        p.fin_mv = fin->moving_var;
+        p.fin_scale = fin->scale;
+        p.fin_shift = fin->shift;
+        p.fin_saved = fin->saved;
+        p.fin_done = fin->counter;
+        p.fin_eps = fin->eps;
+        p.fin_decay = fin->decay;
+        p.fin_unbiased = fin->unbiased_moving;
+    }
     p.M = M;
     p.K = K;
     p.N = Nc;
@@ -1389,13 +1445,14 @@ int tc_prepare_images(int count, const pn2_linear_image *table_dev, cudaStream_t
 
 int tc_linear_fwd(long M, int K, int N, const float *A, int lda, const float *a_scale,
                   const float *a_shift, int a_relu, const float *W, const float *bias, float *Y,
-                  double *stats, float *ws, size_t ws_bytes, bool image_ready, cudaStream_t st) {
+                  double *stats, float *ws, size_t ws_bytes, bool image_ready, const pn2_bn_finalize *fin,
+                  cudaStream_t st) {
     if (!tc_shape_ok(M, K, N) || ws == nullptr || ws_bytes < tc_image_bytes(K, N))
         return PN2_EUNSUPPORTED;
     // all column blocks in one launch; Bt(n,k) = W[k*N + n]
     const int nch = (N + TC_NCHUNK - 1) / TC_NCHUNK;
     return tc::run_chunk(M, K, nch == 1 ? N : TC_NCHUNK, nch, N, A, lda, a_scale, a_shift, a_relu, W, 1, N,
-                         bias, Y, N, stats, stats ? stats + N : nullptr, ws, image_ready, st);
+                         bias, Y, N, stats, stats ? stats + N : nullptr, ws, image_ready, fin, st);
 }
 
 int tc_linear_dgrad(long M, int K, int N, const float *dY, const float *W, float *dX, int ldx,
@@ -1405,7 +1462,7 @@ int tc_linear_dgrad(long M, int K, int N, const float *dY, const float *W, float
         return PN2_EUNSUPPORTED;
     const int nch = (K + TC_NCHUNK - 1) / TC_NCHUNK;
     return tc::run_chunk(M, N, nch == 1 ? K : TC_NCHUNK, nch, K, dY, N, nullptr, nullptr, 0, W, N, 1, nullptr,
-                         dX, ldx, nullptr, nullptr, ws, image_ready, st);
+                         dX, ldx, nullptr, nullptr, ws, image_ready, nullptr, st);
 }
 
 }  // namespace pn2

@@ -901,12 +901,16 @@ PN2_API int pn2_fps(int b, int n, int m, const float *inp, float *temp, int *out
     static const bool prune = !(getenv("PN2_FPS_PRUNE") && getenv("PN2_FPS_PRUNE")[0] == '0');
     if (n <= 4096) return prune && n > 2048 && m > 64 ? launch_fps_pruned<1024, 4>(b, n, m, inp, out, st)
                                                       : launch_fps_reg<1024, 4>(b, n, m, inp, out, st);
-    // PN2_FPS_T512=1 (A/B switch): 512 threads x 16 points instead of 1024 x 8 -- half the warps at the
-    // per-round barrier and in the final arg-max, coarser pruning boxes
-    static const bool t512 = getenv("PN2_FPS_T512") && getenv("PN2_FPS_T512")[0] == '1';
-    if (n <= 8192 && t512 && prune && m > 64) return launch_fps_pruned<512, 16>(b, n, m, inp, out, st);
-    if (n <= 8192) return prune && m > 64 ? launch_fps_pruned<1024, 8>(b, n, m, inp, out, st)
-                                          : launch_fps_reg<1024, 8>(b, n, m, inp, out, st);
+    // 4096 < n <= 8192: 512 threads x 16 points (r02 A/B on B200: 0.457 vs 0.516 ms at 16 x 8192 -> 1024 with 1024 x 8,
+    // bit-identical: half the warps at the per-round barrier and in the final arg-max outweigh the coarser pruning
+    // boxes).  PN2_FPS_T=1024 | 256 selects the other shapes for A/B runs.
+    static const int fps_t = getenv("PN2_FPS_T") ? atoi(getenv("PN2_FPS_T")) : 512;
+    if (n <= 8192) {
+        if (!(prune && m > 64)) return launch_fps_reg<1024, 8>(b, n, m, inp, out, st);
+        if (fps_t == 1024) return launch_fps_pruned<1024, 8>(b, n, m, inp, out, st);
+        if (fps_t == 256) return launch_fps_pruned<256, 32>(b, n, m, inp, out, st);
+        return launch_fps_pruned<512, 16>(b, n, m, inp, out, st);
+    }
     // more than 8192 points: a thread-block cluster per cloud keeps the whole cloud on chip
     // (PN2_FPS_CLUSTER=0/1 overrides the default)
     static const char *cl_env = getenv("PN2_FPS_CLUSTER");

@@ -20,6 +20,7 @@ BatchNorm+ReLU applied while loading A, batch statistics accumulated in the GEMM
 BN+ReLU(+max-pool over nsample) applied by one pass over the pre-activation tensor.
 """
 import contextlib
+import ctypes
 import math
 
 import torch
@@ -340,6 +341,13 @@ def _workspace(L, dev):
 IMAGE_READY = 16  # PN2_GEMM_IMAGE_READY (include/pn2_b200.h)
 
 
+class BnFinalize(ctypes.Structure):
+    """pn2_bn_finalize (include/pn2_b200.h): the train-mode BatchNorm finalize the GEMM's last CTA performs."""
+    _fields_ = [(n, ctypes.c_void_p) for n in ("gamma", "beta", "moving_mean", "moving_var", "scale", "shift",
+                                               "saved", "counter")] + \
+               [("eps", ctypes.c_float), ("decay", ctypes.c_float), ("unbiased_moving", ctypes.c_int)]
+
+
 def _weight_image(L, dgrad, dev, gemm_mode):
     """(workspace, mode) of one GEMM call: the layer's persistent image when the store prepared the
     images for this pass (mode + IMAGE_READY), else the shared per-shape scratch (image rebuilt per call)."""
@@ -374,26 +382,33 @@ class _MLPChain(torch.autograd.Function):
             use_stats = L.bn and is_training
             stats = zero_arena.take(2 * N, dev) if use_stats else None
             ws, mode_i = _weight_image(L, 0, dev, gemm_mode)
-            call("pn2_linear_fwd", M, L.k, N, a_ptr, lda, ptr(a_sc, F32, True),
-                 ptr(a_sh, F32, True), a_relu, ptr(L.w.data, F32), ptr(L.b.data, F32), ptr(Y, F32),
-                 ptr(stats, F64, True), ptr(ws, F32, True), 0 if ws is None else ws.numel() * 4,
-                 mode_i)
             sc = sh = saved = None
-            if L.bn:
+            if use_stats:
+                # GEMM + train-mode BatchNorm finalize in one entry point (the GEMM's last CTA finalises)
                 sc = torch.empty(N, dtype=F32, device=dev)
                 sh = torch.empty(N, dtype=F32, device=dev)
-                if is_training:
-                    saved = torch.empty(2 * N, dtype=F32, device=dev)
-                    upd = not _freeze_moving[0]
-                    call("pn2_bn_train_finalize", N, M, ptr(stats, F64), ptr(L.gamma.data, F32),
-                         ptr(L.beta.data, F32), BN_EPS, decay, 1 if L.rank4 else 0,
-                         ptr(L.mm.data, F32) if upd else None, ptr(L.mv.data, F32) if upd else None,
-                         ptr(sc, F32), ptr(sh, F32), ptr(saved, F32))
-                else:
+                saved = torch.empty(2 * N, dtype=F32, device=dev)
+                counter = zero_arena.take(1, dev)
+                upd = not _freeze_moving[0]
+                fin = BnFinalize(L.gamma.data.data_ptr(), L.beta.data.data_ptr(),
+                                 L.mm.data.data_ptr() if upd else None, L.mv.data.data_ptr() if upd else None,
+                                 sc.data_ptr(), sh.data_ptr(), saved.data_ptr(), counter.data_ptr(), BN_EPS, decay,
+                                 1 if L.rank4 else 0)
+                call("pn2_linear_fwd_bn", M, L.k, N, a_ptr, lda, ptr(a_sc, F32, True), ptr(a_sh, F32, True),
+                     a_relu, ptr(L.w.data, F32), ptr(L.b.data, F32), ptr(Y, F32), ptr(stats, F64),
+                     ctypes.byref(fin), ptr(ws, F32, True), 0 if ws is None else ws.numel() * 4, mode_i)
+            else:
+                call("pn2_linear_fwd", M, L.k, N, a_ptr, lda, ptr(a_sc, F32, True),
+                     ptr(a_sh, F32, True), a_relu, ptr(L.w.data, F32), ptr(L.b.data, F32), ptr(Y, F32),
+                     ptr(stats, F64, True), ptr(ws, F32, True), 0 if ws is None else ws.numel() * 4,
+                     mode_i)
+                if L.bn:  # inference: moving statistics
+                    sc = torch.empty(N, dtype=F32, device=dev)
+                    sh = torch.empty(N, dtype=F32, device=dev)
                     call("pn2_bn_eval_affine", N, ptr(L.gamma.data, F32), ptr(L.beta.data, F32),
                          ptr(L.mm.data, F32), ptr(L.mv.data, F32), BN_EPS, ptr(sc, F32),
                          ptr(sh, F32))
-            elif L.relu:
+            if not L.bn and L.relu:
                 sc = torch.ones(N, dtype=F32, device=dev)
                 sh = torch.zeros(N, dtype=F32, device=dev)
             Ys.append(Y)

@@ -241,3 +241,50 @@ def test_narrow_layers_auto_mode(ffi, M, K, N):
     tol = 2e-5 * max(1.0, np.abs(expw).max())
     np.testing.assert_allclose(dW.cpu().numpy(), expw, atol=tol)
     np.testing.assert_allclose(db.cpu().numpy(), dY.astype(np.float64).sum(0), atol=tol)
+
+
+@pytest.mark.parametrize("M,K,N,rank4", [(16384, 128, 128, 1), (40000, 67, 64, 0), (4096, 259, 256, 1), (100, 32, 32, 1),
+                                        (33000, 32, 9, 0)])
+def test_linear_fwd_with_fused_bn_finalize(ffi, M, K, N, rank4):
+    """pn2_linear_fwd_bn (the GEMM's last CTA finalises the train-mode BatchNorm) against pn2_linear_fwd +
+    pn2_bn_train_finalize: same Y, scale / shift / saved mean+rstd and moving statistics; (100, 32, 32) takes
+    the fp32-kernel fallback inside the same entry point."""
+    import ctypes
+    import torch
+    from pn2_b200.util.tf_util import BnFinalize
+    rs = np.random.RandomState(M + N)
+    lda = (K + 3) // 4 * 4
+    A = np.full((M, lda), np.nan, np.float32)
+    A[:, :K] = rs.normal(size=(M, K))
+    W = (rs.uniform(-1, 1, (K, N)) * np.sqrt(6.0 / (K + N))).astype(np.float32)
+    b = rs.uniform(-0.5, 0.5, N).astype(np.float32)
+    gamma, beta = rs.uniform(0.5, 1.5, N).astype(np.float32), rs.uniform(-0.3, 0.3, N).astype(np.float32)
+    mm0, mv0 = rs.normal(size=N).astype(np.float32), rs.uniform(0.5, 2, N).astype(np.float32)
+    p = ffi.ptr
+    At, Wt, bt, gt, bet = to_cuda(A), to_cuda(W), to_cuda(b), to_cuda(gamma), to_cuda(beta)
+    ws = _ws(ffi, K, N)
+    f32 = lambda n: torch.empty(n, dtype=torch.float32, device="cuda")  # noqa: E731
+    out = {}
+    for fused in (0, 1):
+        Y, stats = torch.empty((M, N), dtype=torch.float32, device="cuda"), torch.zeros(2 * N, dtype=torch.float64, device="cuda")
+        mm, mv, sc, sh, saved = to_cuda(mm0), to_cuda(mv0), f32(N), f32(N), f32(2 * N)
+        if fused:
+            counter = torch.zeros(2, dtype=torch.int32, device="cuda")
+            fin = BnFinalize(gt.data_ptr(), bet.data_ptr(), mm.data_ptr(), mv.data_ptr(), sc.data_ptr(), sh.data_ptr(),
+                             saved.data_ptr(), counter.data_ptr(), 1e-3, 0.7, rank4)
+            ffi.call("pn2_linear_fwd_bn", M, K, N, p(At), lda, None, None, 0, p(Wt), p(bt), p(Y), p(stats),
+                     ctypes.byref(fin), p(ws), ws.numel() * 4, -1)
+        else:
+            ffi.call("pn2_linear_fwd", M, K, N, p(At), lda, None, None, 0, p(Wt), p(bt), p(Y), p(stats), p(ws),
+                     ws.numel() * 4, -1)
+            ffi.call("pn2_bn_train_finalize", N, M, p(stats), p(gt), p(bet), 1e-3, 0.7, rank4, p(mm), p(mv), p(sc),
+                     p(sh), p(saved))
+        torch.cuda.synchronize()
+        out[fused] = [t.cpu().numpy() for t in (Y, sc, sh, saved, mm, mv)]
+    for a, b2, name in zip(out[0], out[1], ("Y", "scale", "shift", "saved", "moving_mean", "moving_var")):
+        np.testing.assert_allclose(b2, a, rtol=2e-6, atol=1e-7, err_msg=name)
+    # and against fp64
+    y64 = A[:, :K].astype(np.float64) @ W.astype(np.float64) + b
+    mean, var = y64.mean(0), y64.var(0)
+    np.testing.assert_allclose(out[1][3][:N], mean, atol=1e-5)
+    np.testing.assert_allclose(out[1][1], gamma / np.sqrt(var + 1e-3), rtol=1e-5)

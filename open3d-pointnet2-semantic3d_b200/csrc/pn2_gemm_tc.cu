@@ -735,13 +735,15 @@ __global__ void __launch_bounds__(THREADS, 1)
     if (p.fin_scale) {
         // every CTA has issued its fp64 statistics atomics (the barrier above); the last one to get here
         // sees all of them (fence + counter: the classic last-block pattern) and finalises the layer
-        __shared__ int s_last;
+        // (the flag lives in the spare word next to the TMEM address: a static __shared__ variable would push
+        //  static + dynamic shared memory past the 227 KB this kernel opts in to)
+        volatile uint32_t *s_last = tmem_slot + 1;
         if (threadIdx.x == 0) {
             __threadfence();
-            s_last = atomicAdd(p.fin_done, 1u) == gridDim.x - 1 ? 1 : 0;
+            *s_last = atomicAdd(p.fin_done, 1u) == gridDim.x - 1 ? 1u : 0u;
         }
         __syncthreads();
-        if (s_last) {
+        if (*s_last) {
             __threadfence();
             const double Md = (double)p.M;
             for (int c = threadIdx.x; c < p.Ntot; c += THREADS) {

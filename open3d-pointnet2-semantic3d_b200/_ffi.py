@@ -160,7 +160,7 @@ def call(name, *args):
         e0.record()
         rc = getattr(lib(), name)(*args, stream())
         e1.record()
-        profile.append((name, e0, e1, args[:3] if name in ("pn2_linear_fwd", "pn2_linear_dgrad", "pn2_linear_wgrad") else None))
+        profile.append((name, e0, e1, args[:3] if name in ("pn2_linear_fwd", "pn2_linear_fwd_bn", "pn2_linear_dgrad", "pn2_linear_wgrad") else None))
     else:
         rc = getattr(lib(), name)(*args, stream())
     launches += 1

@@ -23,6 +23,40 @@
 
 namespace pn2 {
 
+// Packed fp32x2 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2): two independent IEEE round-to-nearest operations per
+// instruction, so results are bit-identical to the scalar forms -- the FPS distance update issues half the FP
+// instructions.  A pair lives in one 64-bit register.
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pack2(float a, float b) {
+    f32x2_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2_t v, float &a, float &b) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ f32x2_t fadd2(f32x2_t a, f32x2_t b) {
+    f32x2_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2_t fmul2(f32x2_t a, f32x2_t b) {
+    f32x2_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2_t ffma2(f32x2_t a, f32x2_t b, f32x2_t c) {
+    f32x2_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+// sqdist_ref for two points at once: fma(dz,dz, fma(dx,dx, dy*dy)) with d = p + (-centroid)
+__device__ __forceinline__ f32x2_t sqdist_ref2(f32x2_t x, f32x2_t y, f32x2_t z, f32x2_t nx, f32x2_t ny, f32x2_t nz) {
+    const f32x2_t dx = fadd2(x, nx), dy = fadd2(y, ny), dz = fadd2(z, nz);
+    return ffma2(dz, dz, ffma2(dx, dx, fmul2(dy, dy)));
+}
+
+
 // ---- tie key: smaller wins.  (k mod 512) major, (k div 512) minor ----------------------
 __device__ __forceinline__ unsigned tie_key(int k) {
     return ((unsigned)(k & 511) << 22) | (unsigned)(k >> 9);
@@ -241,6 +275,14 @@ fps_pruned_kernel(int n, int m, const float *__restrict__ inp, int *__restrict__
         }
     }
 
+    // the coordinates stay packed in pairs for the rounds (FADD2 / FMUL2 / FFMA2)
+    f32x2_t X2[PPT / 2], Y2[PPT / 2], Z2[PPT / 2];
+#pragma unroll
+    for (int i = 0; i < PPT; i += 2) {
+        X2[i >> 1] = pack2(px[i], px[i + 1]);
+        Y2[i >> 1] = pack2(py[i], py[i + 1]);
+        Z2[i >> 1] = pack2(pz[i], pz[i + 1]);
+    }
     int old = 0;
     if (t == 0) dst[0] = 0;
     // cached warp candidate: FLT_MAX forces the first update of a warp that owns real points; a warp
@@ -255,14 +297,22 @@ fps_pruned_kernel(int n, int m, const float *__restrict__ inp, int *__restrict__
         if (dmin < __uint_as_float(wmax)) {  // warp-uniform: some running minimum may change
             float best = -1.f;
             unsigned bkey = 0xFFFFFFFFu;
+            const f32x2_t nx = pack2(-x1, -x1), ny = pack2(-y1, -y1), nz = pack2(-z1, -z1);
 #pragma unroll
-            for (int i = 0; i < PPT; ++i) {
-                float d = sqdist_ref(px[i] - x1, py[i] - y1, pz[i] - z1);
-                float d2 = fminf(d, pd[i]);
-                pd[i] = d2;
-                if (d2 > best) {
-                    best = d2;
+            for (int i = 0; i < PPT; i += 2) {
+                float da, db;
+                unpack2(sqdist_ref2(X2[i >> 1], Y2[i >> 1], Z2[i >> 1], nx, ny, nz), da, db);
+                const float d2a = fminf(da, pd[i]);
+                pd[i] = d2a;
+                if (d2a > best) {
+                    best = d2a;
                     bkey = tk[i];
+                }
+                const float d2b = fminf(db, pd[i + 1]);
+                pd[i + 1] = d2b;
+                if (d2b > best) {
+                    best = d2b;
+                    bkey = tk[i + 1];
                 }
             }
             const bool has = best >= 0.f;

@@ -276,5 +276,10 @@ def pointnet_fp_module(xyz1, xyz2, points1, points2, mlp, is_training, bn_decay,
         x0 = _InterpConcat.apply(points2, points1, idx, weight)
         b, n1, _ = xyz1.shape
         layers = _conv_layers("conv_%d", x0.shape[1], mlp, bn)
-        out = tf_util.mlp_chain(x0, layers, training, bn_decay)
+        # concat order [interpolated | points1]: when points1 needs no gradient (the network input at FP4) only the
+        # interpolated columns of the input gradient are read
+        dx_cols = None
+        if points1 is not None and not points1.requires_grad:
+            dx_cols = (0, points2.shape[2])
+        out = tf_util.mlp_chain(x0, layers, training, bn_decay, dx_cols=dx_cols)
         return out.view(b, n1, mlp[-1])

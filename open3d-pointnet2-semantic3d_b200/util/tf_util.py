@@ -365,7 +365,7 @@ class _MLPChain(torch.autograd.Function):
     on the fly when layer i+1 loads its A operand, and by the final affine(+pool) pass."""
 
     @staticmethod
-    def forward(ctx, x, anchor, layers, is_training, bn_decay, pool_ns, gemm_mode):
+    def forward(ctx, x, anchor, layers, is_training, bn_decay, pool_ns, gemm_mode, dx_cols=None):
         M, K0 = x.shape
         dev = x.device
         # rows may be padded (a column slice of a wider buffer: the SA/FP concat buffers are
@@ -441,6 +441,7 @@ class _MLPChain(torch.autograd.Function):
             if arg is not None:
                 debug_capture[L.w.name[:-len("/weights")] + "/argmax"] = arg
         ctx.layers, ctx.pool_ns, ctx.is_training, ctx.gemm_mode = layers, pool_ns, is_training, gemm_mode
+        ctx.dx_cols = dx_cols
         ctx.x, ctx.Ys, ctx.scs, ctx.shs, ctx.saveds, ctx.arg = x, Ys, scs, shs, saveds, arg
         return out
 
@@ -499,14 +500,30 @@ class _MLPChain(torch.autograd.Function):
                  db, ctx.gemm_mode)
             if i > 0 or ctx.needs_input_grad[0]:
                 dX = torch.empty((M, L.k), dtype=F32, device=dev)
-                ws, mode_i = _weight_image(L, 1, dev, ctx.gemm_mode)
-                call("pn2_linear_dgrad", M, L.k, N, ptr(dY, F32), ptr(L.w.data, F32), ptr(dX, F32),
-                     L.k, ptr(ws, F32, True), 0 if ws is None else ws.numel() * 4, mode_i)
+                k0, k1 = (0, L.k) if (i > 0 or ctx.dx_cols is None) else ctx.dx_cols
+                if (k0, k1) == (0, L.k):
+                    ws, mode_i = _weight_image(L, 1, dev, ctx.gemm_mode)
+                    call("pn2_linear_dgrad", M, L.k, N, ptr(dY, F32), ptr(L.w.data, F32), ptr(dX, F32),
+                         L.k, ptr(ws, F32, True), 0 if ws is None else ws.numel() * 4, mode_i)
+                elif k1 > k0:
+                    # only columns [k0, k1) of the input gradient are consumed (the caller's xyz / skip columns need
+                    # none): dX[:, k] = dY W[k, :]^T is independent per column, so the same entry point runs on
+                    # the row range k0..k1 of W and writes into the column range of dX -- FP4's first layer
+                    # (131 -> 128 columns) drops its second 128-wide column block, 86 -> 32 us
+                    ws, mode_i = _weight_image(L, 1, dev, ctx.gemm_mode)
+                    if not (mode_i >= IMAGE_READY - 1 and k0 == 0 and k1 % 128 == 0 and L.k > 128):
+                        # a prefix of whole 128-column blocks reuses the prepared image; anything else gets a
+                        # per-call image of just those rows
+                        ws, mode_i = (None, 0) if ctx.gemm_mode == 0 else (_workspace(L, dev), ctx.gemm_mode)
+                    call("pn2_linear_dgrad", M, k1 - k0, N, ptr(dY, F32),
+                         ctypes.c_void_p(L.w.data.data_ptr() + 4 * k0 * N),
+                         ctypes.c_void_p(dX.data_ptr() + 4 * k0), L.k, ptr(ws, F32, True),
+                         0 if ws is None else ws.numel() * 4, mode_i)
                 up = dX
             else:
                 up = None
         ctx.Ys = ctx.x = None
-        return up, None, None, None, None, None, None
+        return up, None, None, None, None, None, None, None
 
 
 import os as _os
@@ -516,9 +533,11 @@ import os as _os
 GEMM_MODE = int(_os.environ.get("PN2_GEMM_MODE", "-1"))
 
 
-def mlp_chain(x2d, layers, is_training, bn_decay, pool_ns=0):
+def mlp_chain(x2d, layers, is_training, bn_decay, pool_ns=0, dx_cols=None):
+    """dx_cols = (k0, k1): only these columns of the gradient w.r.t. x2d will be read by the caller (the rest of
+    the returned gradient is left unwritten)."""
     return _MLPChain.apply(x2d, default_store().anchor, layers, _as_bool(is_training), bn_decay,
-                           int(pool_ns), GEMM_MODE)
+                           int(pool_ns), GEMM_MODE, dx_cols)
 
 
 # ------------------------------------------------------------------------------------------

@@ -254,3 +254,51 @@ def test_loss_with_out_of_range_label_is_nan_not_garbage(cuda):
     g[1, 5] = 0
     g[0, 7] = 0
     assert np.isfinite(g).all()
+
+
+def test_full_size_step_properties(cuda):
+    """BASELINE.json configs[1] at its FULL size (16 clouds x 8192 points, semantic.json): the oracle cannot
+    follow here in seconds, so the step is pinned by size-independent properties of what it computes --
+    (1) the same pass twice gives the same loss and gradient up to the fp32-atomics noise floor,
+    (2) linearity in the sample weights (SUM_BY_NONZERO_WEIGHTS: doubling every weight doubles loss and gradient
+        exactly, up to that floor),
+    (3) the captured graph reproduces the eager pass on the same weights and the same dropout counter,
+    (4) clouds whose weights are all zero contribute nothing: their labels can be anything."""
+    import pn2_b200  # noqa: F401
+    import bench
+    from pn2_b200.train_step import Trainer
+    pc, labels, smpw = bench.make_batch(16, 8192, 100)
+    rs = np.random.RandomState(5)
+    smpw = rs.uniform(0.5, 2.0, smpw.shape).astype(np.float32)
+    smpw[3] = 0.0
+    tr = Trainer(bench.HP, bench.NUM_CLASS, device="cuda", seed=0, world_size=1)
+    d = [to_cuda(x) for x in (pc, labels, smpw)]
+
+    def fb(inputs):
+        loss = float(tr.forward_backward(*inputs).item())
+        return loss, tr.grads.clone()
+
+    l0, g0 = fb(d)
+    gmax = float(g0.abs().max())
+    assert np.isfinite(l0) and bool(g0.isfinite().all()) and gmax > 0
+    l1, g1 = fb(d)                                            # (1)
+    noise = float((g1 - g0).abs().max())
+    assert abs(l1 - l0) < 2e-6 * max(1.0, abs(l0)) and noise < 1e-4 * gmax, (l0, l1, noise, gmax)
+    l2, g2 = fb([d[0], d[1], d[2] * 2.0])                     # (2)
+    assert abs(l2 - 2 * l0) < 1e-5 * max(1.0, abs(l0)), (l2, l0)
+    assert float((g2 - 2 * g0).abs().max()) <= 4 * noise + 1e-6 * gmax
+    lab2 = labels.copy()                                      # (4)
+    lab2[3] = (lab2[3] + 3) % 9
+    l3, g3 = fb([d[0], to_cuda(lab2), d[2]])
+    assert abs(l3 - l0) < 2e-6 * max(1.0, abs(l0)), (l3, l0)
+    assert float((g3 - g0).abs().max()) <= 4 * noise + 1e-6 * gmax
+    assert tr.capture(*d), tr._capture_error                  # (3)
+    import torch
+    with torch.cuda.stream(tr.stream):                        # one replay WITHOUT the optimizer step (the learning
+        tr._seed_dev.add_(1)                                  # rate schedule is clipped at 1e-5, never zero)
+        tr._graph.replay()
+    tr.stream.synchronize()
+    l4, g4 = float(tr._static_loss.item()), tr.grads.clone()
+    l5, g5 = fb(d)                                            # eager pass at the same dropout counter
+    assert abs(l4 - l5) < 2e-6 * max(1.0, abs(l5)), (l4, l5)
+    assert float((g4 - g5).abs().max()) <= 4 * noise + 1e-6 * gmax

@@ -1194,8 +1194,10 @@ PN2_API int pn2_bn_bwd_reduce(long M, int N, const float *dZ, int ldz, const flo
     int blocks;
     long rpb = slab_rows(M, &blocks);
     if (vec4_ok(N, ldz, dZ, Y)) {
-        // two resident blocks of work per SM: every block ends with 2N global fp64 atomics
-        long rpb4 = ceil_div<long>(M, 148L * 2);
+        // a few resident blocks of work per SM: every block ends with 2N global fp64 atomics
+        // (PN2_BNRED_BPS: blocks per SM, A/B switch; 80 registers x 256 threads allow 3)
+        static const int bps = getenv("PN2_BNRED_BPS") ? atoi(getenv("PN2_BNRED_BPS")) : 2;
+        long rpb4 = ceil_div<long>(M, 148L * (bps > 0 ? bps : 2));
         if (rpb4 < 32) rpb4 = 32;
         const int blocks4 = (int)ceil_div<long>(M, rpb4);
         bn_bwd_reduce_v4_kernel<<<blocks4, 256, 2 * N * sizeof(double), as_stream(s)>>>(

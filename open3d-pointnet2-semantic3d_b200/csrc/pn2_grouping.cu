@@ -315,6 +315,28 @@ __global__ void group_concat_kernel(int n, int m, int ns, int c, int w, int ld, 
     }
 }
 
+// Feature part of the gradient with vector reductions: one thread per (grouped row, 4 consecutive feature
+// channels) -> ONE red.global.add.v4.f32 instead of four scalar atomics (c % 4 == 0 makes the destination
+// 16-byte aligned; the source row pitch 3+c is odd, so the four gradients are loaded as scalars).
+__global__ void group_concat_grad_feat_v4_kernel(int n, int m, int ns, int c, int w, int poff, long total4,
+                                                 const float *__restrict__ grad_out,
+                                                 const int *__restrict__ idx,
+                                                 float *__restrict__ grad_points) {
+    const int c4 = c >> 2;
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total4;
+         e += (long)gridDim.x * blockDim.x) {
+        const long row = e / c4;
+        const int q = (int)(e - row * c4);
+        const long cloud = row / ((long)m * ns);
+        const int ii = __ldg(idx + row);
+        const float *g = grad_out + row * w + poff + 4 * q;
+        float *dst = grad_points + (cloud * n + ii) * c + 4 * q;
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(__ldg(g)), "f"(__ldg(g + 1)),
+                     "f"(__ldg(g + 2)), "f"(__ldg(g + 3))
+                     : "memory");
+    }
+}
+
 __global__ void group_concat_grad_kernel(int n, int m, int ns, int c, int w, int xoff, int poff,
                                          int use_xyz, long total,
                                          const float *__restrict__ grad_out,
@@ -913,6 +935,17 @@ PN2_API int pn2_group_concat_grad(int b, int n, int m, int nsample, int c, const
     PN2_REQUIRE_PTR(grad_out);
     PN2_REQUIRE_PTR(idx);
     const int xoff = xyz_first ? 0 : c, poff = (use_xyz && xyz_first) ? 3 : 0;
+    if (grad_points && c > 0 && (c % 4) == 0 && (reinterpret_cast<uintptr_t>(grad_points) & 15) == 0) {
+        // feature channels by vector reductions; the xyz columns keep the scalar kernel (and are skipped
+        // altogether when nobody asked for xyz gradients: the model never does)
+        const long total4 = (long)b * m * nsample * (c / 4);
+        group_concat_grad_feat_v4_kernel<<<grid_for(total4, 256), 256, 0, st>>>(n, m, nsample, c, w, poff, total4,
+                                                                                grad_out, idx, grad_points);
+        rc = finish_launch();
+        if (rc) return rc;
+        if (!(use_xyz && (grad_xyz || grad_new_xyz))) return PN2_OK;
+        grad_points = nullptr;  // done
+    }
     group_concat_grad_kernel<<<grid_for(total, 256), 256, 0, st>>>(
         n, m, nsample, c, w, xoff, poff, use_xyz, total, grad_out, idx, grad_points, grad_xyz,
         grad_new_xyz);

@@ -155,6 +155,33 @@ __global__ void three_interpolate_grad_kernel(int m, int c, int n, long total,
     }
 }
 
+// c % 4 == 0: one thread per (row, 4 consecutive channels), three red.global.add.v4.f32 instead of twelve
+// scalar atomics (the source row pitch may be odd -- 131 at FP4 -- so the four gradients load as scalars)
+__global__ void three_interpolate_grad_v4_kernel(int m, int c, int n, long total4,
+                                                 const float *__restrict__ grad_out, int ldg,
+                                                 const int *__restrict__ idx,
+                                                 const float *__restrict__ weight,
+                                                 float *__restrict__ grad_points) {
+    const int c4 = c >> 2;
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total4;
+         e += (long)gridDim.x * blockDim.x) {
+        const long row = e / c4;
+        const int l = 4 * (int)(e - row * c4);
+        const long cloud = row / n;
+        const float *g = grad_out + row * ldg + l;
+        const float g0 = __ldg(g), g1 = __ldg(g + 1), g2 = __ldg(g + 2), g3 = __ldg(g + 3);
+        float *gp = grad_points + cloud * m * c + l;
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            const float wt = __ldg(weight + row * 3 + t);
+            float *dst = gp + (size_t)__ldg(idx + row * 3 + t) * c;
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(__fmul_rn(g0, wt)),
+                         "f"(__fmul_rn(g1, wt)), "f"(__fmul_rn(g2, wt)), "f"(__fmul_rn(g3, wt))
+                         : "memory");
+        }
+    }
+}
+
 __global__ void copy_cols_kernel(long rows, int cols, long total, const float *__restrict__ src,
                                  int lds, float *__restrict__ dst, int ldd, int accumulate) {
     for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total;
@@ -345,8 +372,12 @@ PN2_API int pn2_three_interpolate_grad_ld(int b, int n, int c, int m, const floa
     PN2_REQUIRE_PTR(grad_out);
     PN2_REQUIRE_PTR(idx);
     PN2_REQUIRE_PTR(weight);
-    three_interpolate_grad_kernel<<<grid_for(total, 256), 256, 0, st>>>(
-        m, c, n, total, grad_out, ldg, idx, weight, grad_points);
+    if ((c % 4) == 0 && (reinterpret_cast<uintptr_t>(grad_points) & 15) == 0)
+        three_interpolate_grad_v4_kernel<<<grid_for(total / 4, 256), 256, 0, st>>>(
+            m, c, n, total / 4, grad_out, ldg, idx, weight, grad_points);
+    else
+        three_interpolate_grad_kernel<<<grid_for(total, 256), 256, 0, st>>>(
+            m, c, n, total, grad_out, ldg, idx, weight, grad_points);
     return finish_launch();
 }
 

@@ -1,4 +1,5 @@
 // pn2_api.cu -- ABI bookkeeping: version, error strings, per-device attribute cache.
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -25,6 +26,14 @@ int num_sms() {
         cached[dev] = v;
     }
     return cached[dev];
+}
+
+bool pdl_enabled() {
+    static const bool on = [] {
+        const char *e = getenv("PN2_PDL");
+        return !(e && e[0] == '0');
+    }();
+    return on;
 }
 
 namespace {

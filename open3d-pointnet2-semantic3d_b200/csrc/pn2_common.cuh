@@ -48,6 +48,48 @@ inline int opt_in_dyn_smem(K kernel, size_t bytes) {
                        (int)bytes);
 }
 
+// ---- programmatic dependent launch -------------------------------------------------------------------------
+// Every kernel of this library is launched with the programmatic-stream-serialization attribute and starts with
+// pdl_enter() = `griddepcontrol.wait`: it may become resident as soon as the CTAs of the PREVIOUS kernel of the
+// stream have exited (instead of after that kernel's completion and memory flush), and is held at the wait until
+// that kernel has completed and its writes are visible.  What overlaps is launch latency, CTA scheduling and
+// whatever a kernel does before its wait (barrier init, TMEM allocation in the tensor-core GEMMs) -- never a
+// global-memory access: no kernel reads or writes global memory ahead of its wait
+// (tests/test_host_logic.py::test_every_kernel_waits_for_its_predecessor).  Under stream capture the attribute
+// becomes a programmatic edge of the graph.  PN2_PDL=0 launches everything fully serialised (A/B switch).
+// An EARLY trigger (`griddepcontrol.launch_dependents` at kernel entry, -DPN2_PDL_EARLY_TRIGGER) measured 2 %
+// SLOWER per training step than no PDL at all: the next kernel's CTAs are placed while the SMs still hold CTAs of
+// the current one, wherever there is room, and the grid-stride / persistent kernels then run unbalanced
+// (profiles/README_r02.md, call S).
+bool pdl_enabled();
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_trigger() {
+#ifdef PN2_PDL_EARLY_TRIGGER
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() {
+    pdl_trigger();
+    pdl_wait();
+}
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                     Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);  // errors surface in finish_launch()
+}
+#endif
+
 template <typename T>
 __host__ __device__ constexpr T ceil_div(T a, T b) {
     return (a + b - 1) / b;

@@ -43,7 +43,7 @@ static int launch_gemm(int Mp, int Np, long Kp, const float *A, long a_sm, long 
     if (splits < 1) splits = 1;
     dim3 grid((unsigned)ceil_div(Mp, bm), (unsigned)ceil_div(Np, bn), (unsigned)splits);
 #define PN2_G(BM_, BN_)                                                                        \
-    gemm_simt_kernel<BM_, BN_, A_KC, B_NC, ATOMIC><<<grid, G_THREADS, 0, st>>>(                 \
+    launch_k(gemm_simt_kernel<BM_, BN_, A_KC, B_NC, ATOMIC>, grid, G_THREADS, 0, st,                  \
         Mp, Np, Kp, A, a_sm, a_sk, B, b_sk, b_sn, a_scale, a_shift, a_relu, bias, C, ldc, stats, \
         k_chunk)
     if (bm == 128 && bn == 128) PN2_G(128, 128);
@@ -107,6 +107,7 @@ bn_bwd_reduce_kernel(long M, int N, long rpb, const float *__restrict__ dZ, int 
                      const float *__restrict__ Y, const float *__restrict__ scale,
                      const float *__restrict__ shift, const float *__restrict__ saved, int relu,
                      double *__restrict__ red) {
+    pdl_enter();
     extern __shared__ double sred[];  // [2N] per-block partial sums
     const Slab s = make_slab(M, N, rpb);
     block_zero2(sred, N);
@@ -132,6 +133,7 @@ bn_bwd_apply_kernel(long M, int N, long rpb, const float *__restrict__ dZ, int l
                     const float *__restrict__ gamma, int relu, int bn,
                     const double *__restrict__ red, float *__restrict__ dY,
                     float *__restrict__ dgamma, float *__restrict__ dbeta) {
+    pdl_enter();
     const Slab s = make_slab(M, N, rpb);
     if (!s.active) return;
     const double invM = 1.0 / (double)M;
@@ -186,6 +188,7 @@ bn_bwd_reduce_v4_kernel(long M, int N, long rpb, const float *__restrict__ dZ, i
                         const float *__restrict__ Y, const float *__restrict__ scale,
                         const float *__restrict__ shift, const float *__restrict__ saved, int relu,
                         double *__restrict__ red) {
+    pdl_enter();
     extern __shared__ double sred[];  // [2N] per-block partial sums
     const Slab4 s = make_slab4(M, N, rpb);
     block_zero2(sred, N);
@@ -239,6 +242,7 @@ bn_bwd_apply_v4_kernel(long M, int N, long rpb, const float *__restrict__ dZ, in
                        const float *__restrict__ gamma, int relu, int bn,
                        const double *__restrict__ red, float *__restrict__ dY,
                        float *__restrict__ dgamma, float *__restrict__ dbeta) {
+    pdl_enter();
     const Slab4 s = make_slab4(M, N, rpb);
     if (!s.active) return;
     const double invM = 1.0 / (double)M;
@@ -303,6 +307,7 @@ bn_bwd_reduce_pool_kernel(long G, int ns, int N, const float *__restrict__ dOut,
                           const int *__restrict__ arg, const float *__restrict__ Y,
                           const float *__restrict__ scale, const float *__restrict__ shift,
                           const float *__restrict__ saved, int relu, double *__restrict__ red) {
+    pdl_enter();
     extern __shared__ double sred[];  // [2N] per-block partial sums
     const long rpb = ceil_div<long>(G, (long)gridDim.x);
     const Slab s = make_slab(G, N, rpb);
@@ -335,6 +340,7 @@ bn_bwd_apply_pool_v4_kernel(long G, int ns, int N, long gpb, const float *__rest
                             int relu, int bn, const double *__restrict__ red,
                             float *__restrict__ dY, float *__restrict__ dgamma,
                             float *__restrict__ dbeta) {
+    pdl_enter();
     const Slab4 s = make_slab4(G, N, gpb);
     if (!s.active) return;
     const double invM = 1.0 / (double)(G * ns);
@@ -395,6 +401,7 @@ bn_bwd_apply_pool_kernel(long G, int ns, int N, long rpb, const float *__restric
                          int relu, int bn, const double *__restrict__ red,
                          float *__restrict__ dY, float *__restrict__ dgamma,
                          float *__restrict__ dbeta) {
+    pdl_enter();
     const long M = G * ns;
     const Slab s = make_slab(M, N, rpb);
     if (!s.active) return;
@@ -433,6 +440,7 @@ __global__ void bn_train_finalize_kernel(int N, long M, const double *__restrict
                                          int unbiased_moving, float *__restrict__ moving_mean,
                                          float *__restrict__ moving_var, float *__restrict__ scale,
                                          float *__restrict__ shift, float *__restrict__ saved) {
+    pdl_enter();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= N) return;
     const double mean = stats[c] / (double)M;
@@ -457,6 +465,7 @@ __global__ void bn_eval_affine_kernel(int N, const float *__restrict__ gamma,
                                       const float *__restrict__ mm, const float *__restrict__ mv,
                                       float eps, float *__restrict__ scale,
                                       float *__restrict__ shift) {
+    pdl_enter();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= N) return;
     const double rstd = 1.0 / sqrt((double)mv[c] + (double)eps);
@@ -468,6 +477,7 @@ __global__ void affine_act_kernel(long total, int N, const float *__restrict__ Y
                                   const float *__restrict__ scale,
                                   const float *__restrict__ shift, int relu,
                                   float *__restrict__ Z, int ldz) {
+    pdl_enter();
     for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total;
          e += (long)gridDim.x * blockDim.x) {
         const long r = e / N;
@@ -484,6 +494,7 @@ __global__ void affine_act_v4_kernel(long total4, int nq, const float *__restric
                                      const float *__restrict__ scale,
                                      const float *__restrict__ shift, int relu,
                                      float *__restrict__ Z, int ldz) {
+    pdl_enter();
     for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total4;
          e += (long)gridDim.x * blockDim.x) {
         const long r = e / nq;
@@ -511,6 +522,7 @@ __global__ void __launch_bounds__(128)
 affine_act_maxpool_v4_kernel(long total4, int ns, int N, const float *__restrict__ Y,
                              const float *__restrict__ scale, const float *__restrict__ shift,
                              int relu, float *__restrict__ out, int *__restrict__ arg) {
+    pdl_enter();
     const int nq = N >> 2;
     for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total4;
          e += (long)gridDim.x * blockDim.x) {
@@ -549,6 +561,7 @@ __global__ void affine_act_maxpool_kernel(long total, int ns, int N, const float
                                           const float *__restrict__ scale,
                                           const float *__restrict__ shift, int relu,
                                           float *__restrict__ out, int *__restrict__ arg) {
+    pdl_enter();
     for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total;
          e += (long)gridDim.x * blockDim.x) {
         const long g = e / N;
@@ -578,6 +591,7 @@ __global__ void affine_act_maxpool_kernel(long total, int ns, int N, const float
 // attaining the maximum.  One thread per (group, channel); sums run j = 0..ns-1 in fp32.
 __global__ void pool_weights_kernel(long G, int ns, const float *__restrict__ gxyz, int ld,
                                     float *__restrict__ w) {
+    pdl_enter();
     for (long g = blockIdx.x * (long)blockDim.x + threadIdx.x; g < G; g += (long)gridDim.x * blockDim.x) {
         float tot = 0.f;
         for (int j = 0; j < ns; ++j) {
@@ -595,6 +609,7 @@ __global__ void pool_weights_kernel(long G, int ns, const float *__restrict__ gx
 __global__ void group_pool_kernel(long total, int ns, int N, const float *__restrict__ X,
                                   const float *__restrict__ w, int mode, float *__restrict__ out,
                                   int *__restrict__ arg) {
+    pdl_enter();
     for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
         const long g = e / N;
         const int c = (int)(e - g * N);
@@ -622,6 +637,7 @@ __global__ void group_pool_kernel(long total, int ns, int N, const float *__rest
 __global__ void group_pool_grad_kernel(long total, int ns, int N, const float *__restrict__ dOut,
                                        const float *__restrict__ w, const int *__restrict__ arg, int mode,
                                        float *__restrict__ dX) {
+    pdl_enter();
     for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
         const long row = e / N;
         const int c = (int)(e - row * N);
@@ -641,6 +657,7 @@ __global__ void group_pool_grad_kernel(long total, int ns, int N, const float *_
 __global__ void relu_mask_kernel(long total, int N, const float *__restrict__ Y,
                                  const float *__restrict__ scale, const float *__restrict__ shift,
                                  unsigned char *__restrict__ mask) {
+    pdl_enter();
     for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total;
          e += (long)gridDim.x * blockDim.x) {
         const int c = (int)(e % N);
@@ -663,13 +680,31 @@ __global__ void dropout_kernel(long n, const float *__restrict__ x, float keep_p
                                unsigned long long seed,
                                const unsigned long long *__restrict__ seed_dev,
                                float *__restrict__ out) {
+    pdl_enter();
     if (seed_dev) seed += *seed_dev;
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n;
          i += (long)gridDim.x * blockDim.x)
         out[i] = dropout_keep(seed, i, keep_prob) ? __fmul_rn(__ldg(x + i), inv) : 0.f;
 }
+// four elements per thread (16-byte loads / stores); element i still uses hash(seed, i), so the mask is the same
+__global__ void dropout_v4_kernel(long n4, const float4 *__restrict__ x, float keep_prob, float inv,
+                                  unsigned long long seed, const unsigned long long *__restrict__ seed_dev,
+                                  float4 *__restrict__ out) {
+    pdl_enter();
+    if (seed_dev) seed += *seed_dev;
+    for (long q = blockIdx.x * (long)blockDim.x + threadIdx.x; q < n4; q += (long)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(x + q);
+        float4 o;
+        o.x = dropout_keep(seed, 4 * q, keep_prob) ? __fmul_rn(v.x, inv) : 0.f;
+        o.y = dropout_keep(seed, 4 * q + 1, keep_prob) ? __fmul_rn(v.y, inv) : 0.f;
+        o.z = dropout_keep(seed, 4 * q + 2, keep_prob) ? __fmul_rn(v.z, inv) : 0.f;
+        o.w = dropout_keep(seed, 4 * q + 3, keep_prob) ? __fmul_rn(v.w, inv) : 0.f;
+        out[q] = o;
+    }
+}
 __global__ void dropout_mask_kernel(long n, float keep_prob, unsigned long long seed,
                                     unsigned char *__restrict__ mask) {
+    pdl_enter();
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n;
          i += (long)gridDim.x * blockDim.x)
         mask[i] = dropout_keep(seed, i, keep_prob) ? 1 : 0;
@@ -680,6 +715,7 @@ __global__ void softmax_ce_reduce_kernel(long rows, int C, const float *__restri
                                          const int *__restrict__ labels,
                                          const float *__restrict__ weights,
                                          double *__restrict__ acc) {
+    pdl_enter();
     double s = 0.0, nz = 0.0;
     for (long r = blockIdx.x * (long)blockDim.x + threadIdx.x; r < rows;
          r += (long)gridDim.x * blockDim.x) {
@@ -713,6 +749,7 @@ __global__ void softmax_ce_grad_kernel(long rows, int C, const float *__restrict
                                        const double *__restrict__ acc, float gscale,
                                        const float *__restrict__ gscale_dev,
                                        float *__restrict__ loss, float *__restrict__ dlogits) {
+    pdl_enter();
     const double nz = acc[1] > 0.0 ? acc[1] : 1.0;
     if (blockIdx.x == 0 && threadIdx.x == 0 && loss) *loss = (float)(acc[0] / nz);
     if (!dlogits) return;
@@ -738,6 +775,7 @@ __global__ void softmax_ce_grad_kernel(long rows, int C, const float *__restrict
 __global__ void adam_kernel(long n, float *__restrict__ p, const float *__restrict__ g,
                             float *__restrict__ m, float *__restrict__ v, float lr_t, float b1,
                             float b2, float eps, float gscale) {
+    pdl_enter();
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n;
          i += (long)gridDim.x * blockDim.x) {
         const float gi = g[i] * gscale;
@@ -760,6 +798,7 @@ __global__ void __launch_bounds__(128)
 wgrad_skinny_v4_kernel(long M, int K, int N, long rpb, const float *__restrict__ A, int lda,
                        const float *__restrict__ a_scale, const float *__restrict__ a_shift, int a_relu,
                        const float *__restrict__ dY, float *__restrict__ dW, float *__restrict__ db) {
+    pdl_enter();
     __shared__ float red[4][NMAX][132];  // [warp][n][k within the 128-feature block] (+4: bank spread)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int k0 = blockIdx.y * 128 + lane * 4;
@@ -780,7 +819,7 @@ wgrad_skinny_v4_kernel(long M, int K, int N, long rpb, const float *__restrict__
     const long r0 = (long)blockIdx.x * rpb;
     const long r1 = r0 + rpb < M ? r0 + rpb : M;
     const bool full4 = k0 + 3 < K;
-#pragma unroll 4
+#pragma unroll 8
     for (long r = r0 + warp; r < r1; r += 4) {
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
         const float *ap = A + r * lda + k0;
@@ -817,16 +856,39 @@ wgrad_skinny_v4_kernel(long M, int K, int N, long rpb, const float *__restrict__
     for (int n = 0; n < NMAX; ++n)
         *reinterpret_cast<float4 *>(&red[warp][n][lane * 4]) = make_float4(acc[n][0], acc[n][1], acc[n][2], acc[n][3]);
     __syncthreads();
-    for (int e = threadIdx.x; e < N * 128; e += 128) {
-        const int n = e / 128, kk = e % 128;
-        const int k = blockIdx.y * 128 + kk;
-        if (k >= K) continue;
-        float v = 0.f;
+    // the block's 128 x N slice of dW is one contiguous run of floats: four consecutive ones per thread go out
+    // as ONE vector reduction (the same ~1k addresses take the sums of every block: the L2 atomic units, not
+    // the row loop, bounded this kernel)
+    float *base = dW + (long)blockIdx.y * 128 * N;
+    const int kvalid = K - blockIdx.y * 128 < 128 ? K - blockIdx.y * 128 : 128;
+    const int fvalid = kvalid * N;
+    const bool vec_ok = (reinterpret_cast<uintptr_t>(base) & 15) == 0;
+    for (int q = threadIdx.x; q < N * 32; q += 128) {
+        float v[4];
 #pragma unroll
-        for (int w = 0; w < 4; ++w) v += red[w][n][kk];
-        atomicAdd(dW + (long)k * N + n, v);
+        for (int j = 0; j < 4; ++j) {
+            const int f = 4 * q + j, kk = f / N, n = f - kk * N;
+            v[j] = (red[0][n][kk] + red[1][n][kk]) + (red[2][n][kk] + red[3][n][kk]);
+        }
+        if (vec_ok && 4 * q + 3 < fvalid) {
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(base + 4 * q), "f"(v[0]), "f"(v[1]),
+                         "f"(v[2]), "f"(v[3])
+                         : "memory");
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (4 * q + j < fvalid) atomicAdd(base + 4 * q + j, v[j]);
+        }
     }
-    if (db && blockIdx.y == 0 && lane < N) atomicAdd(db + lane, bsum);
+    if (db && blockIdx.y == 0) {
+        // one atomic per column and block
+        __syncthreads();
+        if (lane < N) red[warp][0][lane] = bsum;
+        __syncthreads();
+        if (threadIdx.x < N)
+            atomicAdd(db + threadIdx.x, (red[0][0][threadIdx.x] + red[1][0][threadIdx.x]) +
+                                            (red[2][0][threadIdx.x] + red[3][0][threadIdx.x]));
+    }
 }
 
 // dW[K,N] += f(A)^T dY for narrow outputs (N <= 16: the 9-class head).  Thread = feature k with N
@@ -837,6 +899,7 @@ __global__ void __launch_bounds__(128)
 wgrad_skinny_kernel(long M, int K, int N, long rpb, const float *__restrict__ A, int lda,
                     const float *__restrict__ a_scale, const float *__restrict__ a_shift, int a_relu,
                     const float *__restrict__ dY, float *__restrict__ dW) {
+    pdl_enter();
     __shared__ float sdy[64 * NMAX];
     const int k = blockIdx.y * 128 + threadIdx.x;
     const bool kok = k < K;
@@ -875,6 +938,7 @@ wgrad_skinny_kernel(long M, int K, int N, long rpb, const float *__restrict__ A,
 
 __global__ void colsum_kernel(long M, int N, long rpb, const float *__restrict__ X,
                               float *__restrict__ out) {
+    pdl_enter();
     const Slab s = make_slab(M, N, rpb);
     if (!s.active) return;
     for (int c = s.cx; c < N; c += s.lanes) {
@@ -1042,10 +1106,11 @@ PN2_API int pn2_linear_wgrad(long M, int K, int N, const float *A, int lda, cons
         static const bool old_skinny = getenv("PN2_WGRAD_SKINNY_V1") && getenv("PN2_WGRAD_SKINNY_V1")[0] == '1';
         const bool v4 = !old_skinny && (lda % 4 == 0) && (reinterpret_cast<uintptr_t>(A) & 15) == 0;
         if (v4) {  // warp per 128 features, float4 rows, bias gradient in the same pass
-            long rpb = ceil_div<long>(M, 148L * 6);
-            rpb = ceil_div<long>(rpb, 4L) * 4;
+            static const int bps = getenv("PN2_SKINNY_BPS") ? atoi(getenv("PN2_SKINNY_BPS")) : 3;
+            long rpb = ceil_div<long>(M, 148L * (bps > 0 ? bps : 3));
+            rpb = ceil_div<long>(rpb, 8L) * 8;
             dim3 grid((unsigned)ceil_div<long>(M, rpb), (unsigned)ceil_div(K, 128));
-            wgrad_skinny_v4_kernel<16><<<grid, 128, 0, st>>>(M, K, N, rpb, A, lda, a_scale, a_shift, a_relu, dY,
+            launch_k(wgrad_skinny_v4_kernel<16>, grid, 128, 0, st, M, K, N, rpb, A, lda, a_scale, a_shift, a_relu, dY,
                                                              dW, db);
             rc = finish_launch();
             if (rc) return rc;
@@ -1055,7 +1120,7 @@ PN2_API int pn2_linear_wgrad(long M, int K, int N, const float *A, int lda, cons
             long rpb = ceil_div<long>(M, 148L * 7);
             rpb = ceil_div<long>(rpb, 64L) * 64;
             dim3 grid((unsigned)ceil_div<long>(M, rpb), (unsigned)ceil_div(K, 128));
-            wgrad_skinny_kernel<16><<<grid, 128, 0, st>>>(M, K, N, rpb, A, lda, a_scale, a_shift, a_relu, dY, dW);
+            launch_k(wgrad_skinny_kernel<16>, grid, 128, 0, st, M, K, N, rpb, A, lda, a_scale, a_shift, a_relu, dY, dW);
             rc = finish_launch();
             if (rc) return rc;
         }
@@ -1079,7 +1144,7 @@ PN2_API int pn2_linear_wgrad(long M, int K, int N, const float *A, int lda, cons
         if (rc == PN2_OK && db) {
             long rpb = ceil_div<long>(M, 64L);
             if (rpb < 32) rpb = 32;
-            colsum_kernel<<<(int)ceil_div<long>(M, rpb), 256, 0, st>>>(M, N, rpb, dY, db);
+            launch_k(colsum_kernel, (int)ceil_div<long>(M, rpb), 256, 0, st, M, N, rpb, dY, db);
             rc = finish_launch();
         }
         return rc;
@@ -1100,7 +1165,7 @@ PN2_API int pn2_linear_wgrad(long M, int K, int N, const float *A, int lda, cons
         long rpb = ceil_div<long>(M, 64L);
         if (rpb < 32) rpb = 32;
         int blocks = (int)ceil_div<long>(M, rpb);
-        colsum_kernel<<<blocks, 256, 0, st>>>(M, N, rpb, dY, db);
+        launch_k(colsum_kernel, blocks, 256, 0, st, M, N, rpb, dY, db);
         rc = finish_launch();
     }
     return rc;
@@ -1118,7 +1183,7 @@ PN2_API int pn2_bn_train_finalize(int N, long M, const double *stats, const floa
     PN2_REQUIRE_PTR(shift);
     PN2_REQUIRE_PTR(saved);
     PN2_REQUIRE((moving_mean == nullptr) == (moving_var == nullptr));
-    bn_train_finalize_kernel<<<ceil_div(N, 128), 128, 0, as_stream(s)>>>(
+    launch_k(bn_train_finalize_kernel, ceil_div(N, 128), 128, 0, as_stream(s), 
         N, M, stats, gamma, beta, eps, decay, unbiased_moving, moving_mean, moving_var, scale, shift,
         saved);
     return finish_launch();
@@ -1134,7 +1199,7 @@ PN2_API int pn2_bn_eval_affine(int N, const float *gamma, const float *beta,
     PN2_REQUIRE_PTR(moving_var);
     PN2_REQUIRE_PTR(scale);
     PN2_REQUIRE_PTR(shift);
-    bn_eval_affine_kernel<<<ceil_div(N, 128), 128, 0, as_stream(s)>>>(
+    launch_k(bn_eval_affine_kernel, ceil_div(N, 128), 128, 0, as_stream(s), 
         N, gamma, beta, moving_mean, moving_var, eps, scale, shift);
     return finish_launch();
 }
@@ -1151,10 +1216,10 @@ PN2_API int pn2_affine_act(long M, int N, const float *Y, const float *scale, co
                     (scale == nullptr ||
                      ((reinterpret_cast<uintptr_t>(scale) | reinterpret_cast<uintptr_t>(shift)) & 15) == 0);
     if (v4)
-        affine_act_v4_kernel<<<grid_for(total / 4, 256), 256, 0, as_stream(s)>>>(total / 4, N / 4, Y, scale,
+        launch_k(affine_act_v4_kernel, grid_for(total / 4, 256), 256, 0, as_stream(s), total / 4, N / 4, Y, scale,
                                                                                shift, relu, Z, ldz);
     else
-        affine_act_kernel<<<grid_for(total, 256), 256, 0, as_stream(s)>>>(total, N, Y, scale, shift,
+        launch_k(affine_act_kernel, grid_for(total, 256), 256, 0, as_stream(s), total, N, Y, scale, shift,
                                                                           relu, Z, ldz);
     return finish_launch();
 }
@@ -1172,10 +1237,10 @@ PN2_API int pn2_affine_act_maxpool(long G, int ns, int N, const float *Y, const 
                     (scale == nullptr ||
                      ((reinterpret_cast<uintptr_t>(scale) | reinterpret_cast<uintptr_t>(shift)) & 15) == 0);
     if (v4)
-        affine_act_maxpool_v4_kernel<<<grid_for(total / 4, 128), 128, 0, as_stream(s)>>>(
+        launch_k(affine_act_maxpool_v4_kernel, grid_for(total / 4, 128), 128, 0, as_stream(s), 
             total / 4, ns, N, Y, scale, shift, relu, out, arg);
     else
-        affine_act_maxpool_kernel<<<grid_for(total, 128), 128, 0, as_stream(s)>>>(
+        launch_k(affine_act_maxpool_kernel, grid_for(total, 128), 128, 0, as_stream(s), 
             total, ns, N, Y, scale, shift, relu, out, arg);
     return finish_launch();
 }
@@ -1200,11 +1265,11 @@ PN2_API int pn2_bn_bwd_reduce(long M, int N, const float *dZ, int ldz, const flo
         long rpb4 = ceil_div<long>(M, 148L * (bps > 0 ? bps : 2));
         if (rpb4 < 32) rpb4 = 32;
         const int blocks4 = (int)ceil_div<long>(M, rpb4);
-        bn_bwd_reduce_v4_kernel<<<blocks4, 256, 2 * N * sizeof(double), as_stream(s)>>>(
+        launch_k(bn_bwd_reduce_v4_kernel, blocks4, 256, 2 * N * sizeof(double), as_stream(s), 
             M, N, rpb4, dZ, ldz, Y, scale, shift, saved, relu, red);
     }
     else
-        bn_bwd_reduce_kernel<<<blocks, 256, 2 * N * sizeof(double), as_stream(s)>>>(
+        launch_k(bn_bwd_reduce_kernel, blocks, 256, 2 * N * sizeof(double), as_stream(s), 
             M, N, rpb, dZ, ldz, Y, scale, shift, saved, relu, red);
     return finish_launch();
 }
@@ -1230,11 +1295,11 @@ PN2_API int pn2_bn_bwd_apply(long M, int N, const float *dZ, int ldz, const floa
     long rpb = slab_rows(M, &blocks);
     if (vec4_ok(N, ldz, dZ, Y) && (reinterpret_cast<uintptr_t>(dY) & 15) == 0 &&
         (scale == nullptr || ((reinterpret_cast<uintptr_t>(scale) | reinterpret_cast<uintptr_t>(shift)) & 15) == 0))
-        bn_bwd_apply_v4_kernel<<<blocks, 256, 0, as_stream(s)>>>(M, N, rpb, dZ, ldz, Y, scale, shift,
+        launch_k(bn_bwd_apply_v4_kernel, blocks, 256, 0, as_stream(s), M, N, rpb, dZ, ldz, Y, scale, shift,
                                                                  saved, gamma, relu, bn, red, dY, dgamma,
                                                                  dbeta);
     else
-        bn_bwd_apply_kernel<<<blocks, 256, 0, as_stream(s)>>>(M, N, rpb, dZ, ldz, Y, scale, shift, saved,
+        launch_k(bn_bwd_apply_kernel, blocks, 256, 0, as_stream(s), M, N, rpb, dZ, ldz, Y, scale, shift, saved,
                                                               gamma, relu, bn, red, dY, dgamma, dbeta);
     return finish_launch();
 }
@@ -1256,7 +1321,7 @@ PN2_API int pn2_bn_bwd_reduce_pool(long G, int ns, int N, const float *dOut, con
     if (blocks > 148L * 4) blocks = 148L * 4;
     if (blocks > G) blocks = G;
     if (blocks < 1) blocks = 1;
-    bn_bwd_reduce_pool_kernel<<<(int)blocks, 256, 2 * N * sizeof(double), as_stream(s)>>>(
+    launch_k(bn_bwd_reduce_pool_kernel, (int)blocks, 256, 2 * N * sizeof(double), as_stream(s), 
         G, ns, N, dOut, arg, Y, scale, shift, saved, relu, red);
     return finish_launch();
 }
@@ -1286,13 +1351,13 @@ PN2_API int pn2_bn_bwd_apply_pool(long G, int ns, int N, const float *dOut, cons
     if (v4) {
         long gpb = ceil_div<long>(G, 148L * 8);
         if (gpb < 1) gpb = 1;
-        bn_bwd_apply_pool_v4_kernel<<<(int)ceil_div<long>(G, gpb), 256, 0, as_stream(s)>>>(
+        launch_k(bn_bwd_apply_pool_v4_kernel, (int)ceil_div<long>(G, gpb), 256, 0, as_stream(s), 
             G, ns, N, gpb, dOut, arg, Y, scale, shift, saved, gamma, relu, bn, red, dY, dgamma, dbeta);
         return finish_launch();
     }
     int blocks;
     long rpb = slab_rows(G * ns, &blocks);
-    bn_bwd_apply_pool_kernel<<<blocks, 256, 0, as_stream(s)>>>(G, ns, N, rpb, dOut, arg, Y, scale,
+    launch_k(bn_bwd_apply_pool_kernel, blocks, 256, 0, as_stream(s), G, ns, N, rpb, dOut, arg, Y, scale,
                                                                shift, saved, gamma, relu, bn, red, dY,
                                                                dgamma, dbeta);
     return finish_launch();
@@ -1303,7 +1368,7 @@ PN2_API int pn2_pool_weights(long G, int ns, const float *grouped_xyz, int ld, f
     if (G == 0) return PN2_OK;
     PN2_REQUIRE_PTR(grouped_xyz);
     PN2_REQUIRE_PTR(w);
-    pool_weights_kernel<<<grid_for(G, 128), 128, 0, as_stream(s)>>>(G, ns, grouped_xyz, ld, w);
+    launch_k(pool_weights_kernel, grid_for(G, 128), 128, 0, as_stream(s), G, ns, grouped_xyz, ld, w);
     return finish_launch();
 }
 
@@ -1315,7 +1380,7 @@ PN2_API int pn2_group_pool(long G, int ns, int N, const float *X, const float *w
     PN2_REQUIRE_PTR(out);
     if (mode == 2) PN2_REQUIRE_PTR(w);
     if (mode == 3) PN2_REQUIRE_PTR(arg);
-    group_pool_kernel<<<grid_for(G * N, 128), 128, 0, as_stream(s)>>>(G * N, ns, N, X, w, mode, out, arg);
+    launch_k(group_pool_kernel, grid_for(G * N, 128), 128, 0, as_stream(s), G * N, ns, N, X, w, mode, out, arg);
     return finish_launch();
 }
 
@@ -1327,7 +1392,7 @@ PN2_API int pn2_group_pool_grad(long G, int ns, int N, const float *dOut, const 
     PN2_REQUIRE_PTR(dX);
     if (mode == 2) PN2_REQUIRE_PTR(w);
     if (mode == 3) PN2_REQUIRE_PTR(arg);
-    group_pool_grad_kernel<<<grid_for(G * ns * N, 256), 256, 0, as_stream(s)>>>(G * ns * N, ns, N, dOut, w, arg,
+    launch_k(group_pool_grad_kernel, grid_for(G * ns * N, 256), 256, 0, as_stream(s), G * ns * N, ns, N, dOut, w, arg,
                                                                                 mode, dX);
     return finish_launch();
 }
@@ -1339,7 +1404,7 @@ PN2_API int pn2_relu_mask(long M, int N, const float *Y, const float *scale, con
     if (M == 0) return PN2_OK;
     PN2_REQUIRE_PTR(Y);
     PN2_REQUIRE_PTR(mask);
-    relu_mask_kernel<<<grid_for(M * N, 256), 256, 0, as_stream(s)>>>(M * N, N, Y, scale, shift, mask);
+    launch_k(relu_mask_kernel, grid_for(M * N, 256), 256, 0, as_stream(s), M * N, N, Y, scale, shift, mask);
     return finish_launch();
 }
 
@@ -1349,8 +1414,13 @@ PN2_API int pn2_dropout(long n, const float *x, float keep_prob, unsigned long l
     if (n == 0) return PN2_OK;
     PN2_REQUIRE_PTR(x);
     PN2_REQUIRE_PTR(out);
-    dropout_kernel<<<grid_for(n, 256), 256, 0, as_stream(s)>>>(n, x, keep_prob, 1.0f / keep_prob,
-                                                               seed, seed_dev, out);
+    if ((n % 4) == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0)
+        launch_k(dropout_v4_kernel, grid_for(n / 4, 256), 256, 0, as_stream(s), 
+            n / 4, reinterpret_cast<const float4 *>(x), keep_prob, 1.0f / keep_prob, seed, seed_dev,
+            reinterpret_cast<float4 *>(out));
+    else
+        launch_k(dropout_kernel, grid_for(n, 256), 256, 0, as_stream(s), n, x, keep_prob, 1.0f / keep_prob,
+                                                                   seed, seed_dev, out);
     return finish_launch();
 }
 
@@ -1359,7 +1429,7 @@ PN2_API int pn2_dropout_mask(long n, float keep_prob, unsigned long long seed,
     PN2_REQUIRE(n >= 0 && keep_prob > 0.f && keep_prob <= 1.f);
     if (n == 0) return PN2_OK;
     PN2_REQUIRE_PTR(mask);
-    dropout_mask_kernel<<<grid_for(n, 256), 256, 0, as_stream(s)>>>(n, keep_prob, seed, mask);
+    launch_k(dropout_mask_kernel, grid_for(n, 256), 256, 0, as_stream(s), n, keep_prob, seed, mask);
     return finish_launch();
 }
 
@@ -1370,7 +1440,7 @@ PN2_API int pn2_softmax_ce_reduce(long rows, int C, const float *logits, const i
     PN2_REQUIRE_PTR(logits);
     PN2_REQUIRE_PTR(labels);
     PN2_REQUIRE_PTR(acc);
-    softmax_ce_reduce_kernel<<<grid_for(rows, 256), 256, 0, as_stream(s)>>>(rows, C, logits, labels,
+    launch_k(softmax_ce_reduce_kernel, grid_for(rows, 256), 256, 0, as_stream(s), rows, C, logits, labels,
                                                                            weights, acc);
     return finish_launch();
 }
@@ -1384,7 +1454,7 @@ PN2_API int pn2_softmax_ce_grad(long rows, int C, const float *logits, const int
     PN2_REQUIRE_PTR(logits);
     PN2_REQUIRE_PTR(labels);
     PN2_REQUIRE_PTR(acc);
-    softmax_ce_grad_kernel<<<grid_for(rows, 256), 256, 0, as_stream(s)>>>(
+    launch_k(softmax_ce_grad_kernel, grid_for(rows, 256), 256, 0, as_stream(s), 
         rows, C, logits, labels, weights, acc, gscale, gscale_dev, loss, dlogits);
     return finish_launch();
 }
@@ -1399,7 +1469,7 @@ PN2_API int pn2_adam_step(long n, float *p, const float *g, float *m, float *v, 
     PN2_REQUIRE_PTR(m);
     PN2_REQUIRE_PTR(v);
     const double lr_t = (double)lr * sqrt(1.0 - pow((double)beta2, t)) / (1.0 - pow((double)beta1, t));
-    adam_kernel<<<grid_for(n, 256), 256, 0, as_stream(s)>>>(n, p, g, m, v, (float)lr_t, beta1, beta2,
+    launch_k(adam_kernel, grid_for(n, 256), 256, 0, as_stream(s), n, p, g, m, v, (float)lr_t, beta1, beta2,
                                                             eps, gscale);
     return finish_launch();
 }

@@ -59,6 +59,7 @@ __device__ __forceinline__ bool in_box(const double *__restrict__ p, const doubl
 }
 
 __global__ void __launch_bounds__(BS_THREADS) box_sample_kernel(const BoxParams p) {
+    pdl_enter();
     typedef cub::BlockScan<int, BS_THREADS> Scan;
     typedef cub::BlockReduce<int, BS_THREADS> ReduceI;
     typedef cub::BlockReduce<double, BS_THREADS> ReduceD;
@@ -271,6 +272,6 @@ PN2_API int pn2_box_sample(int B, long P, int num_point, int feat, const double 
     p.out_labels = out_labels;
     p.out_index = out_index;
     p.out_count = out_count;
-    box_sample_kernel<<<B, BS_THREADS, 0, as_stream(s)>>>(p);
+    launch_k(box_sample_kernel, B, BS_THREADS, 0, as_stream(s), p);
     return finish_launch();
 }

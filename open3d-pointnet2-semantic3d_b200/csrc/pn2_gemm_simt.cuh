@@ -35,6 +35,7 @@ gemm_simt_kernel(int Mp, int Np, long Kp, const float *__restrict__ A, long a_sm
                  const float *__restrict__ a_scale, const float *__restrict__ a_shift, int a_relu,
                  const float *__restrict__ bias, float *__restrict__ C, long ldc,
                  double *__restrict__ stats, long k_chunk) {
+    pdl_enter();
     constexpr int TM = BM / 16, TN = BN / 16;
     constexpr int LDA = BM + 4, LDB = BN + 4;
     constexpr int A_PER = BM * G_BK / G_THREADS, B_PER = BN * G_BK / G_THREADS;

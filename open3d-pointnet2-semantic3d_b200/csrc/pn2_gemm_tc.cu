@@ -188,6 +188,7 @@ __host__ __device__ __forceinline__ uint32_t sw128_offset(int row, int k) {
 __global__ void tc_prep_b_kernel(int N, int Ntot, int K, int Npad, int KC, int nchunks,
                                  const float *__restrict__ src, long s_n, long s_k,
                                  float *__restrict__ image) {
+    pdl_enter();
     const long total = (long)nchunks * KC * Npad * BK;
     for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total;
          e += (long)gridDim.x * blockDim.x) {
@@ -213,6 +214,7 @@ __global__ void tc_prep_b_kernel(int N, int Ntot, int K, int Npad, int KC, int n
 // All weight images of a step in ONE launch: blockIdx.y = table entry, blockIdx.x strides over its
 // elements (same element mapping as tc_prep_b_kernel).
 __global__ void tc_prep_images_kernel(const pn2_linear_image *__restrict__ table) {
+    pdl_enter();
     const pn2_linear_image d = table[blockIdx.y];
     for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < d.total;
          e += (long)gridDim.x * blockDim.x) {
@@ -290,6 +292,7 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap *tm, int c0, int 
 __global__ void __launch_bounds__(THREADS, 1)
     tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmY,
                    const Params p) {
+    pdl_trigger();
     extern __shared__ __align__(1024) unsigned char smem[];
     // carve:  [resident B: KC x (B_hi | B_lo)]            (p.b_res: weights loaded once per CTA)
     //         stages x [A_hi 16K | A_lo 16K (| B_hi | B_lo when B is streamed per chunk)]
@@ -341,8 +344,6 @@ __global__ void __launch_bounds__(THREADS, 1)
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (threadIdx.x < 128)
-        sbias[threadIdx.x] = (p.bias && (int)threadIdx.x < Nv) ? __ldg(p.bias + n0 + threadIdx.x) : 0.f;
     if (warp == W_MMA) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                          smem_u32(tmem_slot)),
@@ -350,6 +351,11 @@ __global__ void __launch_bounds__(THREADS, 1)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    // barrier init and TMEM allocation above overlap the tail of the previous kernel; nothing before this line
+    // touches global memory (the tensor maps are kernel parameters)
+    pdl_wait();
+    if (threadIdx.x < 128)
+        sbias[threadIdx.x] = (p.bias && (int)threadIdx.x < Nv) ? __ldg(p.bias + n0 + threadIdx.x) : 0.f;
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -918,7 +924,7 @@ static int run_chunk(long M, int K, int Nc, int nchunks, int Ntot, const float *
         const long total = (long)nchunks * p.KC * p.Npad * BK;
         int pb = (int)((total + 255) / 256);
         if (pb > 148 * 8) pb = 148 * 8;
-        tc_prep_b_kernel<<<pb, 256, 0, st>>>(Nc, Ntot, K, p.Npad, p.KC, nchunks, bsrc, s_n, s_k, ws);
+        launch_k(tc_prep_b_kernel, pb, 256, 0, st, Nc, Ntot, K, p.Npad, p.KC, nchunks, bsrc, s_n, s_k, ws);
         rc = finish_launch();
         if (rc) return rc;
     }
@@ -932,7 +938,7 @@ static int run_chunk(long M, int K, int Nc, int nchunks, int Ntot, const float *
     if (per_chunk < 1) per_chunk = 1;
     if (per_chunk > tiles) per_chunk = tiles;
     const int grid = (int)per_chunk * nchunks;
-    tc_gemm_kernel<<<grid, THREADS, smem, st>>>(tmA, tmY, p);
+    launch_k(tc_gemm_kernel, grid, THREADS, smem, st, tmA, tmY, p);
     return finish_launch();
 }
 
@@ -1008,6 +1014,7 @@ struct WParams {
 __global__ void __launch_bounds__(W_THREADS, 1)
     tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG,
                     const WParams p) {
+    pdl_trigger();
     extern __shared__ __align__(1024) unsigned char smem[];
     // carve: W_STAGES x [X_hi | X_lo | G_hi | G_lo], W_RAW x [X raw | G raw], barriers
     const uint32_t a_bytes = (uint32_t)p.rows * p.MG * 128;
@@ -1048,6 +1055,7 @@ __global__ void __launch_bounds__(W_THREADS, 1)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    pdl_wait();  // everything above (barrier init, TMEM allocation) overlaps the previous kernel's tail
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -1372,7 +1380,7 @@ static int run(long M, int K, int Kdo, int N, const float *A, int lda, const flo
     int rc = tc::opt_in_smem(reinterpret_cast<const void *>(tc_wgrad_kernel), 1);
     if (rc) return rc;
     const int grid = (int)(p.units < num_sms() ? p.units : num_sms());
-    tc_wgrad_kernel<<<grid, W_THREADS, smem, st>>>(tmX, tmG, p);
+    launch_k(tc_wgrad_kernel, grid, W_THREADS, smem, st, tmX, tmG, p);
     return finish_launch();
 }
 
@@ -1441,7 +1449,7 @@ size_t tc_image_bytes_for(int K, int N, bool dgrad) {
 int tc_prepare_images(int count, const pn2_linear_image *table_dev, cudaStream_t st) {
     if (count <= 0) return PN2_OK;
     dim3 grid(32, (unsigned)count);
-    tc::tc_prep_images_kernel<<<grid, 256, 0, st>>>(table_dev);
+    launch_k(tc::tc_prep_images_kernel, grid, 256, 0, st, table_dev);
     return finish_launch();
 }
 

@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(BQ_THREADS)
 ball_query_stream_kernel(int n, int m, float thr, int nsample, const float *__restrict__ xyz1,
                          const float *__restrict__ xyz2, int *__restrict__ idx,
                          int *__restrict__ pts_cnt) {
+    pdl_enter();
     __shared__ __align__(128) float tile[2][BQ_TILE * 3];
     __shared__ __align__(8) uint64_t full[2];
 
@@ -170,6 +171,7 @@ __global__ void __launch_bounds__(BQ_THREADS)
 ball_query_resident_kernel(int n, int m, float thr, int nsample, int use_tma,
                            const float *__restrict__ xyz1, const float *__restrict__ xyz2,
                            int *__restrict__ idx, int *__restrict__ pts_cnt) {
+    pdl_enter();
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int QPB = BQ_THREADS / SPLIT;
     const int npad = ((n + SPLIT * 4 - 1) / (SPLIT * 4)) * (SPLIT * 4);  // whole rounds
@@ -266,6 +268,7 @@ template <typename VT>
 __global__ void group_point_kernel(int n, int cv, long rows_per_cloud, long total,
                                    const VT *__restrict__ points, const int *__restrict__ idx,
                                    VT *__restrict__ out) {
+    pdl_enter();
     // cv = channels in units of VT; e = row*cv + l
     for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total;
          e += (long)gridDim.x * blockDim.x) {
@@ -281,6 +284,7 @@ __global__ void group_point_grad_kernel(int n, int c, long rows_per_cloud, long 
                                         const float *__restrict__ grad_out,
                                         const int *__restrict__ idx,
                                         float *__restrict__ grad_points) {
+    pdl_enter();
     for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total;
          e += (long)gridDim.x * blockDim.x) {
         long row = e / c;
@@ -297,6 +301,7 @@ __global__ void group_concat_kernel(int n, int m, int ns, int c, int w, int ld, 
                                     const float *__restrict__ new_xyz,
                                     const float *__restrict__ points,
                                     const int *__restrict__ idx, float *__restrict__ out) {
+    pdl_enter();
     for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total;
          e += (long)gridDim.x * blockDim.x) {
         long row = e / w;
@@ -315,6 +320,42 @@ __global__ void group_concat_kernel(int n, int m, int ns, int c, int w, int ld, 
     }
 }
 
+// c % 4 == 0: the feature channels of a grouped row as float4 gathers (one thread per row and channel quad, 32-bit
+// index arithmetic, the neighbour index read once per quad); the destination columns start at an odd offset
+// (3 + 4q behind the centred xyz) so they are written as four scalars, consecutive across the threads of a row.
+__global__ void group_concat_feat_v4_kernel(int n, int m_ns, int c, int ld, int poff, unsigned total4,
+                                            const float *__restrict__ points, const int *__restrict__ idx,
+                                            float *__restrict__ out) {
+    pdl_enter();
+    const unsigned c4 = (unsigned)c >> 2;
+    for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < total4; e += gridDim.x * blockDim.x) {
+        const unsigned row = e / c4, q = e - row * c4;
+        const unsigned cloud = row / (unsigned)m_ns;
+        const int ii = __ldg(idx + row);
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(points + ((size_t)cloud * n + ii) * c) + q);
+        float *o = out + (size_t)row * ld + poff + 4 * q;
+        o[0] = v.x;
+        o[1] = v.y;
+        o[2] = v.z;
+        o[3] = v.w;
+    }
+}
+// the three centred coordinates of every grouped row
+__global__ void group_concat_xyz_kernel(int n, int ns, int m, int ld, int xoff, unsigned rows,
+                                        const float *__restrict__ xyz, const float *__restrict__ new_xyz,
+                                        const int *__restrict__ idx, float *__restrict__ out) {
+    pdl_enter();
+    for (unsigned row = blockIdx.x * blockDim.x + threadIdx.x; row < rows; row += gridDim.x * blockDim.x) {
+        const unsigned grp = row / (unsigned)ns, cloud = grp / (unsigned)m;
+        const int ii = __ldg(idx + row);
+        const float *p = xyz + ((size_t)cloud * n + ii) * 3, *q = new_xyz + (size_t)grp * 3;
+        float *o = out + (size_t)row * ld + xoff;
+        o[0] = __fsub_rn(__ldg(p), __ldg(q));
+        o[1] = __fsub_rn(__ldg(p + 1), __ldg(q + 1));
+        o[2] = __fsub_rn(__ldg(p + 2), __ldg(q + 2));
+    }
+}
+
 // Feature part of the gradient with vector reductions: one thread per (grouped row, 4 consecutive feature
 // channels) -> ONE red.global.add.v4.f32 instead of four scalar atomics (c % 4 == 0 makes the destination
 // 16-byte aligned; the source row pitch 3+c is odd, so the four gradients are loaded as scalars).
@@ -322,6 +363,7 @@ __global__ void group_concat_grad_feat_v4_kernel(int n, int m, int ns, int c, in
                                                  const float *__restrict__ grad_out,
                                                  const int *__restrict__ idx,
                                                  float *__restrict__ grad_points) {
+    pdl_enter();
     const int c4 = c >> 2;
     for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total4;
          e += (long)gridDim.x * blockDim.x) {
@@ -344,6 +386,7 @@ __global__ void group_concat_grad_kernel(int n, int m, int ns, int c, int w, int
                                          float *__restrict__ grad_points,
                                          float *__restrict__ grad_xyz,
                                          float *__restrict__ grad_new_xyz) {
+    pdl_enter();
     for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total;
          e += (long)gridDim.x * blockDim.x) {
         long row = e / w;
@@ -503,6 +546,7 @@ __device__ __forceinline__ int selection_passes(const Row &row, int n, int k, un
 __global__ void __launch_bounds__(32 * SEL_WARPS)
 selection_sort_kernel(long rows, int n, int k, const float *__restrict__ dist, int *__restrict__ outi,
                       float *__restrict__ out) {
+    pdl_enter();
     extern __shared__ unsigned sel_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int words = (n + 31) >> 5;
@@ -547,6 +591,7 @@ template <int C>
 __global__ void __launch_bounds__(32 * SEL_WARPS)
 knn_point_kernel(int n, int c, int m, int k, const float *__restrict__ xyz1, const float *__restrict__ xyz2,
                  float *__restrict__ val, int *__restrict__ idx) {
+    pdl_enter();
     extern __shared__ unsigned sel_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int words = (n + 31) >> 5;
@@ -626,6 +671,7 @@ __device__ __forceinline__ bool finite3(float x, float y, float z) {
 __global__ void grid_count_kernel(int n, long total, unsigned tmask, float inv,
                                   const float *__restrict__ xyz, int *__restrict__ cursor,
                                   int *__restrict__ flag) {
+    pdl_enter();
     for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total;
          e += (long)gridDim.x * blockDim.x) {
         const long cloud = e / n;
@@ -639,6 +685,7 @@ __global__ void grid_count_kernel(int n, long total, unsigned tmask, float inv,
 // pass 2: starts = exclusive scan of the populations (one CTA per cloud), cursor = starts
 __global__ void __launch_bounds__(1024)
 grid_scan_kernel(int T, int *__restrict__ cursor, int *__restrict__ starts, int starts_pitch) {
+    pdl_enter();
     typedef cub::BlockScan<int, 1024> Scan;
     __shared__ typename Scan::TempStorage tmp;
     int *cur = cursor + (long)blockIdx.x * T;
@@ -662,6 +709,7 @@ grid_scan_kernel(int T, int *__restrict__ cursor, int *__restrict__ starts, int 
 __global__ void grid_fill_kernel(int n, long total, unsigned tmask, float inv,
                                  const float *__restrict__ xyz, int *__restrict__ cursor,
                                  float4 *__restrict__ sorted) {
+    pdl_enter();
     for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total;
          e += (long)gridDim.x * blockDim.x) {
         const long cloud = e / n;
@@ -680,6 +728,7 @@ ball_query_grid_kernel(int n, int m, long queries, unsigned tmask, int starts_pi
                        const float *__restrict__ xyz2, const int *__restrict__ starts,
                        const float4 *__restrict__ sorted, const int *__restrict__ flag,
                        int *__restrict__ idx, int *__restrict__ pts_cnt) {
+    pdl_enter();
     __shared__ int hits[GQ_WARPS][GQ_CAP];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt = (1u << lane) - 1u;
@@ -821,7 +870,7 @@ PN2_API int pn2_query_ball_point(int b, int n, int m, float radius, int nsample,
         auto kern = ball_query_resident_kernel<SP>;                                             \
         rc = opt_in_dyn_smem(kern, res_smem);                                                   \
         if (rc) return rc;                                                                      \
-        kern<<<grid, BQ_THREADS, res_smem, st>>>(n, m, thr, nsample, tma_ok ? 1 : 0, xyz1,     \
+        launch_k(kern, grid, BQ_THREADS, res_smem, st, n, m, thr, nsample, tma_ok ? 1 : 0, xyz1,     \
                                                  xyz2, idx, pts_cnt);                           \
     } while (0)
         if (split == 2) PN2_LAUNCH_RES(2);
@@ -832,10 +881,10 @@ PN2_API int pn2_query_ball_point(int b, int n, int m, float radius, int nsample,
     }
     dim3 grid((unsigned)ceil_div(m, BQ_THREADS), (unsigned)b);
     if (tma_ok)
-        ball_query_stream_kernel<true><<<grid, BQ_THREADS, 0, st>>>(n, m, thr, nsample, xyz1, xyz2,
+        launch_k(ball_query_stream_kernel<true>, grid, BQ_THREADS, 0, st, n, m, thr, nsample, xyz1, xyz2,
                                                                     idx, pts_cnt);
     else
-        ball_query_stream_kernel<false><<<grid, BQ_THREADS, 0, st>>>(n, m, thr, nsample, xyz1,
+        launch_k(ball_query_stream_kernel<false>, grid, BQ_THREADS, 0, st, n, m, thr, nsample, xyz1,
                                                                      xyz2, idx, pts_cnt);
     return finish_launch();
 }
@@ -853,12 +902,12 @@ PN2_API int pn2_group_point(int b, int n, int c, int m, int nsample, const float
                      (reinterpret_cast<uintptr_t>(out) % 16 == 0);
     if (vec) {
         long total = rows * (c / 4);
-        group_point_kernel<float4><<<grid_for(total, 256), 256, 0, st>>>(
+        launch_k(group_point_kernel<float4>, grid_for(total, 256), 256, 0, st, 
             n, c / 4, (long)m * nsample, total, reinterpret_cast<const float4 *>(points), idx,
             reinterpret_cast<float4 *>(out));
     } else {
         long total = rows * c;
-        group_point_kernel<float><<<grid_for(total, 256), 256, 0, st>>>(
+        launch_k(group_point_kernel<float>, grid_for(total, 256), 256, 0, st, 
             n, c, (long)m * nsample, total, points, idx, out);
     }
     return finish_launch();
@@ -876,7 +925,7 @@ PN2_API int pn2_group_point_grad(int b, int n, int c, int m, int nsample, const 
     if (total == 0) return PN2_OK;
     PN2_REQUIRE_PTR(grad_out);
     PN2_REQUIRE_PTR(idx);
-    group_point_grad_kernel<<<grid_for(total, 256), 256, 0, st>>>(n, c, (long)m * nsample, total,
+    launch_k(group_point_grad_kernel, grid_for(total, 256), 256, 0, st, n, c, (long)m * nsample, total,
                                                                   grad_out, idx, grad_points);
     return finish_launch();
 }
@@ -898,7 +947,19 @@ PN2_API int pn2_group_concat_ld(int b, int n, int m, int nsample, int c, const f
     }
     if (c > 0) PN2_REQUIRE_PTR(points);
     const int xoff = xyz_first ? 0 : c, poff = (use_xyz && xyz_first) ? 3 : 0;
-    group_concat_kernel<<<grid_for(total, 256), 256, 0, as_stream(s)>>>(
+    const long rows = (long)b * m * nsample;
+    if (c > 0 && (c % 4) == 0 && (reinterpret_cast<uintptr_t>(points) & 15) == 0 && rows * (c / 4) < (1L << 32) &&
+        rows < (1L << 31)) {
+        cudaStream_t st = as_stream(s);
+        launch_k(group_concat_feat_v4_kernel, grid_for(rows * (c / 4), 256), 256, 0, st, 
+            n, m * nsample, c, ld, poff, (unsigned)(rows * (c / 4)), points, idx, out);
+        int rc = finish_launch();
+        if (rc || !use_xyz) return rc;
+        launch_k(group_concat_xyz_kernel, grid_for(rows, 256), 256, 0, st, n, nsample, m, ld, xoff, (unsigned)rows, xyz,
+                                                                    new_xyz, idx, out);
+        return finish_launch();
+    }
+    launch_k(group_concat_kernel, grid_for(total, 256), 256, 0, as_stream(s), 
         n, m, nsample, c, w, ld, xoff, poff, use_xyz, total, xyz, new_xyz, points, idx, out);
     return finish_launch();
 }
@@ -939,14 +1000,14 @@ PN2_API int pn2_group_concat_grad(int b, int n, int m, int nsample, int c, const
         // feature channels by vector reductions; the xyz columns keep the scalar kernel (and are skipped
         // altogether when nobody asked for xyz gradients: the model never does)
         const long total4 = (long)b * m * nsample * (c / 4);
-        group_concat_grad_feat_v4_kernel<<<grid_for(total4, 256), 256, 0, st>>>(n, m, nsample, c, w, poff, total4,
+        launch_k(group_concat_grad_feat_v4_kernel, grid_for(total4, 256), 256, 0, st, n, m, nsample, c, w, poff, total4,
                                                                                 grad_out, idx, grad_points);
         rc = finish_launch();
         if (rc) return rc;
         if (!(use_xyz && (grad_xyz || grad_new_xyz))) return PN2_OK;
         grad_points = nullptr;  // done
     }
-    group_concat_grad_kernel<<<grid_for(total, 256), 256, 0, st>>>(
+    launch_k(group_concat_grad_kernel, grid_for(total, 256), 256, 0, st, 
         n, m, nsample, c, w, xoff, poff, use_xyz, total, grad_out, idx, grad_points, grad_xyz,
         grad_new_xyz);
     return finish_launch();
@@ -972,7 +1033,7 @@ PN2_API int pn2_selection_sort(int b, int n, int m, int k, const float *dist, in
     if (rc) return rc;
     long blocks = ceil_div<long>(rows, SEL_WARPS);
     if (blocks > 148L * 8) blocks = 148L * 8;
-    selection_sort_kernel<<<(unsigned)blocks, 32 * SEL_WARPS, smem, as_stream(s)>>>(rows, n, k, dist, outi, out);
+    launch_k(selection_sort_kernel, (unsigned)blocks, 32 * SEL_WARPS, smem, as_stream(s), rows, n, k, dist, outi, out);
     return finish_launch();
 }
 
@@ -998,11 +1059,11 @@ PN2_API int pn2_knn_point(int b, int n, int c, int m, int k, const float *xyz1, 
     if (c == 3) {
         rc = opt_in_dyn_smem(knn_point_kernel<3>, smem);
         if (rc) return rc;
-        knn_point_kernel<3><<<grid, 32 * SEL_WARPS, smem, as_stream(s)>>>(n, c, m, k, xyz1, xyz2, val, idx);
+        launch_k(knn_point_kernel<3>, grid, 32 * SEL_WARPS, smem, as_stream(s), n, c, m, k, xyz1, xyz2, val, idx);
     } else {
         rc = opt_in_dyn_smem(knn_point_kernel<0>, smem);
         if (rc) return rc;
-        knn_point_kernel<0><<<grid, 32 * SEL_WARPS, smem, as_stream(s)>>>(n, c, m, k, xyz1, xyz2, val, idx);
+        launch_k(knn_point_kernel<0>, grid, 32 * SEL_WARPS, smem, as_stream(s), n, c, m, k, xyz1, xyz2, val, idx);
     }
     return finish_launch();
 }
@@ -1044,19 +1105,19 @@ PN2_API int pn2_query_ball_point_grid(int b, int n, int m, float radius, int nsa
     const long total = (long)b * n;
     long blocks = ceil_div<long>(total, 256);
     if (blocks > 148L * 16) blocks = 148L * 16;
-    grid_count_kernel<<<(int)blocks, 256, 0, st>>>(n, total, (unsigned)(T - 1), inv, xyz1, cursor, flag);
+    launch_k(grid_count_kernel, (int)blocks, 256, 0, st, n, total, (unsigned)(T - 1), inv, xyz1, cursor, flag);
     rc = finish_launch();
     if (rc) return rc;
-    grid_scan_kernel<<<b, 1024, 0, st>>>(T, cursor, starts, pitch);
+    launch_k(grid_scan_kernel, b, 1024, 0, st, T, cursor, starts, pitch);
     rc = finish_launch();
     if (rc) return rc;
-    grid_fill_kernel<<<(int)blocks, 256, 0, st>>>(n, total, (unsigned)(T - 1), inv, xyz1, cursor, sorted);
+    launch_k(grid_fill_kernel, (int)blocks, 256, 0, st, n, total, (unsigned)(T - 1), inv, xyz1, cursor, sorted);
     rc = finish_launch();
     if (rc) return rc;
     const long queries = (long)b * m;
     const long qblocks = ceil_div<long>(queries, GQ_WARPS);
     PN2_REQUIRE(qblocks < (1l << 31));
-    ball_query_grid_kernel<<<(unsigned)qblocks, GQ_WARPS * 32, 0, st>>>(
+    launch_k(ball_query_grid_kernel, (unsigned)qblocks, GQ_WARPS * 32, 0, st, 
         n, m, queries, (unsigned)(T - 1), pitch, thr, inv, rpad, nsample, xyz1, xyz2, starts, sorted, flag,
         idx, pts_cnt);
     return finish_launch();

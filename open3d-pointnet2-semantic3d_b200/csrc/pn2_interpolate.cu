@@ -23,6 +23,7 @@ constexpr int NN_TILE = 1024;  // known points per stage: 24 KB of doubles
 __global__ void __launch_bounds__(NN_THREADS)
 three_nn_kernel(int n, int m, const float *__restrict__ xyz1, const float *__restrict__ xyz2,
                 float *__restrict__ dist, int *__restrict__ idx) {
+    pdl_enter();
     __shared__ __align__(16) double kx[NN_TILE], ky[NN_TILE], kz[NN_TILE];
     const int cloud = blockIdx.y;
     const int j = blockIdx.x * NN_THREADS + threadIdx.x;
@@ -83,6 +84,7 @@ three_nn_kernel(int n, int m, const float *__restrict__ xyz1, const float *__res
 //   d = max(d,1e-10); norm = (1/d0 + 1/d1) + 1/d2; w = (1/d)/norm
 __global__ void fp_weights_kernel(long rows, const float *__restrict__ dist,
                                   float *__restrict__ weight) {
+    pdl_enter();
     for (long r = blockIdx.x * (long)blockDim.x + threadIdx.x; r < rows;
          r += (long)gridDim.x * blockDim.x) {
         float d0 = fmaxf(__ldg(dist + r * 3), 1e-10f);
@@ -107,6 +109,7 @@ __global__ void three_interpolate_kernel(int m, int c, int n, long total,
                                          const int *__restrict__ idx,
                                          const float *__restrict__ weight,
                                          float *__restrict__ out, int ldo) {
+    pdl_enter();
     const int cv = VEC4 ? c / 4 : c;
     for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total;
          e += (long)gridDim.x * blockDim.x) {
@@ -140,6 +143,7 @@ __global__ void three_interpolate_grad_kernel(int m, int c, int n, long total,
                                               const int *__restrict__ idx,
                                               const float *__restrict__ weight,
                                               float *__restrict__ grad_points) {
+    pdl_enter();
     for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total;
          e += (long)gridDim.x * blockDim.x) {
         long row = e / c;
@@ -162,6 +166,7 @@ __global__ void three_interpolate_grad_v4_kernel(int m, int c, int n, long total
                                                  const int *__restrict__ idx,
                                                  const float *__restrict__ weight,
                                                  float *__restrict__ grad_points) {
+    pdl_enter();
     const int c4 = c >> 2;
     for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total4;
          e += (long)gridDim.x * blockDim.x) {
@@ -184,6 +189,7 @@ __global__ void three_interpolate_grad_v4_kernel(int m, int c, int n, long total
 
 __global__ void copy_cols_kernel(long rows, int cols, long total, const float *__restrict__ src,
                                  int lds, float *__restrict__ dst, int ldd, int accumulate) {
+    pdl_enter();
     for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total;
          e += (long)gridDim.x * blockDim.x) {
         long r = e / cols;
@@ -191,6 +197,24 @@ __global__ void copy_cols_kernel(long rows, int cols, long total, const float *_
         float v = __ldg(src + r * lds + j);
         if (accumulate) dst[r * ldd + j] += v;
         else dst[r * ldd + j] = v;
+    }
+}
+
+__global__ void copy_cols_v4_kernel(unsigned rows, unsigned cols4, const float4 *__restrict__ src, unsigned lds4,
+                                    float4 *__restrict__ dst, unsigned ldd4, int accumulate) {
+    pdl_enter();
+    const unsigned total = rows * cols4;
+    for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        const unsigned r = e / cols4, j = e - r * cols4;
+        const float4 v = __ldg(src + (size_t)r * lds4 + j);
+        float4 *d = dst + (size_t)r * ldd4 + j;
+        if (accumulate) {
+            float4 o = *d;
+            o.x += v.x; o.y += v.y; o.z += v.z; o.w += v.w;
+            *d = o;
+        } else {
+            *d = v;
+        }
     }
 }
 
@@ -214,6 +238,7 @@ __global__ void __launch_bounds__(KV_THREADS)
 knn_vote_kernel(int ns, int nd, int k, const float *__restrict__ sparse,
                 const int *__restrict__ labels, const float *__restrict__ dense,
                 int *__restrict__ out_labels, unsigned char *__restrict__ out_colors) {
+    pdl_enter();
     __shared__ __align__(16) double kx[NN_TILE], ky[NN_TILE], kz[NN_TILE];
     const long j = (long)blockIdx.x * KV_THREADS + threadIdx.x;
     const bool valid = j < nd;
@@ -315,7 +340,7 @@ PN2_API int pn2_three_nn(int b, int n, int m, const float *xyz1, const float *xy
     PN2_REQUIRE_PTR(dist);
     PN2_REQUIRE_PTR(idx);
     dim3 grid((unsigned)ceil_div(n, NN_THREADS), (unsigned)b);
-    three_nn_kernel<<<grid, NN_THREADS, 0, as_stream(s)>>>(n, m, xyz1, xyz2, dist, idx);
+    launch_k(three_nn_kernel, grid, NN_THREADS, 0, as_stream(s), n, m, xyz1, xyz2, dist, idx);
     return finish_launch();
 }
 
@@ -324,7 +349,7 @@ PN2_API int pn2_fp_weights(int rows, const float *dist, float *weight, pn2_strea
     if (rows == 0) return PN2_OK;
     PN2_REQUIRE_PTR(dist);
     PN2_REQUIRE_PTR(weight);
-    fp_weights_kernel<<<grid_for(rows, 256), 256, 0, as_stream(s)>>>(rows, dist, weight);
+    launch_k(fp_weights_kernel, grid_for(rows, 256), 256, 0, as_stream(s), rows, dist, weight);
     return finish_launch();
 }
 
@@ -343,11 +368,11 @@ PN2_API int pn2_three_interpolate_ld(int b, int m, int c, int n, const float *po
     cudaStream_t st = as_stream(s);
     if (vec) {
         long total = (long)b * n * (c / 4);
-        three_interpolate_kernel<true><<<grid_for(total, 256), 256, 0, st>>>(
+        launch_k(three_interpolate_kernel<true>, grid_for(total, 256), 256, 0, st, 
             m, c, n, total, points, idx, weight, out, ldo);
     } else {
         long total = (long)b * n * c;
-        three_interpolate_kernel<false><<<grid_for(total, 256), 256, 0, st>>>(
+        launch_k(three_interpolate_kernel<false>, grid_for(total, 256), 256, 0, st, 
             m, c, n, total, points, idx, weight, out, ldo);
     }
     return finish_launch();
@@ -373,10 +398,10 @@ PN2_API int pn2_three_interpolate_grad_ld(int b, int n, int c, int m, const floa
     PN2_REQUIRE_PTR(idx);
     PN2_REQUIRE_PTR(weight);
     if ((c % 4) == 0 && (reinterpret_cast<uintptr_t>(grad_points) & 15) == 0)
-        three_interpolate_grad_v4_kernel<<<grid_for(total / 4, 256), 256, 0, st>>>(
+        launch_k(three_interpolate_grad_v4_kernel, grid_for(total / 4, 256), 256, 0, st, 
             m, c, n, total / 4, grad_out, ldg, idx, weight, grad_points);
     else
-        three_interpolate_grad_kernel<<<grid_for(total, 256), 256, 0, st>>>(
+        launch_k(three_interpolate_grad_kernel, grid_for(total, 256), 256, 0, st, 
             m, c, n, total, grad_out, ldg, idx, weight, grad_points);
     return finish_launch();
 }
@@ -394,8 +419,14 @@ PN2_API int pn2_copy_cols(long rows, int cols, const float *src, int lds, float 
     if (total == 0) return PN2_OK;
     PN2_REQUIRE_PTR(src);
     PN2_REQUIRE_PTR(dst);
-    copy_cols_kernel<<<grid_for(total, 256), 256, 0, as_stream(s)>>>(rows, cols, total, src, lds,
-                                                                     dst, ldd, accumulate);
+    if ((cols % 4) == 0 && (lds % 4) == 0 && (ldd % 4) == 0 && total < (1L << 32) &&
+        ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0)
+        launch_k(copy_cols_v4_kernel, grid_for(total / 4, 256), 256, 0, as_stream(s), 
+            (unsigned)rows, (unsigned)(cols / 4), reinterpret_cast<const float4 *>(src), (unsigned)(lds / 4),
+            reinterpret_cast<float4 *>(dst), (unsigned)(ldd / 4), accumulate);
+    else
+        launch_k(copy_cols_kernel, grid_for(total, 256), 256, 0, as_stream(s), rows, cols, total, src, lds,
+                                                                         dst, ldd, accumulate);
     return finish_launch();
 }
 
@@ -417,7 +448,7 @@ PN2_API int pn2_interpolate_label_with_color(int num_sparse, int num_dense,
     cudaStream_t st = as_stream(s);
     const unsigned grid = (unsigned)ceil_div<long>(num_dense, KV_THREADS);
 #define PN2_LAUNCH_VOTE(KM)                                                                    \
-    knn_vote_kernel<KM><<<grid, KV_THREADS, 0, st>>>(num_sparse, num_dense, knn, sparse_points, \
+    launch_k(knn_vote_kernel<KM>, grid, KV_THREADS, 0, st, num_sparse, num_dense, knn, sparse_points, \
                                                      sparse_labels, dense_points, dense_labels, \
                                                      dense_colors)
     if (knn <= 4) PN2_LAUNCH_VOTE(4);

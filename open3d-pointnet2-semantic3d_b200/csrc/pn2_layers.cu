@@ -201,6 +201,7 @@ using namespace pn2;
 
 namespace pn2 {
 __global__ void fill_f32_kernel(long n, float value, float *__restrict__ dst) {
+    pdl_enter();
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) dst[i] = value;
 }
 }  // namespace pn2
@@ -356,6 +357,6 @@ PN2_API int pn2_fill_f32(long n, float value, float *dst, pn2_stream_t s) {
     PN2_REQUIRE_PTR(dst);
     long blocks = (n + 255) / 256;
     if (blocks > 148L * 8) blocks = 148L * 8;
-    fill_f32_kernel<<<(int)blocks, 256, 0, as_stream(s)>>>(n, value, dst);
+    launch_k(fill_f32_kernel, (int)blocks, 256, 0, as_stream(s), n, value, dst);
     return finish_launch();
 }

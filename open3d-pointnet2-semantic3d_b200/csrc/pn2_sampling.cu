@@ -68,6 +68,7 @@ __device__ __forceinline__ int key_to_k(unsigned key) {
 template <int THREADS, int PPT>
 __global__ void __launch_bounds__(THREADS, 1)
 fps_reg_kernel(int n, int m, const float *__restrict__ inp, int *__restrict__ out) {
+    pdl_enter();
     constexpr int NW = THREADS / 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long *slots = reinterpret_cast<unsigned long long *>(smem_raw);  // [2][32]
@@ -151,6 +152,7 @@ fps_reg_kernel(int n, int m, const float *__restrict__ inp, int *__restrict__ ou
 template <int THREADS, int PPT>
 __global__ void __launch_bounds__(THREADS, 1)
 fps_pruned_kernel(int n, int m, const float *__restrict__ inp, int *__restrict__ out) {
+    pdl_enter();
     constexpr int NW = THREADS / 32;
     typedef cub::BlockRadixSort<unsigned, THREADS, PPT, int> Sort;
     typedef cub::BlockReduce<float, THREADS> Reduce;
@@ -337,6 +339,7 @@ fps_pruned_kernel(int n, int m, const float *__restrict__ inp, int *__restrict__
 template <int THREADS, int PPT>
 __global__ void __launch_bounds__(THREADS, 1)
 fps_smem_kernel(int n, int m, const float *__restrict__ inp, int *__restrict__ out) {
+    pdl_enter();
     constexpr int NW = THREADS / 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long *slots = reinterpret_cast<unsigned long long *>(smem_raw);
@@ -412,6 +415,7 @@ constexpr bool kFpsClusterDefault = true;  // verified on the B200: bit-identica
 template <int PPT>
 __global__ void __launch_bounds__(1024, 1)
 fps_cluster_kernel(int n, int m, const float *__restrict__ inp, int *__restrict__ out) {
+    pdl_enter();
     namespace cg = cooperative_groups;
     constexpr int THREADS = 1024, SLICE = THREADS * PPT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -536,6 +540,7 @@ __device__ __forceinline__ void mbar_wait_acquire_cluster(void *bar, unsigned pa
 template <int PPT>
 __global__ void __launch_bounds__(1024, 1)
 fps_cluster_mb_kernel(int n, int m, const float *__restrict__ inp, int *__restrict__ out) {
+    pdl_enter();
     namespace cg = cooperative_groups;
     constexpr int THREADS = 1024, SLICE = THREADS * PPT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -638,6 +643,7 @@ fps_cluster_mb_kernel(int n, int m, const float *__restrict__ inp, int *__restri
 __global__ void __launch_bounds__(1024, 1)
 fps_stream_kernel(int n, int m, const float *__restrict__ inp, float *__restrict__ temp,
                   int *__restrict__ out) {
+    pdl_enter();
     constexpr int THREADS = 1024, NW = 32;
     __shared__ unsigned long long slots[64];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -687,7 +693,7 @@ static int launch_fps_reg(int b, int n, int m, const float *inp, int *out, cudaS
         int rc = opt_in_dyn_smem(kern, smem);
         if (rc) return rc;
     }
-    kern<<<b, THREADS, smem, st>>>(n, m, inp, out);
+    launch_k(kern, b, THREADS, smem, st, n, m, inp, out);
     return finish_launch();
 }
 
@@ -702,7 +708,7 @@ static int launch_fps_pruned(int b, int n, int m, const float *inp, int *out, cu
     auto kern = fps_pruned_kernel<THREADS, PPT>;
     int rc = opt_in_dyn_smem(kern, smem);
     if (rc) return rc;
-    kern<<<b, THREADS, smem, st>>>(n, m, inp, out);
+    launch_k(kern, b, THREADS, smem, st, n, m, inp, out);
     return finish_launch();
 }
 
@@ -712,7 +718,7 @@ static int launch_fps_smem(int b, int n, int m, const float *inp, int *out, cuda
     auto kern = fps_smem_kernel<THREADS, PPT>;
     int rc = opt_in_dyn_smem(kern, smem);
     if (rc) return rc;
-    kern<<<b, THREADS, smem, st>>>(n, m, inp, out);
+    launch_k(kern, b, THREADS, smem, st, n, m, inp, out);
     return finish_launch();
 }
 
@@ -734,11 +740,13 @@ static int launch_fps_cluster(int b, int cs, int n, int m, const float *inp, int
     cfg.blockDim = dim3(1024, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = (unsigned)cs;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     int clusters = 0;
@@ -746,6 +754,7 @@ static int launch_fps_cluster(int b, int cs, int n, int m, const float *inp, int
         cudaGetLastError();
         return PN2_EUNSUPPORTED;  // this cluster shape cannot be co-scheduled on the device
     }
+    if (pdl_enabled()) cfg.numAttrs = 2;
     rc = cuda_status(cudaLaunchKernelEx(&cfg, kern, n, m, inp, out));
     if (rc) return rc;
     return finish_launch();
@@ -774,6 +783,7 @@ static int dispatch_fps_cluster(int b, int n, int m, const float *inp, int *out,
 // ---- gather_point / grad ---------------------------------------------------------------
 __global__ void gather_point_kernel(int n, int m, long total, const float *__restrict__ inp,
                                     const int *__restrict__ idx, float *__restrict__ out) {
+    pdl_enter();
     // one thread per output float: e = (cloud*m + j)*3 + c ; coalesced writes
     for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total;
          e += (long)gridDim.x * blockDim.x) {
@@ -789,6 +799,7 @@ __global__ void gather_point_grad_kernel(int n, int m, long total,
                                          const float *__restrict__ out_g,
                                          const int *__restrict__ idx,
                                          float *__restrict__ inp_g) {
+    pdl_enter();
     for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total;
          e += (long)gridDim.x * blockDim.x) {
         long row = e / 3;
@@ -814,6 +825,7 @@ constexpr int kScanChunk = 8192;  // part of the rounding sequence (tf_sampling.
 
 __global__ void __launch_bounds__(kScanThreads)
 prob_cdf_kernel(int n, const float *__restrict__ inp, float *__restrict__ out) {
+    pdl_enter();
     __shared__ float warp_tot[32];
     __shared__ float chunk_total;
     const unsigned full = 0xffffffffu;
@@ -917,6 +929,7 @@ prob_cdf_kernel(int n, const float *__restrict__ inp, float *__restrict__ out) {
 // hit the same few CDF entries for every thread and stay in L1.
 __global__ void prob_search_kernel(int b, int n, int m, int base, const float *__restrict__ cdf,
                                    const float *__restrict__ query, int *__restrict__ result) {
+    pdl_enter();
     for (int i = blockIdx.y; i < b; i += gridDim.y) {
         const float *c = cdf + (size_t)i * n;
         const float total = __ldg(c + n - 1);
@@ -977,7 +990,7 @@ PN2_API int pn2_fps(int b, int n, int m, const float *inp, float *temp, int *out
     // beyond what a cluster holds (or no cluster available): streaming kernel; it needs the
     // (b,n) scratch the reference also requires (tf_sampling.cpp:143-146 allocates (32,n))
     if (temp == nullptr) return PN2_ENULL;
-    fps_stream_kernel<<<b, 1024, 0, st>>>(n, m, inp, temp, out);
+    launch_k(fps_stream_kernel, b, 1024, 0, st, n, m, inp, temp, out);
     return finish_launch();
 }
 
@@ -1008,7 +1021,7 @@ PN2_API int pn2_gather_point(int b, int n, int m, const float *inp, const int *i
     int threads = 256;
     long blocks = ceil_div<long>(total, threads);
     if (blocks > 148L * 16) blocks = 148L * 16;
-    gather_point_kernel<<<(int)blocks, threads, 0, as_stream(s)>>>(n, m, total, inp, idx, out);
+    launch_k(gather_point_kernel, (int)blocks, threads, 0, as_stream(s), n, m, total, inp, idx, out);
     return finish_launch();
 }
 
@@ -1027,7 +1040,7 @@ PN2_API int pn2_gather_point_grad(int b, int n, int m, const float *out_g, const
     int threads = 256;
     long blocks = ceil_div<long>(total, threads);
     if (blocks > 148L * 16) blocks = 148L * 16;
-    gather_point_grad_kernel<<<(int)blocks, threads, 0, st>>>(n, m, total, out_g, idx, inp_g);
+    launch_k(gather_point_grad_kernel, (int)blocks, threads, 0, st, n, m, total, out_g, idx, inp_g);
     return finish_launch();
 }
 
@@ -1036,7 +1049,7 @@ PN2_API int pn2_cumsum(int b, int n, const float *inp, float *out, pn2_stream_t 
     if (b == 0) return PN2_OK;
     PN2_REQUIRE_PTR(inp);
     PN2_REQUIRE_PTR(out);
-    prob_cdf_kernel<<<b, kScanThreads, 0, as_stream(s)>>>(n, inp, out);
+    launch_k(prob_cdf_kernel, b, kScanThreads, 0, as_stream(s), n, inp, out);
     return finish_launch();
 }
 
@@ -1049,13 +1062,13 @@ PN2_API int pn2_prob_sample(int b, int n, int m, const float *inp_p, const float
     PN2_REQUIRE_PTR(temp);  // (b,n) floats: the CDF, as in the reference (tf_sampling.cpp:104-108)
     PN2_REQUIRE_PTR(out);
     cudaStream_t st = as_stream(s);
-    prob_cdf_kernel<<<b, kScanThreads, 0, st>>>(n, inp_p, temp);
+    launch_k(prob_cdf_kernel, b, kScanThreads, 0, st, n, inp_p, temp);
     int rc = finish_launch();
     if (rc) return rc;
     int base = 1;
     while (base < n) base <<= 1;
     const int threads = 256;
     dim3 grid((unsigned)min(ceil_div(m, threads), 148 * 8), (unsigned)min(b, 65535));
-    prob_search_kernel<<<grid, threads, 0, st>>>(b, n, m, base, temp, inp_r, out);
+    launch_k(prob_search_kernel, grid, threads, 0, st, b, n, m, base, temp, inp_r, out);
     return finish_launch();
 }

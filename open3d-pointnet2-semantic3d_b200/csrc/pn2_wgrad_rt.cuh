@@ -23,6 +23,7 @@ __global__ void __launch_bounds__(WRT_THREADS)
 wgrad_rt_kernel(long M, int K, int N, const float *__restrict__ A, int lda,
                 const float *__restrict__ a_scale, const float *__restrict__ a_shift, int a_relu,
                 const float *__restrict__ dY, float *__restrict__ dW, long rows_per_cta, int tk, int tn) {
+    pdl_enter();
     constexpr int WRT_UNROLL = 32 / TK;
     extern __shared__ float tile[];  // [tk*TK][tn*4]
     const int G = tk * tn;
@@ -124,10 +125,10 @@ static int wgrad_rt(long M, int K, int N, const float *A, int lda, const float *
     const long rows_per_cta = ceil_div<long>(M, ctas);
     const size_t smem = (size_t)tk * TKsel * tn * 4 * sizeof(float);
     if (TKsel == 4)
-        wgrad_rt_kernel<4><<<(unsigned)ctas, WRT_THREADS, smem, st>>>(M, K, N, A, lda, a_scale, a_shift, a_relu,
+        launch_k(wgrad_rt_kernel<4>, (unsigned)ctas, WRT_THREADS, smem, st, M, K, N, A, lda, a_scale, a_shift, a_relu,
                                                                      dY, dW, rows_per_cta, tk, tn);
     else
-        wgrad_rt_kernel<8><<<(unsigned)ctas, WRT_THREADS, smem, st>>>(M, K, N, A, lda, a_scale, a_shift, a_relu,
+        launch_k(wgrad_rt_kernel<8>, (unsigned)ctas, WRT_THREADS, smem, st, M, K, N, A, lda, a_scale, a_shift, a_relu,
                                                                      dY, dW, rows_per_cta, tk, tn);
     return finish_launch();
 }

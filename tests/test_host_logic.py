@@ -232,3 +232,50 @@ def test_load_state_dict_is_strict_about_shapes_and_foreign_keys():
     st2.load_state_dict({"fc1/weights": np.zeros((128, 128), np.float32)})
     L2 = tf_util.make_layer("fc1", 128, 128, False, None, kernel_rank=3)
     assert tuple(L2.w.data.shape) == (1, 128, 128)
+
+
+def test_every_kernel_waits_for_its_predecessor():
+    """Programmatic dependent launch (csrc/pn2_common.cuh): every kernel of the library is launched with the
+    programmatic-serialization attribute, so every `__global__` function has to execute griddepcontrol.wait
+    (pdl_enter / pdl_wait) before it touches global memory -- a kernel without it would start
+    reading while its predecessor is still writing.  Static check over the sources: the wait is there, it comes
+    before the first global-memory access idiom, and no launch bypasses launch_k."""
+    import glob
+    import re
+    src_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                           "open3d-pointnet2-semantic3d_b200", "csrc")
+    kernels = 0
+    for path in sorted(glob.glob(os.path.join(src_dir, "*.cu")) + glob.glob(os.path.join(src_dir, "*.cuh"))):
+        text = open(path).read()
+        assert "<<<" not in re.sub(r"//[^\n]*", "", text), "%s launches a kernel outside launch_k" % path
+        for m in re.finditer(r"__global__", text):
+            i, depth, seen = m.end(), 0, False
+            while True:  # body start: the first '{' outside parentheses after the parameter list
+                c = text[i]
+                if c == "(":
+                    depth, seen = depth + 1, True
+                elif c == ")":
+                    depth -= 1
+                elif c == "{" and depth == 0 and seen:
+                    break
+                elif c == ";" and depth == 0:
+                    i = -1
+                    break
+                i += 1
+            if i < 0:
+                continue  # a declaration
+            j, depth = i, 0
+            while True:
+                depth += {"{": 1, "}": -1}.get(text[j], 0)
+                if depth == 0:
+                    break
+                j += 1
+            body = text[i:j]
+            name = re.findall(r"(\w+)\s*\($", text[m.end():i].split("(")[0] + "(")  # best effort, for the message
+            w = re.search(r"pdl_enter\(\)|pdl_wait\(\)", body)
+            assert w, "%s: kernel %s never waits for its predecessor" % (os.path.basename(path), name)
+            before = body[:w.start()]
+            for idiom in ("__ldg", "__ldcg", "atomicAdd", "cp.async", "ld.global", "st.global", "red.global"):
+                assert idiom not in before, "%s: %s before the dependency wait" % (os.path.basename(path), idiom)
+            kernels += 1
+    assert kernels >= 60

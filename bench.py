@@ -407,7 +407,8 @@ def run_ours(args):
     b, n = args.batch, args.npoint
     pc, labels, smpw = make_batch(b, n, 100 + rank)
     d_pc, d_lab, d_w = (torch.as_tensor(x).to(dev) for x in (pc, labels, smpw))
-    trainer = Trainer(HP, NUM_CLASS, device=dev, seed=0, world_size=world)
+    ahead = not (args.no_ahead or args.no_graph)
+    trainer = Trainer(HP, NUM_CLASS, device=dev, seed=0, world_size=world, geometry_ahead=ahead)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
 
     def barrier():
@@ -614,6 +615,9 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": workload_name(b, n), "global_batch": b * world,
                        "parallelism": "dp%d" % world, "cuda_graph": bool(use_graph),
+                       "geometry_ahead": ("every replay = dense stage of the current batch + sampling / neighbour "
+                                          "search of the next batch on a second stream of the same graph; K steps "
+                                          "run K of each") if (ahead and use_graph) else False,
                        "cuda_graph_error": (trainer._capture_error or "")[:1500] or None,
                        "l2": "256 MB flush write between timed steps; a step also streams >1 GB of "
                              "activations, far beyond the 126 MB L2"},
@@ -641,6 +645,9 @@ def main():
     ap.add_argument("--npoint", type=int, default=8192)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of a CUDA graph")
+    ap.add_argument("--no-ahead", action="store_true",
+                    help="compute the geometry (FPS, ball query, 3-NN) of a batch inside its own step instead of "
+                         "one batch ahead on a second stream")
     ap.add_argument("--no-extra", action="store_true",
                     help="skip the config-1 row and the 6-feature-channel line (N=1 only)")
     args = ap.parse_args()

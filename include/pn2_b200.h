@@ -40,6 +40,14 @@ int pn2_abi_version(void);
 const char *pn2_strerror(int code);
 /* last CUDA error string seen by a failing launch on this thread ("" if none) */
 const char *pn2_last_cuda_error(void);
+/* SM budget of the PERSISTENT kernels (the tensor-core GEMMs launch one CTA per SM): with sms > 0 they size
+ * their grids for `sms` SMs and leave the rest of the device to kernels running concurrently on another stream
+ * (train_step.py runs the weight-independent sampling / neighbour search of the NEXT batch next to the dense
+ * forward pass, the reference overlaps its host-side batch preparation the same way, train.py:134-196).
+ * 0 = all SMs.  Process-wide; grid sizes are fixed at launch (and baked into a captured graph).
+ * pn2_get_sm_budget returns the SM count the next persistent launch would use. */
+int pn2_set_sm_budget(int sms);
+int pn2_get_sm_budget(void);
 
 /* ===== group 1: one entry point per reference launcher ======================= */
 

@@ -24,6 +24,8 @@ SIGNATURES = {
     "pn2_abi_version": [],
     "pn2_strerror": [_i],
     "pn2_last_cuda_error": [],
+    "pn2_set_sm_budget": [_i],
+    "pn2_get_sm_budget": [],
     "pn2_ball_threshold": [_f],
     "pn2_fps": [_i, _i, _i, _vp, _vp, _vp, _vp],
     "pn2_fps_cluster": [_i, _i, _i, _vp, _vp, _vp],

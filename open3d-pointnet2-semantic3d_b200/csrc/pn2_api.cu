@@ -2,6 +2,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <mutex>
 
 #include "pn2_common.cuh"
@@ -15,7 +16,9 @@ void set_last_cuda_error(const char *msg) {
     g_last_err[sizeof(g_last_err) - 1] = 0;
 }
 
-int num_sms() {
+static std::atomic<int> g_sm_budget{0};
+
+static int device_sms() {
     static int cached[64] = {0};
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return kNumSMsB200;
@@ -26,6 +29,12 @@ int num_sms() {
         cached[dev] = v;
     }
     return cached[dev];
+}
+
+// SMs the persistent kernels size their grids for: all of them, or the budget set by pn2_set_sm_budget
+int num_sms() {
+    const int all = device_sms(), b = g_sm_budget.load(std::memory_order_relaxed);
+    return b > 0 && b < all ? b : all;
 }
 
 bool pdl_enabled() {
@@ -81,3 +90,11 @@ PN2_API const char *pn2_strerror(int code) {
 }
 
 PN2_API const char *pn2_last_cuda_error(void) { return pn2::g_last_err; }
+
+PN2_API int pn2_set_sm_budget(int sms) {
+    if (sms < 0) return PN2_EINVAL;
+    const int prev = pn2::g_sm_budget.exchange(sms, std::memory_order_relaxed);
+    (void)prev;
+    return PN2_OK;
+}
+PN2_API int pn2_get_sm_budget(void) { return pn2::num_sms(); }

@@ -68,6 +68,26 @@ def get_model(point_cloud, is_training, num_class, hyperparams, bn_decay=None):
     return net, end_points
 
 
+def get_geometry(point_cloud, hyperparams):
+    """The weight-independent part of get_model for one batch -- per SA layer the sampled centres and their
+    ball-query neighbours, per FP layer the three nearest known points and their weights -- as a GeometryTape
+    in get_model's call order (util/pointnet_util.py).  `with replay_geometry(tape): get_model(...)` then runs
+    only the dense stage.  Same kernels, same results as computing them inside the layers."""
+    from .util import pointnet_util as pu
+    tape = pu.GeometryTape()
+    with torch.no_grad(), pu.replay_geometry(None):
+        xyz = [point_cloud[:, :, 0:3].contiguous() if hyperparams["use_color"] else point_cloud]
+        for l in (1, 2, 3, 4):
+            npoint, radius, nsample = (hyperparams["l%d_%s" % (l, k)] for k in ("npoint", "radius", "nsample"))
+            new_xyz, idx = pu.sampling_geometry(npoint, radius, nsample, xyz[-1])
+            tape.add("sample", (npoint, float(radius), nsample, tuple(xyz[-1].shape)), (new_xyz, idx))
+            xyz.append(new_xyz)
+        for lo in (3, 2, 1, 0):
+            idx, weight = pu.interpolation_geometry(xyz[lo], xyz[lo + 1])
+            tape.add("interp", (tuple(xyz[lo].shape), tuple(xyz[lo + 1].shape)), (idx, weight))
+    return tape
+
+
 class _SoftmaxCE(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pred, label, smpw):

@@ -12,15 +12,27 @@ the default stream (eager warm-up) with a capture stream made the engine create 
 uncaptured work (cudaErrorStreamCaptureIsolation) at the end of the captured backward, which is
 how graph mode silently fell back to eager launches in round 1.  The caller's current stream is
 joined at the start and at the end of every step, so callers keep ordinary stream semantics.
+
+Geometry one batch ahead (``Trainer(..., geometry_ahead=True)``, graph mode): farthest point sampling,
+gather, ball query, 3-NN and the interpolation weights depend on the coordinates only, yet they head the
+critical path of a step (~0.9 of ~4.1 ms at B=16 x 8192; FPS alone keeps 16 of 148 SMs busy for 0.5 ms while
+132 idle).  In this mode one replay runs the dense stage (grouping, shared MLPs, loss, backward) of the
+CURRENT batch from a precomputed GeometryTape and, forked onto a second stream inside the same graph, the
+geometry of the NEXT batch; the persistent tensor-core GEMMs of the forward pass size their grids for the SMs
+the sampling kernels leave free (pn2_set_sm_budget).  The reference overlaps its host-side batch preparation
+with training the same way (train.py:134-196).  Nothing is cached or skipped: K replays run K dense stages and
+K geometry stages, on the same kernels, and the values the dense stage consumes are the ones the plain step
+computes (tests/test_train_step_gpu.py compares the two step by step).
 """
 import gc
+import os
 
 import torch
 import torch.distributed as dist
 
-from . import model
+from . import _ffi, model
 from ._ffi import F32, call, ptr
-from .util import tf_util
+from .util import pointnet_util, tf_util
 
 
 def get_learning_rate(step, params):
@@ -64,8 +76,9 @@ class Trainer:
     a fresh mask and both modes walk through the same mask sequence.
     """
 
-    def __init__(self, params, num_class, device="cuda", seed=0, world_size=1):
+    def __init__(self, params, num_class, device="cuda", seed=0, world_size=1, geometry_ahead=False):
         self.params, self.num_class, self.world_size = params, num_class, world_size
+        self.geometry_ahead = bool(geometry_ahead)
         self.device = torch.device(device)
         if self.device.type == "cuda" and self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
@@ -81,6 +94,10 @@ class Trainer:
         self._capture_error = None
         self.launches_per_replay = 0
         self.timing = None  # bench.py: dict that receives CUDA events around the collective
+        # geometry one batch ahead: the tape the dense stage of the current batch consumes, the inputs of the
+        # batch whose geometry is computed meanwhile, the stream that computes it
+        self._tape = self._next = None
+        self._side = torch.cuda.Stream(device=self.device) if self.geometry_ahead else None
 
     # ---- variables ----------------------------------------------------------------------------
     def _ensure_flat(self):
@@ -96,7 +113,10 @@ class Trainer:
         return [v.data for v in self.store.vars.values() if not v.trainable]
 
     # ---- one forward + loss + backward on self.stream --------------------------------------------
-    def _fb(self, point_cloud, labels, smpw):
+    def _fb(self, point_cloud, labels, smpw, ahead=None):
+        """``ahead`` = (point_cloud, labels, smpw) of the NEXT batch: the dense stage of this pass takes its
+        geometry from self._tape while the geometry of the next batch is computed on the side stream; at the
+        end the tape and the current inputs are overwritten with the next batch's."""
         bn_decay = get_bn_decay(self.step_count, self.params)
         tf_util.set_default_store(self.store)
         tf_util.set_dropout_seed_device(self._seed_dev)
@@ -104,16 +124,44 @@ class Trainer:
         self.store.anchor = torch.zeros(1, device=self.device, requires_grad=True)
         tf_util.zero_arena.reset(self.device)  # one memset for every layer's fp64 accumulators
         self.store.prepare_images()            # one launch: every layer's 3xTF32 weight images
+        nxt = None
+        if ahead is not None:
+            self._side.wait_stream(self.stream)  # fork
+            with torch.cuda.stream(self._side):
+                nxt = model.get_geometry(ahead[0], self.params)
         try:
-            pred, _ = model.get_model(point_cloud, True, self.num_class, self.params, bn_decay=bn_decay)
-            self.store.zero_grad()
-            loss = model.get_loss(pred, labels, smpw)
-            loss.backward()
+            with pointnet_util.replay_geometry(self._tape if ahead is not None else None):
+                self._sm_budget(point_cloud.shape[0] if ahead is not None else 0)
+                try:
+                    pred, _ = model.get_model(point_cloud, True, self.num_class, self.params, bn_decay=bn_decay)
+                finally:
+                    if os.environ.get("PN2_AHEAD_SCOPE", "fwd") != "step":
+                        self._sm_budget(0)
+                self.store.zero_grad()
+                loss = model.get_loss(pred, labels, smpw)
+                loss.backward()
         finally:
+            self._sm_budget(0)
             tf_util.zero_arena.disarm()
             tf_util.set_dropout_seed_device(None)
             self.store.images_fresh = False  # the optimizer step that follows changes the weights
+        if ahead is not None:
+            self.stream.wait_stream(self._side)  # join: the dense stage has read its tape, the next one is complete
+            torch._foreach_copy_(self._tape.tensors(), nxt.tensors())
+            torch._foreach_copy_([point_cloud, labels, smpw], list(ahead))
+            if not torch.cuda.is_current_stream_capturing():
+                for t in nxt.tensors():
+                    t.record_stream(self.stream)  # allocated on the side stream, last read on this one
         return loss.detach()
+
+    def _sm_budget(self, reserve):
+        """Leave ``reserve`` SMs (one per cloud: the FPS kernel runs one CTA per cloud) to the geometry stream."""
+        if not self.geometry_ahead:
+            return
+        if reserve:
+            reserve = int(os.environ.get("PN2_AHEAD_RESERVE", min(int(reserve), 32)))
+        total = torch.cuda.get_device_properties(self.device).multi_processor_count
+        _ffi.lib().pn2_set_sm_budget(total - reserve if 0 < reserve < total else 0)
 
     def _create_variables(self, point_cloud):
         """The first forward pass creates the variables (the reference builds its graph once,
@@ -184,7 +232,6 @@ class Trainer:
         replay leave no trace: moving statistics are frozen / restored, the dropout counter is not
         advanced, no optimizer step is taken.  Returns False (eager mode stays) if capture fails;
         the reason is kept, untruncated, in ``self._capture_error``."""
-        from . import _ffi
         self._graph = None
         self._capture_error = None
         caller = torch.cuda.current_stream(self.device)
@@ -193,7 +240,16 @@ class Trainer:
             with torch.cuda.stream(self.stream):
                 src = self._to_device(point_cloud, labels, smpw)
                 self._create_variables(src[0])
-                if self._static is None or any(a.shape != b.shape for a, b in zip(self._static, src)):
+                ahead = None
+                if self.geometry_ahead:
+                    # the pipeline state survives a (re-)capture: with next = current, the warm-up passes and
+                    # the validation replay recompute the tape of the current batch and copy the batch onto itself
+                    if self._tape is None:
+                        self._prime(src)
+                    for d, s in zip(self._next, self._static):
+                        d.copy_(s)
+                    ahead = self._next
+                elif self._static is None or any(a.shape != b.shape for a, b in zip(self._static, src)):
                     self._static = [t.clone() for t in src]
                 else:
                     for d, s in zip(self._static, src):
@@ -202,13 +258,15 @@ class Trainer:
                 static = self._static
                 with tf_util.frozen_moving_stats():
                     for _ in range(2):  # every kernel / workspace / gradient buffer exists
-                        self._fb(*static)
+                        self._fb(*static, ahead=ahead)
                 self.stream.synchronize()
+                if self._side is not None:
+                    self._side.synchronize()
                 gc.collect()  # no autograd graph of an earlier pass survives into the capture
                 g = torch.cuda.CUDAGraph()
                 n0 = _ffi.launches
                 with torch.cuda.graph(g, stream=self.stream, capture_error_mode="thread_local"):
-                    loss = self._fb(*static)
+                    loss = self._fb(*static, ahead=ahead)
                 self.launches_per_replay = _ffi.launches - n0
                 # validation replay (would raise on a broken graph), then undo its EMA update
                 keep = [t.clone() for t in self._moving()]
@@ -230,6 +288,32 @@ class Trainer:
         caller.wait_stream(self.stream)
         return self._graph is not None
 
+    # ---- geometry one batch ahead -----------------------------------------------------------------------
+    def _prime(self, src):
+        self._static = [t.clone() for t in src]
+        self._next = [t.clone() for t in src]
+        self._tape = model.get_geometry(self._static[0], self.params)
+
+    def prime(self, point_cloud, labels, smpw):
+        """geometry_ahead mode: load the FIRST batch (its geometry is computed here, on the replica's stream).
+        Every ``step_graph(batch)`` after that trains on the batch loaded before it and returns that batch's
+        loss, while the geometry of ``batch`` is computed alongside."""
+        if not self.geometry_ahead:
+            raise ValueError("prime() belongs to Trainer(..., geometry_ahead=True)")
+        caller = torch.cuda.current_stream(self.device)
+        self.stream.wait_stream(caller)
+        with torch.cuda.stream(self.stream):
+            src = self._to_device(point_cloud, labels, smpw)
+            self._create_variables(src[0])
+            if self._tape is None or any(a.shape != b.shape for a, b in zip(self._static, src)):
+                self._prime(src)
+                self._graph = None
+            else:
+                for d, s in zip(self._static, src):
+                    d.copy_(s)
+                torch._foreach_copy_(self._tape.tensors(), model.get_geometry(self._static[0], self.params).tensors())
+        caller.wait_stream(self.stream)
+
     def stage(self, point_cloud, labels, smpw):
         """Start the host->device copy of the NEXT batch on the copy stream (pinned host tensors);
         ``step_graph()`` without arguments consumes it.  This is the double-buffered input feed
@@ -249,7 +333,8 @@ class Trainer:
 
     def step_graph(self, point_cloud=None, labels=None, smpw=None):
         """One step by graph replay.  Inputs: device tensors, pinned host tensors (copied in on the
-        replica's stream), or nothing at all = the batch handed to ``stage()``."""
+        replica's stream), or nothing at all = the batch handed to ``stage()``.  In geometry_ahead mode the
+        inputs are the NEXT batch (see ``prime``); the loss returned is that of the batch trained on."""
         staged = point_cloud is None
         if staged:
             if self._staged_event is None:
@@ -257,22 +342,35 @@ class Trainer:
             src = self._staging
         else:
             src = (point_cloud, labels, smpw)
-        if self._graph is None:
-            if staged:
-                torch.cuda.current_stream(self.device).wait_event(self._staged_event)
-            return self.step(*src)
-        if get_bn_decay(self.step_count, self.params) != self._graph_bn_decay or \
-                any(a.shape != b.shape for a, b in zip(self._static, src)):
-            if staged:
-                torch.cuda.current_stream(self.device).wait_event(self._staged_event)
-            if not self.capture(*src):
+        if self.geometry_ahead:
+            # the batch handed in is the one whose geometry this replay computes; the dense stage trains on the
+            # batch of the previous call (prime() loaded the first one)
+            if self._tape is None:
+                raise ValueError("geometry_ahead: call prime(first_batch) before the first step_graph(next_batch)")
+            if any(a.shape != b.shape for a, b in zip(self._static, src)):
+                raise ValueError("geometry_ahead needs a fixed batch shape")
+            if self._graph is None or get_bn_decay(self.step_count, self.params) != self._graph_bn_decay:
+                if not self.capture(*self._static):
+                    raise _ffi.Pn2Error("geometry_ahead needs graph mode; capture failed: %s" % self._capture_error)
+            inputs = self._next
+        else:
+            if self._graph is None:
+                if staged:
+                    torch.cuda.current_stream(self.device).wait_event(self._staged_event)
                 return self.step(*src)
+            if get_bn_decay(self.step_count, self.params) != self._graph_bn_decay or \
+                    any(a.shape != b.shape for a, b in zip(self._static, src)):
+                if staged:
+                    torch.cuda.current_stream(self.device).wait_event(self._staged_event)
+                if not self.capture(*src):
+                    return self.step(*src)
+            inputs = self._static
         caller = torch.cuda.current_stream(self.device)
         self.stream.wait_stream(caller)
         with torch.cuda.stream(self.stream):
             if staged:
                 self.stream.wait_event(self._staged_event)
-            for dst, s in zip(self._static, src):
+            for dst, s in zip(inputs, src):
                 if dst.data_ptr() != s.data_ptr():
                     dst.copy_(s, non_blocking=True)
             if staged:

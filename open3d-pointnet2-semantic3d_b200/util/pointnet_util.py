@@ -28,6 +28,75 @@ def _pad4(w):
     return (w + 3) // 4 * 4
 
 
+# ---- geometry tape ---------------------------------------------------------------------------------
+# Farthest point sampling, gather_point, ball query, three_nn and the interpolation weights depend on the
+# point coordinates only, never on the weights.  `sampling_geometry` / `interpolation_geometry` are the two
+# places the layers compute them; with a GeometryTape set (`replay_geometry`) the layers take the precomputed
+# tensors from it instead, in call order -- which lets train_step.Trainer run the geometry of the NEXT batch
+# on a second stream next to the dense stage of the current one (model.get_geometry builds the tape).
+class GeometryTape:
+    """Results of the weight-independent ops of one forward pass, in the order the layers ask for them."""
+
+    def __init__(self):
+        self.entries, self.pos = [], 0
+
+    def add(self, kind, key, value):
+        self.entries.append((kind, tuple(key), tuple(value)))
+
+    def tensors(self):
+        return [t for _, _, v in self.entries for t in v]
+
+    def take(self, kind, key):
+        if self.pos == len(self.entries):  # another forward pass over the same batch
+            self.pos = 0
+        k, want, value = self.entries[self.pos]
+        if k != kind or want != tuple(key):
+            raise RuntimeError("geometry tape out of order: the model asked for %s%r where the tape holds %s%r"
+                               % (kind, tuple(key), k, want))
+        self.pos += 1
+        return value
+
+
+_tape = None
+
+
+class replay_geometry:
+    """Context manager: the layers inside take their geometry from ``tape`` (None = compute it)."""
+
+    def __init__(self, tape):
+        self.tape = tape
+
+    def __enter__(self):
+        global _tape
+        self.prev, _tape = _tape, self.tape
+        if self.tape is not None:
+            self.tape.pos = 0
+        return self.tape
+
+    def __exit__(self, *exc):
+        global _tape
+        _tape = self.prev
+        return False
+
+
+def sampling_geometry(npoint, radius, nsample, xyz):
+    """new_xyz (B,npoint,3) and the ball-query neighbour indices (B,npoint,nsample) of an SA layer
+    (pointnet_util.py:39-46)."""
+    if _tape is not None:
+        return _tape.take("sample", (npoint, float(radius), nsample, tuple(xyz.shape)))
+    new_xyz = gather_point(xyz, farthest_point_sample(npoint, xyz))
+    idx, _ = query_ball_point(radius, nsample, xyz, new_xyz)
+    return new_xyz, idx
+
+
+def interpolation_geometry(xyz1, xyz2):
+    """three nearest known points and their normalised inverse-distance weights (pointnet_util.py:299-303)."""
+    if _tape is not None:
+        return _tape.take("interp", (tuple(xyz1.shape), tuple(xyz2.shape)))
+    dist, idx = three_nn(xyz1, xyz2)
+    return idx, fp_weights(dist)
+
+
 class _GroupConcat(torch.autograd.Function):
     """(B,m,ns,3+C) = [xyz[idx]-new_xyz | points[idx]] (xyz_first) or [points | xyz] (MSG)."""
 
@@ -71,11 +140,11 @@ class _GroupConcat(torch.autograd.Function):
 def sample_and_group(npoint, radius, nsample, xyz, points, knn=False, use_xyz=True):
     """pointnet_util.py:18-60.  Returns new_xyz (B,npoint,3), new_points (B,npoint,nsample,3+C)
     with channel order [xyz, features], idx (B,npoint,nsample), grouped_xyz (centred)."""
-    new_xyz = gather_point(xyz, farthest_point_sample(npoint, xyz))
     if knn:
+        new_xyz = gather_point(xyz, farthest_point_sample(npoint, xyz))
         _, idx = knn_point(nsample, xyz, new_xyz)
     else:
-        idx, _ = query_ball_point(radius, nsample, xyz, new_xyz)
+        new_xyz, idx = sampling_geometry(npoint, radius, nsample, xyz)
     if points is not None and use_xyz:
         # one fused pass writes [xyz - centre | features]; grouped_xyz is its first 3 channels
         new_points = _GroupConcat.apply(xyz, new_xyz, points, idx, True, True)
@@ -271,8 +340,7 @@ def pointnet_fp_module(xyz1, xyz2, points1, points2, mlp, is_training, bn_decay,
     -> (B,n1,mlp[-1]);  concat order [interpolated, points1] (:307-309)."""
     training = tf_util._as_bool(is_training)
     with tf_util.variable_scope(scope):
-        dist, idx = three_nn(xyz1, xyz2)
-        weight = fp_weights(dist)
+        idx, weight = interpolation_geometry(xyz1, xyz2)
         x0 = _InterpConcat.apply(points2, points1, idx, weight)
         b, n1, _ = xyz1.shape
         layers = _conv_layers("conv_%d", x0.shape[1], mlp, bn)

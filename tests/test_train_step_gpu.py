@@ -129,28 +129,39 @@ def test_two_training_steps_match_oracle(cuda):
     torch.cuda.synchronize()
 
 
-def _run_steps(mode, batches, seed0=77):
-    """3 steps on a fresh Trainer (same initial weights every time): 'eager' | 'graph' | 'staged'."""
+def _run_steps(mode, batches, seed0=77, hp=None):
+    """len(batches) steps on a fresh Trainer (same initial weights every time): 'eager' | 'graph' | 'staged' |
+    'ahead' | 'ahead_staged'."""
+    hp = hp or HP_SMALL
     import torch
     from pn2_b200.train_step import Trainer
     from pn2_b200.util import tf_util
     from oracle import layers_ref as lr
-    tr = Trainer(HP_SMALL, 9, device="cuda", seed=0, world_size=1)
-    load_oracle_params(tr, lr.init_model_params(HP_SMALL, 9, seed=1))
+    ahead = mode.startswith("ahead")
+    tr = Trainer(hp, 9, device="cuda", seed=0, world_size=1, geometry_ahead=ahead)
+    load_oracle_params(tr, lr.init_model_params(hp, 9, seed=1))
     tf_util.set_dropout_seed(seed0)
     dev = [tuple(to_cuda(x) for x in bt) for bt in batches]
     losses, moving1 = [], None
+    if ahead:
+        tr.prime(*dev[0])
     if mode != "eager":
         assert tr.capture(*dev[0]), tr._capture_error
         assert tr.launches_per_replay > 100
-    if mode == "staged":
+    if mode in ("staged", "ahead_staged"):
         host = [tuple(torch.as_tensor(x).pin_memory() for x in bt) for bt in batches]
-        tr.stage(*host[0])
+        tr.stage(*host[1 if ahead else 0])
     for i in range(len(batches)):
+        nxt = min(i + 1, len(batches) - 1)  # ahead modes: the batch whose geometry step i computes
         if mode == "eager":
             loss = tr.step(*dev[i])
         elif mode == "graph":
             loss = tr.step_graph(*dev[i])
+        elif mode == "ahead":
+            loss = tr.step_graph(*dev[nxt])
+        elif mode == "ahead_staged":
+            loss = tr.step_graph()
+            tr.stage(*host[min(nxt + 1, len(batches) - 1)])
         else:
             loss = tr.step_graph()
             if i + 1 < len(batches):
@@ -197,6 +208,42 @@ def test_graph_replay_matches_eager_steps(cuda):
     # a defect of the kind this test exists for: the same batch replayed (inputs not refreshed) is far outside
     l_stale = [l_a[0]] * 3
     assert max(abs(a - b) for a, b in zip(l_stale, l_a)) > 1e-2
+
+
+def test_geometry_ahead_trains_like_the_plain_graph_steps(cuda):
+    """Trainer(geometry_ahead=True): every replay runs the dense stage of the batch loaded one call earlier and, on
+    a second stream of the same graph, the sampling / neighbour search of the batch handed in.  4 steps on 4
+    different batches must train like 4 plain graph steps.  The learning rate sits at the schedule's floor (1e-5),
+    so the chaotic part of graph-vs-eager above (Adam turning the sign of near-zero gradients into +-lr moves) is
+    100x smaller and the bound can be tight at EVERY step: a dense stage fed with the geometry, the colours, the
+    labels or the dropout mask of the wrong batch moves the loss by > 1e-3 (checked at the end).  The tape left behind must be
+    bit-identical to the geometry of the last batch handed in, and the SM budget of the persistent kernels must be
+    back at the whole device."""
+    import torch
+    import pn2_b200  # noqa: F401
+    from pn2_b200 import _ffi, model
+    hp = dict(HP_SMALL, learning_rate=1e-5)
+    batches = small_batches(4)
+    l_g, mv_g, w_g, _ = _run_steps("graph", batches, hp=hp)
+    l_h, _, w_h, _ = _run_steps("graph", batches, hp=hp)
+    noise = max(abs(a - b) for a, b in zip(l_g, l_h))
+    for mode in ("ahead", "ahead_staged"):
+        l_x, mv_x, w_x, tr = _run_steps(mode, batches, hp=hp)
+        assert tr._graph is not None and tr._capture_error is None
+        print("losses graph %s %s %s (graph-vs-graph noise %.3g)" % (l_g, mode, l_x, noise))
+        assert abs(l_x[0] - l_g[0]) < 2e-6, (mode, l_x, l_g)
+        for k in mv_g:
+            np.testing.assert_allclose(mv_x[k], mv_g[k], rtol=1e-6, atol=1e-7, err_msg="%s %s" % (mode, k))
+        assert max(abs(a - b) for a, b in zip(l_x, l_g)) <= 1e-4, (mode, l_x, l_g, noise)
+        dw = max(float(np.abs(w_x[k] - w_g[k]).max()) for k in w_g if "moving" not in k)
+        assert dw <= 1e-4, (mode, dw)  # 4 steps x (at most ~2 lr per sign flip)
+        fresh = model.get_geometry(to_cuda(batches[-1][0]), hp)
+        assert len(fresh.tensors()) == len(tr._tape.tensors()) == 16
+        for a, b in zip(tr._tape.tensors(), fresh.tensors()):
+            assert a.dtype == b.dtype and torch.equal(a, b)
+        assert _ffi.lib().pn2_get_sm_budget() == torch.cuda.get_device_properties(0).multi_processor_count
+    # the batches differ enough for a mix-up to show: every pair of step losses is >= 10x the bound apart
+    assert min(abs(a - b) for i, a in enumerate(l_g) for b in l_g[i + 1:]) > 1e-3, l_g
 
 
 def test_eager_step_after_capture_draws_fresh_dropout_masks(cuda):

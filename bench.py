@@ -492,6 +492,7 @@ def run_ours(args):
     trainer.timing = {}
     torch.cuda.synchronize()
     psteps = min(args.steps, 3)
+    side_sms, trainer.wgrad_sms = trainer.wgrad_sms, 0  # every kernel alone on the device: no overlapped streams
     for _ in range(psteps):
         flush.zero_()
         # keep the launch queue backlogged (a ~25 ms spin kernel first): the events around every
@@ -499,6 +500,7 @@ def run_ours(args):
         torch.cuda._sleep(50_000_000)
         trainer.step(d_pc, d_lab, d_w)
     torch.cuda.synchronize()
+    trainer.wgrad_sms = side_sms
     barrier()
     if rank == 0:
         agg = {}
@@ -615,6 +617,7 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": workload_name(b, n), "global_batch": b * world,
                        "parallelism": "dp%d" % world, "cuda_graph": bool(use_graph),
+                       "wgrad_stream_sms": trainer.wgrad_sms,
                        "geometry_ahead": ("every replay = dense stage of the current batch + sampling / neighbour "
                                           "search of the next batch on a second stream of the same graph; K steps "
                                           "run K of each") if (ahead and use_graph) else False,

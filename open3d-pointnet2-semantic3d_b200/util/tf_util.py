@@ -301,6 +301,26 @@ class _ZeroArena:
 
 zero_arena = _ZeroArena()
 
+
+# ---- weight gradients on a second stream -------------------------------------------------------------------
+# In the backward pass of a shared-MLP chain the weight gradient of a layer (dW = A^T dY) and everything else
+# (dX = dY W^T, then the BatchNorm backward of the layer below) are independent once dY exists.  With a side
+# stream set here, the chains issue every pn2_linear_wgrad on it (ordered behind the kernel that produced dY by an
+# event) with the persistent kernel sized for `wgrad_sms` SMs, and the input-gradient GEMMs for the rest of the
+# device, so the tensor-core wgrad runs next to the HBM-bound BatchNorm kernels of the main chain instead of
+# after them.  The owner (train_step.Trainer) joins the side stream before the gradients are consumed.
+_wgrad_side = [None, 0]
+
+
+def set_wgrad_stream(stream, wgrad_sms=0):
+    """stream: torch.cuda.Stream for the weight-gradient launches (None = same stream as everything else)."""
+    _wgrad_side[0], _wgrad_side[1] = stream, int(wgrad_sms)
+
+
+def _sm_budget(sms):
+    from .. import _ffi
+    _ffi.lib().pn2_set_sm_budget(int(sms))
+
 # Test hook: a dict here makes every shared-MLP chain record its ReLU masks ("<scope>/relu_mask", uint8
 # (M,N)) and max-pool winners ("<scope>/argmax", int32 (G,N)).  The fp64 oracle then differentiates the
 # SAME piecewise-linear function (an element whose pre-activation is within fp32 rounding of zero may
@@ -495,9 +515,29 @@ class _MLPChain(torch.autograd.Function):
             # fp32 rounding noise of an M-term sum.
             db = None if L.bn else ptr(L.b.ensure_grad(), F32)
             L.b.ensure_grad()
-            call("pn2_linear_wgrad", M, L.k, N, a_ptr, lda, ptr(a_sc, F32, True),
-                 ptr(a_sh, F32, True), a_relu, ptr(dY, F32), ptr(L.w.ensure_grad(), F32),
-                 db, ctx.gemm_mode)
+            dw = ptr(L.w.ensure_grad(), F32)
+            side, side_sms = _wgrad_side
+            if side is None:
+                call("pn2_linear_wgrad", M, L.k, N, a_ptr, lda, ptr(a_sc, F32, True),
+                     ptr(a_sh, F32, True), a_relu, ptr(dY, F32), dw, db, ctx.gemm_mode)
+            else:
+                main = torch.cuda.current_stream(dev)
+                side.wait_stream(main)  # dY (and, first time round, the zeroed gradient buffer) is complete
+                total = torch.cuda.get_device_properties(dev).multi_processor_count
+                # the first layer of a chain whose input needs no gradient ends the backward pass (SA1): nothing runs
+                # next to its weight gradient, so it gets the whole device
+                last = i == 0 and not ctx.needs_input_grad[0] and _os.environ.get("PN2_WGRAD_TAIL_FULL", "1") != "0"
+                with torch.cuda.stream(side):
+                    _sm_budget(0 if last else side_sms)
+                    try:
+                        call("pn2_linear_wgrad", M, L.k, N, a_ptr, lda, ptr(a_sc, F32, True),
+                             ptr(a_sh, F32, True), a_relu, ptr(dY, F32), dw, db, ctx.gemm_mode)
+                    finally:
+                        _sm_budget(total - side_sms if 0 < side_sms < total else 0)
+                # buffers of this pass that the side stream reads after this function has dropped them
+                for t in (dY, x if i == 0 else Ys[i - 1], a_sc, a_sh):
+                    if t is not None:
+                        t.record_stream(side)
             if i > 0 or ctx.needs_input_grad[0]:
                 dX = torch.empty((M, L.k), dtype=F32, device=dev)
                 k0, k1 = (0, L.k) if (i > 0 or ctx.dx_cols is None) else ctx.dx_cols
@@ -523,6 +563,8 @@ class _MLPChain(torch.autograd.Function):
             else:
                 up = None
         ctx.Ys = ctx.x = None
+        if _wgrad_side[0] is not None:
+            _sm_budget(0)
         return up, None, None, None, None, None, None, None
 
 

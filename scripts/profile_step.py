@@ -11,7 +11,7 @@ b = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 pc, labels, smpw = bench.make_batch(b, 8192, 100)
 dev = torch.device("cuda", 0)
 d_pc, d_lab, d_w = (torch.as_tensor(x).to(dev) for x in (pc, labels, smpw))
-tr = Trainer(bench.HP, bench.NUM_CLASS, device=dev, seed=0, world_size=1)
+tr = Trainer(bench.HP, bench.NUM_CLASS, device=dev, seed=0, world_size=1, wgrad_sms=0)  # every kernel at its full grid
 for _ in range(3):
     tr.step(d_pc, d_lab, d_w)
 torch.cuda.synchronize()

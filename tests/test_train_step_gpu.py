@@ -129,7 +129,7 @@ def test_two_training_steps_match_oracle(cuda):
     torch.cuda.synchronize()
 
 
-def _run_steps(mode, batches, seed0=77, hp=None):
+def _run_steps(mode, batches, seed0=77, hp=None, **trainer_kw):
     """len(batches) steps on a fresh Trainer (same initial weights every time): 'eager' | 'graph' | 'staged' |
     'ahead' | 'ahead_staged'."""
     hp = hp or HP_SMALL
@@ -138,7 +138,7 @@ def _run_steps(mode, batches, seed0=77, hp=None):
     from pn2_b200.util import tf_util
     from oracle import layers_ref as lr
     ahead = mode.startswith("ahead")
-    tr = Trainer(hp, 9, device="cuda", seed=0, world_size=1, geometry_ahead=ahead)
+    tr = Trainer(hp, 9, device="cuda", seed=0, world_size=1, geometry_ahead=ahead, **trainer_kw)
     load_oracle_params(tr, lr.init_model_params(hp, 9, seed=1))
     tf_util.set_dropout_seed(seed0)
     dev = [tuple(to_cuda(x) for x in bt) for bt in batches]
@@ -244,6 +244,26 @@ def test_geometry_ahead_trains_like_the_plain_graph_steps(cuda):
         assert _ffi.lib().pn2_get_sm_budget() == torch.cuda.get_device_properties(0).multi_processor_count
     # the batches differ enough for a mix-up to show: every pair of step losses is >= 10x the bound apart
     assert min(abs(a - b) for i, a in enumerate(l_g) for b in l_g[i + 1:]) > 1e-3, l_g
+
+
+def test_weight_gradients_on_a_second_stream_train_alike(cuda):
+    """Trainer(wgrad_sms=k): every pn2_linear_wgrad of the backward pass runs on a second stream (k SMs for its
+    persistent kernel) next to the input-gradient / BatchNorm-backward chain.  Same gradients, so 4 steps at the
+    learning-rate floor must match the single-stream trainer at every step -- eagerly, by graph replay, and combined
+    with the geometry-ahead mode; a weight gradient read before it is complete (a missing join) or computed from a
+    recycled buffer would move the weights and with them the next losses."""
+    import pn2_b200  # noqa: F401
+    hp = dict(HP_SMALL, learning_rate=1e-5)
+    batches = small_batches(4)
+    l_g, mv_g, w_g, _ = _run_steps("graph", batches, hp=hp, wgrad_sms=0)
+    for mode in ("eager", "graph", "ahead"):
+        l_x, mv_x, w_x, tr = _run_steps(mode, batches, hp=hp, wgrad_sms=48)
+        assert tr.wgrad_sms == 48 and tr._wstream is not None
+        print("losses single-stream %s, wgrad stream (%s) %s" % (l_g, mode, l_x))
+        assert max(abs(a - b) for a, b in zip(l_x, l_g)) <= 1e-4, (mode, l_x, l_g)
+        assert abs(l_x[0] - l_g[0]) < 2e-6, (mode, l_x, l_g)
+        dw = max(float(np.abs(w_x[k] - w_g[k]).max()) for k in w_g if "moving" not in k)
+        assert dw <= 1e-4, (mode, dw)
 
 
 def test_eager_step_after_capture_draws_fresh_dropout_masks(cuda):

@@ -2,7 +2,7 @@
 (SURVEY.md section 5).  Sizes are small (the sanitizer slows kernels 10-100x) but cover every dispatch branch:
   FPS reg / pruned / cluster(handshake), ball query resident / stream / grid, gathers + grads, 3-NN, interpolation,
   fused kNN + selection sort, tcgen05 forward / dgrad / wgrad (wide, narrow alt-epilogue, K > 512), BN kernels,
-  poolings, loss, dropout, Adam, box sampling, label vote, prob_sample."""
+  poolings, loss, dropout, Adam, box sampling, label vote, prob_sample, the Trainer with its side streams."""
 import os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -73,6 +73,12 @@ if section("layers"):
         out = pu.pointnet_fp_module(xyz, nx, pts, f, [32, 16], True, 0.5, "fp_" + pooling)
         pred = tf_util.conv1d(tf_util.dropout(out, True, "dp"), 9, 1, scope="fc_" + pooling, activation_fn=None)
         model.get_loss(pred, cu(rs.randint(0, 9, (2, 512)).astype(np.int32)), cu(np.ones((2, 512), np.float32))).backward()
+    # channel counts that are multiples of 4: the float4 paths of group_concat (forward and gradient), copy_cols and
+    # three_interpolate_grad
+    nx1, f1, _ = pu.pointnet_sa_module(xyz, pts, 64, 0.3, 16, [16, 32], None, False, True, 0.5, "v4_sa1")
+    nx2, f2, _ = pu.pointnet_sa_module(nx1, f1, 16, 0.6, 8, [32, 64], None, False, True, 0.5, "v4_sa2")
+    up = pu.pointnet_fp_module(nx1, nx2, f1, f2, [32, 32], True, 0.5, "v4_fp1")
+    tf_util.dropout(up, True, "v4_dp").sum().backward()
     n = 1000
     p_, g_, m_, v_ = (torch.randn(n, device=dev) for _ in range(4)); v_.abs_()
     call("pn2_adam_step", n, ptr(p_), ptr(g_), ptr(m_), ptr(v_), 1e-3, 0.9, 0.999, 1e-8, 3, 1.0)
@@ -81,5 +87,21 @@ if section("feed"):
     fd = SemanticFileData(pts, rs.randint(0, 9, 30000), rs.random_sample((30000, 3)), 10.0, 10.0)
     fd.sample_batch(3, 2048, rng=np.random.RandomState(1), augment=True, seed=5)
     fd.sample_batch(2, 8192, rng=np.random.RandomState(2), seed=6)
+if section("trainer"):
+    # the training step with its side streams: weight gradients on a second stream, geometry one batch ahead inside the
+    # captured graph, programmatic dependent launch on every kernel
+    from pn2_b200.train_step import Trainer
+    hp = {"use_color": 1, "batch_size": 2, "learning_rate": 0.001, "decay_step": 200000, "learning_rate_decay_rate": 0.7,
+          "bn_init_decay": 0.5, "bn_decay_decay_rate": 0.5, "bn_decay_clip": 0.99,
+          "l1_npoint": 128, "l1_radius": 0.2, "l1_nsample": 16, "l2_npoint": 64, "l2_radius": 0.4, "l2_nsample": 16,
+          "l3_npoint": 16, "l3_radius": 0.8, "l3_nsample": 16, "l4_npoint": 8, "l4_radius": 1.2, "l4_nsample": 8}
+    bt = [(cu(rs.random_sample((2, 512, 6)).astype(np.float32)), cu(rs.randint(0, 9, (2, 512)).astype(np.int32)),
+           cu(np.ones((2, 512), np.float32))) for _ in range(2)]
+    tr = Trainer(hp, 9, device=dev, seed=0, geometry_ahead=True, wgrad_sms=48)
+    tr.step(*bt[0])
+    tr.prime(*bt[0])
+    assert tr.capture(*bt[0]), tr._capture_error
+    tr.step_graph(*bt[1])
+    tr.step_graph(*bt[0])
 torch.cuda.synchronize()
 print("SANITIZE_RUN_OK")

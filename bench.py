@@ -330,7 +330,7 @@ def config1_row(dev, reps=30):
     return row
 
 
-def cfeat6_line(dev, b, n, steps, warmup, flush):
+def cfeat6_line(dev, b, n, steps, warmup, flush, ahead=True):
     """the same SSG step with BASELINE.json's "(3+6)" wording -- 6 feature channels next to
     xyz (SA1 K = 9, FP4 K = 134) instead of semantic.json's 3; device-resident inputs, graph replay."""
     import torch
@@ -342,7 +342,7 @@ def cfeat6_line(dev, b, n, steps, warmup, flush):
     labels = rs.randint(1, 9, (b, n)).astype(np.int32)
     smpw = np.ones((b, n), np.float32)
     d = [torch.as_tensor(x).to(dev) for x in (pc, labels, smpw)]
-    tr = Trainer(hp, NUM_CLASS, device=dev, seed=0, world_size=1)
+    tr = Trainer(hp, NUM_CLASS, device=dev, seed=0, world_size=1, geometry_ahead=ahead)  # same mode as the headline
     tr.step(*d)
     graph = tr.capture(*d)
     fn = tr.step_graph if graph else tr.step
@@ -358,7 +358,8 @@ def cfeat6_line(dev, b, n, steps, warmup, flush):
     torch.cuda.synchronize()
     ms = sum(a.elapsed_time(bb) for a, bb in ev) / steps
     return {"workload": "ssg_train_step_B%d_N%d_xyz3+feat6 (BASELINE.json wording)" % (b, n),
-            "ms_per_step": ms, "value": b * n / (ms * 1e-3), "unit": UNIT, "cuda_graph": bool(graph)}
+            "ms_per_step": ms, "value": b * n / (ms * 1e-3), "unit": UNIT, "cuda_graph": bool(graph),
+            "geometry_ahead": bool(ahead and graph)}
 
 
 def fused_chain_bytes(b):
@@ -605,7 +606,7 @@ def run_ours(args):
         except Exception as e:  # noqa: BLE001
             cfg1 = {"error": repr(e)[:300]}
         try:
-            cf6 = cfeat6_line(dev, b, n, min(args.steps, 10), args.warmup, flush)
+            cf6 = cfeat6_line(dev, b, n, min(args.steps, 10), args.warmup, flush, ahead=ahead)
         except Exception as e:  # noqa: BLE001
             cf6 = {"error": repr(e)[:300]}
 

@@ -43,6 +43,9 @@ HP = {  # semantic.json (reference), verbatim values
 }
 
 
+NBATCH = 4  # distinct batches the timed loops rotate through
+
+
 def make_batch(b, n, seed):
     """xyz uniform in a 10 x 10 x 5 box centred like _center_box
     (semantic_dataset.py:109-121), colours U[0,1), labels 1..8, weights 1."""
@@ -406,8 +409,12 @@ def run_ours(args):
                                 timeout=datetime.timedelta(seconds=180))
     dev = torch.device("cuda", local)
     b, n = args.batch, args.npoint
-    pc, labels, smpw = make_batch(b, n, 100 + rank)
-    d_pc, d_lab, d_w = (torch.as_tensor(x).to(dev) for x in (pc, labels, smpw))
+    # NBATCH distinct synthetic batches, rotated step by step (resident in HBM for `value`, in pinned host memory for
+    # `e2e`): every step samples, groups and trains on data the previous step has not seen
+    host_batches = [make_batch(b, n, 100 + rank + 1000 * j) for j in range(NBATCH)]
+    pc, labels, smpw = host_batches[0]
+    dev_batches = [tuple(torch.as_tensor(x).to(dev) for x in hb) for hb in host_batches]
+    d_pc, d_lab, d_w = dev_batches[0]
     ahead = not (args.no_ahead or args.no_graph)
     trainer = Trainer(HP, NUM_CLASS, device=dev, seed=0, world_size=world, geometry_ahead=ahead)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
@@ -426,8 +433,8 @@ def run_ours(args):
               file=sys.stderr)
     step_fn = trainer.step_graph if use_graph else trainer.step
     launches_per_step = None
-    for _ in range(max(args.warmup, 3)):
-        step_fn(d_pc, d_lab, d_w)
+    for i in range(max(args.warmup, 3)):
+        step_fn(*dev_batches[i % NBATCH])
     barrier()
 
     # ---- device-resident timing ---------------------------------------------------------
@@ -439,7 +446,7 @@ def run_ours(args):
     for i in range(args.steps):
         flush.zero_()
         ev[i][0].record()
-        step_fn(d_pc, d_lab, d_w)
+        step_fn(*dev_batches[i % NBATCH])
         ev[i][1].record()
     barrier()
     calls = _ffi.launches - calls0
@@ -458,7 +465,8 @@ def run_ours(args):
     # stream, Trainer.step_graph() consumes it (double-buffered input feed, like the reference's prefetch
     # queue, train.py:134-196).  Every timed step contains exactly one H2D copy of a full batch and one D2H
     # read of the loss; the same 256 MB L2 flush as above runs between steps, outside the events.
-    h_pc, h_lab, h_w = (torch.as_tensor(x).pin_memory() for x in (pc, labels, smpw))
+    pinned = [tuple(torch.as_tensor(x).pin_memory() for x in hb) for hb in host_batches]
+    h_pc, h_lab, h_w = pinned[0]
     h_loss = torch.empty((), dtype=torch.float32).pin_memory()
     ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
            for _ in range(args.steps)]
@@ -472,9 +480,9 @@ def run_ours(args):
         ev2[i][0].record()
         if use_graph:
             loss = trainer.step_graph()               # consumes the staged batch
-            trainer.stage(h_pc, h_lab, h_w)           # H2D of the next batch overlaps this step
+            trainer.stage(*pinned[(i + 1) % NBATCH])  # H2D of the next batch overlaps this step
         else:
-            loss = trainer.step(h_pc, h_lab, h_w)     # eager: H2D on the replica's stream
+            loss = trainer.step(*pinned[i % NBATCH])  # eager: H2D on the replica's stream
         h_loss.copy_(loss, non_blocking=True)         # device -> host read of the step's result
         ev2[i][1].record()
         ev2[i][1].synchronize()
@@ -619,6 +627,8 @@ def run_ours(args):
             "config": {"workload": workload_name(b, n), "global_batch": b * world,
                        "parallelism": "dp%d" % world, "cuda_graph": bool(use_graph),
                        "wgrad_stream_sms": trainer.wgrad_sms,
+                       "batches": "%d distinct synthetic batches rotated step by step (resident in HBM for value, "
+                                  "pinned host memory for e2e)" % NBATCH,
                        "geometry_ahead": ("every replay = dense stage of the current batch + sampling / neighbour "
                                           "search of the next batch on a second stream of the same graph; K steps "
                                           "run K of each") if (ahead and use_graph) else False,

@@ -293,6 +293,10 @@ __global__ void __launch_bounds__(THREADS, 1)
     tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmY,
                    const Params p) {
     pdl_trigger();
+    if (threadIdx.x == 0) {  // the descriptors are kernel parameters: fetched while the previous kernel drains
+        if (p.a_tma) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        if (p.y_tma) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmY) : "memory");
+    }
     extern __shared__ __align__(1024) unsigned char smem[];
     // carve:  [resident B: KC x (B_hi | B_lo)]            (p.b_res: weights loaded once per CTA)
     //         stages x [A_hi 16K | A_lo 16K (| B_hi | B_lo when B is streamed per chunk)]
@@ -354,8 +358,6 @@ __global__ void __launch_bounds__(THREADS, 1)
     // barrier init and TMEM allocation above overlap the tail of the previous kernel; nothing before this line
     // touches global memory (the tensor maps are kernel parameters)
     pdl_wait();
-    if (threadIdx.x < 128)
-        sbias[threadIdx.x] = (p.bias && (int)threadIdx.x < Nv) ? __ldg(p.bias + n0 + threadIdx.x) : 0.f;
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -596,6 +598,11 @@ __global__ void __launch_bounds__(THREADS, 1)
         const int q4 = warp & 3, wg = warp >> 2;
         unsigned char *buf = epi_b + warp * 4096;
         const int nblk = (Nv + 31) / 32;
+        // the bias vector is the epilogue's business alone: loaded here, behind a barrier of the epilogue warps only,
+        // so that the loader / transform / MMA roles do not sit out a global-load round trip at kernel start
+        if (threadIdx.x < 128)
+            sbias[threadIdx.x] = (p.bias && (int)threadIdx.x < Nv) ? __ldg(p.bias + n0 + threadIdx.x) : 0.f;
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * W_EPI) : "memory");
         // BatchNorm statistics: per lane-column fp64 sums of (y - c) and (y - c)^2 with a constant
         // shift c (the first value this lane sees in the column) so that neither the fp32 partial
         // sums over 32 rows nor the final variance suffer cancellation; un-shifted once at the end.
@@ -1015,6 +1022,10 @@ __global__ void __launch_bounds__(W_THREADS, 1)
     tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG,
                     const WParams p) {
     pdl_trigger();
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmG) : "memory");
+    }
     extern __shared__ __align__(1024) unsigned char smem[];
     // carve: W_STAGES x [X_hi | X_lo | G_hi | G_lo], W_RAW x [X raw | G raw], barriers
     const uint32_t a_bytes = (uint32_t)p.rows * p.MG * 128;

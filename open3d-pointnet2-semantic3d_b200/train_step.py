@@ -133,7 +133,17 @@ class Trainer:
         # a fresh autograd anchor per pass: no leaf (or its gradient accumulator) outlives the pass
         self.store.anchor = torch.zeros(1, device=self.device, requires_grad=True)
         tf_util.zero_arena.reset(self.device)  # one memset for every layer's fp64 accumulators
-        self.store.prepare_images()            # one launch: every layer's 3xTF32 weight images
+        if self._wstream is not None and os.environ.get("PN2_PREP_SIDE", "1") != "0":
+            # one launch: every layer's 3xTF32 weight images -- on the side stream, the first GEMM waits for it
+            # (the main stream meanwhile gathers and centres SA1's groups)
+            self._wstream.wait_stream(self.stream)
+            with torch.cuda.stream(self._wstream):
+                self.store.prepare_images()
+                ev = torch.cuda.Event()
+                ev.record(self._wstream)
+            tf_util.set_images_event(ev)
+        else:
+            self.store.prepare_images()
         nxt = None
         if ahead is not None:
             self._side.wait_stream(self.stream)  # fork
@@ -160,6 +170,7 @@ class Trainer:
                         self.stream.wait_stream(self._wstream)  # join: every weight gradient is complete
         finally:
             self._sm_budget(0)
+            tf_util.set_images_event(None)
             tf_util.zero_arena.disarm()
             tf_util.set_dropout_seed_device(None)
             self.store.images_fresh = False  # the optimizer step that follows changes the weights

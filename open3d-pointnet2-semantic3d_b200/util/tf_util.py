@@ -317,6 +317,15 @@ def set_wgrad_stream(stream, wgrad_sms=0):
     _wgrad_side[0], _wgrad_side[1] = stream, int(wgrad_sms)
 
 
+# Event the first GEMM of a pass has to wait for (the weight images of the step, prepared on a side stream while
+# the main stream already gathers the first layer's input); consumed by the first shared-MLP chain that runs.
+_images_event = [None]
+
+
+def set_images_event(ev):
+    _images_event[0] = ev
+
+
 def _sm_budget(sms):
     from .. import _ffi
     _ffi.lib().pn2_set_sm_budget(int(sms))
@@ -388,6 +397,9 @@ class _MLPChain(torch.autograd.Function):
     def forward(ctx, x, anchor, layers, is_training, bn_decay, pool_ns, gemm_mode, dx_cols=None):
         M, K0 = x.shape
         dev = x.device
+        if _images_event[0] is not None:
+            torch.cuda.current_stream(dev).wait_event(_images_event[0])
+            _images_event[0] = None
         # rows may be padded (a column slice of a wider buffer: the SA/FP concat buffers are
         # allocated with a 16-byte aligned row pitch for the TMA tensor maps)
         if not (x.stride(1) == 1 and x.stride(0) >= K0):

@@ -260,7 +260,9 @@ class Trainer:
         (bn_decay) trigger a re-capture when they change.  The warm-up passes and the validation
         replay leave no trace: moving statistics are frozen / restored, the dropout counter is not
         advanced, no optimizer step is taken.  Returns False (eager mode stays) if capture fails;
-        the reason is kept, untruncated, in ``self._capture_error``."""
+        the reason is kept, untruncated, in ``self._capture_error``.  In geometry_ahead mode the graph is
+        captured around the batch loaded by ``prime()`` (the arguments prime the pipeline if it is empty and are
+        otherwise ignored): the pipeline state survives a re-capture."""
         self._graph = None
         self._capture_error = None
         caller = torch.cuda.current_stream(self.device)

@@ -739,6 +739,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    pdl_trigger_late();  // all tiles of this CTA are done: what follows is the TMEM release and the statistics finalize
     if (warp == W_MMA) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
@@ -1319,6 +1320,7 @@ __global__ void __launch_bounds__(W_THREADS, 1)
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    pdl_trigger_late();
     if (warp == W_WMMA) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),

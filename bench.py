@@ -639,7 +639,10 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 4, "last_loss": last,
                     "feed": "Trainer.stage(pinned host batch) + Trainer.step_graph(): one H2D batch copy and one "
-                            "D2H loss read per step, the copy of batch i+1 overlaps step i"},
+                            "D2H loss read per step, the copy of batch i+1 overlaps step i" +
+                            ("; geometry-ahead: the batch copied in during step i is sampled / grouped by step i+1's "
+                             "replay and trained on by step i+2's, the loss read is that of the batch trained on"
+                             if (ahead and use_graph) else "")},
             "gpu_launches": calls,
             "roofline": roofline, "cpu_baseline": cpu, "breakdown_ms_per_step": breakdown,
             "collective": collective, "config1": cfg1, "cfeat6": cf6, "linear_calls": linear_table,

@@ -102,6 +102,10 @@ class Trainer:
         # geometry one batch ahead: the tape the dense stage of the current batch consumes, the inputs of the
         # batch whose geometry is computed meanwhile, the stream that computes it
         self._tape = self._next = None
+        # SMs the forward GEMMs leave free in a pass WITHOUT a geometry stream (0 = none).  A test hook: the fp32
+        # partial sums of the BatchNorm statistics depend on which tiles a CTA owns, i.e. on the grid size, so a
+        # single-stream reference for the geometry-ahead mode has to run its forward GEMMs on the same grid
+        self.forward_reserve = 0
         # SMs the weight-gradient GEMMs get on their own stream during the backward pass (0 = same stream as the
         # rest).  64 of 148 measured best at B=16 x 8192 (3.52 -> 3.30 ms per step; 48: 3.35, 80: 3.36, a stream
         # priority for the main chain changed nothing)
@@ -151,7 +155,7 @@ class Trainer:
                 nxt = model.get_geometry(ahead[0], self.params)
         try:
             with pointnet_util.replay_geometry(self._tape if ahead is not None else None):
-                self._sm_budget(point_cloud.shape[0] if ahead is not None else 0)
+                self._sm_budget(point_cloud.shape[0] if ahead is not None else self.forward_reserve)
                 try:
                     pred, _ = model.get_model(point_cloud, True, self.num_class, self.params, bn_decay=bn_decay)
                 finally:
@@ -185,7 +189,7 @@ class Trainer:
 
     def _sm_budget(self, reserve):
         """Leave ``reserve`` SMs (one per cloud: the FPS kernel runs one CTA per cloud) to the geometry stream."""
-        if not self.geometry_ahead:
+        if not self.geometry_ahead and not self.forward_reserve:
             return
         if reserve:
             reserve = int(os.environ.get("PN2_AHEAD_RESERVE", min(int(reserve), 32)))

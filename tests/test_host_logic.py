@@ -279,3 +279,65 @@ def test_every_kernel_waits_for_its_predecessor():
                 assert idiom not in before, "%s: %s before the dependency wait" % (os.path.basename(path), idiom)
             kernels += 1
     assert kernels >= 60
+
+
+def test_geometry_tape_records_and_replays_in_model_order(monkeypatch):
+    """model.get_geometry runs the weight-independent ops of get_model (FPS, gather, ball query per SA layer; 3-NN and
+    weights per FP layer) in the model's order and files the results in a GeometryTape; under replay_geometry the
+    layers' two geometry hooks hand the stored tensors back WITHOUT launching anything, insist on the recorded order and
+    arguments, and compute again inside replay_geometry(None).  Device ops faked on the CPU."""
+    import torch
+    import pn2_b200  # noqa: F401
+    from pn2_b200 import model
+    from pn2_b200.util import pointnet_util as pu
+    calls = []
+
+    def fps(npoint, xyz):
+        calls.append(("fps", npoint, tuple(xyz.shape)))
+        return torch.zeros(xyz.shape[0], npoint, dtype=torch.int32)
+
+    def gather(xyz, idx):
+        calls.append(("gather", tuple(xyz.shape), tuple(idx.shape)))
+        return torch.full((xyz.shape[0], idx.shape[1], 3), float(len(calls)))
+
+    def ball(radius, nsample, xyz, new_xyz):
+        calls.append(("ball", radius, nsample, tuple(xyz.shape), tuple(new_xyz.shape)))
+        return torch.full((xyz.shape[0], new_xyz.shape[1], nsample), len(calls), dtype=torch.int32), None
+
+    def three_nn(xyz1, xyz2):
+        calls.append(("three_nn", tuple(xyz1.shape), tuple(xyz2.shape)))
+        return torch.ones(xyz1.shape[0], xyz1.shape[1], 3), torch.full((xyz1.shape[0], xyz1.shape[1], 3), len(calls), dtype=torch.int32)
+
+    def weights(dist):
+        calls.append(("weights", tuple(dist.shape)))
+        return dist / 3
+
+    for name, fn in (("farthest_point_sample", fps), ("gather_point", gather), ("query_ball_point", ball),
+                     ("three_nn", three_nn), ("fp_weights", weights)):
+        monkeypatch.setattr(pu, name, fn)
+    hp = {"use_color": 1, "l1_npoint": 32, "l1_radius": 0.5, "l1_nsample": 8, "l2_npoint": 16, "l2_radius": 1.0,
+          "l2_nsample": 8, "l3_npoint": 8, "l3_radius": 2.0, "l3_nsample": 4, "l4_npoint": 4, "l4_radius": 4.0,
+          "l4_nsample": 4}
+    pc = torch.rand(2, 64, 6)
+    tape = model.get_geometry(pc, hp)
+    assert [c[0] for c in calls] == ["fps", "gather", "ball"] * 4 + ["three_nn", "weights"] * 4
+    assert [c[1] for c in calls if c[0] == "fps"] == [32, 16, 8, 4]
+    assert [c for c in calls if c[0] == "three_nn"] == [("three_nn", (2, 8, 3), (2, 4, 3)), ("three_nn", (2, 16, 3), (2, 8, 3)),
+                                                         ("three_nn", (2, 32, 3), (2, 16, 3)), ("three_nn", (2, 64, 3), (2, 32, 3))]
+    assert [k for k, _, _ in tape.entries] == ["sample"] * 4 + ["interp"] * 4 and len(tape.tensors()) == 16
+    n = len(calls)
+    xyz = pc[:, :, :3].contiguous()
+    with pu.replay_geometry(tape):
+        new_xyz, idx = pu.sampling_geometry(32, 0.5, 8, xyz)
+        assert new_xyz is tape.entries[0][2][0] and idx is tape.entries[0][2][1] and len(calls) == n  # nothing launched
+        with pu.replay_geometry(None):   # e.g. get_geometry of the next batch while a tape is installed
+            pu.sampling_geometry(32, 0.5, 8, xyz)
+        assert len(calls) == n + 3
+        with pytest.raises(RuntimeError, match="out of order"):
+            pu.interpolation_geometry(xyz, new_xyz)          # the tape holds layer 2's sampling next
+        tape.pos = 1
+        with pytest.raises(RuntimeError, match="out of order"):
+            pu.sampling_geometry(16, 1.0, 8, xyz)            # right op, wrong input shape
+    assert pu._tape is None
+    pu.sampling_geometry(32, 0.5, 8, xyz)                    # no tape: computed in place
+    assert len(calls) == n + 6

@@ -419,3 +419,29 @@ def test_full_size_geometry_ahead_replay_equals_the_plain_pass(cuda):
         assert torch.equal(a, b)
     for a, b in zip(tr._static, B):                               # the inputs moved up as well
         assert torch.equal(a, b)
+
+
+def test_weight_gradient_stream_gives_the_same_gradient(cuda):
+    """The gradient itself (not its effect through Adam, which at the learning-rate floor hides everything but the
+    sign): one eager forward_backward with the weight gradients on their own stream (48 SMs; the whole device) against
+    the single-stream pass on the same weights, batch and dropout mask.  The forward GEMMs run on the full grid in both,
+    so the activations are bit-identical and only the summation order of the weight gradients differs."""
+    import pn2_b200  # noqa: F401
+    from pn2_b200.train_step import Trainer
+    (pc, labels, smpw), = small_batches(1, b=4, n=2048)
+    d = tuple(to_cuda(x) for x in (pc, labels, smpw))
+    ref = Trainer(HP_SMALL, 9, device="cuda", seed=0, world_size=1, wgrad_sms=0)
+    ref._seed_dev.add_(1)
+    l0 = float(ref.forward_backward(*d).item())
+    g0 = ref.grads.clone()
+    ref.forward_backward(*d)
+    noise, gmax = float((ref.grads - g0).abs().max()), float(g0.abs().max())
+    assert gmax > 0 and noise < 1e-4 * gmax
+    for sms in (48, 148):
+        tr = Trainer(HP_SMALL, 9, device="cuda", seed=0, world_size=1, wgrad_sms=sms)
+        assert tr._wstream is not None
+        tr._seed_dev.add_(1)
+        l1 = float(tr.forward_backward(*d).item())
+        dg = float((tr.grads - g0).abs().max())
+        assert abs(l1 - l0) < 2e-6 * max(1.0, abs(l0)), (sms, l1, l0)
+        assert dg <= 4 * noise + 1e-5 * gmax, (sms, dg, noise, gmax)
